@@ -1,0 +1,304 @@
+"""Pins the CPU oracle against golden vectors dumped from the reference's own code
+(tests/golden/tier0/make_golden.py) and against known answers in the reference's unit tests."""
+import numpy as np
+import pytest
+
+from oracle import acs, atmosphere, balloon, constants as C, env as env_lib, geometry, opensimplex4
+from oracle import safety, solar, stable_init, thermal, wind
+from tests import golden_io
+from tests.golden import fields as golden_fields
+
+KAT = golden_io.load_kat()
+TRAJ = golden_io.load_traj()
+FF, IF = KAT['float_fields'], KAT['int_fields']
+RTOL = 1e-12
+
+
+def close(a, b, rtol=RTOL, atol=0.0):
+  np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
+
+
+# ---------------------------------------------------------------- atmosphere
+
+def test_atmosphere_tables_and_lookups():
+  for row in KAT['atmosphere']:
+    atm = atmosphere.Atmosphere([row['alpha']])
+    close(atm.lapse[0], row['lapse']); close(atm.t_tr[0], row['t_tr']); close(atm.p_tr[0], row['p_tr'])
+    for p, h, t, rho in row['at_pressure']:
+      hh, tt = atm.at_pressure(np.array([p]))
+      close(hh[0], h, atol=1e-9); close(tt[0], t)
+      close(p / (C.DRY_AIR_SPECIFIC_GAS_CONSTANT * tt[0]), rho)
+    for h, p, t, rho in row['at_height']:
+      pp, tt = atm.at_height(np.array([h]))
+      close(pp[0], p); close(tt[0], t)
+
+
+def test_atmosphere_survey_known_answers():
+  # SURVEY.md section 8c (alpha = 0.5), values produced by the reference.
+  atm = atmosphere.Atmosphere([0.5])
+  close(atm.p_tr[0, 1], 8806.321178176613); close(atm.p_tr[0, 7], 0.23965710887498662)
+  h, t = atm.at_pressure(np.array([9000.0]))
+  close(h[0], 16880.48843206775); close(t[0], 188.0608740347664)
+  p, _ = atm.at_height(np.array([C.ALT_MIN_ALTITUDE_M]))
+  close(p[0], 12027.731351001139)
+
+
+def test_atmosphere_out_of_range_asserts():
+  atm = atmosphere.Atmosphere([0.5])
+  with pytest.raises(AssertionError):
+    atm.at_pressure(np.array([0.1]))
+  with pytest.raises(AssertionError):
+    atm.at_pressure(np.array([2e5]))
+
+
+# ---------------------------------------------------------------- solar
+
+def test_solar_calculator_matches_reference():
+  rows = np.array(KAT['solar']['calculator'])
+  el, az, flux = solar.solar_calculator(rows[:, 0], rows[:, 1], rows[:, 2].astype(np.int64))
+  close(el, rows[:, 3], rtol=1e-10, atol=1e-11); close(az, rows[:, 4], rtol=1e-9, atol=1e-9)
+  close(flux, rows[:, 5])
+
+
+def test_solar_calculator_reference_unit_test_table():
+  # env/balloon/solar_test.py:47-102 (asserted to 1 decimal there).
+  table = [(37.3894, -122.0819, 1382123322, 41.6, None, None),
+           (37.3861, -122.0828, 1374188880, 49.14, 258.56, 1320.16),
+           (-35.1234, -71.5720, 1367743680, -32.63, 92.41, 1342.24),
+           (-70.0, -105.0, 1358237160, 1.93, 166.82, 1412.20),
+           (0.0, 0.0, 1357041600, 67.03, 177.84, 1413.17),
+           (0.0, 180.0, 1357041600, -67.02, 182.16, 1413.17)]
+  for lat, lng, ts, e_el, e_az, e_flux in table:
+    el, az, flux = solar.solar_calculator(np.radians([lat]), np.radians([lng]), np.array([ts]))
+    assert abs(el[0] - e_el) < 0.05
+    if e_az is not None:
+      assert abs(az[0] - e_az) < 0.05 and abs(flux[0] - e_flux) < 0.05
+  # env/features_test.py:482-496
+  el, _, _ = solar.solar_calculator(np.array([0.0]), np.array([0.0]), np.array([1379786400]))
+  assert abs(el[0] - (-1.57684695242166)) < 1e-7
+
+
+def test_civil_calendar_equals_linear_julian_day():
+  # The GPU path uses JD = 2440587.5 + days-since-epoch; prove it equals solar.py:71-75.
+  ts = np.arange(0, 2_000_000_000, 86400 * 13 + 7919, dtype=np.int64)
+  y, m, d, _ = solar.civil_from_unix(ts)
+  y, m, d = y.astype(float), m.astype(float), d.astype(float)
+  jdn = (367.0 * y - np.floor(7.0 * (y + np.floor((m + 9.0) / 12.0)) / 4.0)
+         - np.floor(3.0 * (np.floor((y + (m - 9.0) / 7.0) / 100.0) + 1.0) / 4.0)
+         + np.floor(275.0 * m / 9.0) + d + 1721028.5)
+  np.testing.assert_array_equal(jdn, 2440587.5 + ts // 86400)
+
+
+def test_solar_attenuation_power_shadow():
+  for el, p, att, w in KAT['solar']['power']:
+    close(solar.solar_atmospheric_attenuation(el, p), att, atol=1e-15)
+    close(solar.solar_power(el, p), w, atol=1e-12)
+  # env/balloon/solar_test.py:120-196 (5 places)
+  for el, p, e in [(0.0, 101325.0, 0.000186), (30.0, 101325.0, 0.577255), (90.0, 20000.0, 0.946635),
+                   (0.0, 5000.0, 0.620610), (60.0, 5000.0, 0.984287), (90.0, 0.0, 1.0)]:
+    assert abs(solar.solar_atmospheric_attenuation(el, p) - e) < 5e-6
+  # env/balloon/solar_test.py:198-210
+  for el, h, e in [(90.0, 3.0, 0.4392), (45.0, 3.0, 0.4392), (30.0, 3.0, 1.0), (0.0, 3.0, 1.0),
+                   (30.0, 1.0, 0.4392), (0.0, 1.0, 1.0)]:
+    assert solar.balloon_shadow(el, h) == e
+  with pytest.raises(ValueError):
+    solar.solar_atmospheric_attenuation(91.0, 5000.0)
+  with pytest.raises(ValueError):
+    solar.solar_atmospheric_attenuation(0.0, 101326.0)
+
+
+def test_sunrise_sunset_matches_reference():
+  rows = np.array(KAT['solar']['sunrise_sunset'])
+  sr, ss = solar.get_next_sunrise_sunset(rows[:, 0], rows[:, 1], rows[:, 2].astype(np.int64))
+  np.testing.assert_array_equal(sr, rows[:, 3].astype(np.int64))
+  np.testing.assert_array_equal(ss, rows[:, 4].astype(np.int64))
+
+
+def test_sunrise_sunset_reference_unit_test_table():
+  # env/balloon/solar_test.py:212-242 at (0, 0): exact datetimes.
+  import datetime as dt
+  ts = lambda *a: int(dt.datetime(*a, tzinfo=dt.timezone.utc).timestamp())
+  for now, e_sr, e_ss in [((2013, 9, 21, 9), (2013, 9, 22, 5, 36), (2013, 9, 21, 18, 9)),
+                          ((2013, 9, 21, 15), (2013, 9, 22, 5, 36), (2013, 9, 21, 18, 9)),
+                          ((2013, 9, 21, 21), (2013, 9, 22, 5, 36), (2013, 9, 22, 18, 9)),
+                          ((2013, 9, 22, 3), (2013, 9, 22, 5, 36), (2013, 9, 22, 18, 9))]:
+    sr, ss = solar.get_next_sunrise_sunset([0.0], [0.0], [ts(*now)])
+    assert sr[0] == ts(*e_sr) and ss[0] == ts(*e_ss)
+
+
+# ---------------------------------------------------------------- thermal / acs / geometry
+
+def test_thermal_matches_reference():
+  rows = np.array(KAT['thermal'])
+  got = thermal.d_balloon_temperature_dt(*[rows[:, j] for j in range(8)])
+  close(got, rows[:, 8], rtol=1e-10, atol=1e-15)
+
+
+def test_acs_matches_reference():
+  rows = np.array(KAT['acs'])
+  w = acs.get_most_efficient_power(rows[:, 0])
+  eff = acs.get_fan_efficiency(rows[:, 0], w)
+  close(w, rows[:, 1], rtol=1e-12); close(eff, rows[:, 2], atol=1e-14)
+  close(acs.get_mass_flow(w, eff), rows[:, 3], atol=1e-15)
+  g = np.array(KAT['eff_grid'])
+  close(acs.get_fan_efficiency(g[:, 0], g[:, 1]), g[:, 2], atol=1e-14)
+  # env/balloon/acs_test.py:26-63: table corners
+  assert abs(acs.get_fan_efficiency(1.05, 100.0) - 0.4) < 1e-12
+  assert abs(acs.get_fan_efficiency(1.35, 400.0) - 0.13) < 1e-12
+  assert acs.get_most_efficient_power(1.0) == 100.0 and acs.get_most_efficient_power(1.35) == 400.0
+
+
+def test_geometry_matches_reference():
+  rows = np.array(KAT['geometry'])
+  lat, lng = geometry.latlng_from_offset(rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3])
+  close(lat, rows[:, 4], atol=1e-15); close(lng, rows[:, 5], atol=1e-14)
+
+
+def test_superpressure_and_volume():
+  rows = np.array(KAT['superpressure'])
+  vol, sp = balloon.calculate_superpressure_and_volume(rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3])
+  close(vol, rows[:, 4]); close(sp, rows[:, 5], rtol=1e-9, atol=1e-9)
+  # env/balloon/balloon_test.py:85-91
+  b = balloon.make_batch(1, center_lat=0.0, center_lng=0.0, date_time=1364203532, pressure=5235.0)
+  b.superpressure[:] = 1234.0
+  assert abs(b.pressure_ratio()[0] - 1.2357) < 5e-5
+
+
+def test_stable_init_matches_reference():
+  rows = np.array(KAT['stable_init'])
+  atm = atmosphere.Atmosphere(rows[:, 0])
+  p = stable_init.calculate_stable_params_for_pressure(
+      rows[:, 1], 6830.0, rows[:, 2], rows[:, 3], rows[:, 4].astype(np.int64), rows[:, 5], atm)
+  close(p['ambient_temperature'], rows[:, 6]); close(p['internal_temperature'], rows[:, 7], rtol=1e-10)
+  close(p['mols_air'], rows[:, 8], rtol=1e-10); close(p['envelope_volume'], rows[:, 9], rtol=1e-10)
+  close(p['superpressure'], rows[:, 10], rtol=1e-8, atol=1e-8)
+
+
+# ---------------------------------------------------------------- safety layers
+
+def test_envelope_safety_sequence():
+  state = np.array([C.ENV_NOMINAL])
+  for sp, a, out, st, paused in KAT['safety']['envelope']:
+    got, state = safety.envelope_safety_get_action(np.array([a]), np.array([sp]), state)
+    assert (int(got[0]), int(state[0]), int(state[0] != C.ENV_NOMINAL)) == (out, st, paused)
+
+
+def test_envelope_safety_reference_table():
+  # env/balloon/envelope_safety_test.py:28-116 (fresh layer each row).
+  exp = {50.0: (2, 2, 2), 200.0: (1, 1, 2), 1000.0: (0, 1, 2), 2180.0: (1, 1, 2), 2280.0: (2, 2, 2)}
+  for sp, outs in exp.items():
+    for a in (0, 1, 2):
+      got, _ = safety.envelope_safety_get_action(np.array([a]), np.array([sp]), np.array([0]))
+      assert got[0] == outs[a]
+
+
+def test_altitude_safety_sequence():
+  k = KAT['safety']['altitude']
+  atm = atmosphere.Atmosphere([k['alpha']])
+  state = np.array([C.ALT_NOMINAL])
+  for p, a, out, st in k['rows']:
+    h, _ = atm.at_pressure(np.array([p]))
+    got, state = safety.altitude_safety_get_action(np.array([a]), h, state)
+    assert (int(got[0]), int(state[0])) == (out, st)
+
+
+def test_power_safety_sequence():
+  k = KAT['safety']['power']
+  sunrise_h, sunset = np.array([k['init'][0]]), np.array([k['init'][1]])
+  paused = np.array([False])
+  for ts, charge, a, out, e_paused, e_sr, e_ss in k['rows']:
+    got, sunrise_h, sunset, paused = safety.power_safety_get_action(
+        np.array([a]), np.array([ts]), np.array([charge]), sunrise_h, sunset, paused)
+    assert (int(got[0]), int(paused[0]), int(sunrise_h[0]), int(sunset[0])) == (out, e_paused, e_sr, e_ss)
+
+
+# ---------------------------------------------------------------- wind
+
+def test_grid_interpolation_matches_reference():
+  rows = np.array(KAT['interp'])
+  bank = golden_fields.field_bank()
+  u, v = wind.get_forecast(bank, rows[:, 0].astype(int), rows[:, 1], rows[:, 2], rows[:, 3],
+                           rows[:, 4].astype(np.int64))
+  close(u, rows[:, 5], rtol=1e-12, atol=1e-13); close(v, rows[:, 6], rtol=1e-12, atol=1e-13)
+
+
+def test_grid_interpolation_reference_properties():
+  # env/grid_based_wind_field_test.py:160-223: boomerang equalities and boundary clamping.
+  bank = golden_fields.field_bank()
+  f = np.array([2])
+  g = lambda x, y, p, t: np.array(wind.get_forecast(bank, f, [x], [y], [p], [t])).ravel()
+  h = 3600
+  for a, b in [(46 * h, 50 * h), (46 * h, 142 * h), (46 * h, 146 * h)]:
+    close(g(1e4, 2e4, 9000.0, a), g(1e4, 2e4, 9000.0, b), rtol=1e-6)
+  close(g(7e5, 0.0, 9000.0, 0), g(5e5, 0.0, 9000.0, 0)); close(g(0.0, -9e5, 9000.0, 0), g(0.0, -5e5, 9000.0, 0))
+  close(g(0.0, 0.0, 100.0, 0), g(0.0, 0.0, 5000.0, 0)); close(g(0.0, 0.0, 2e4, 0), g(0.0, 0.0, 14000.0, 0))
+  # midpoint linearity on the x axis (:86-158)
+  lo, hi, mid = g(-5e5, 0.0, 5000.0, 0), g(-4.5e5, 0.0, 5000.0, 0), g(-4.75e5, 0.0, 5000.0, 0)
+  close(mid, 0.5 * (lo + hi), rtol=1e-6)
+
+
+def test_opensimplex_port_self_kat():
+  k = KAT['opensimplex_port']
+  perm = opensimplex4.make_perm(k['seed'])
+  np.testing.assert_array_equal(perm, np.array(k['perm'], np.uint8))
+  pts = np.array(k['points'])
+  close(opensimplex4.noise4d(perm, *pts.T), k['values'], rtol=1e-12, atol=1e-15)
+  assert abs(opensimplex4.noise4d_scalar(perm, 0.0, 0.0, 0.0, 0.0)) < 1e-30   # zero at the origin
+
+
+def test_opensimplex_port_statistics_and_continuity():
+  # Statistical anchor to the reference's constant OPENSIMPLEX_VARIANCE = 0.0569
+  # (env/simplex_wind_noise.py:69); the port sums every in-range vertex, measured 0.0616.
+  rng = np.random.default_rng(0)
+  perm = opensimplex4.make_perm(99)
+  pts = rng.uniform(-60, 60, (60000, 4))
+  v = opensimplex4.noise4d(perm, *pts.T)
+  assert abs(v.mean()) < 0.01 and 0.05 < v.var() < 0.07 and np.abs(v).max() < 1.0
+  eps = 1e-7
+  v2 = opensimplex4.noise4d(perm, *(pts[:5000] + eps).T)
+  assert np.abs(v2 - v[:5000]).max() < 1e-5       # C0-continuous (no missed vertices)
+
+
+# ---------------------------------------------------------------- trajectories through BalloonEnv.step
+
+def test_trajectories_match_reference():
+  """All golden scenarios, stepped as ONE batch through the oracle's BalloonEnv.step restatement."""
+  names = sorted(TRAJ)
+  scs = [TRAJ[n] for n in names]
+  env = golden_io.oracle_env_for_scenarios(scs, FF, IF)
+  horizon = max(len(sc['actions']) for sc in scs)
+  for t in range(horizon):
+    acts = np.array([sc['actions'][t] if t < len(sc['actions']) else 1 for sc in scs])
+    u, v = env.arena.ground_truth_at_balloon()
+    reward, done, _ = env.step(acts)
+    s = env.arena.state
+    for e, (name, sc) in enumerate(zip(names, scs)):
+      if t >= len(sc['actions']):
+        continue
+      close([u[e], v[e]], sc['wind'][t], rtol=1e-6, atol=1e-6)
+      for j, k in enumerate(FF):
+        # x, y cross zero and inherit the reference's fp32 rounding of the query point
+        # (grid_based_wind_field.py:181): absolute floor of 1 mm.
+        atol = 1e-3 if k in ('x', 'y') else 1e-9
+        close(getattr(s, k)[e], sc['f'][t, j], rtol=1e-6 if k in ('x', 'y') else 1e-7, atol=atol)
+      for j, k in enumerate(IF):
+        if k in ('sunrise_h', 'sunset') and not sc['power_safety']:
+          continue
+        assert getattr(s, k)[e] == sc['i'][t, j], (name, t, k)
+      close(reward[e], sc['reward'][t], rtol=1e-8, atol=1e-9)
+      assert bool(done[e]) == bool(sc['done'][t]), (name, t)
+
+
+def test_terminal_status_precedence_and_noop_after_done():
+  # env/balloon/balloon.py:479-482,541-542: OUT_OF_POWER > ZEROPRESSURE > BURST.
+  assert TRAJ['zeropressure']['i'][-1][IF.index('status')] == C.STATUS_ZEROPRESSURE
+  assert TRAJ['burst']['i'][-1][IF.index('status')] == C.STATUS_BURST
+  assert TRAJ['all_terminal']['i'][-1][IF.index('status')] == C.STATUS_OUT_OF_POWER
+  sc = TRAJ['burst']
+  env = golden_io.oracle_env_for_scenario(sc, FF, IF)
+  env.step(np.array([sc['actions'][0]]))
+  before = env.arena.state.copy()
+  r, done, _ = env.step(np.array([1]))
+  assert done[0] and r[0] == 0.0
+  for k in FF + IF:
+    np.testing.assert_array_equal(getattr(before, k), getattr(env.arena.state, k))
