@@ -1,0 +1,144 @@
+/* ble_b200.h -- C ABI of the B200-native batched Balloon Learning Environment transition function.
+ *
+ * Drop-in boundary for the reference's simulator injection point:
+ *   BalloonEnv(arena: BalloonArenaInterface)            env/balloon_env.py:113,144-148
+ *   BalloonArenaInterface.{reset, step, get/set_simulator_state, get/set_balloon_state,
+ *                          get_measurements}             env/balloon_arena.py:42-120
+ * (paths relative to /root/reference/balloon_learning_environment/).  The reference is pure
+ * Python and has no FFI; INTEGRATION.md shows the ctypes binding a maintainer would add and the
+ * `CudaBalloonArena(BalloonArenaInterface)` adaptor that sits on top of these entry points.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative ble_status; nothing throws or aborts
+ *     across the ABI; ble_last_error() returns a static/handle-owned message.
+ *   - all array arguments are caller-owned DEVICE pointers unless the name ends in `_host`;
+ *     they must stay valid until the work queued on `stream` completes.  Calls are stream-ordered
+ *     and asynchronous (no hidden synchronisation) except the `_host` variants, which return
+ *     after the results have landed in host memory.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).
+ *   - one handle per GPU; a handle is not thread-safe.
+ *   - N = number of balloons (environments) of the handle.  Stepping a balloon whose status is
+ *     not OK is a no-op with reward 0 and done = 1 (the reference asserts instead,
+ *     env/balloon/balloon.py:288).
+ */
+#ifndef BLE_B200_H_
+#define BLE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ble_handle ble_handle;
+
+typedef enum {
+  BLE_OK = 0,
+  BLE_ERR_INVALID_ARGUMENT = -1,
+  BLE_ERR_CUDA = -2,
+  BLE_ERR_NOT_READY = -3,      /* e.g. stepping before fields / state were provided
+                                  (reference: RuntimeError, env/grid_based_wind_field.py:86-87) */
+  BLE_ERR_OUT_OF_MEMORY = -4,
+  BLE_ERR_UNSUPPORTED = -5
+} ble_status;
+
+/* Arithmetic of the physics kernels. */
+#define BLE_PRECISION_FP32 0   /* production: fp32 math, fp64 only for Julian time / height secant */
+#define BLE_PRECISION_FP64 1   /* audit: follows the reference's fp64 arithmetic */
+
+/* Forecast wind model (env/wind_field.py). */
+#define BLE_WIND_GRID 0        /* GridBasedWindField: per-balloon [21,21,10,9,2] grids             */
+#define BLE_WIND_SIMPLE_STATIC 1  /* SimpleStaticWindField (env/wind_field.py:149-184)             */
+
+typedef struct {
+  int32_t precision;           /* BLE_PRECISION_*                                                   */
+  int32_t wind_model;          /* BLE_WIND_*                                                        */
+  int32_t enable_noise;        /* 1: ground truth = forecast + simplex noise (wind_field.py:125-145) */
+  int32_t reserved;
+} ble_config;
+
+/* State exchange: two row-major device matrices, one row per field, N columns.
+ * f64 rows (BLE_F_*) mirror the float fields of BalloonState (env/balloon/balloon.py:73-208),
+ * i64 rows (BLE_I_*) the discrete ones plus the three safety layers' internal state. */
+enum {
+  BLE_F_X = 0, BLE_F_Y, BLE_F_PRESSURE, BLE_F_AMBIENT_TEMPERATURE, BLE_F_INTERNAL_TEMPERATURE,
+  BLE_F_ENVELOPE_VOLUME, BLE_F_SUPERPRESSURE, BLE_F_MOLS_AIR, BLE_F_MOLS_LIFT_GAS,
+  BLE_F_BATTERY_CHARGE /* Wh */, BLE_F_ACS_POWER /* W */, BLE_F_ACS_MASS_FLOW, BLE_F_SOLAR_CHARGING,
+  BLE_F_POWER_LOAD, BLE_F_CENTER_LAT /* rad */, BLE_F_CENTER_LNG /* rad */, BLE_F_UPWELLING_INFRARED,
+  BLE_F_ATMOSPHERE_ALPHA /* lapse blend, env/balloon/standard_atmosphere.py:82-84 */,
+  BLE_NUM_F
+};
+enum {
+  BLE_I_DATE_TIME = 0 /* UNIX s */, BLE_I_TIME_ELAPSED /* s */, BLE_I_LAST_COMMAND, BLE_I_STATUS,
+  BLE_I_ENVELOPE_STATE, BLE_I_ALTITUDE_STATE, BLE_I_POWER_PAUSED,
+  BLE_I_SUNRISE_H /* PowerSafetyLayer._sunrise_with_hysteresis, UNIX s */, BLE_I_SUNSET,
+  BLE_I_POWER_SAFETY_ENABLED,
+  BLE_NUM_I
+};
+typedef struct {
+  double* f64;    /* [BLE_NUM_F][N] */
+  int64_t* i64;   /* [BLE_NUM_I][N] */
+} ble_state_soa;
+
+/* Lifetime. Replaces BalloonArena.__init__ (env/balloon_arena.py:126-159). */
+int ble_create(int device, int64_t n_envs, const ble_config* config, ble_handle** out);
+int ble_destroy(ble_handle* h);
+const char* ble_last_error(const ble_handle* h /* may be NULL: error of the last failed ble_create */);
+int64_t ble_num_envs(const ble_handle* h);
+
+/* Wind fields: F grids in the reference's native layout float32 [F,21,21,10,9,2]
+ * (GridWindFieldSampler.sample_field, env/grid_wind_field_sampler.py:33-41) and the balloon ->
+ * grid map int32 [N].  The handle keeps its own re-laid-out copy (32-byte (pressure,time) cells). */
+int ble_upload_fields(ble_handle* h, const float* fields, int64_t n_fields,
+                      const int32_t* env_to_field, void* stream);
+
+/* Simplex noise parameters, SimplexWindNoise.reset_wind_noise (env/wind_field.py:196-207,
+ * env/simplex_wind_noise.py:98-114): seeds int64 [N,2,5] (component u/v, harmonic),
+ * offsets float32 [N,2,5,4].  Builds the 256-entry permutation tables on the device. */
+int ble_set_noise(ble_handle* h, const int64_t* seeds, const float* offsets, void* stream);
+
+/* get/set_balloon_state (env/balloon_arena.py:213-220) for all N balloons. */
+int ble_state_upload(ble_handle* h, const ble_state_soa* state, void* stream);
+int ble_state_download(ble_handle* h, ble_state_soa* state, void* stream);
+
+/* BalloonArena.reset (env/balloon_arena.py:161-182) for balloons with mask[i] != 0 (NULL = all):
+ * samples atmosphere, start time, position, pressure, upwelling IR from seeds[i] (distributions of
+ * utils/sampling.py:37-152 and env/balloon_arena.py:228-268), runs the power-safety sunrise/sunset
+ * search and the stable-init solve (env/balloon/stable_init.py:132-157), and re-seeds the noise. */
+int ble_reset(ble_handle* h, const uint64_t* seeds, const uint8_t* mask, void* stream);
+
+/* Deterministic part of reset only: recompute sunrise/sunset + (optionally) stable-init from the
+ * currently uploaded x, y, pressure, date_time, ... (BalloonState.__post_init__,
+ * env/balloon/balloon.py:210-215; stable_init.cold_start_to_stable_params). */
+int ble_init_derived(ble_handle* h, int32_t run_stable_init, void* stream);
+
+/* BalloonEnv.step for all balloons (env/balloon_env.py:157-190 -> env/balloon_arena.py:184-202 ->
+ * env/balloon/balloon.py:263-328): actions int32 [N] in {0 DOWN, 1 STAY, 2 UP};
+ * reward float32 [N] (perciatelli_reward_function), done uint8 [N],
+ * wind_uv float32 [N,2] = ground-truth wind applied during the step (may be NULL). */
+int ble_step(ble_handle* h, const int32_t* actions, float* reward, uint8_t* done, float* wind_uv,
+             void* stream);
+
+/* Same, with HOST buffers (pageable or pinned): copies actions in, steps, copies reward/done out
+ * and waits.  This is the call a Python/NumPy user of the reference makes per step. */
+int ble_step_host(ble_handle* h, const int32_t* actions_host, float* reward_host,
+                  uint8_t* done_host, void* stream);
+
+/* BalloonArena.get_measurements' wind_at_balloon (env/balloon_arena.py:222-226,270-275):
+ * ground-truth wind at every balloon's CURRENT state, float32 [N,2]. */
+int ble_wind_at_balloon(ble_handle* h, float* wind_uv, void* stream);
+
+/* GridBasedWindField.get_forecast for M arbitrary points (env/grid_based_wind_field.py:70-94):
+ * xyzt float32 [M,4] = (x km, y km, pressure Pa, elapsed hours), field_idx int32 [M] (grid index,
+ * NOT balloon index), uv float32 [M,2].  Clip + time boomerang + fp32 point rounding as the
+ * reference, 16-corner multilinear interpolation. */
+int ble_wind_gather(ble_handle* h, const float* xyzt, const int32_t* field_idx, float* uv,
+                    int64_t m, void* stream);
+
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+int64_t ble_launch_count(const ble_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* BLE_B200_H_ */

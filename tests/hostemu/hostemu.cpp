@@ -1,0 +1,129 @@
+// TEST-ONLY host replay of balloon_learning_environment_b200/csrc/ble_physics.cuh + ble_wind.cuh.
+//
+// There is no GPU in the build container, so the numerics of the templated device functions
+// (fp32 production path and fp64 audit path) are checked here by compiling the SAME headers
+// with g++ and driving them from pytest through ctypes.  This library is never loaded by the
+// product package; the product path has no CPU fallback.
+#include <cstdint>
+#include <cstring>
+#include "../../balloon_learning_environment_b200/csrc/ble_physics.cuh"
+#include "../../balloon_learning_environment_b200/csrc/ble_wind.cuh"
+#include "../../include/ble_b200.h"
+
+using namespace ble;
+
+template <typename Real>
+static void step_impl(int64_t n, double* f, int64_t* iv, const int32_t* actions, const double* wind,
+                      double* reward, int32_t* eff_out) {
+  auto F = [&](int r, int64_t e) -> double& { return f[int64_t(r) * n + e]; };
+  auto I = [&](int r, int64_t e) -> int64_t& { return iv[int64_t(r) * n + e]; };
+  for (int64_t e = 0; e < n; ++e) {
+    reward[e] = 0.0;
+    eff_out[e] = kStay;
+    if (I(BLE_I_STATUS, e) != kOk) continue;
+    BalloonState<Real> s;
+    s.x = Real(F(BLE_F_X, e)); s.y = Real(F(BLE_F_Y, e)); s.pressure = Real(F(BLE_F_PRESSURE, e));
+    s.t_ambient = Real(F(BLE_F_AMBIENT_TEMPERATURE, e)); s.t_internal = Real(F(BLE_F_INTERNAL_TEMPERATURE, e));
+    s.volume = Real(F(BLE_F_ENVELOPE_VOLUME, e)); s.superpressure = Real(F(BLE_F_SUPERPRESSURE, e));
+    s.mols_air = Real(F(BLE_F_MOLS_AIR, e)); s.charge = Real(F(BLE_F_BATTERY_CHARGE, e));
+    s.acs_power = Real(F(BLE_F_ACS_POWER, e)); s.acs_flow = Real(F(BLE_F_ACS_MASS_FLOW, e));
+    s.solar_w = Real(F(BLE_F_SOLAR_CHARGING, e)); s.load_w = Real(F(BLE_F_POWER_LOAD, e));
+    s.lat0 = Real(F(BLE_F_CENTER_LAT, e)); s.lng0 = Real(F(BLE_F_CENTER_LNG, e));
+    s.ir = Real(F(BLE_F_UPWELLING_INFRARED, e)); s.mols_gas = Real(F(BLE_F_MOLS_LIFT_GAS, e));
+    s.date_time = I(BLE_I_DATE_TIME, e); s.time_elapsed = int32_t(I(BLE_I_TIME_ELAPSED, e));
+    s.status = int(I(BLE_I_STATUS, e));
+    Atmosphere<Real> atm; atm.init(F(BLE_F_ATMOSPHERE_ALPHA, e));
+    SafetyState ss;
+    ss.sunrise_h = I(BLE_I_SUNRISE_H, e); ss.sunset = I(BLE_I_SUNSET, e);
+    ss.envelope_state = int(I(BLE_I_ENVELOPE_STATE, e)); ss.altitude_state = int(I(BLE_I_ALTITUDE_STATE, e));
+    ss.power_paused = int(I(BLE_I_POWER_PAUSED, e)); ss.power_safety_enabled = int(I(BLE_I_POWER_SAFETY_ENABLED, e));
+    ss.last_command = int(I(BLE_I_LAST_COMMAND, e));
+    int eff;
+    const Real r = agent_step<Real>(s, atm, ss, actions[e], Real(wind[2 * e]), Real(wind[2 * e + 1]), &eff);
+    reward[e] = double(r); eff_out[e] = eff;
+    F(BLE_F_X, e) = s.x; F(BLE_F_Y, e) = s.y; F(BLE_F_PRESSURE, e) = s.pressure;
+    F(BLE_F_AMBIENT_TEMPERATURE, e) = s.t_ambient; F(BLE_F_INTERNAL_TEMPERATURE, e) = s.t_internal;
+    F(BLE_F_ENVELOPE_VOLUME, e) = s.volume; F(BLE_F_SUPERPRESSURE, e) = s.superpressure;
+    F(BLE_F_MOLS_AIR, e) = s.mols_air; F(BLE_F_BATTERY_CHARGE, e) = s.charge;
+    F(BLE_F_ACS_POWER, e) = s.acs_power; F(BLE_F_ACS_MASS_FLOW, e) = s.acs_flow;
+    F(BLE_F_SOLAR_CHARGING, e) = s.solar_w; F(BLE_F_POWER_LOAD, e) = s.load_w;
+    I(BLE_I_DATE_TIME, e) = s.date_time; I(BLE_I_TIME_ELAPSED, e) = s.time_elapsed;
+    I(BLE_I_STATUS, e) = s.status; I(BLE_I_LAST_COMMAND, e) = ss.last_command;
+    I(BLE_I_ENVELOPE_STATE, e) = ss.envelope_state; I(BLE_I_ALTITUDE_STATE, e) = ss.altitude_state;
+    I(BLE_I_POWER_PAUSED, e) = ss.power_paused; I(BLE_I_SUNRISE_H, e) = ss.sunrise_h;
+    I(BLE_I_SUNSET, e) = ss.sunset;
+  }
+}
+
+extern "C" {
+
+void emu_step(int precision, int64_t n, double* f, int64_t* iv, const int32_t* actions,
+              const double* wind, double* reward, int32_t* eff) {
+  if (precision == BLE_PRECISION_FP64) step_impl<double>(n, f, iv, actions, wind, reward, eff);
+  else step_impl<float>(n, f, iv, actions, wind, reward, eff);
+}
+
+void emu_solar(int precision, int64_t n, const double* lat, const double* lng, const int64_t* ts,
+               double* el, double* flux) {
+  for (int64_t i = 0; i < n; ++i) {
+    if (precision == BLE_PRECISION_FP64) {
+      solar_calculator<double>(lat[i], lng[i], ts[i], &el[i], &flux[i]);
+    } else {
+      float e, fl; solar_calculator<float>(float(lat[i]), float(lng[i]), ts[i], &e, &fl);
+      el[i] = e; flux[i] = fl;
+    }
+  }
+}
+
+void emu_noise(int precision, int64_t n, const int64_t* seeds, const double* xyzw, double* out) {
+  uint8_t perm[256], scratch[256];
+  for (int64_t i = 0; i < n; ++i) {
+    simplex_make_perm(seeds[i], perm, scratch);
+    const double* p = xyzw + 4 * i;
+    out[i] = precision == BLE_PRECISION_FP64 ? simplex_noise4<double>(perm, p[0], p[1], p[2], p[3])
+                                             : double(simplex_noise4<float>(perm, p[0], p[1], p[2], p[3]));
+  }
+}
+
+void emu_perm(int64_t seed, uint8_t* perm) { uint8_t scratch[256]; simplex_make_perm(seed, perm, scratch); }
+
+// fields: native layout [F,21,21,10,9,2]; xyzt: (x km, y km, p, hours) float32
+void emu_interp(int precision, int64_t m, const float* fields, const int32_t* fidx, const float* xyzt,
+                double* uv) {
+  for (int64_t i = 0; i < m; ++i) {
+    const float* base = fields + int64_t(fidx[i]) * kFieldFloats;
+    auto ld = [&](int64_t ci) {
+      // decode the cell index back to (ix, iy, pc, tc) and gather from the native layout
+      const int tc = int((ci / kCellFloats) % kTC); const int pc = int((ci / (kCellFloats * kTC)) % kPC);
+      const int iy = int((ci / kColumnFloats) % kNY); const int ix = int(ci / (kColumnFloats * kNY));
+      float8 c;
+      c.a = {base[native_index(ix, iy, pc, tc, 0)], base[native_index(ix, iy, pc, tc, 1)],
+             base[native_index(ix, iy, pc, tc + 1, 0)], base[native_index(ix, iy, pc, tc + 1, 1)]};
+      c.b = {base[native_index(ix, iy, pc + 1, tc, 0)], base[native_index(ix, iy, pc + 1, tc, 1)],
+             base[native_index(ix, iy, pc + 1, tc + 1, 0)], base[native_index(ix, iy, pc + 1, tc + 1, 1)]};
+      return c;
+    };
+    const FieldPoint q = make_field_point(xyzt[4 * i], xyzt[4 * i + 1], xyzt[4 * i + 2], xyzt[4 * i + 3]);
+    if (precision == BLE_PRECISION_FP64) {
+      double u, v; interp_cells<double>(q, ld, &u, &v); uv[2 * i] = u; uv[2 * i + 1] = v;
+    } else {
+      float u, v; interp_cells<float>(q, ld, &u, &v); uv[2 * i] = u; uv[2 * i + 1] = v;
+    }
+  }
+}
+
+void emu_sunrise_sunset(int64_t n, const double* lat, const double* lng, const int64_t* ts,
+                        int64_t* sunrise, int64_t* sunset) {
+  for (int64_t i = 0; i < n; ++i) next_sunrise_sunset(lat[i], lng[i], ts[i], &sunrise[i], &sunset[i]);
+}
+
+void emu_stable(int64_t n, const double* alpha, const double* p, const double* lat, const double* lng,
+                const int64_t* ts, const double* ir, double* out /*[n,5]*/) {
+  for (int64_t i = 0; i < n; ++i) {
+    const StableParams s = stable_params(alpha[i], p[i], 6830.0, lat[i], lng[i], ts[i], ir[i]);
+    out[5 * i] = s.t_ambient; out[5 * i + 1] = s.t_internal; out[5 * i + 2] = s.mols_air;
+    out[5 * i + 3] = s.volume; out[5 * i + 4] = s.superpressure;
+  }
+}
+
+}  // extern "C"

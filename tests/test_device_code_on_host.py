@@ -1,0 +1,175 @@
+"""Numerics of the CUDA device headers, replayed on the CPU (no GPU in the build container).
+
+tests/hostemu compiles balloon_learning_environment_b200/csrc/ble_physics.cuh + ble_wind.cuh
+with g++ and these tests hold them to the oracle / the reference goldens:
+  * fp64 instantiation: tight tolerance, discrete decisions bit-exact;
+  * fp32 instantiation (production arithmetic): 1e-4 relative on state after a step.
+The same comparisons run against the real kernels in tests/test_gpu_parity.py (-m gpu).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import balloon, constants as C, opensimplex4, solar, stable_init, atmosphere, wind
+from tests import golden_io, hostemu
+from tests.golden import fields as golden_fields
+
+LIB = hostemu.load()
+KAT = golden_io.load_kat()
+TRAJ = golden_io.load_traj()
+FF, IF = KAT['float_fields'], KAT['int_fields']
+P = hostemu.ptr
+
+
+def test_solar_fp64_and_fp32():
+  rows = np.array(KAT['solar']['calculator'])
+  lat, lng, ts = rows[:, 0].copy(), rows[:, 1].copy(), rows[:, 2].astype(np.int64)
+  for prec, tol_el, tol_flux in ((1, 1e-9, 1e-12), (0, 2e-4, 2e-6)):
+    el = np.zeros(len(ts)); flux = np.zeros(len(ts))
+    LIB.emu_solar(prec, ctypes.c_int64(len(ts)), P(lat), P(lng), P(ts), P(el), P(flux))
+    assert np.abs(el - rows[:, 3]).max() < tol_el          # degrees
+    np.testing.assert_allclose(flux, rows[:, 5], rtol=tol_flux)
+
+
+def test_noise_matches_oracle():
+  rng = np.random.default_rng(5)
+  seeds = rng.integers(0, 1634753849, 64)
+  pts = rng.uniform(-200, 200, (64, 4))
+  perm = np.zeros(256, np.uint8)
+  LIB.emu_perm(ctypes.c_int64(int(seeds[0])), P(perm))
+  np.testing.assert_array_equal(perm, opensimplex4.make_perm(int(seeds[0])))
+  want = np.array([opensimplex4.noise4d_scalar(opensimplex4.make_perm(int(s)), *p)
+                   for s, p in zip(seeds, pts)])
+  for prec, tol in ((1, 1e-13), (0, 2e-6)):
+    out = np.zeros(64)
+    LIB.emu_noise(prec, ctypes.c_int64(64), P(seeds.astype(np.int64)), P(pts), P(out))
+    assert np.abs(out - want).max() < tol
+
+
+def test_interp_matches_reference_kat():
+  rows = np.array(KAT['interp'])
+  bank = np.ascontiguousarray(golden_fields.field_bank())
+  xyzt = np.stack([rows[:, 1] / 1000.0, rows[:, 2] / 1000.0, rows[:, 3], rows[:, 4] / 3600.0], 1)
+  # the C-ABI takes float32 (x km, y km, p, hours); only keep rows that are exact in float32
+  keep = np.all(xyzt.astype(np.float32).astype(np.float64) == xyzt, axis=1)
+  assert keep.sum() >= 20
+  x32 = np.ascontiguousarray(xyzt[keep].astype(np.float32)); fidx = rows[keep, 0].astype(np.int32)
+  for prec, tol in ((1, 1e-12), (0, 2e-5)):
+    uv = np.zeros((len(fidx), 2))
+    LIB.emu_interp(prec, ctypes.c_int64(len(fidx)), P(bank), P(fidx), P(x32), P(uv))
+    np.testing.assert_allclose(uv, rows[keep][:, 5:7], rtol=tol, atol=tol)
+
+
+def test_interp_random_points_vs_oracle():
+  rng = np.random.default_rng(9)
+  bank = np.ascontiguousarray(golden_fields.field_bank())
+  m = 4000
+  xyzt = np.stack([rng.uniform(-600, 600, m), rng.uniform(-600, 600, m), rng.uniform(4000, 15000, m),
+                   rng.uniform(0, 200, m)], 1).astype(np.float32)
+  xyzt[:8, 3] = [0, 6, 47.999, 48, 48.001, 96, 144, 95.99]
+  fidx = rng.integers(0, 4, m).astype(np.int32)
+  hours = xyzt[:, 3].astype(np.float64)
+  pts = wind.prepare_points(xyzt[:, 0].astype(np.float64) * 1000, xyzt[:, 1].astype(np.float64) * 1000,
+                            xyzt[:, 2].astype(np.float64), hours * 3600.0)
+  want = wind.interpolate(bank, fidx, pts)
+  for prec, tol in ((1, 1e-11), (0, 3e-5)):
+    uv = np.zeros((m, 2))
+    LIB.emu_interp(prec, ctypes.c_int64(m), P(bank), P(fidx), P(np.ascontiguousarray(xyzt)), P(uv))
+    assert np.abs(uv - want).max() < tol * 20.0        # |wind| up to ~20 m/s
+
+
+def test_sunrise_sunset_and_stable_init_fp64():
+  rows = np.array(KAT['solar']['sunrise_sunset'])
+  n = len(rows)
+  sr = np.zeros(n, np.int64); ss = np.zeros(n, np.int64)
+  LIB.emu_sunrise_sunset(ctypes.c_int64(n), P(rows[:, 0].copy()), P(rows[:, 1].copy()),
+                         P(rows[:, 2].astype(np.int64)), P(sr), P(ss))
+  np.testing.assert_array_equal(sr, rows[:, 3].astype(np.int64))
+  np.testing.assert_array_equal(ss, rows[:, 4].astype(np.int64))
+  rows = np.array(KAT['stable_init'])
+  out = np.zeros((len(rows), 5))
+  LIB.emu_stable(ctypes.c_int64(len(rows)), P(rows[:, 0].copy()), P(rows[:, 1].copy()), P(rows[:, 2].copy()),
+                 P(rows[:, 3].copy()), P(rows[:, 4].astype(np.int64)), P(rows[:, 5].copy()), P(out))
+  np.testing.assert_allclose(out[:, :4], rows[:, 6:10], rtol=1e-9)
+  np.testing.assert_allclose(out[:, 4], rows[:, 10], rtol=1e-7, atol=1e-7)
+
+
+def _scenario_batch():
+  names = sorted(TRAJ)
+  scs = [TRAJ[n] for n in names]
+  env = golden_io.oracle_env_for_scenarios(scs, FF, IF)
+  alpha = np.array([float(sc['alpha']) for sc in scs])
+  psl = np.array([int(sc['power_safety']) for sc in scs])
+  return names, scs, env, alpha, psl
+
+
+def test_trajectories_fp64_device_code_matches_reference():
+  """fp64 instantiation of the device code, driven with the reference's recorded winds."""
+  names, scs, env, alpha, psl = _scenario_batch()
+  f, i = hostemu.pack_state(env.arena.state, alpha, psl)
+  horizon = max(len(sc['actions']) for sc in scs)
+  for t in range(horizon):
+    acts = np.array([sc['actions'][t] if t < len(sc['actions']) else 1 for sc in scs], np.int32)
+    w = np.array([sc['wind'][t] if t < len(sc['actions']) else (0.0, 0.0) for sc in scs])
+    reward, _ = hostemu.emu_step(LIB, 1, f, i, acts, w)
+    for e, sc in enumerate(scs):
+      if t >= len(sc['actions']):
+        continue
+      for j, k in enumerate(FF):
+        got = f[hostemu.F_ROWS.index(k), e]
+        # The dynamics take sqrt(|lift - mass|) across equilibrium, which amplifies
+        # rounding-order differences (~5e-10 per crossing): 1e-5 over 960 steps.
+        atol = 1e-2 if k in ('x', 'y') else 1e-6
+        np.testing.assert_allclose(got, sc['f'][t, j], rtol=1e-5, atol=atol, err_msg=f'{names[e]} t={t} {k}')
+      for j, k in enumerate(IF):
+        if k in ('sunrise_h', 'sunset') and not sc['power_safety']:
+          continue
+        assert i[hostemu.I_ROWS.index(k), e] == sc['i'][t, j], (names[e], t, k)
+      np.testing.assert_allclose(reward[e], sc['reward'][t], rtol=1e-6, atol=1e-8)
+
+
+def _single_step_errors(prec):
+  names, scs, env, alpha, psl = _scenario_batch()
+  worst, mism, total, rworst = {}, 0, 0, 0.0
+  for e, sc in enumerate(scs):
+    n = len(sc['actions'])
+    idx = np.arange(0, n - 1)
+    if idx.size == 0:
+      continue
+    # state BEFORE step t+1 is the recorded state after step t
+    b = golden_io.batch_from_rows(FF, IF, sc['f'][idx], sc['i'][idx])
+    f, i = hostemu.pack_state(b, alpha[e], psl[e])
+    acts = sc['actions'][idx + 1].astype(np.int32)
+    reward, _ = hostemu.emu_step(LIB, prec, f, i, acts, sc['wind'][idx + 1])
+    want_f, want_i = sc['f'][idx + 1], sc['i'][idx + 1]
+    for j, k in enumerate(FF):
+      got = f[hostemu.F_ROWS.index(k)]
+      ref = want_f[:, j]
+      # relative error, with a floor at a small fraction of each field's typical magnitude for
+      # the fields that pass through zero
+      scale = np.maximum(np.abs(ref), {'x': 1e4, 'y': 1e4, 'acs_mass_flow': 1e-2, 'superpressure': 100.0,
+                                       'solar_charging': 50.0, 'acs_power': 100.0,
+                                       'mols_air': 100.0}.get(k, 1e-30))
+      worst[k] = max(worst.get(k, 0.0), float((np.abs(got - ref) / scale).max()))
+    for j, k in enumerate(IF):
+      if k in ('sunrise_h', 'sunset') and not sc['power_safety']:
+        continue
+      mism += int((i[hostemu.I_ROWS.index(k)] != want_i[:, j]).sum())
+      total += len(idx)
+    rworst = max(rworst, float(np.abs(reward - sc['reward'][idx + 1]).max()))
+  return worst, mism, total, rworst
+
+
+def test_single_steps_fp64_device_code_tight():
+  worst, mism, total, rworst = _single_step_errors(1)
+  assert max(worst.values()) < 1e-8, worst
+  assert mism == 0 and rworst < 1e-9
+
+
+def test_single_steps_fp32_device_code_within_1e4():
+  worst, mism, total, rworst = _single_step_errors(0)
+  print(worst)
+  assert max(worst.values()) < 1e-4, worst
+  assert mism == 0, (mism, total)
+  assert rworst < 1e-4
