@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI in include/ble_b200.h.
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is present the
+import / create call raises.
+"""
+import ctypes
+import os
+
+from balloon_learning_environment_b200 import _build
+
+_c = ctypes
+_LIB = None
+
+BLE_OK = 0
+PRECISION = {'fp32': 0, 'fp64': 1}
+WIND_MODEL = {'grid': 0, 'simple_static': 1}
+
+# Row order of the state exchange matrices (include/ble_b200.h, BLE_F_* / BLE_I_*).
+F_ROWS = ('x', 'y', 'pressure', 'ambient_temperature', 'internal_temperature', 'envelope_volume',
+          'superpressure', 'mols_air', 'mols_lift_gas', 'battery_charge', 'acs_power', 'acs_mass_flow',
+          'solar_charging', 'power_load', 'center_lat', 'center_lng', 'upwelling_infrared',
+          'atmosphere_alpha')
+I_ROWS = ('date_time', 'time_elapsed', 'last_command', 'status', 'envelope_state', 'altitude_state',
+          'power_paused', 'sunrise_h', 'sunset', 'power_safety_enabled')
+
+EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_upload_fields',
+           'ble_set_noise', 'ble_state_upload', 'ble_state_download', 'ble_reset', 'ble_init_derived',
+           'ble_step', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_launch_count')
+
+
+class BleConfig(_c.Structure):
+  _fields_ = [('precision', _c.c_int32), ('wind_model', _c.c_int32), ('enable_noise', _c.c_int32),
+              ('reserved', _c.c_int32)]
+
+
+class BleStateSoa(_c.Structure):
+  _fields_ = [('f64', _c.c_void_p), ('i64', _c.c_void_p)]
+
+
+class BleError(RuntimeError):
+  pass
+
+
+def library_path():
+  return _build.LIB_PATH
+
+
+def load(build_if_missing=True):
+  """Loads libble_b200.so (building it in-tree first if it is missing and nvcc is present)."""
+  global _LIB
+  if _LIB is not None:
+    return _LIB
+  path = library_path()
+  if not os.path.exists(path):
+    if not build_if_missing:
+      raise BleError(f'{path} is missing; run `python -m balloon_learning_environment_b200._build`')
+    _build.build()
+  lib = _c.CDLL(path)
+  vp, i64, i32 = _c.c_void_p, _c.c_int64, _c.c_int32
+  lib.ble_create.argtypes = [_c.c_int, i64, _c.POINTER(BleConfig), _c.POINTER(vp)]
+  lib.ble_destroy.argtypes = [vp]
+  lib.ble_last_error.argtypes = [vp]
+  lib.ble_last_error.restype = _c.c_char_p
+  lib.ble_num_envs.argtypes = [vp]
+  lib.ble_num_envs.restype = i64
+  lib.ble_launch_count.argtypes = [vp]
+  lib.ble_launch_count.restype = i64
+  lib.ble_upload_fields.argtypes = [vp, vp, i64, vp, vp]
+  lib.ble_set_noise.argtypes = [vp, vp, vp, vp]
+  lib.ble_state_upload.argtypes = [vp, _c.POINTER(BleStateSoa), vp]
+  lib.ble_state_download.argtypes = [vp, _c.POINTER(BleStateSoa), vp]
+  lib.ble_reset.argtypes = [vp, vp, vp, vp]
+  lib.ble_init_derived.argtypes = [vp, i32, vp]
+  lib.ble_step.argtypes = [vp, vp, vp, vp, vp, vp]
+  lib.ble_step_host.argtypes = [vp, vp, vp, vp, vp]
+  lib.ble_wind_at_balloon.argtypes = [vp, vp, vp]
+  lib.ble_wind_gather.argtypes = [vp, vp, vp, vp, i64, vp]
+  for name in EXPORTS:
+    if name not in ('ble_last_error', 'ble_num_envs', 'ble_launch_count'):
+      getattr(lib, name).restype = _c.c_int
+  _LIB = lib
+  return lib
+
+
+def check(lib, handle, rc, what):
+  if rc != BLE_OK:
+    msg = lib.ble_last_error(handle)
+    raise BleError(f'{what} failed (code {rc}): {msg.decode() if msg else "?"}')

@@ -1,0 +1,244 @@
+"""Batched, GPU-resident Balloon Learning Environment (host side).
+
+`BatchedBalloonArena` mirrors the reference's `BalloonArena` (env/balloon_arena.py:123-275) and
+`BatchedBalloonEnv` its `BalloonEnv` (env/balloon_env.py:105-300) for N balloons at once.  All
+numerics run in hand-written CUDA behind the C ABI of include/ble_b200.h; PyTorch only owns the
+device buffers and the stream.  There is no CPU path.
+"""
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from balloon_learning_environment_b200 import _lib
+
+# AltitudeControlCommand (env/balloon/control.py:21-25) and BalloonStatus (env/balloon/balloon.py:66-70)
+DOWN, STAY, UP = 0, 1, 2
+STATUS_OK, STATUS_OUT_OF_POWER, STATUS_BURST, STATUS_ZEROPRESSURE = 0, 1, 2, 3
+FIELD_SHAPE = (21, 21, 10, 9, 2)     # generative/vae.py:38-51
+
+
+class Discrete:
+  """Minimal stand-in for gym.spaces.Discrete (env/balloon_env.py:262-264)."""
+
+  def __init__(self, n: int):
+    self.n = n
+
+  def __repr__(self):
+    return f'Discrete({self.n})'
+
+
+def _ptr(t: Optional[torch.Tensor]):
+  return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class BatchedBalloonArena:
+  """N balloons, each flying in its own (or a shared) wind field.  Device-resident state.
+
+  Reference: BalloonArena (env/balloon_arena.py:123-275).  Differences that come with batching:
+  `step` takes a tensor of N commands; a balloon whose status is not OK is left untouched
+  (the reference asserts, env/balloon/balloon.py:288).
+  """
+
+  def __init__(self, num_envs: int, *, device: str = 'cuda:0', precision: str = 'fp32',
+               wind_model: str = 'grid', enable_noise: bool = True):
+    if not torch.cuda.is_available():
+      raise _lib.BleError('BatchedBalloonArena needs a CUDA device (no CPU fallback exists)')
+    self._lib = _lib.load()
+    self.device = torch.device(device)
+    self.num_envs = int(num_envs)
+    self.precision = precision
+    self.wind_model = wind_model
+    self.enable_noise = bool(enable_noise)
+    cfg = _lib.BleConfig(_lib.PRECISION[precision], _lib.WIND_MODEL[wind_model], int(enable_noise), 0)
+    handle = ctypes.c_void_p()
+    dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+    rc = self._lib.ble_create(dev_index, self.num_envs, ctypes.byref(cfg), ctypes.byref(handle))
+    _lib.check(self._lib, None, rc, 'ble_create')
+    self._h = handle
+    n = self.num_envs
+    with torch.cuda.device(self.device):
+      self._reward = torch.zeros(n, dtype=torch.float32, device=self.device)
+      self._done = torch.zeros(n, dtype=torch.uint8, device=self.device)
+      self._wind = torch.zeros(n, 2, dtype=torch.float32, device=self.device)
+    self._keepalive = []
+
+  # -- plumbing ---------------------------------------------------------------------------------
+  def _stream(self):
+    return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+  def _check(self, rc, what):
+    _lib.check(self._lib, self._h, rc, what)
+
+  def close(self):
+    if getattr(self, '_h', None) is not None:
+      torch.cuda.synchronize(self.device)
+      self._lib.ble_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+  @property
+  def launch_count(self) -> int:
+    return int(self._lib.ble_launch_count(self._h))
+
+  # -- wind -------------------------------------------------------------------------------------
+  def set_wind_fields(self, fields: torch.Tensor, env_to_field: Optional[torch.Tensor] = None):
+    """fields: float32 [F,21,21,10,9,2] (GridWindFieldSampler.sample_field layout); env_to_field int32 [N]."""
+    fields = fields.to(self.device, torch.float32).contiguous()
+    if tuple(fields.shape[1:]) != FIELD_SHAPE:
+      raise ValueError(f'fields must have shape [F, {FIELD_SHAPE}], got {tuple(fields.shape)}')
+    if env_to_field is not None:
+      env_to_field = env_to_field.to(self.device, torch.int32).contiguous()
+      if env_to_field.numel() != self.num_envs:
+        raise ValueError('env_to_field must have one entry per balloon')
+      if int(env_to_field.max()) >= fields.shape[0] or int(env_to_field.min()) < 0:
+        raise ValueError('env_to_field refers to a field that was not provided')
+    self._n_fields = int(fields.shape[0])
+    rc = self._lib.ble_upload_fields(self._h, _ptr(fields), fields.shape[0], _ptr(env_to_field), self._stream())
+    self._check(rc, 'ble_upload_fields')
+    self._keepalive = [fields, env_to_field]
+
+  def set_wind_noise(self, seeds: torch.Tensor, offsets: torch.Tensor):
+    """seeds int64 [N,2,5], offsets float32 [N,2,5,4] (env/simplex_wind_noise.py:98-114)."""
+    seeds = seeds.to(self.device, torch.int64).contiguous()
+    offsets = offsets.to(self.device, torch.float32).contiguous()
+    if tuple(seeds.shape) != (self.num_envs, 2, 5) or tuple(offsets.shape) != (self.num_envs, 2, 5, 4):
+      raise ValueError('seeds must be [N,2,5] and offsets [N,2,5,4]')
+    self._check(self._lib.ble_set_noise(self._h, _ptr(seeds), _ptr(offsets), self._stream()), 'ble_set_noise')
+    torch.cuda.current_stream(self.device).synchronize()
+
+  def wind_forecast(self, xyzt: torch.Tensor, field_idx: torch.Tensor) -> torch.Tensor:
+    """GridBasedWindField.get_forecast for M points: xyzt float32 [M,4] (x km, y km, Pa, hours)."""
+    xyzt = xyzt.to(self.device, torch.float32).contiguous()
+    field_idx = field_idx.to(self.device, torch.int32).contiguous()
+    m = xyzt.shape[0]
+    uv = torch.empty(m, 2, dtype=torch.float32, device=self.device)
+    rc = self._lib.ble_wind_gather(self._h, _ptr(xyzt), _ptr(field_idx), _ptr(uv), m, self._stream())
+    self._check(rc, 'ble_wind_gather')
+    return uv
+
+  def wind_at_balloon(self) -> torch.Tensor:
+    """Ground-truth wind at the balloons' current state, float32 [N,2] (get_measurements)."""
+    uv = torch.empty(self.num_envs, 2, dtype=torch.float32, device=self.device)
+    self._check(self._lib.ble_wind_at_balloon(self._h, _ptr(uv), self._stream()), 'ble_wind_at_balloon')
+    return uv
+
+  # -- state ------------------------------------------------------------------------------------
+  def set_state(self, f64: torch.Tensor, i64: torch.Tensor):
+    """set_balloon_state for all balloons: f64 [18,N] / i64 [10,N] in the row order of _lib.F_ROWS/I_ROWS."""
+    f64 = f64.to(self.device, torch.float64).contiguous()
+    i64 = i64.to(self.device, torch.int64).contiguous()
+    if tuple(f64.shape) != (len(_lib.F_ROWS), self.num_envs) or tuple(i64.shape) != (len(_lib.I_ROWS), self.num_envs):
+      raise ValueError('state matrices have the wrong shape')
+    soa = _lib.BleStateSoa(f64.data_ptr(), i64.data_ptr())
+    self._check(self._lib.ble_state_upload(self._h, ctypes.byref(soa), self._stream()), 'ble_state_upload')
+    torch.cuda.current_stream(self.device).synchronize()
+
+  def get_state(self) -> Tuple[torch.Tensor, torch.Tensor]:
+    f64 = torch.empty(len(_lib.F_ROWS), self.num_envs, dtype=torch.float64, device=self.device)
+    i64 = torch.empty(len(_lib.I_ROWS), self.num_envs, dtype=torch.int64, device=self.device)
+    soa = _lib.BleStateSoa(f64.data_ptr(), i64.data_ptr())
+    self._check(self._lib.ble_state_download(self._h, ctypes.byref(soa), self._stream()), 'ble_state_download')
+    return f64, i64
+
+  def get_state_dict(self) -> Dict[str, torch.Tensor]:
+    f64, i64 = self.get_state()
+    out = {k: f64[r] for r, k in enumerate(_lib.F_ROWS)}
+    out.update({k: i64[r] for r, k in enumerate(_lib.I_ROWS)})
+    return out
+
+  def init_derived(self, run_stable_init: bool = True):
+    """Recompute power-safety sunrise/sunset (+ stable init) from the uploaded state."""
+    self._check(self._lib.ble_init_derived(self._h, int(run_stable_init), self._stream()), 'ble_init_derived')
+
+  # -- reset / step -----------------------------------------------------------------------------
+  def reset(self, seeds: torch.Tensor, mask: Optional[torch.Tensor] = None):
+    """BalloonArena.reset for every balloon (or those with mask != 0), one 64-bit seed each."""
+    seeds = seeds.to(self.device).contiguous()
+    if seeds.dtype not in (torch.int64, torch.uint64) or seeds.numel() != self.num_envs:
+      raise ValueError('seeds must be an int64 tensor with one entry per balloon')
+    if mask is not None:
+      mask = mask.to(self.device, torch.uint8).contiguous()
+    self._check(self._lib.ble_reset(self._h, _ptr(seeds), _ptr(mask), self._stream()), 'ble_reset')
+    torch.cuda.current_stream(self.device).synchronize()
+
+  def step(self, actions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """actions int32 [N] -> (reward f32 [N], done u8 [N], wind_uv f32 [N,2]); stream-ordered, async."""
+    if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
+      actions = actions.to(self.device, torch.int32).contiguous()
+    rc = self._lib.ble_step(self._h, _ptr(actions), _ptr(self._reward), _ptr(self._done), _ptr(self._wind),
+                            self._stream())
+    self._check(rc, 'ble_step')
+    return self._reward, self._done, self._wind
+
+  def step_host(self, actions: np.ndarray, reward: np.ndarray, done: np.ndarray):
+    """Host-buffer step: int32 [N] in; float32 [N] / uint8 [N] out (copies inside, blocking)."""
+    assert actions.dtype == np.int32 and reward.dtype == np.float32 and done.dtype == np.uint8
+    rc = self._lib.ble_step_host(self._h, ctypes.c_void_p(actions.ctypes.data),
+                                 ctypes.c_void_p(reward.ctypes.data), ctypes.c_void_p(done.ctypes.data),
+                                 self._stream())
+    self._check(rc, 'ble_step_host')
+
+
+class BatchedBalloonEnv:
+  """Vectorised BalloonEnv: `step(actions[N]) -> (obs, reward[N], done[N], info)`.
+
+  Reference: BalloonEnv (env/balloon_env.py:105-300).  `action_space.n == 3`.  The observation is
+  produced by `feature_constructor(arena)` when one is given (the Perciatelli 1099-feature
+  constructor is a later row of the scope table); without one `obs` is None.
+  """
+
+  def __init__(self, num_envs: int, *, device: str = 'cuda:0', precision: str = 'fp32',
+               wind_model: str = 'grid', enable_noise: bool = True, seed: int = 0,
+               arena: Optional[BatchedBalloonArena] = None, feature_constructor=None):
+    self.arena = arena if arena is not None else BatchedBalloonArena(
+        num_envs, device=device, precision=precision, wind_model=wind_model, enable_noise=enable_noise)
+    self.num_envs = self.arena.num_envs
+    self.device = self.arena.device
+    self.feature_constructor = feature_constructor
+    self._generator = torch.Generator(device='cpu')
+    self.seed(seed)
+
+  @property
+  def action_space(self) -> Discrete:
+    return Discrete(3)
+
+  @property
+  def reward_range(self) -> Tuple[float, float]:
+    return (0.0, 1.0)
+
+  def seed(self, seed: int) -> None:
+    self._generator.manual_seed(int(seed))
+
+  def reset(self, *, seed: Optional[int] = None):
+    if seed is not None:
+      self.seed(seed)
+    seeds = torch.randint(0, 2**62, (self.num_envs,), dtype=torch.int64, generator=self._generator)
+    self.arena.reset(seeds)
+    return self._observe()
+
+  def _observe(self):
+    if self.feature_constructor is None:
+      return None
+    return self.feature_constructor(self.arena)
+
+  def step(self, actions: torch.Tensor):
+    reward, done, _ = self.arena.step(actions)
+    info = {'done': done}
+    return self._observe(), reward, done, info
+
+  def get_info(self) -> Dict[str, torch.Tensor]:
+    """_get_info (env/balloon_env.py:280-290) for all balloons."""
+    st = self.arena.get_state_dict()
+    status = st['status']
+    return {'out_of_power': status == STATUS_OUT_OF_POWER, 'envelope_burst': status == STATUS_BURST,
+            'zeropressure': status == STATUS_ZEROPRESSURE, 'time_elapsed': st['time_elapsed']}
+
+  def close(self):
+    self.arena.close()

@@ -1,0 +1,826 @@
+// CUDA engine + C ABI (include/ble_b200.h) for the batched BLE transition function.
+// Target: sm_100a (B200).  One handle per GPU, one thread per balloon in the physics kernel,
+// one thread per (balloon, noise harmonic) in the noise kernel with TMA bulk staging of the
+// permutation tables.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/ble_b200.h"
+#include "ble_physics.cuh"
+#include "ble_wind.cuh"
+
+namespace ble {
+
+// ---------------------------------------------------------------------------------------------
+// Device-side state layout (struct of arrays, one row per field, N columns)
+// ---------------------------------------------------------------------------------------------
+enum RRow : int {
+  R_X = 0, R_Y, R_P, R_TAMB, R_TINT, R_VOL, R_SP, R_MOLS_AIR, R_CHARGE, R_ACS_W, R_ACS_FLOW, R_SOLAR_W,
+  R_LOAD_W,                                          // 13 dynamic rows (read + written every step)
+  R_LAT0, R_LNG0, R_IR, R_MOLS_GAS,                  // per-episode constants
+  R_L0, R_L1, R_L2, R_T1, R_T2, R_P1, R_P2, R_P3,    // atmosphere layers 0..2 derived from alpha
+  R_COUNT
+};
+enum LRow : int { L_DATE_TIME = 0, L_SUNRISE_H, L_SUNSET, L_COUNT };
+
+// flags word: status[0:2) last_command[2:4) envelope[4:7) altitude[7:9) paused[9] psl[10] atm_err[11]
+__host__ __device__ inline uint32_t pack_flags(int status, int last_cmd, int env, int alt, int paused,
+                                               int psl, int atm_err) {
+  return uint32_t(status) | (uint32_t(last_cmd) << 2) | (uint32_t(env) << 4) | (uint32_t(alt) << 7) |
+         (uint32_t(paused) << 9) | (uint32_t(psl) << 10) | (uint32_t(atm_err) << 11);
+}
+
+template <typename Real>
+struct DevState {
+  int64_t n;
+  Real* r;            // [R_COUNT][n]
+  double* alpha;      // [n]
+  int64_t* l;         // [L_COUNT][n]
+  int32_t* t_elapsed; // [n]
+  uint32_t* flags;    // [n]
+  // wind
+  const float* cells;        // [F][kCellFieldFloats]
+  const int32_t* env_field;  // [n]
+  const uint8_t* perm;       // [10][n][256], each table rotated by 4*(env%32) bytes
+  const float* offsets;      // [10][4][n]
+  Real* noise_partial;       // [10][n]
+  int wind_model, enable_noise;
+};
+
+template <typename Real>
+__device__ __forceinline__ Real& RR(const DevState<Real>& d, int row, int64_t e) { return d.r[int64_t(row) * d.n + e]; }
+
+// ---------------------------------------------------------------------------------------------
+// State upload / download (get/set_balloon_state, env/balloon_arena.py:213-220)
+// ---------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void k_state_upload(DevState<Real> d, const double* __restrict__ f, const int64_t* __restrict__ iv) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  const int64_t n = d.n;
+  auto F = [&](int row) { return f[int64_t(row) * n + e]; };
+  auto I = [&](int row) { return iv[int64_t(row) * n + e]; };
+  RR(d, R_X, e) = Real(F(BLE_F_X)); RR(d, R_Y, e) = Real(F(BLE_F_Y)); RR(d, R_P, e) = Real(F(BLE_F_PRESSURE));
+  RR(d, R_TAMB, e) = Real(F(BLE_F_AMBIENT_TEMPERATURE)); RR(d, R_TINT, e) = Real(F(BLE_F_INTERNAL_TEMPERATURE));
+  RR(d, R_VOL, e) = Real(F(BLE_F_ENVELOPE_VOLUME)); RR(d, R_SP, e) = Real(F(BLE_F_SUPERPRESSURE));
+  RR(d, R_MOLS_AIR, e) = Real(F(BLE_F_MOLS_AIR)); RR(d, R_CHARGE, e) = Real(F(BLE_F_BATTERY_CHARGE));
+  RR(d, R_ACS_W, e) = Real(F(BLE_F_ACS_POWER)); RR(d, R_ACS_FLOW, e) = Real(F(BLE_F_ACS_MASS_FLOW));
+  RR(d, R_SOLAR_W, e) = Real(F(BLE_F_SOLAR_CHARGING)); RR(d, R_LOAD_W, e) = Real(F(BLE_F_POWER_LOAD));
+  RR(d, R_LAT0, e) = Real(F(BLE_F_CENTER_LAT)); RR(d, R_LNG0, e) = Real(F(BLE_F_CENTER_LNG));
+  RR(d, R_IR, e) = Real(F(BLE_F_UPWELLING_INFRARED)); RR(d, R_MOLS_GAS, e) = Real(F(BLE_F_MOLS_LIFT_GAS));
+  const double alpha = F(BLE_F_ATMOSPHERE_ALPHA);
+  d.alpha[e] = alpha;
+  Atmosphere<Real> atm; atm.init(alpha);
+  RR(d, R_L0, e) = atm.l0; RR(d, R_L1, e) = atm.l1; RR(d, R_L2, e) = atm.l2;
+  RR(d, R_T1, e) = atm.t1; RR(d, R_T2, e) = atm.t2;
+  RR(d, R_P1, e) = atm.p1; RR(d, R_P2, e) = atm.p2; RR(d, R_P3, e) = atm.p3;
+  d.l[int64_t(L_DATE_TIME) * n + e] = I(BLE_I_DATE_TIME);
+  d.l[int64_t(L_SUNRISE_H) * n + e] = I(BLE_I_SUNRISE_H);
+  d.l[int64_t(L_SUNSET) * n + e] = I(BLE_I_SUNSET);
+  d.t_elapsed[e] = int32_t(I(BLE_I_TIME_ELAPSED));
+  d.flags[e] = pack_flags(int(I(BLE_I_STATUS)), int(I(BLE_I_LAST_COMMAND)), int(I(BLE_I_ENVELOPE_STATE)),
+                          int(I(BLE_I_ALTITUDE_STATE)), int(I(BLE_I_POWER_PAUSED)),
+                          int(I(BLE_I_POWER_SAFETY_ENABLED)), 0);
+}
+
+template <typename Real>
+__global__ void k_state_download(DevState<Real> d, double* __restrict__ f, int64_t* __restrict__ iv) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  const int64_t n = d.n;
+  auto F = [&](int row) -> double& { return f[int64_t(row) * n + e]; };
+  auto I = [&](int row) -> int64_t& { return iv[int64_t(row) * n + e]; };
+  F(BLE_F_X) = double(RR(d, R_X, e)); F(BLE_F_Y) = double(RR(d, R_Y, e)); F(BLE_F_PRESSURE) = double(RR(d, R_P, e));
+  F(BLE_F_AMBIENT_TEMPERATURE) = double(RR(d, R_TAMB, e)); F(BLE_F_INTERNAL_TEMPERATURE) = double(RR(d, R_TINT, e));
+  F(BLE_F_ENVELOPE_VOLUME) = double(RR(d, R_VOL, e)); F(BLE_F_SUPERPRESSURE) = double(RR(d, R_SP, e));
+  F(BLE_F_MOLS_AIR) = double(RR(d, R_MOLS_AIR, e)); F(BLE_F_MOLS_LIFT_GAS) = double(RR(d, R_MOLS_GAS, e));
+  F(BLE_F_BATTERY_CHARGE) = double(RR(d, R_CHARGE, e)); F(BLE_F_ACS_POWER) = double(RR(d, R_ACS_W, e));
+  F(BLE_F_ACS_MASS_FLOW) = double(RR(d, R_ACS_FLOW, e)); F(BLE_F_SOLAR_CHARGING) = double(RR(d, R_SOLAR_W, e));
+  F(BLE_F_POWER_LOAD) = double(RR(d, R_LOAD_W, e)); F(BLE_F_CENTER_LAT) = double(RR(d, R_LAT0, e));
+  F(BLE_F_CENTER_LNG) = double(RR(d, R_LNG0, e)); F(BLE_F_UPWELLING_INFRARED) = double(RR(d, R_IR, e));
+  F(BLE_F_ATMOSPHERE_ALPHA) = d.alpha[e];
+  const uint32_t fl = d.flags[e];
+  I(BLE_I_DATE_TIME) = d.l[int64_t(L_DATE_TIME) * n + e];
+  I(BLE_I_TIME_ELAPSED) = d.t_elapsed[e];
+  I(BLE_I_LAST_COMMAND) = (fl >> 2) & 3; I(BLE_I_STATUS) = fl & 3;
+  I(BLE_I_ENVELOPE_STATE) = (fl >> 4) & 7; I(BLE_I_ALTITUDE_STATE) = (fl >> 7) & 3;
+  I(BLE_I_POWER_PAUSED) = (fl >> 9) & 1;
+  I(BLE_I_SUNRISE_H) = d.l[int64_t(L_SUNRISE_H) * n + e];
+  I(BLE_I_SUNSET) = d.l[int64_t(L_SUNSET) * n + e];
+  I(BLE_I_POWER_SAFETY_ENABLED) = (fl >> 10) & 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wind field re-layout: native [F,21,21,10,9,2] -> 32-byte (pressure, time) cells
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fields_to_cells(const float* __restrict__ native, float* __restrict__ cells, int64_t n_cells) {
+  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;   // global cell index
+  if (c >= n_cells) return;
+  const int64_t cells_per_field = int64_t(kNX) * kNY * kPC * kTC;
+  const int64_t f = c / cells_per_field;
+  int64_t r = c - f * cells_per_field;
+  const int tc = int(r % kTC); r /= kTC;
+  const int pc = int(r % kPC); r /= kPC;
+  const int iy = int(r % kNY);
+  const int ix = int(r / kNY);
+  const float* src = native + f * kFieldFloats;
+  float4 a, b;
+  a.x = src[native_index(ix, iy, pc, tc, 0)];     a.y = src[native_index(ix, iy, pc, tc, 1)];
+  a.z = src[native_index(ix, iy, pc, tc + 1, 0)]; a.w = src[native_index(ix, iy, pc, tc + 1, 1)];
+  b.x = src[native_index(ix, iy, pc + 1, tc, 0)];     b.y = src[native_index(ix, iy, pc + 1, tc, 1)];
+  b.z = src[native_index(ix, iy, pc + 1, tc + 1, 0)]; b.w = src[native_index(ix, iy, pc + 1, tc + 1, 1)];
+  float4* dst = reinterpret_cast<float4*>(cells + c * kCellFloats);
+  dst[0] = a;
+  dst[1] = b;
+}
+
+struct CellLoader {
+  const float* base;
+  __device__ __forceinline__ float8 operator()(int64_t idx) const {
+    const float4* p = reinterpret_cast<const float4*>(base + idx);
+    float8 c;
+    c.a = __ldg(p);
+    c.b = __ldg(p + 1);
+    return c;
+  }
+};
+
+// GridBasedWindField.get_forecast for M arbitrary points (C ABI ble_wind_gather).
+template <typename Real>
+__global__ void __launch_bounds__(256)
+k_wind_gather(const float* __restrict__ cells, const float4* __restrict__ xyzt,
+              const int32_t* __restrict__ field_idx, float2* __restrict__ uv, int64_t m) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= m) return;
+  const float4 q4 = __ldg(xyzt + i);
+  const int32_t f = __ldg(field_idx + i);
+  const FieldPoint q = make_field_point(double(q4.x), double(q4.y), double(q4.z), double(q4.w));
+  CellLoader ld{cells + int64_t(f) * kCellFieldFloats};
+  Real u, v;
+  interp_cells<Real>(q, ld, &u, &v);
+  uv[i] = make_float2(float(u), float(v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Noise: permutation tables (reset time) and the per-step noise kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void k_make_perms(int64_t n, const int64_t* __restrict__ seeds /*[n,2,5]*/,
+                             const float* __restrict__ offsets_in /*[n,2,5,4]*/, const uint8_t* __restrict__ mask,
+                             uint8_t* __restrict__ perm /*[10][n][256]*/, float* __restrict__ offsets /*[10][4][n]*/) {
+  const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (t >= n * 10) return;
+  const int64_t e = t / 10;
+  const int h10 = int(t - e * 10);
+  if (mask != nullptr && mask[e] == 0) return;
+  uint8_t table[256], scratch[256];
+  simplex_make_perm(seeds[e * 10 + h10], table, scratch);
+  uint8_t* dst = perm + (int64_t(h10) * n + e) * 256;
+  const int rot = int(e & 31) * 4;       // bank-conflict-free rotation, undone at lookup time
+  for (int j = 0; j < 256; ++j) dst[(j + rot) & 255] = table[j];
+  for (int c = 0; c < 4; ++c) offsets[(int64_t(h10) * 4 + c) * n + e] = offsets_in[(e * 10 + h10) * 4 + c];
+}
+
+struct RotatedPerm {      // view of one rotated table in shared memory
+  const uint8_t* t;
+  int rot;
+  __device__ __forceinline__ int operator[](int i) const { return t[(i + rot) & 255]; }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+constexpr int kNoiseBlock = 128;
+
+// One thread per (balloon, harmonic).  blockIdx.y = harmonic (0..9), blockIdx.x = block of 128
+// consecutive balloons, whose 128 x 256 B permutation tables are contiguous in HBM and are
+// staged into shared memory with ONE TMA bulk copy (cp.async.bulk) tracked by an mbarrier.
+template <typename Real>
+__global__ void __launch_bounds__(kNoiseBlock)
+k_noise(DevState<Real> d) {
+  extern __shared__ __align__(128) uint8_t s_perm[];     // kNoiseBlock * 256 bytes
+  __shared__ __align__(8) uint64_t s_bar;
+  const int h10 = blockIdx.y;
+  const int64_t e0 = int64_t(blockIdx.x) * kNoiseBlock;
+  const int count = int(min(int64_t(kNoiseBlock), d.n - e0));
+  const uint32_t bar = smem_u32(&s_bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = uint32_t(count) * 256u;
+    const uint8_t* src = d.perm + (int64_t(h10) * d.n + e0) * 256;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(s_perm)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  }
+  // coordinates while the copy is in flight (NoisyWindHarmonic.get_noise, simplex_wind_noise.py:116-146)
+  const int64_t e = e0 + threadIdx.x;
+  const bool live = threadIdx.x < count;
+  double X = 0, Y = 0, Z = 0, W = 0;
+  if (live) {
+    double wgt, sx, sy, sp, st;
+    harmonic_params(h10, &wgt, &sx, &sy, &sp, &st);
+    const double x_km = double(RR(d, R_X, e)) / 1000.0, y_km = double(RR(d, R_Y, e)) / 1000.0;
+    const double p = double(RR(d, R_P, e)), t_h = double(d.t_elapsed[e]) / 3600.0;
+    X = x_km / sx + double(d.offsets[(int64_t(h10) * 4 + 0) * d.n + e]);
+    Y = y_km / sy + double(d.offsets[(int64_t(h10) * 4 + 1) * d.n + e]);
+    Z = p / sp + double(d.offsets[(int64_t(h10) * 4 + 2) * d.n + e]);
+    W = t_h / st + double(d.offsets[(int64_t(h10) * 4 + 3) * d.n + e]);
+  }
+  // wait for the TMA transaction (phase 0)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar) : "memory");
+  if (live) {
+    RotatedPerm perm{s_perm + threadIdx.x * 256, int(e & 31) * 4};
+    const Real v = simplex_noise4<Real>(perm, X, Y, Z, W);
+    d.noise_partial[int64_t(h10) * d.n + e] = Real(kNoiseMagnitude) * v;
+  }
+}
+
+// forecast + noise at the balloon's current state (WindField.get_ground_truth, env/wind_field.py:125-145)
+template <typename Real>
+__device__ __forceinline__ void wind_at_balloon(const DevState<Real>& d, int64_t e, Real x, Real y, Real p,
+                                                int32_t t_elapsed, Real* u, Real* v) {
+  if (d.wind_model == BLE_WIND_SIMPLE_STATIC) {
+    static_wind<Real>(p, u, v);
+  } else {
+    const FieldPoint q = make_field_point(double(x) / 1000.0, double(y) / 1000.0, double(p),
+                                          double(t_elapsed) / 3600.0);
+    CellLoader ld{d.cells + int64_t(d.env_field[e]) * kCellFieldFloats};
+    interp_cells<Real>(q, ld, u, v);
+  }
+  if (d.enable_noise) {
+    // NoisyWindComponent.get_noise (:180-211): weighted mean of 5 harmonics, variance-rescaled
+    const double wu[5] = {0.1445, 0.2766, 0.2627, 0.2137, 0.1025};
+    const double wv[5] = {0.2716, 0.2684, 0.2348, 0.1186, 0.1066};
+    Real nu = Real(0), nv = Real(0);
+    double swu = 0, swu2 = 0, swv = 0, swv2 = 0;
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      nu += d.noise_partial[int64_t(h) * d.n + e] * Real(wu[h]);
+      nv += d.noise_partial[int64_t(5 + h) * d.n + e] * Real(wv[h]);
+      swu += wu[h]; swu2 += wu[h] * wu[h]; swv += wv[h]; swv2 += wv[h] * wv[h];
+    }
+    nu = nu / Real(swu) * Real(sqrt(swu / swu2));
+    nv = nv / Real(swv) * Real(sqrt(swv / swv2));
+    *u += nu;
+    *v += nv;
+  }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128)
+k_wind_at_balloon(DevState<Real> d, float2* __restrict__ uv) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  Real u, v;
+  wind_at_balloon<Real>(d, e, RR(d, R_X, e), RR(d, R_Y, e), RR(d, R_P, e), d.t_elapsed[e], &u, &v);
+  uv[e] = make_float2(float(u), float(v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// The fused physics step: wind at balloon -> safety layers -> 18 Euler sub-steps -> reward/done
+// ---------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(128)
+k_step(DevState<Real> d, const int32_t* __restrict__ actions, float* __restrict__ reward,
+       uint8_t* __restrict__ done, float2* __restrict__ wind_uv) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  const uint32_t fl = d.flags[e];
+  if ((fl & 3u) != uint32_t(kOk)) {          // finished balloon: no-op (documented divergence)
+    reward[e] = 0.f;
+    done[e] = 1;
+    if (wind_uv != nullptr) wind_uv[e] = make_float2(0.f, 0.f);
+    return;
+  }
+  BalloonState<Real> s;
+  s.x = RR(d, R_X, e); s.y = RR(d, R_Y, e); s.pressure = RR(d, R_P, e);
+  s.t_ambient = RR(d, R_TAMB, e); s.t_internal = RR(d, R_TINT, e); s.volume = RR(d, R_VOL, e);
+  s.superpressure = RR(d, R_SP, e); s.mols_air = RR(d, R_MOLS_AIR, e); s.charge = RR(d, R_CHARGE, e);
+  s.acs_power = RR(d, R_ACS_W, e); s.acs_flow = RR(d, R_ACS_FLOW, e);
+  s.solar_w = RR(d, R_SOLAR_W, e); s.load_w = RR(d, R_LOAD_W, e);
+  s.lat0 = RR(d, R_LAT0, e); s.lng0 = RR(d, R_LNG0, e); s.ir = RR(d, R_IR, e); s.mols_gas = RR(d, R_MOLS_GAS, e);
+  s.date_time = d.l[int64_t(L_DATE_TIME) * d.n + e];
+  s.time_elapsed = d.t_elapsed[e];
+  s.status = kOk;
+  Atmosphere<Real> atm;
+  atm.alpha = Real(d.alpha[e]);
+  atm.l0 = RR(d, R_L0, e); atm.l1 = RR(d, R_L1, e); atm.l2 = RR(d, R_L2, e);
+  atm.t1 = RR(d, R_T1, e); atm.t2 = RR(d, R_T2, e);
+  atm.p1 = RR(d, R_P1, e); atm.p2 = RR(d, R_P2, e); atm.p3 = RR(d, R_P3, e);
+  atm.ok = true;
+  SafetyState ss;
+  ss.sunrise_h = d.l[int64_t(L_SUNRISE_H) * d.n + e];
+  ss.sunset = d.l[int64_t(L_SUNSET) * d.n + e];
+  ss.last_command = int((fl >> 2) & 3); ss.envelope_state = int((fl >> 4) & 7);
+  ss.altitude_state = int((fl >> 7) & 3); ss.power_paused = int((fl >> 9) & 1);
+  ss.power_safety_enabled = int((fl >> 10) & 1);
+
+  Real u, v;
+  wind_at_balloon<Real>(d, e, s.x, s.y, s.pressure, s.time_elapsed, &u, &v);   // PRE-step lookup
+  int action = actions[e];
+  action = action < 0 ? 0 : (action > 2 ? 2 : action);
+  int eff;
+  const Real r = agent_step<Real>(s, atm, ss, action, u, v, &eff);
+
+  RR(d, R_X, e) = s.x; RR(d, R_Y, e) = s.y; RR(d, R_P, e) = s.pressure;
+  RR(d, R_TAMB, e) = s.t_ambient; RR(d, R_TINT, e) = s.t_internal; RR(d, R_VOL, e) = s.volume;
+  RR(d, R_SP, e) = s.superpressure; RR(d, R_MOLS_AIR, e) = s.mols_air; RR(d, R_CHARGE, e) = s.charge;
+  RR(d, R_ACS_W, e) = s.acs_power; RR(d, R_ACS_FLOW, e) = s.acs_flow;
+  RR(d, R_SOLAR_W, e) = s.solar_w; RR(d, R_LOAD_W, e) = s.load_w;
+  d.l[int64_t(L_DATE_TIME) * d.n + e] = s.date_time;
+  d.l[int64_t(L_SUNRISE_H) * d.n + e] = ss.sunrise_h;
+  d.l[int64_t(L_SUNSET) * d.n + e] = ss.sunset;
+  d.t_elapsed[e] = s.time_elapsed;
+  d.flags[e] = pack_flags(s.status, ss.last_command, ss.envelope_state, ss.altitude_state, ss.power_paused,
+                          ss.power_safety_enabled, atm.ok ? 0 : 1);
+  reward[e] = float(r);
+  done[e] = (s.status != kOk) ? 1 : 0;
+  if (wind_uv != nullptr) wind_uv[e] = make_float2(float(u), float(v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reset (env/balloon_arena.py:161-182,228-268; utils/sampling.py:37-152)
+// ---------------------------------------------------------------------------------------------
+struct Philox {          // Philox4x32-10, one stream per (seed, balloon)
+  uint32_t key[2], ctr[4], out[4];
+  int have;
+  __device__ void init(uint64_t seed, uint64_t stream) {
+    key[0] = uint32_t(seed); key[1] = uint32_t(seed >> 32);
+    ctr[0] = 0; ctr[1] = 0; ctr[2] = uint32_t(stream); ctr[3] = uint32_t(stream >> 32);
+    have = 0;
+  }
+  __device__ void round(uint32_t* c, const uint32_t* k) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __device__ uint32_t next() {
+    if (have == 0) {
+      uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+      uint32_t k[2] = {key[0], key[1]};
+      for (int i = 0; i < 10; ++i) { round(c, k); k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
+      out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+      if (++ctr[0] == 0) ++ctr[1];
+      have = 4;
+    }
+    return out[--have];
+  }
+  __device__ double uniform() {       // [0, 1) with 53 bits
+    const uint64_t a = next(), b = next();
+    return double(((a << 32) | b) >> 11) * (1.0 / 9007199254740992.0);
+  }
+  __device__ float uniform_f32() { return float(next() >> 8) * (1.0f / 16777216.0f); }   // [0,1), 24 bits
+  __device__ double normal() {        // Box-Muller
+    const double u1 = 1.0 - uniform(), u2 = uniform();
+    return sqrt(-2.0 * log(u1)) * cos(2.0 * kPi * u2);
+  }
+  __device__ double gamma(double a) { // Marsaglia-Tsang, a >= 1
+    const double dd = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
+    for (;;) {
+      const double x = normal();
+      double v = 1.0 + c * x;
+      if (v <= 0.0) continue;
+      v = v * v * v;
+      const double u = 1.0 - uniform();
+      if (log(u) < 0.5 * x * x + dd - dd * v + dd * log(v)) return dd * v;
+    }
+  }
+};
+
+// Deterministic derived state: power-safety sunrise/sunset (+30 min hysteresis) and, optionally,
+// the stable-init solve.  Always fp64 (see ble_physics.cuh).
+template <typename Real>
+__device__ void init_derived_one(DevState<Real>& d, int64_t e, bool run_stable_init) {
+  const double alpha = d.alpha[e];
+  const double x = double(RR(d, R_X, e)), y = double(RR(d, R_Y, e));
+  const double lat0 = double(RR(d, R_LAT0, e)), lng0 = double(RR(d, R_LNG0, e));
+  const int64_t ts = d.l[int64_t(L_DATE_TIME) * d.n + e];
+  double lat, lng;
+  latlng_from_offset<double>(lat0, lng0, x, y, &lat, &lng);
+  int64_t sunrise, sunset;
+  const bool ok = next_sunrise_sunset(lat, lng, ts, &sunrise, &sunset);   // PowerSafetyLayer.__init__
+  d.l[int64_t(L_SUNRISE_H) * d.n + e] = sunrise + 30 * 60;                // power_safety.py:45-50
+  d.l[int64_t(L_SUNSET) * d.n + e] = sunset;
+  uint32_t fl = d.flags[e];
+  fl &= ~((7u << 4) | (3u << 7) | (1u << 9));     // envelope/altitude NOMINAL, not paused (balloon.py:210-215)
+  if (!ok) fl |= (1u << 11);
+  if (run_stable_init) {                           // stable_init.cold_start_to_stable_params :132-157
+    const StableParams sp = stable_params(alpha, double(RR(d, R_P, e)), double(RR(d, R_MOLS_GAS, e)),
+                                          lat, lng, ts, double(RR(d, R_IR, e)));
+    RR(d, R_TAMB, e) = Real(sp.t_ambient); RR(d, R_TINT, e) = Real(sp.t_internal);
+    RR(d, R_MOLS_AIR, e) = Real(sp.mols_air); RR(d, R_VOL, e) = Real(sp.volume);
+    RR(d, R_SP, e) = Real(sp.superpressure);
+    if (!sp.ok) fl |= (1u << 11);
+  }
+  d.flags[e] = fl;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128) k_init_derived(DevState<Real> d, int run_stable_init) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  init_derived_one<Real>(d, e, run_stable_init != 0);
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128)
+k_reset(DevState<Real> d, const uint64_t* __restrict__ seeds, const uint8_t* __restrict__ mask,
+        int64_t* __restrict__ noise_seeds /*[n,2,5]*/, float* __restrict__ noise_offsets /*[n,2,5,4]*/) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  if (mask != nullptr && mask[e] == 0) return;
+  Philox rng;
+  rng.init(seeds[e], uint64_t(e));
+  // Atmosphere.reset: alpha ~ U(0,1)  (standard_atmosphere.py:82)
+  const double alpha = rng.uniform();
+  // sampling.sample_time: uniform second in [2011-01-01, 2014-12-31)  (utils/sampling.py:65-83)
+  const int64_t t0 = 1293840000;               // 2011-01-01T00:00:00Z
+  const int64_t range = 126144000;             // 1460 days
+  const int64_t ts = t0 + int64_t(rng.uniform() * double(range));
+  // _initialize_balloon (env/balloon_arena.py:228-268)
+  const double ga = rng.gamma(1.2), gb = rng.gamma(2.0);
+  const double radius_m = 200.0e3 * (ga / (ga + gb));                      // 200 km * Beta(1.2, 2.0)
+  const double theta = rng.uniform() * 2.0 * kPi;
+  const double x = cos(theta) * radius_m, y = sin(theta) * radius_m;
+  const double lat_deg = -10.0 + 20.0 * rng.uniform();                     // sample_location :37-61
+  const double lng_deg = -175.0 + 350.0 * rng.uniform();
+  double pmax, tmp;
+  atm_at_height_generic(alpha, kAltMin, &pmax, &tmp);                      // sample_pressure :86-111
+  const double pressure = 6500.0 + (pmax - 6500.0) * rng.uniform();
+  double ir;
+  do {                                                                     // sample_upwelling_infrared :114-152
+    const double z = 2.0 + 315.0 * rng.normal();
+    ir = 315.0 * (1.0 / (1.0 + exp(-z)));
+  } while (!(ir >= 225.0));
+
+  d.alpha[e] = alpha;
+  Atmosphere<Real> atm; atm.init(alpha);
+  RR(d, R_L0, e) = atm.l0; RR(d, R_L1, e) = atm.l1; RR(d, R_L2, e) = atm.l2;
+  RR(d, R_T1, e) = atm.t1; RR(d, R_T2, e) = atm.t2;
+  RR(d, R_P1, e) = atm.p1; RR(d, R_P2, e) = atm.p2; RR(d, R_P3, e) = atm.p3;
+  // BalloonState defaults (env/balloon/balloon.py:175-208)
+  RR(d, R_X, e) = Real(x); RR(d, R_Y, e) = Real(y); RR(d, R_P, e) = Real(pressure);
+  RR(d, R_TAMB, e) = Real(206.0); RR(d, R_TINT, e) = Real(206.0); RR(d, R_VOL, e) = Real(1804.0);
+  RR(d, R_SP, e) = Real(0); RR(d, R_MOLS_AIR, e) = Real(0); RR(d, R_CHARGE, e) = Real(2905.6);
+  RR(d, R_ACS_W, e) = Real(0); RR(d, R_ACS_FLOW, e) = Real(0); RR(d, R_SOLAR_W, e) = Real(0);
+  RR(d, R_LOAD_W, e) = Real(0);
+  RR(d, R_LAT0, e) = Real(lat_deg * (kPi / 180.0)); RR(d, R_LNG0, e) = Real(lng_deg * (kPi / 180.0));
+  RR(d, R_IR, e) = Real(ir); RR(d, R_MOLS_GAS, e) = Real(6830.0);
+  d.l[int64_t(L_DATE_TIME) * d.n + e] = ts;
+  d.t_elapsed[e] = 0;
+  d.flags[e] = pack_flags(kOk, kStay, kEnvNominal, kAltNominal, 0, 1, 0);
+  init_derived_one<Real>(d, e, true);
+  // SimplexWindNoise.reset_wind_noise (simplex_wind_noise.py:98-114)
+  for (int h = 0; h < 10; ++h) {
+    noise_seeds[e * 10 + h] = int64_t(rng.uniform() * 1634753849.0);
+    for (int c = 0; c < 4; ++c) noise_offsets[(e * 10 + h) * 4 + c] = rng.uniform_f32() * 2.0f - 1.0f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side engine
+// ---------------------------------------------------------------------------------------------
+struct EngineBase {
+  virtual ~EngineBase() {}
+  virtual int upload_fields(const float*, int64_t, const int32_t*, cudaStream_t) = 0;
+  virtual int set_noise(const int64_t*, const float*, const uint8_t*, cudaStream_t) = 0;
+  virtual int state_upload(const ble_state_soa*, cudaStream_t) = 0;
+  virtual int state_download(ble_state_soa*, cudaStream_t) = 0;
+  virtual int reset(const uint64_t*, const uint8_t*, cudaStream_t) = 0;
+  virtual int init_derived(int, cudaStream_t) = 0;
+  virtual int step(const int32_t*, float*, uint8_t*, float*, cudaStream_t) = 0;
+  virtual int step_host(const int32_t*, float*, uint8_t*, cudaStream_t) = 0;
+  virtual int wind_at(float*, cudaStream_t) = 0;
+  virtual int wind_gather(const float*, const int32_t*, float*, int64_t, cudaStream_t) = 0;
+  int64_t n = 0;
+  int64_t launches = 0;
+  std::string err;
+};
+
+#define BLE_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+      return e_ == cudaErrorMemoryAllocation ? BLE_ERR_OUT_OF_MEMORY : BLE_ERR_CUDA;       \
+    }                                                                                      \
+  } while (0)
+
+template <typename Real>
+struct Engine : EngineBase {
+  DevState<Real> d{};
+  ble_config cfg{};
+  int device = 0;
+  float* cells = nullptr; int64_t n_fields = 0;
+  int32_t* env_field = nullptr;
+  uint8_t* perm = nullptr; float* offsets = nullptr;
+  int64_t* noise_seeds = nullptr; float* noise_offsets_in = nullptr;
+  bool have_state = false, have_fields = false, have_noise = false;
+  // ble_step_host staging
+  int32_t* h_actions = nullptr; float* h_reward = nullptr; uint8_t* h_done = nullptr;
+  int32_t* d_actions = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr;
+
+  int create(int dev, int64_t n_envs, const ble_config& c) {
+    device = dev; n = n_envs; cfg = c;
+    BLE_CUDA(cudaSetDevice(device));
+    d.n = n;
+    BLE_CUDA(cudaMalloc(&d.r, sizeof(Real) * R_COUNT * n));
+    BLE_CUDA(cudaMalloc(&d.alpha, sizeof(double) * n));
+    BLE_CUDA(cudaMalloc(&d.l, sizeof(int64_t) * L_COUNT * n));
+    BLE_CUDA(cudaMalloc(&d.t_elapsed, sizeof(int32_t) * n));
+    BLE_CUDA(cudaMalloc(&d.flags, sizeof(uint32_t) * n));
+    BLE_CUDA(cudaMalloc(&env_field, sizeof(int32_t) * n));
+    BLE_CUDA(cudaMemset(env_field, 0, sizeof(int32_t) * n));
+    BLE_CUDA(cudaMalloc(&d.noise_partial, sizeof(Real) * 10 * n));
+    BLE_CUDA(cudaMemset(d.noise_partial, 0, sizeof(Real) * 10 * n));
+    BLE_CUDA(cudaMalloc(&d_actions, sizeof(int32_t) * n));
+    BLE_CUDA(cudaMalloc(&d_reward, sizeof(float) * n));
+    BLE_CUDA(cudaMalloc(&d_done, sizeof(uint8_t) * n));
+    BLE_CUDA(cudaMallocHost(&h_actions, sizeof(int32_t) * n));
+    BLE_CUDA(cudaMallocHost(&h_reward, sizeof(float) * n));
+    BLE_CUDA(cudaMallocHost(&h_done, sizeof(uint8_t) * n));
+    d.env_field = env_field;
+    d.wind_model = cfg.wind_model;
+    d.enable_noise = 0;
+    BLE_CUDA(cudaFuncSetAttribute(k_noise<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseBlock * 256));
+    return BLE_OK;
+  }
+
+  ~Engine() override {
+    cudaSetDevice(device);
+    cudaFree(d.r); cudaFree(d.alpha); cudaFree(d.l); cudaFree(d.t_elapsed); cudaFree(d.flags);
+    cudaFree(env_field); cudaFree(d.noise_partial); cudaFree(cells); cudaFree(perm); cudaFree(offsets);
+    cudaFree(noise_seeds); cudaFree(noise_offsets_in);
+    cudaFree(d_actions); cudaFree(d_reward); cudaFree(d_done);
+    cudaFreeHost(h_actions); cudaFreeHost(h_reward); cudaFreeHost(h_done);
+  }
+
+  static unsigned grid_for(int64_t items, int block) { return unsigned((items + block - 1) / block); }
+
+  int upload_fields(const float* fields, int64_t nf, const int32_t* map, cudaStream_t s) override {
+    if (fields == nullptr || nf <= 0) { err = "upload_fields: fields must be non-null, n_fields > 0"; return BLE_ERR_INVALID_ARGUMENT; }
+    BLE_CUDA(cudaSetDevice(device));
+    if (nf != n_fields) {
+      BLE_CUDA(cudaStreamSynchronize(s));
+      cudaFree(cells); cells = nullptr;
+      BLE_CUDA(cudaMalloc(&cells, sizeof(float) * kCellFieldFloats * nf));
+      n_fields = nf;
+    }
+    const int64_t n_cells = nf * int64_t(kNX) * kNY * kPC * kTC;
+    k_fields_to_cells<<<grid_for(n_cells, 256), 256, 0, s>>>(fields, cells, n_cells);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    if (map != nullptr) BLE_CUDA(cudaMemcpyAsync(env_field, map, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
+    d.cells = cells;
+    have_fields = true;
+    return BLE_OK;
+  }
+
+  int ensure_noise_buffers() {
+    if (perm == nullptr) {
+      BLE_CUDA(cudaMalloc(&perm, size_t(10) * n * 256));
+      BLE_CUDA(cudaMalloc(&offsets, sizeof(float) * 40 * n));
+      d.perm = perm; d.offsets = offsets;
+    }
+    return BLE_OK;
+  }
+
+  int set_noise(const int64_t* seeds, const float* offs, const uint8_t* mask, cudaStream_t s) override {
+    if (seeds == nullptr || offs == nullptr) { err = "set_noise: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    BLE_CUDA(cudaSetDevice(device));
+    int rc = ensure_noise_buffers();
+    if (rc != BLE_OK) return rc;
+    k_make_perms<<<grid_for(n * 10, 64), 64, 0, s>>>(n, seeds, offs, mask, perm, offsets);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    have_noise = true;
+    d.enable_noise = cfg.enable_noise ? 1 : 0;
+    return BLE_OK;
+  }
+
+  int state_upload(const ble_state_soa* st, cudaStream_t s) override {
+    if (st == nullptr || st->f64 == nullptr || st->i64 == nullptr) { err = "state_upload: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    BLE_CUDA(cudaSetDevice(device));
+    k_state_upload<Real><<<grid_for(n, 128), 128, 0, s>>>(d, st->f64, st->i64);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    have_state = true;
+    return BLE_OK;
+  }
+
+  int state_download(ble_state_soa* st, cudaStream_t s) override {
+    if (st == nullptr || st->f64 == nullptr || st->i64 == nullptr) { err = "state_download: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    if (!have_state) { err = "state_download: no state (call ble_reset or ble_state_upload first)"; return BLE_ERR_NOT_READY; }
+    BLE_CUDA(cudaSetDevice(device));
+    k_state_download<Real><<<grid_for(n, 128), 128, 0, s>>>(d, st->f64, st->i64);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
+  int reset(const uint64_t* seeds, const uint8_t* mask, cudaStream_t s) override {
+    if (seeds == nullptr) { err = "reset: seeds must be non-null"; return BLE_ERR_INVALID_ARGUMENT; }
+    if (mask != nullptr && !have_state) { err = "reset: a masked reset needs an initial full reset"; return BLE_ERR_NOT_READY; }
+    BLE_CUDA(cudaSetDevice(device));
+    int rc = ensure_noise_buffers();
+    if (rc != BLE_OK) return rc;
+    if (noise_seeds == nullptr) {
+      BLE_CUDA(cudaMalloc(&noise_seeds, sizeof(int64_t) * 10 * n));
+      BLE_CUDA(cudaMalloc(&noise_offsets_in, sizeof(float) * 40 * n));
+    }
+    k_reset<Real><<<grid_for(n, 128), 128, 0, s>>>(d, seeds, mask, noise_seeds, noise_offsets_in);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    k_make_perms<<<grid_for(n * 10, 64), 64, 0, s>>>(n, noise_seeds, noise_offsets_in, mask, perm, offsets);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    have_state = true; have_noise = true;
+    d.enable_noise = cfg.enable_noise ? 1 : 0;
+    return BLE_OK;
+  }
+
+  int init_derived(int run_stable_init, cudaStream_t s) override {
+    if (!have_state) { err = "init_derived: no state uploaded"; return BLE_ERR_NOT_READY; }
+    BLE_CUDA(cudaSetDevice(device));
+    k_init_derived<Real><<<grid_for(n, 128), 128, 0, s>>>(d, run_stable_init);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
+  int check_ready(const char* who) {
+    if (!have_state) { err = std::string(who) + ": no balloon state (call ble_reset or ble_state_upload)"; return BLE_ERR_NOT_READY; }
+    if (cfg.wind_model == BLE_WIND_GRID && !have_fields) {
+      err = std::string(who) + ": no wind fields (call ble_upload_fields before stepping)";   // grid_based_wind_field.py:86-87
+      return BLE_ERR_NOT_READY;
+    }
+    if (cfg.enable_noise && !have_noise) { err = std::string(who) + ": noise enabled but not seeded (ble_set_noise / ble_reset)"; return BLE_ERR_NOT_READY; }
+    return BLE_OK;
+  }
+
+  int launch_noise(cudaStream_t s) {
+    if (!d.enable_noise) return BLE_OK;
+    dim3 grid(grid_for(n, kNoiseBlock), 10);
+    k_noise<Real><<<grid, kNoiseBlock, kNoiseBlock * 256, s>>>(d);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
+  int step(const int32_t* actions, float* reward, uint8_t* done, float* wind_uv, cudaStream_t s) override {
+    if (actions == nullptr || reward == nullptr || done == nullptr) { err = "step: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    int rc = check_ready("step");
+    if (rc != BLE_OK) return rc;
+    BLE_CUDA(cudaSetDevice(device));
+    rc = launch_noise(s);
+    if (rc != BLE_OK) return rc;
+    k_step<Real><<<grid_for(n, 128), 128, 0, s>>>(d, actions, reward, done, reinterpret_cast<float2*>(wind_uv));
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
+  int step_host(const int32_t* actions_host, float* reward_host, uint8_t* done_host, cudaStream_t s) override {
+    if (actions_host == nullptr || reward_host == nullptr || done_host == nullptr) { err = "step_host: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    BLE_CUDA(cudaSetDevice(device));
+    std::memcpy(h_actions, actions_host, sizeof(int32_t) * n);
+    BLE_CUDA(cudaMemcpyAsync(d_actions, h_actions, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    int rc = step(d_actions, d_reward, d_done, nullptr, s);
+    if (rc != BLE_OK) return rc;
+    BLE_CUDA(cudaMemcpyAsync(h_reward, d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+    BLE_CUDA(cudaMemcpyAsync(h_done, d_done, sizeof(uint8_t) * n, cudaMemcpyDeviceToHost, s));
+    BLE_CUDA(cudaStreamSynchronize(s));
+    std::memcpy(reward_host, h_reward, sizeof(float) * n);
+    std::memcpy(done_host, h_done, sizeof(uint8_t) * n);
+    return BLE_OK;
+  }
+
+  int wind_at(float* uv, cudaStream_t s) override {
+    if (uv == nullptr) { err = "wind_at_balloon: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    int rc = check_ready("wind_at_balloon");
+    if (rc != BLE_OK) return rc;
+    BLE_CUDA(cudaSetDevice(device));
+    rc = launch_noise(s);
+    if (rc != BLE_OK) return rc;
+    k_wind_at_balloon<Real><<<grid_for(n, 128), 128, 0, s>>>(d, reinterpret_cast<float2*>(uv));
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
+  int wind_gather(const float* xyzt, const int32_t* fidx, float* uv, int64_t m, cudaStream_t s) override {
+    if (m < 0 || (m > 0 && (xyzt == nullptr || fidx == nullptr || uv == nullptr))) { err = "wind_gather: bad argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    if (!have_fields) { err = "wind_gather: no wind fields (call ble_upload_fields first)"; return BLE_ERR_NOT_READY; }
+    if (m == 0) return BLE_OK;
+    BLE_CUDA(cudaSetDevice(device));
+    k_wind_gather<Real><<<grid_for(m, 256), 256, 0, s>>>(cells, reinterpret_cast<const float4*>(xyzt), fidx,
+                                                       reinterpret_cast<float2*>(uv), m);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+};
+
+}  // namespace ble
+
+// -----------------------------------------------------------------------------------------------
+// C ABI
+// -----------------------------------------------------------------------------------------------
+struct ble_handle {
+  ble::EngineBase* eng;
+};
+
+static thread_local std::string g_create_error;
+
+extern "C" {
+
+int ble_create(int device, int64_t n_envs, const ble_config* config, ble_handle** out) {
+  if (out == nullptr || config == nullptr || n_envs <= 0) {
+    g_create_error = "ble_create: out/config must be non-null and n_envs > 0";
+    return BLE_ERR_INVALID_ARGUMENT;
+  }
+  if (config->precision != BLE_PRECISION_FP32 && config->precision != BLE_PRECISION_FP64) {
+    g_create_error = "ble_create: unknown precision"; return BLE_ERR_INVALID_ARGUMENT;
+  }
+  if (config->wind_model != BLE_WIND_GRID && config->wind_model != BLE_WIND_SIMPLE_STATIC) {
+    g_create_error = "ble_create: unknown wind_model"; return BLE_ERR_INVALID_ARGUMENT;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    g_create_error = "ble_create: CUDA device not available (this library has no CPU fallback)";
+    return BLE_ERR_CUDA;
+  }
+  ble::EngineBase* eng = nullptr;
+  int rc;
+  if (config->precision == BLE_PRECISION_FP64) {
+    auto* e = new (std::nothrow) ble::Engine<double>();
+    if (e == nullptr) { g_create_error = "ble_create: host allocation failed"; return BLE_ERR_OUT_OF_MEMORY; }
+    rc = e->create(device, n_envs, *config); eng = e;
+  } else {
+    auto* e = new (std::nothrow) ble::Engine<float>();
+    if (e == nullptr) { g_create_error = "ble_create: host allocation failed"; return BLE_ERR_OUT_OF_MEMORY; }
+    rc = e->create(device, n_envs, *config); eng = e;
+  }
+  if (rc != BLE_OK) { g_create_error = eng->err; delete eng; return rc; }
+  auto* h = new (std::nothrow) ble_handle{eng};
+  if (h == nullptr) { delete eng; g_create_error = "ble_create: host allocation failed"; return BLE_ERR_OUT_OF_MEMORY; }
+  *out = h;
+  return BLE_OK;
+}
+
+int ble_destroy(ble_handle* h) {
+  if (h == nullptr) return BLE_ERR_INVALID_ARGUMENT;
+  delete h->eng;
+  delete h;
+  return BLE_OK;
+}
+
+const char* ble_last_error(const ble_handle* h) { return h == nullptr ? g_create_error.c_str() : h->eng->err.c_str(); }
+int64_t ble_num_envs(const ble_handle* h) { return h == nullptr ? 0 : h->eng->n; }
+int64_t ble_launch_count(const ble_handle* h) { return h == nullptr ? 0 : h->eng->launches; }
+
+#define BLE_H(h) if ((h) == nullptr) return BLE_ERR_INVALID_ARGUMENT
+
+int ble_upload_fields(ble_handle* h, const float* fields, int64_t n_fields, const int32_t* env_to_field, void* stream) {
+  BLE_H(h); return h->eng->upload_fields(fields, n_fields, env_to_field, cudaStream_t(stream));
+}
+int ble_set_noise(ble_handle* h, const int64_t* seeds, const float* offsets, void* stream) {
+  BLE_H(h); return h->eng->set_noise(seeds, offsets, nullptr, cudaStream_t(stream));
+}
+int ble_state_upload(ble_handle* h, const ble_state_soa* state, void* stream) {
+  BLE_H(h); return h->eng->state_upload(state, cudaStream_t(stream));
+}
+int ble_state_download(ble_handle* h, ble_state_soa* state, void* stream) {
+  BLE_H(h); return h->eng->state_download(state, cudaStream_t(stream));
+}
+int ble_reset(ble_handle* h, const uint64_t* seeds, const uint8_t* mask, void* stream) {
+  BLE_H(h); return h->eng->reset(seeds, mask, cudaStream_t(stream));
+}
+int ble_init_derived(ble_handle* h, int32_t run_stable_init, void* stream) {
+  BLE_H(h); return h->eng->init_derived(run_stable_init, cudaStream_t(stream));
+}
+int ble_step(ble_handle* h, const int32_t* actions, float* reward, uint8_t* done, float* wind_uv, void* stream) {
+  BLE_H(h); return h->eng->step(actions, reward, done, wind_uv, cudaStream_t(stream));
+}
+int ble_step_host(ble_handle* h, const int32_t* actions_host, float* reward_host, uint8_t* done_host, void* stream) {
+  BLE_H(h); return h->eng->step_host(actions_host, reward_host, done_host, cudaStream_t(stream));
+}
+int ble_wind_at_balloon(ble_handle* h, float* wind_uv, void* stream) {
+  BLE_H(h); return h->eng->wind_at(wind_uv, cudaStream_t(stream));
+}
+int ble_wind_gather(ble_handle* h, const float* xyzt, const int32_t* field_idx, float* uv, int64_t m, void* stream) {
+  BLE_H(h); return h->eng->wind_gather(xyzt, field_idx, uv, m, cudaStream_t(stream));
+}
+
+}  // extern "C"

@@ -150,8 +150,8 @@ BLE_HD Real gradient_dot(int hash, Real dx, Real dy, Real dz, Real dw) {
 // Candidate c in [0, 80): m = c / 5 is the cube corner (bit k of m = offset along axis k),
 // e = c % 5: 0 = the corner itself, 1..4 = step one further out along axis e-1
 // (offset 1 -> 2, offset 0 -> -1).  `perm` is this generator's 256-entry table.
-template <typename Real>
-BLE_HD Real simplex_noise4(const uint8_t* perm, double x, double y, double z, double w) {
+template <typename Real, typename Perm>
+BLE_HD Real simplex_noise4(const Perm& perm, double x, double y, double z, double w) {
   const double s = (x + y + z + w) * kStretch4;
   const double fx = floor(x + s), fy = floor(y + s), fz = floor(z + s), fw = floor(w + s);
   const double q = (fx + fy + fz + fw) * kSquish4;

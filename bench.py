@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the batched BLE transition function (BASELINE.json: env-steps/s at batch 65,536).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--num-envs 65536]
+
+One "step" = one BalloonEnv.step (wind lookup + safety layers + 18 physics sub-steps + reward)
+for every balloon of the batch.  Default workload = BASELINE.json configs[2]: 65,536 balloons,
+random agent, one wind field per balloon (synthetic fields: the VAE decoder is reset-time only).
+N > 1 (torchrun) shards the balloons across ranks with no data-path collective: strong scaling.
+
+`--impl reference` times the CPU oracle port (oracle/, the restated reference algorithm) on the
+host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'env_steps_per_s'
+UNIT = 'env-steps/s'
+GATHER_BYTES_PER_LOOKUP = 156        # 16 B query + 4 B field index + 128 B corners + 8 B result
+
+
+def load_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    with open(path) as f:
+      return float(json.load(f)['hbm_gbs']), 'measured'
+  return 6650.0, 'fallback'
+
+
+class ClockSampler(threading.Thread):
+  """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+  def run(self):
+    q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    while not self._stop_evt.is_set():
+      try:
+        out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+          self.rows.append([c.strip() for c in out.split(',')])
+      except Exception:  # pylint: disable=broad-except
+        pass
+      self._stop_evt.wait(0.2)
+
+  def stop(self):
+    self._stop_evt.set()
+    self.join(timeout=3)
+    if not self.rows:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    reasons = [n for j, n in enumerate(names) if any(r[2 + j].lower().startswith('active') for r in self.rows)]
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+            'reasons': reasons, 'samples': len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (oracle port): the only place bench.py touches oracle/
+# ---------------------------------------------------------------------------------------------
+def _oracle_worker(args):
+  n, steps, seed = args
+  os.environ.setdefault('OMP_NUM_THREADS', '1')
+  from oracle import atmosphere, balloon, env as oenv, stable_init, wind
+  rng = np.random.default_rng(seed)
+  alpha = rng.uniform(0, 1, n)
+  atm = atmosphere.Atmosphere(alpha)
+  radius = 200e3 * rng.beta(1.2, 2.0, n); theta = rng.uniform(0, 2 * np.pi, n)
+  pmax, _ = atm.at_height(np.full(n, 15240.0))
+  b = balloon.make_batch(n, center_lat=np.radians(rng.uniform(-10, 10, n)), center_lng=np.radians(rng.uniform(-175, 175, n)),
+                         date_time=1293840000 + rng.integers(0, 126144000, n), x=radius * np.cos(theta),
+                         y=radius * np.sin(theta), pressure=rng.uniform(6500, pmax), upwelling_infrared=315.0)
+  stable_init.cold_start_to_stable_params(b, atm)
+  n_fields = min(n, 64)                                     # per-balloon fields: the CPU does not care
+  fields = (rng.standard_normal((n_fields, 21, 21, 10, 9, 2)) * np.array([5.4, 1.5])).astype(np.float32)
+  noise = wind.SimplexWindNoise(rng.integers(0, 1634753849, (n, 2, 5)), rng.uniform(-1, 1, (n, 2, 5, 4)))
+  e = oenv.OracleEnv(oenv.OracleArena(b, atm, fields=fields, field_idx=rng.integers(0, n_fields, n), noise=noise))
+  e.step(rng.integers(0, 3, n))                              # warm-up (imports, allocations)
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    e.step(rng.integers(0, 3, n))
+  return time.perf_counter() - t0
+
+
+def cpu_oracle_throughput(n_per_worker, steps, workers):
+  """env-steps/s of the oracle port on `workers` host processes (1 = scalar baseline)."""
+  if workers <= 1:
+    dt = _oracle_worker((n_per_worker, steps, 0))
+    return n_per_worker * steps / dt
+  import multiprocessing as mp
+  with mp.get_context('spawn').Pool(workers) as pool:
+    times = pool.map(_oracle_worker, [(n_per_worker, steps, s) for s in range(workers)])
+  return workers * n_per_worker * steps / max(times)
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  cores = os.cpu_count() or 1
+  n_per_worker = 2048
+  # warm-up + K steps, each step a bounded sample (cores x 2,048 balloons) of the 65,536-balloon batch
+  t0 = time.perf_counter()
+  value = cpu_oracle_throughput(n_per_worker, max(1, args.steps), cores)
+  wall = time.perf_counter() - t0
+  sample = f'{cores} processes x {n_per_worker} balloons x {max(1, args.steps)} steps of the oracle port (NumPy fp64)'
+  line = {
+      'metric': METRIC, 'value': value, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': 1e3 * args.num_envs / value, 'higher_is_better': True,
+      'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+      'config': {'workload': f'batch={args.num_envs} balloons, random agent, per-balloon wind field + simplex noise '
+                             '(BASELINE configs[2]); CPU arm runs a bounded sample'},
+      'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+      'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'wall_s': wall,
+  }
+  print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def synthetic_fields(torch, n_fields, device, seed, chunk=2048):
+  """[F,21,21,10,9,2] fp32 with VAE-like magnitudes (u ~ 5.4 N(0,1), v ~ 1.5 N(0,1))."""
+  g = torch.Generator(device=device); g.manual_seed(seed)
+  out = torch.empty(n_fields, 21, 21, 10, 9, 2, dtype=torch.float32, device=device)
+  scale = torch.tensor([5.4, 1.5], device=device)
+  for s in range(0, n_fields, chunk):
+    e = min(n_fields, s + chunk)
+    out[s:e] = torch.randn(e - s, 21, 21, 10, 9, 2, generator=g, device=device) * scale
+  return out
+
+
+def run_b200(args):
+  import torch
+  import torch.distributed as dist
+  from balloon_learning_environment_b200 import batched_env
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
+  torch.cuda.set_device(local_rank)
+  device = torch.device(f'cuda:{local_rank}')
+  n_total = args.num_envs
+  n = n_total // world                                       # strong scaling: fixed total batch
+  assert n * world == n_total, 'num-envs must be divisible by the number of GPUs'
+
+  arena = batched_env.BatchedBalloonArena(n, device=str(device), precision='fp32', wind_model='grid', enable_noise=True)
+  n_fields = n if args.shared_fields == 0 else args.shared_fields
+  fields = synthetic_fields(torch, n_fields, device, seed=1234 + rank)
+  env_to_field = (torch.arange(n, dtype=torch.int32, device=device) % n_fields)
+  arena.set_wind_fields(fields, env_to_field)
+  torch.cuda.synchronize()
+  del fields
+  arena._keepalive = [None, env_to_field]
+  torch.cuda.empty_cache()
+  g = torch.Generator(device='cpu'); g.manual_seed(2024 + rank)
+  arena.reset(torch.randint(0, 2**62, (n,), dtype=torch.int64, generator=g))
+
+  total = args.warmup + args.steps
+  gd = torch.Generator(device=device); gd.manual_seed(7 + rank)
+  actions = torch.randint(0, 3, (total, n), dtype=torch.int32, device=device, generator=gd)   # RandomAgent
+  actions_host = actions.cpu().numpy()
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---- device-resident timing -------------------------------------------------------------
+  for t in range(args.warmup):
+    arena.step(actions[t])
+  barrier()
+  launches0 = arena.launch_count
+  sampler = ClockSampler(local_rank); sampler.start()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev0.record()
+  for t in range(args.warmup, total):
+    arena.step(actions[t])
+  ev1.record()
+  barrier()
+  ms = ev0.elapsed_time(ev1)
+  clocks = sampler.stop()
+  launches = arena.launch_count - launches0
+  live_frac = float((arena.get_state_dict()['status'] == 0).float().mean())
+
+  # ---- end to end through the host-buffer C ABI call ----------------------------------------
+  reward_h = np.zeros(n, np.float32); done_h = np.zeros(n, np.uint8)
+  e2e_steps = args.steps
+  for t in range(min(3, args.warmup)):
+    arena.step_host(actions_host[t], reward_h, done_h)
+  barrier()
+  t0 = time.perf_counter()
+  for t in range(e2e_steps):
+    arena.step_host(actions_host[args.warmup + t % args.steps], reward_h, done_h)
+  torch.cuda.synchronize()
+  e2e_s = time.perf_counter() - t0
+
+  # ---- wind-gather roofline (dominant HBM kernel named by BASELINE.json's metric) -----------
+  m = n * 8
+  gq = torch.Generator(device=device); gq.manual_seed(99 + rank)
+  xyzt = torch.empty(m, 4, dtype=torch.float32, device=device)
+  xyzt[:, 0].uniform_(-500, 500, generator=gq); xyzt[:, 1].uniform_(-500, 500, generator=gq)
+  xyzt[:, 2].uniform_(5000, 14000, generator=gq); xyzt[:, 3].uniform_(0, 48, generator=gq)
+  fidx = (torch.randperm(m, device=device, generator=gq) % n_fields).to(torch.int32)
+  for _ in range(3):
+    arena.wind_forecast(xyzt, fidx)
+  torch.cuda.synchronize()
+  g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  reps = 10
+  g0.record()
+  for _ in range(reps):
+    arena.wind_forecast(xyzt, fidx)
+  g1.record()
+  torch.cuda.synchronize()
+  gather_ms = g0.elapsed_time(g1) / reps
+  gather_gbs = GATHER_BYTES_PER_LOOKUP * m / (gather_ms * 1e-3) / 1e9
+
+  if world > 1:
+    tmax = torch.tensor([ms, e2e_s, gather_ms], device=device, dtype=torch.float64)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms, e2e_s, gather_ms_max = [float(v) for v in tmax]
+    lsum = torch.tensor([launches], device=device, dtype=torch.int64)
+    dist.all_reduce(lsum)
+    launches = int(lsum)
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  peak, peak_src = load_peaks()
+  value = n_total * args.steps / (ms * 1e-3)
+  e2e_value = n_total * e2e_steps / e2e_s
+  line = {
+      'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+      'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': f'batch={n_total} balloons, random agent, one synthetic wind field per balloon '
+                             f'({n_fields} fields/GPU) + simplex noise, 18 sub-steps per step (BASELINE configs[2])',
+                 'num_envs': n_total, 'envs_per_gpu': n, 'fields_per_gpu': n_fields,
+                 'l2': 'inputs larger than L2 (per-balloon fields + 2.5 KB noise tables per balloon)',
+                 'live_fraction_after_run': live_frac},
+      'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 4 * n_total, 'd2h_bytes_per_step': 5 * n_total,
+              'api': 'ble_step_host (host int32 actions in, host float32 reward + uint8 done out)'},
+      'gpu_launches': launches,
+      'clocks': clocks,
+      'roofline': {'kernel': 'k_wind_gather', 'bound': 'hbm', 'achieved': gather_gbs, 'peak': peak, 'unit': 'GB/s',
+                   'frac': gather_gbs / peak, 'traffic': None, 'peak_source': peak_src,
+                   'lookups_per_launch': m, 'bytes_per_lookup': GATHER_BYTES_PER_LOOKUP, 'ms_per_launch': gather_ms},
+  }
+  if world == 1 and not args.no_cpu_baseline:
+    t0 = time.perf_counter()
+    v1 = cpu_oracle_throughput(2048, 40, 1)
+    line['cpu_baseline'] = {'value': v1, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                            'sample': '1 process x 2048 balloons x 40 steps of the oracle port (NumPy fp64), '
+                                      f'{time.perf_counter() - t0:.1f} s'}
+  print(json.dumps(line), flush=True)
+  arena.close()
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=50)
+  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--num-envs', type=int, default=65536)
+  ap.add_argument('--shared-fields', type=int, default=0, help='0 = one field per balloon; else size of a shared pool')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_b200(args)
+
+
+if __name__ == '__main__':
+  main()

@@ -80,8 +80,8 @@ void emu_noise(int precision, int64_t n, const int64_t* seeds, const double* xyz
   for (int64_t i = 0; i < n; ++i) {
     simplex_make_perm(seeds[i], perm, scratch);
     const double* p = xyzw + 4 * i;
-    out[i] = precision == BLE_PRECISION_FP64 ? simplex_noise4<double>(perm, p[0], p[1], p[2], p[3])
-                                             : double(simplex_noise4<float>(perm, p[0], p[1], p[2], p[3]));
+    out[i] = precision == BLE_PRECISION_FP64 ? simplex_noise4<double>((const uint8_t*)perm, p[0], p[1], p[2], p[3])
+                                             : double(simplex_noise4<float>((const uint8_t*)perm, p[0], p[1], p[2], p[3]));
   }
 }
 

@@ -1,0 +1,54 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol of include/ble_b200.h;
+the host logic rejects bad input; the product never reaches for the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+  from balloon_learning_environment_b200 import _lib
+  lib = _lib.load()
+  header = open(os.path.join(ROOT, 'include', 'ble_b200.h')).read()
+  declared = sorted(set(re.findall(r'\b(ble_[a-z_]+)\s*\(', header)))
+  assert len(declared) >= 15
+  for name in declared:
+    assert hasattr(lib, name), f'{name} declared in include/ble_b200.h but not exported'
+  assert set(declared) == set(_lib.EXPORTS)
+
+
+def test_create_without_gpu_fails_loudly():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('a GPU is present')
+  from balloon_learning_environment_b200 import _lib, batched_env
+  lib = _lib.load()
+  cfg = _lib.BleConfig(0, 0, 1, 0)
+  h = ctypes.c_void_p()
+  rc = lib.ble_create(0, 16, ctypes.byref(cfg), ctypes.byref(h))
+  assert rc == -2 and b'no CPU fallback' in lib.ble_last_error(None)
+  assert lib.ble_create(0, 0, ctypes.byref(cfg), ctypes.byref(h)) == -1       # invalid argument
+  with pytest.raises(_lib.BleError):
+    batched_env.BatchedBalloonArena(4)
+
+
+def test_row_order_matches_header_enums():
+  from balloon_learning_environment_b200 import _lib
+  header = open(os.path.join(ROOT, 'include', 'ble_b200.h')).read()
+  f_names = re.findall(r'BLE_F_([A-Z_]+)', header.split('BLE_NUM_F')[0].split('enum {')[-1])
+  i_names = re.findall(r'BLE_I_([A-Z_]+)', header.split('BLE_NUM_I')[0].split('enum {')[-1])
+  assert [n.lower() for n in f_names] == list(_lib.F_ROWS)
+  assert [n.lower() for n in i_names] == list(_lib.I_ROWS)
+
+
+def test_product_package_does_not_import_the_oracle():
+  pkg = os.path.join(ROOT, 'balloon_learning_environment_b200')
+  for dirpath, _, files in os.walk(pkg):
+    for fn in files:
+      if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+        text = open(os.path.join(dirpath, fn)).read()
+        assert not re.search(r'^\s*(from|import)\s+oracle', text, re.M), fn
+        assert not re.search(r'#include\s+".*hostemu', text), fn

@@ -1,0 +1,374 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference
+goldens.  Run on the B200 box with `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star): fp32 state within 1e-4 relative of the reference after a
+step; discrete decisions (effective action masks -> safety-layer states, status, last command,
+time) bit-exact.  The fp64 audit build of the same kernels is held to ~1e-8.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+from oracle import atmosphere as atmosphere_lib
+from oracle import balloon as balloon_lib
+from oracle import constants as C
+from oracle import env as env_lib
+from oracle import solar as solar_lib
+from oracle import stable_init as stable_init_lib
+from oracle import wind as wind_lib
+from tests import golden_io
+from tests.golden import fields as golden_fields
+
+pytestmark = pytest.mark.gpu
+
+KAT = golden_io.load_kat()
+TRAJ = golden_io.load_traj()
+FF, IF = KAT['float_fields'], KAT['int_fields']
+
+# relative-error floors for fields that pass through zero (fraction of typical magnitude)
+FLOORS = {'x': 1e4, 'y': 1e4, 'acs_mass_flow': 1e-2, 'superpressure': 100.0, 'solar_charging': 50.0,
+          'acs_power': 100.0, 'mols_air': 100.0}
+
+
+@pytest.fixture(scope='module')
+def ble():
+  if not torch.cuda.is_available():
+    pytest.skip('no CUDA device')
+  import balloon_learning_environment_b200 as pkg
+  from balloon_learning_environment_b200 import _lib, batched_env
+  _lib.load()          # raises if the CUDA library is missing: GPU tests must not silently skip it
+  return batched_env
+
+
+def pack(batch, alpha, psl):
+  from balloon_learning_environment_b200 import _lib
+  n = batch.n
+  f = np.empty((len(_lib.F_ROWS), n)); i = np.empty((len(_lib.I_ROWS), n), np.int64)
+  for r, k in enumerate(_lib.F_ROWS):
+    f[r] = alpha if k == 'atmosphere_alpha' else getattr(batch, k)
+  for r, k in enumerate(_lib.I_ROWS):
+    i[r] = np.broadcast_to(np.asarray(psl, np.int64), (n,)) if k == 'power_safety_enabled' else getattr(batch, k)
+  return torch.from_numpy(f), torch.from_numpy(i)
+
+
+def state_np(arena):
+  from balloon_learning_environment_b200 import _lib
+  f, i = arena.get_state()
+  torch.cuda.synchronize()
+  f, i = f.cpu().numpy(), i.cpu().numpy()
+  d = {k: f[r] for r, k in enumerate(_lib.F_ROWS)}
+  d.update({k: i[r] for r, k in enumerate(_lib.I_ROWS)})
+  return d
+
+
+def rel_err(got, ref, key):
+  scale = np.maximum(np.abs(ref), FLOORS.get(key, 1e-30))
+  return float((np.abs(got - ref) / scale).max())
+
+
+# ------------------------------------------------------------------------------ wind gather
+
+@pytest.mark.parametrize('precision,tol', [('fp64', 1e-11), ('fp32', 3e-5)])
+def test_wind_gather_matches_oracle(ble, precision, tol):
+  rng = np.random.default_rng(9)
+  bank = golden_fields.field_bank()
+  arena = ble.BatchedBalloonArena(8, precision=precision, enable_noise=False)
+  arena.set_wind_fields(torch.from_numpy(bank), torch.zeros(8, dtype=torch.int32))
+  m = 20000
+  xyzt = np.stack([rng.uniform(-600, 600, m), rng.uniform(-600, 600, m), rng.uniform(4000, 15000, m),
+                   rng.uniform(0, 200, m)], 1).astype(np.float32)
+  xyzt[:10, 3] = [0, 6, 47.999, 48, 48.001, 96, 144, 95.99, 191.9, 0.001]
+  xyzt[10:14, 0] = [-500, 500, -500.001, 499.999]
+  xyzt[14:18, 2] = [5000, 14000, 4999.9, 14000.1]
+  fidx = rng.integers(0, 4, m).astype(np.int32)
+  uv = arena.wind_forecast(torch.from_numpy(xyzt), torch.from_numpy(fidx)).cpu().numpy()
+  pts = wind_lib.prepare_points(xyzt[:, 0].astype(np.float64) * 1000, xyzt[:, 1].astype(np.float64) * 1000,
+                                xyzt[:, 2].astype(np.float64), xyzt[:, 3].astype(np.float64) * 3600.0)
+  want = wind_lib.interpolate(bank, fidx, pts)
+  scale = 20.0 if precision == 'fp32' else 1.0
+  assert np.abs(uv - want).max() < max(tol * scale, 3e-6 if precision == 'fp64' else 0)  # fp32 output cast
+  arena.close()
+
+
+def test_wind_gather_reference_kat_and_empty(ble):
+  rows = np.array(KAT['interp'])
+  bank = golden_fields.field_bank()
+  arena = ble.BatchedBalloonArena(4, precision='fp64', enable_noise=False)
+  arena.set_wind_fields(torch.from_numpy(bank))
+  xyzt = np.stack([rows[:, 1] / 1000.0, rows[:, 2] / 1000.0, rows[:, 3], rows[:, 4] / 3600.0], 1)
+  keep = np.all(xyzt.astype(np.float32).astype(np.float64) == xyzt, axis=1)
+  uv = arena.wind_forecast(torch.from_numpy(xyzt[keep].astype(np.float32)),
+                           torch.from_numpy(rows[keep, 0].astype(np.int32))).cpu().numpy()
+  np.testing.assert_allclose(uv, rows[keep][:, 5:7], rtol=1e-6, atol=2e-6)      # float32 output
+  empty = arena.wind_forecast(torch.zeros(0, 4), torch.zeros(0, dtype=torch.int32))
+  assert tuple(empty.shape) == (0, 2)
+  arena.close()
+
+
+# ------------------------------------------------------------------------------ noise
+
+@pytest.mark.parametrize('precision,tol', [('fp64', 1e-6), ('fp32', 3e-4)])
+def test_noise_matches_oracle(ble, precision, tol):
+  rng = np.random.default_rng(3)
+  n = 1000                                      # not a multiple of the 128-balloon noise block
+  arena = ble.BatchedBalloonArena(n, precision=precision, enable_noise=True)
+  arena.set_wind_fields(torch.zeros(1, *ble.FIELD_SHAPE))          # forecast == 0 -> wind == noise
+  seeds = rng.integers(0, 1634753849, (n, 2, 5))
+  offsets = (rng.uniform(0, 1, (n, 2, 5, 4)).astype(np.float32) * 2 - 1)
+  arena.set_wind_noise(torch.from_numpy(seeds), torch.from_numpy(offsets))
+  b = balloon_lib.make_batch(n, center_lat=0.0, center_lng=0.0, date_time=1364203532)
+  b.x = rng.uniform(-8e5, 8e5, n); b.y = rng.uniform(-8e5, 8e5, n)
+  b.pressure = rng.uniform(5000, 14000, n); b.time_elapsed = rng.integers(0, 400000, n) // 10 * 10
+  f, i = pack(b, 0.5, 1)
+  arena.set_state(f, i)
+  got = arena.wind_at_balloon().cpu().numpy().astype(np.float64)
+  st = state_np(arena)                          # fp32 build rounds x, y, p on upload
+  noise = wind_lib.SimplexWindNoise(seeds, offsets.astype(np.float64))
+  du, dv = noise.get_wind_noise(st['x'], st['y'], st['pressure'], st['time_elapsed'])
+  assert np.abs(got[:, 0] - du).max() < tol and np.abs(got[:, 1] - dv).max() < tol
+  assert np.abs(du).max() > 0.5                 # the comparison is not vacuous
+  arena.close()
+
+
+# ------------------------------------------------------------------------------ one step vs the reference
+
+def _all_recorded_states():
+  """Every recorded (state_t, action_{t+1}) -> (state_{t+1}, reward, wind) pair of the goldens."""
+  names = sorted(TRAJ)
+  fs, is_, acts, want_f, want_i, want_r, want_w, alpha, psl, field, seeds, offs = ([] for _ in range(12))
+  for name in names:
+    sc = TRAJ[name]
+    n = len(sc['actions'])
+    idx = np.arange(0, n - 1)
+    if idx.size == 0:
+      continue
+    fs.append(sc['f'][idx]); is_.append(sc['i'][idx]); acts.append(sc['actions'][idx + 1])
+    want_f.append(sc['f'][idx + 1]); want_i.append(sc['i'][idx + 1]); want_r.append(sc['reward'][idx + 1])
+    want_w.append(sc['wind'][idx + 1])
+    alpha.append(np.full(idx.size, float(sc['alpha']))); psl.append(np.full(idx.size, int(sc['power_safety'])))
+    field.append(np.full(idx.size, int(sc['field'])))
+    seeds.append(np.broadcast_to(sc['seeds'], (idx.size, 2, 5))); offs.append(np.broadcast_to(sc['offsets'], (idx.size, 2, 5, 4)))
+  cat = np.concatenate
+  return dict(f=cat(fs), i=cat(is_), actions=cat(acts), want_f=cat(want_f), want_i=cat(want_i),
+              want_r=cat(want_r), want_w=cat(want_w), alpha=cat(alpha), psl=cat(psl), field=cat(field),
+              seeds=cat(seeds), offsets=cat(offs))
+
+
+@pytest.mark.parametrize('precision,tol,wtol', [('fp64', 1e-8, 2e-6), ('fp32', 1e-4, 5e-4)])
+def test_single_step_matches_reference(ble, precision, tol, wtol):
+  """~4,400 recorded reference states advanced by ONE BalloonEnv.step on the GPU."""
+  rec = _all_recorded_states()
+  grid = rec['field'] >= 0                      # SimpleStaticWindField scenario runs in its own arena
+  for model, sel in (('grid', grid), ('simple_static', ~grid)):
+    n = int(sel.sum())
+    arena = ble.BatchedBalloonArena(n, precision=precision, wind_model=model, enable_noise=True)
+    if model == 'grid':
+      arena.set_wind_fields(torch.from_numpy(golden_fields.field_bank()),
+                            torch.from_numpy(rec['field'][sel].astype(np.int32)))
+    arena.set_wind_noise(torch.from_numpy(rec['seeds'][sel].copy()),
+                         torch.from_numpy(rec['offsets'][sel].astype(np.float32)))
+    b = golden_io.batch_from_rows(FF, IF, rec['f'][sel], rec['i'][sel])
+    arena.set_state(*pack(b, rec['alpha'][sel], rec['psl'][sel]))
+    reward, done, wind = arena.step(torch.from_numpy(rec['actions'][sel].astype(np.int32)))
+    torch.cuda.synchronize()
+    st = state_np(arena)
+    assert np.abs(wind.cpu().numpy() - rec['want_w'][sel]).max() < wtol
+    worst = {k: rel_err(st[k], rec['want_f'][sel][:, j], k) for j, k in enumerate(FF)}
+    assert max(worst.values()) < tol, worst
+    for j, k in enumerate(IF):
+      mism = st[k] != rec['want_i'][sel][:, j]
+      if k in ('sunrise_h', 'sunset'):
+        mism = mism & (rec['psl'][sel] == 1)
+      assert not mism.any(), (k, int(mism.sum()))
+    assert np.abs(reward.cpu().numpy() - rec['want_r'][sel]).max() < max(tol, 2e-7)
+    np.testing.assert_array_equal(done.cpu().numpy() != 0, rec['want_i'][sel][:, IF.index('status')] != 0)
+    arena.close()
+
+
+def test_fp64_trajectories_match_reference(ble):
+  """The ten golden scenarios rolled out on the GPU (fp64 audit kernels), own wind lookups."""
+  names = sorted(TRAJ)
+  scs = [TRAJ[n] for n in names]
+  oenv = golden_io.oracle_env_for_scenarios(scs, FF, IF)
+  field = np.array([int(sc['field']) for sc in scs])
+  alpha = np.array([float(sc['alpha']) for sc in scs]); psl = np.array([int(sc['power_safety']) for sc in scs])
+  grid = field >= 0
+  for model, sel in (('grid', grid), ('simple_static', ~grid)):
+    idx = np.nonzero(sel)[0]
+    arena = ble.BatchedBalloonArena(len(idx), precision='fp64', wind_model=model, enable_noise=True)
+    if model == 'grid':
+      arena.set_wind_fields(torch.from_numpy(golden_fields.field_bank()), torch.from_numpy(field[idx].astype(np.int32)))
+    arena.set_wind_noise(torch.from_numpy(np.stack([scs[e]['seeds'] for e in idx])),
+                         torch.from_numpy(np.stack([scs[e]['offsets'] for e in idx]).astype(np.float32)))
+    arena.set_state(*pack(oenv.arena.state.select(idx), alpha[idx], psl[idx]))
+    horizon = max(len(scs[e]['actions']) for e in idx)
+    for t in range(horizon):
+      acts = np.array([scs[e]['actions'][t] if t < len(scs[e]['actions']) else 1 for e in idx], np.int32)
+      reward, done, wind = arena.step(torch.from_numpy(acts))
+      if t % 16 and t != horizon - 1 and t > 4:
+        continue
+      st = state_np(arena)
+      rw = reward.cpu().numpy()
+      for col, e in enumerate(idx):
+        sc = scs[e]
+        if t >= len(sc['actions']):
+          continue
+        for j, k in enumerate(FF):
+          atol = 1e-2 if k in ('x', 'y') else 1e-6
+          np.testing.assert_allclose(st[k][col], sc['f'][t, j], rtol=1e-5, atol=atol, err_msg=f'{names[e]} t={t} {k}')
+        for j, k in enumerate(IF):
+          if k in ('sunrise_h', 'sunset') and not sc['power_safety']:
+            continue
+          assert st[k][col] == sc['i'][t, j], (names[e], t, k)
+        np.testing.assert_allclose(rw[col], sc['reward'][t], rtol=1e-5, atol=1e-6)
+    arena.close()
+
+
+# ------------------------------------------------------------------------------ reset
+
+def test_reset_derived_state_matches_oracle_and_distributions(ble):
+  n = 4096
+  arena = ble.BatchedBalloonArena(n, precision='fp64', enable_noise=True)
+  arena.set_wind_fields(torch.from_numpy(golden_fields.field_bank()[:1]))
+  seeds = torch.arange(n, dtype=torch.int64) * 7919 + 12345
+  arena.reset(seeds)
+  st = state_np(arena)
+  # distributions (utils/sampling.py:37-152, env/balloon_arena.py:228-268)
+  a = st['atmosphere_alpha']
+  assert 0 <= a.min() and a.max() < 1 and abs(a.mean() - 0.5) < 0.03
+  r_km = np.hypot(st['x'], st['y']) / 1000.0
+  assert r_km.max() <= 200.0 and abs(r_km.mean() - 200 * 1.2 / 3.2) < 4.0          # Beta(1.2, 2) mean
+  assert abs(np.degrees(st['center_lat'])).max() <= 10.0 and abs(np.degrees(st['center_lng'])).max() <= 175.0
+  t0, t1 = 1293840000, 1293840000 + 126144000
+  assert st['date_time'].min() >= t0 and st['date_time'].max() < t1
+  assert st['upwelling_infrared'].min() >= 225.0 and st['upwelling_infrared'].max() <= 315.0
+  atm = atmosphere_lib.Atmosphere(a)
+  pmax, _ = atm.at_height(np.full(n, C.ALT_MIN_ALTITUDE_M))
+  assert (st['pressure'] >= 6500.0).all() and (st['pressure'] <= pmax).all()
+  assert (st['status'] == 0).all() and (st['battery_charge'] == 2905.6).all() and (st['time_elapsed'] == 0).all()
+  # deterministic part: stable init + power-safety sunrise/sunset == oracle on the same draws
+  b = balloon_lib.make_batch(n, center_lat=st['center_lat'], center_lng=st['center_lng'], date_time=st['date_time'],
+                             x=st['x'], y=st['y'], pressure=st['pressure'], upwelling_infrared=st['upwelling_infrared'])
+  stable_init_lib.cold_start_to_stable_params(b, atm)
+  for k in ('ambient_temperature', 'internal_temperature', 'mols_air', 'envelope_volume', 'superpressure'):
+    np.testing.assert_allclose(st[k], getattr(b, k), rtol=1e-9, atol=1e-7, err_msg=k)
+  np.testing.assert_array_equal(st['sunrise_h'], b.sunrise_h)
+  np.testing.assert_array_equal(st['sunset'], b.sunset)
+  # same seeds -> same state; masked reset leaves unmasked balloons alone
+  arena.reset(seeds)
+  st2 = state_np(arena)
+  for k in st:
+    np.testing.assert_array_equal(st[k], st2[k])
+  mask = torch.zeros(n, dtype=torch.uint8); mask[::2] = 1
+  arena.reset(seeds + 1, mask)
+  st3 = state_np(arena)
+  assert (st3['x'][1::2] == st['x'][1::2]).all() and (st3['x'][::2] != st['x'][::2]).any()
+  arena.close()
+
+
+# ------------------------------------------------------------------------------ fp32 rollout vs oracle
+
+def test_fp32_rollout_tracks_oracle(ble):
+  """256 balloons from a device reset, 40 agent steps: fp32 kernels vs the fp64 oracle fed the same
+  actions.  State must stay within 1e-4 relative per step when re-synchronised each step, and
+  decisions must agree."""
+  n, steps = 256, 40
+  rng = np.random.default_rng(11)
+  arena = ble.BatchedBalloonArena(n, precision='fp32', enable_noise=True)
+  bank = golden_fields.field_bank()
+  fidx = rng.integers(0, 2, n).astype(np.int32)
+  arena.set_wind_fields(torch.from_numpy(bank), torch.from_numpy(fidx))
+  arena.reset(torch.arange(n, dtype=torch.int64) + 99)
+  seeds = rng.integers(0, 1634753849, (n, 2, 5)); offsets = rng.uniform(-1, 1, (n, 2, 5, 4)).astype(np.float32)
+  arena.set_wind_noise(torch.from_numpy(seeds), torch.from_numpy(offsets))
+  noise = wind_lib.SimplexWindNoise(seeds, offsets.astype(np.float64))
+  mism_total = 0
+  worst = {}
+  for t in range(steps):
+    st = state_np(arena)
+    b = balloon_lib.BalloonBatch(**{k: st[k].copy() for k in balloon_lib.FLOAT_FIELDS + balloon_lib.INT_FIELDS})
+    atm = atmosphere_lib.Atmosphere(st['atmosphere_alpha'])
+    oenv = env_lib.OracleEnv(env_lib.OracleArena(b, atm, fields=bank, field_idx=fidx, noise=noise))
+    acts = rng.integers(0, 3, n).astype(np.int32)
+    want_r, want_done, _ = oenv.step(acts)
+    reward, done, wind = arena.step(torch.from_numpy(acts))
+    got = state_np(arena)
+    for k in balloon_lib.FLOAT_FIELDS:
+      worst[k] = max(worst.get(k, 0.0), rel_err(got[k], getattr(b, k), k))
+    for k in ('status', 'last_command', 'envelope_state', 'altitude_state', 'power_paused', 'time_elapsed',
+              'date_time', 'sunrise_h', 'sunset'):
+      mism_total += int((got[k] != getattr(b, k)).sum())
+    assert np.abs(reward.cpu().numpy() - want_r).max() < 2e-4
+  assert max(worst.values()) < 1e-4, worst
+  assert mism_total == 0, mism_total
+  arena.close()
+
+
+# ------------------------------------------------------------------------------ API behaviour
+
+def test_errors_and_host_step(ble):
+  from balloon_learning_environment_b200 import _lib
+  arena = ble.BatchedBalloonArena(64, precision='fp32', enable_noise=False)
+  with pytest.raises(_lib.BleError):          # stepping before reset/fields (grid_based_wind_field.py:86-87)
+    arena.step(torch.zeros(64, dtype=torch.int32))
+  arena.set_wind_fields(torch.from_numpy(golden_fields.field_bank()[:1]))
+  with pytest.raises(_lib.BleError):
+    arena.step(torch.zeros(64, dtype=torch.int32))
+  arena.reset(torch.arange(64, dtype=torch.int64))
+  twin = ble.BatchedBalloonArena(64, precision='fp32', enable_noise=False)
+  twin.set_wind_fields(torch.from_numpy(golden_fields.field_bank()[:1]))
+  twin.reset(torch.arange(64, dtype=torch.int64))
+  acts = np.random.default_rng(0).integers(0, 3, 64).astype(np.int32)
+  r_host = np.zeros(64, np.float32); d_host = np.zeros(64, np.uint8)
+  arena.step_host(acts, r_host, d_host)
+  r_dev, d_dev, _ = twin.step(torch.from_numpy(acts))
+  np.testing.assert_array_equal(r_host, r_dev.cpu().numpy())
+  np.testing.assert_array_equal(d_host, d_dev.cpu().numpy())
+  assert arena.launch_count > 0
+  arena.close(); twin.close()
+
+
+def test_full_size_properties(ble):
+  """BASELINE.json size (65,536 balloons): size-independent invariants of the transition."""
+  n = 65536
+  rng = np.random.default_rng(5)
+  env = ble.BatchedBalloonEnv(n, precision='fp32', enable_noise=True, seed=3)
+  bank = golden_fields.field_bank()
+  env.arena.set_wind_fields(torch.from_numpy(bank), torch.from_numpy(rng.integers(0, 4, n).astype(np.int32)))
+  env.reset(seed=3)
+  s0 = state_np(env.arena)
+  acts = torch.from_numpy(rng.integers(0, 3, n).astype(np.int32)).cuda()
+  _, reward, done, _ = env.step(acts)
+  wind = env.arena._wind.cpu().numpy().astype(np.float64)
+  s1 = state_np(env.arena)
+  ok = s1['status'] == 0
+  assert ok.mean() > 0.99
+  np.testing.assert_array_equal(s1['time_elapsed'][ok], 180)
+  np.testing.assert_array_equal(s1['date_time'][ok] - s0['date_time'][ok], 180)
+  np.testing.assert_allclose((s1['x'] - s0['x'])[ok], wind[ok, 0] * 180.0, rtol=2e-5, atol=0.2)   # x += u dt
+  np.testing.assert_allclose((s1['y'] - s0['y'])[ok], wind[ok, 1] * 180.0, rtol=2e-5, atol=0.2)
+  assert (s1['battery_charge'] >= 0).all() and (s1['battery_charge'] <= 3058.56 + 1e-3).all()
+  r = reward.cpu().numpy()
+  assert (r >= 0).all() and (r <= 1).all()
+  np.testing.assert_array_equal(s1['last_command'][ok], acts.cpu().numpy()[ok])
+  # determinism: a twin env with the same seeds and actions lands in the same state, bit for bit
+  twin = ble.BatchedBalloonEnv(n, precision='fp32', enable_noise=True, seed=3)
+  twin.arena.set_wind_fields(torch.from_numpy(bank), env.arena._keepalive[1])
+  twin.reset(seed=3)
+  twin.step(acts)
+  s1b = state_np(twin.arena)
+  for k in s1:
+    np.testing.assert_array_equal(s1[k], s1b[k])
+  # finished balloons are frozen: force a terminal status and step again
+  f, i = env.arena.get_state()
+  from balloon_learning_environment_b200 import _lib
+  i[_lib.I_ROWS.index('status'), :100] = 2
+  env.arena.set_state(f, i)
+  before = state_np(env.arena)
+  _, reward, done, _ = env.step(acts)
+  after = state_np(env.arena)
+  for k in before:
+    np.testing.assert_array_equal(before[k][:100], after[k][:100])
+  assert (done.cpu().numpy()[:100] == 1).all() and (reward.cpu().numpy()[:100] == 0).all()
+  env.close(); twin.close()
