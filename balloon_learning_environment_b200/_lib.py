@@ -23,9 +23,13 @@ F_ROWS = ('x', 'y', 'pressure', 'ambient_temperature', 'internal_temperature', '
 I_ROWS = ('date_time', 'time_elapsed', 'last_command', 'status', 'envelope_state', 'altitude_state',
           'power_paused', 'sunrise_h', 'sunset', 'power_safety_enabled')
 
+D_ROWS = ('lat', 'lng', 'solar_elevation', 'solar_flux', 'excess_energy', 'navigation_is_paused',
+          'pressure_ratio', 'battery_soc', 'altitude')
+
 EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_upload_fields',
            'ble_set_noise', 'ble_state_upload', 'ble_state_download', 'ble_reset', 'ble_init_derived',
-           'ble_step', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_launch_count')
+           'ble_step', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_derived',
+           'ble_launch_count')
 
 
 class BleConfig(_c.Structure):
@@ -75,6 +79,7 @@ def load(build_if_missing=True):
   lib.ble_step_host.argtypes = [vp, vp, vp, vp, vp]
   lib.ble_wind_at_balloon.argtypes = [vp, vp, vp]
   lib.ble_wind_gather.argtypes = [vp, vp, vp, vp, i64, vp]
+  lib.ble_derived.argtypes = [vp, vp, vp]
   for name in EXPORTS:
     if name not in ('ble_last_error', 'ble_num_envs', 'ble_launch_count'):
       getattr(lib, name).restype = _c.c_int

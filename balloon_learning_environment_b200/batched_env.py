@@ -153,6 +153,12 @@ class BatchedBalloonArena:
     out.update({k: i64[r] for r, k in enumerate(_lib.I_ROWS)})
     return out
 
+  def get_derived(self) -> Dict[str, torch.Tensor]:
+    """BalloonState's derived properties (latlng, excess_energy, navigation_is_paused, ...)."""
+    out = torch.empty(len(_lib.D_ROWS), self.num_envs, dtype=torch.float64, device=self.device)
+    self._check(self._lib.ble_derived(self._h, _ptr(out), self._stream()), 'ble_derived')
+    return {k: out[r] for r, k in enumerate(_lib.D_ROWS)}
+
   def init_derived(self, run_stable_init: bool = True):
     """Recompute power-safety sunrise/sunset (+ stable init) from the uploaded state."""
     self._check(self._lib.ble_init_derived(self._h, int(run_stable_init), self._stream()), 'ble_init_derived')

@@ -19,11 +19,14 @@ namespace ble {
 // ---------------------------------------------------------------------------------------------
 // Device-side state layout (struct of arrays, one row per field, N columns)
 // ---------------------------------------------------------------------------------------------
-enum RRow : int {
-  R_X = 0, R_Y, R_P, R_TAMB, R_TINT, R_VOL, R_SP, R_MOLS_AIR, R_CHARGE, R_ACS_W, R_ACS_FLOW, R_SOLAR_W,
-  R_LOAD_W,                                          // 13 dynamic rows (read + written every step)
+enum DRow : int {     // fp64 rows: the stiff integrator variables (see ble_physics.cuh) + atmosphere
+  D_X = 0, D_Y, D_P, D_TAMB, D_TINT, D_VOL, D_SP, D_MOLS_AIR, D_CHARGE,   // 9 dynamic rows (read + written every step)
+  D_ALPHA, D_L0, D_L1, D_L2, D_T1, D_T2, D_P1, D_P2, D_P3,              // per-episode atmosphere (layers 0..2)
+  D_COUNT
+};
+enum RRow : int {     // `Real` rows (fp32 in production)
+  R_ACS_W = 0, R_ACS_FLOW, R_SOLAR_W, R_LOAD_W,      // diagnostics written every step
   R_LAT0, R_LNG0, R_IR, R_MOLS_GAS,                  // per-episode constants
-  R_L0, R_L1, R_L2, R_T1, R_T2, R_P1, R_P2, R_P3,    // atmosphere layers 0..2 derived from alpha
   R_COUNT
 };
 enum LRow : int { L_DATE_TIME = 0, L_SUNRISE_H, L_SUNSET, L_COUNT };
@@ -38,8 +41,8 @@ __host__ __device__ inline uint32_t pack_flags(int status, int last_cmd, int env
 template <typename Real>
 struct DevState {
   int64_t n;
+  double* dd;         // [D_COUNT][n]
   Real* r;            // [R_COUNT][n]
-  double* alpha;      // [n]
   int64_t* l;         // [L_COUNT][n]
   int32_t* t_elapsed; // [n]
   uint32_t* flags;    // [n]
@@ -54,6 +57,26 @@ struct DevState {
 
 template <typename Real>
 __device__ __forceinline__ Real& RR(const DevState<Real>& d, int row, int64_t e) { return d.r[int64_t(row) * d.n + e]; }
+template <typename Real>
+__device__ __forceinline__ double& DD(const DevState<Real>& d, int row, int64_t e) { return d.dd[int64_t(row) * d.n + e]; }
+
+template <typename Real>
+__device__ __forceinline__ void store_atmosphere(const DevState<Real>& d, int64_t e, const Atmosphere& atm) {
+  DD(d, D_ALPHA, e) = atm.alpha;
+  DD(d, D_L0, e) = atm.l0; DD(d, D_L1, e) = atm.l1; DD(d, D_L2, e) = atm.l2;
+  DD(d, D_T1, e) = atm.t1; DD(d, D_T2, e) = atm.t2;
+  DD(d, D_P1, e) = atm.p1; DD(d, D_P2, e) = atm.p2; DD(d, D_P3, e) = atm.p3;
+}
+template <typename Real>
+__device__ __forceinline__ Atmosphere load_atmosphere(const DevState<Real>& d, int64_t e) {
+  Atmosphere atm;
+  atm.alpha = DD(d, D_ALPHA, e);
+  atm.l0 = DD(d, D_L0, e); atm.l1 = DD(d, D_L1, e); atm.l2 = DD(d, D_L2, e);
+  atm.t1 = DD(d, D_T1, e); atm.t2 = DD(d, D_T2, e);
+  atm.p1 = DD(d, D_P1, e); atm.p2 = DD(d, D_P2, e); atm.p3 = DD(d, D_P3, e);
+  atm.ok = true;
+  return atm;
+}
 
 // ---------------------------------------------------------------------------------------------
 // State upload / download (get/set_balloon_state, env/balloon_arena.py:213-220)
@@ -65,20 +88,16 @@ __global__ void k_state_upload(DevState<Real> d, const double* __restrict__ f, c
   const int64_t n = d.n;
   auto F = [&](int row) { return f[int64_t(row) * n + e]; };
   auto I = [&](int row) { return iv[int64_t(row) * n + e]; };
-  RR(d, R_X, e) = Real(F(BLE_F_X)); RR(d, R_Y, e) = Real(F(BLE_F_Y)); RR(d, R_P, e) = Real(F(BLE_F_PRESSURE));
-  RR(d, R_TAMB, e) = Real(F(BLE_F_AMBIENT_TEMPERATURE)); RR(d, R_TINT, e) = Real(F(BLE_F_INTERNAL_TEMPERATURE));
-  RR(d, R_VOL, e) = Real(F(BLE_F_ENVELOPE_VOLUME)); RR(d, R_SP, e) = Real(F(BLE_F_SUPERPRESSURE));
-  RR(d, R_MOLS_AIR, e) = Real(F(BLE_F_MOLS_AIR)); RR(d, R_CHARGE, e) = Real(F(BLE_F_BATTERY_CHARGE));
+  DD(d, D_X, e) = F(BLE_F_X); DD(d, D_Y, e) = F(BLE_F_Y); DD(d, D_P, e) = F(BLE_F_PRESSURE);
+  DD(d, D_TAMB, e) = F(BLE_F_AMBIENT_TEMPERATURE); DD(d, D_TINT, e) = F(BLE_F_INTERNAL_TEMPERATURE);
+  DD(d, D_VOL, e) = F(BLE_F_ENVELOPE_VOLUME); DD(d, D_SP, e) = F(BLE_F_SUPERPRESSURE);
+  DD(d, D_MOLS_AIR, e) = F(BLE_F_MOLS_AIR); DD(d, D_CHARGE, e) = F(BLE_F_BATTERY_CHARGE);
   RR(d, R_ACS_W, e) = Real(F(BLE_F_ACS_POWER)); RR(d, R_ACS_FLOW, e) = Real(F(BLE_F_ACS_MASS_FLOW));
   RR(d, R_SOLAR_W, e) = Real(F(BLE_F_SOLAR_CHARGING)); RR(d, R_LOAD_W, e) = Real(F(BLE_F_POWER_LOAD));
   RR(d, R_LAT0, e) = Real(F(BLE_F_CENTER_LAT)); RR(d, R_LNG0, e) = Real(F(BLE_F_CENTER_LNG));
   RR(d, R_IR, e) = Real(F(BLE_F_UPWELLING_INFRARED)); RR(d, R_MOLS_GAS, e) = Real(F(BLE_F_MOLS_LIFT_GAS));
-  const double alpha = F(BLE_F_ATMOSPHERE_ALPHA);
-  d.alpha[e] = alpha;
-  Atmosphere<Real> atm; atm.init(alpha);
-  RR(d, R_L0, e) = atm.l0; RR(d, R_L1, e) = atm.l1; RR(d, R_L2, e) = atm.l2;
-  RR(d, R_T1, e) = atm.t1; RR(d, R_T2, e) = atm.t2;
-  RR(d, R_P1, e) = atm.p1; RR(d, R_P2, e) = atm.p2; RR(d, R_P3, e) = atm.p3;
+  Atmosphere atm; atm.init(F(BLE_F_ATMOSPHERE_ALPHA));
+  store_atmosphere(d, e, atm);
   d.l[int64_t(L_DATE_TIME) * n + e] = I(BLE_I_DATE_TIME);
   d.l[int64_t(L_SUNRISE_H) * n + e] = I(BLE_I_SUNRISE_H);
   d.l[int64_t(L_SUNSET) * n + e] = I(BLE_I_SUNSET);
@@ -95,15 +114,15 @@ __global__ void k_state_download(DevState<Real> d, double* __restrict__ f, int64
   const int64_t n = d.n;
   auto F = [&](int row) -> double& { return f[int64_t(row) * n + e]; };
   auto I = [&](int row) -> int64_t& { return iv[int64_t(row) * n + e]; };
-  F(BLE_F_X) = double(RR(d, R_X, e)); F(BLE_F_Y) = double(RR(d, R_Y, e)); F(BLE_F_PRESSURE) = double(RR(d, R_P, e));
-  F(BLE_F_AMBIENT_TEMPERATURE) = double(RR(d, R_TAMB, e)); F(BLE_F_INTERNAL_TEMPERATURE) = double(RR(d, R_TINT, e));
-  F(BLE_F_ENVELOPE_VOLUME) = double(RR(d, R_VOL, e)); F(BLE_F_SUPERPRESSURE) = double(RR(d, R_SP, e));
-  F(BLE_F_MOLS_AIR) = double(RR(d, R_MOLS_AIR, e)); F(BLE_F_MOLS_LIFT_GAS) = double(RR(d, R_MOLS_GAS, e));
-  F(BLE_F_BATTERY_CHARGE) = double(RR(d, R_CHARGE, e)); F(BLE_F_ACS_POWER) = double(RR(d, R_ACS_W, e));
+  F(BLE_F_X) = DD(d, D_X, e); F(BLE_F_Y) = DD(d, D_Y, e); F(BLE_F_PRESSURE) = DD(d, D_P, e);
+  F(BLE_F_AMBIENT_TEMPERATURE) = DD(d, D_TAMB, e); F(BLE_F_INTERNAL_TEMPERATURE) = DD(d, D_TINT, e);
+  F(BLE_F_ENVELOPE_VOLUME) = DD(d, D_VOL, e); F(BLE_F_SUPERPRESSURE) = DD(d, D_SP, e);
+  F(BLE_F_MOLS_AIR) = DD(d, D_MOLS_AIR, e); F(BLE_F_MOLS_LIFT_GAS) = double(RR(d, R_MOLS_GAS, e));
+  F(BLE_F_BATTERY_CHARGE) = DD(d, D_CHARGE, e); F(BLE_F_ACS_POWER) = double(RR(d, R_ACS_W, e));
   F(BLE_F_ACS_MASS_FLOW) = double(RR(d, R_ACS_FLOW, e)); F(BLE_F_SOLAR_CHARGING) = double(RR(d, R_SOLAR_W, e));
   F(BLE_F_POWER_LOAD) = double(RR(d, R_LOAD_W, e)); F(BLE_F_CENTER_LAT) = double(RR(d, R_LAT0, e));
   F(BLE_F_CENTER_LNG) = double(RR(d, R_LNG0, e)); F(BLE_F_UPWELLING_INFRARED) = double(RR(d, R_IR, e));
-  F(BLE_F_ATMOSPHERE_ALPHA) = d.alpha[e];
+  F(BLE_F_ATMOSPHERE_ALPHA) = DD(d, D_ALPHA, e);
   const uint32_t fl = d.flags[e];
   I(BLE_I_DATE_TIME) = d.l[int64_t(L_DATE_TIME) * n + e];
   I(BLE_I_TIME_ELAPSED) = d.t_elapsed[e];
@@ -226,8 +245,8 @@ k_noise(DevState<Real> d) {
   if (live) {
     double wgt, sx, sy, sp, st;
     harmonic_params(h10, &wgt, &sx, &sy, &sp, &st);
-    const double x_km = double(RR(d, R_X, e)) / 1000.0, y_km = double(RR(d, R_Y, e)) / 1000.0;
-    const double p = double(RR(d, R_P, e)), t_h = double(d.t_elapsed[e]) / 3600.0;
+    const double x_km = double(DD(d, D_X, e)) / 1000.0, y_km = double(DD(d, D_Y, e)) / 1000.0;
+    const double p = double(DD(d, D_P, e)), t_h = double(d.t_elapsed[e]) / 3600.0;
     X = x_km / sx + double(d.offsets[(int64_t(h10) * 4 + 0) * d.n + e]);
     Y = y_km / sy + double(d.offsets[(int64_t(h10) * 4 + 1) * d.n + e]);
     Z = p / sp + double(d.offsets[(int64_t(h10) * 4 + 2) * d.n + e]);
@@ -247,13 +266,12 @@ k_noise(DevState<Real> d) {
 
 // forecast + noise at the balloon's current state (WindField.get_ground_truth, env/wind_field.py:125-145)
 template <typename Real>
-__device__ __forceinline__ void wind_at_balloon(const DevState<Real>& d, int64_t e, Real x, Real y, Real p,
+__device__ __forceinline__ void wind_at_balloon(const DevState<Real>& d, int64_t e, double x, double y, double p,
                                                 int32_t t_elapsed, Real* u, Real* v) {
   if (d.wind_model == BLE_WIND_SIMPLE_STATIC) {
-    static_wind<Real>(p, u, v);
+    static_wind<Real>(Real(p), u, v);
   } else {
-    const FieldPoint q = make_field_point(double(x) / 1000.0, double(y) / 1000.0, double(p),
-                                          double(t_elapsed) / 3600.0);
+    const FieldPoint q = make_field_point(x / 1000.0, y / 1000.0, p, double(t_elapsed) / 3600.0);
     CellLoader ld{d.cells + int64_t(d.env_field[e]) * kCellFieldFloats};
     interp_cells<Real>(q, ld, u, v);
   }
@@ -282,7 +300,7 @@ k_wind_at_balloon(DevState<Real> d, float2* __restrict__ uv) {
   const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (e >= d.n) return;
   Real u, v;
-  wind_at_balloon<Real>(d, e, RR(d, R_X, e), RR(d, R_Y, e), RR(d, R_P, e), d.t_elapsed[e], &u, &v);
+  wind_at_balloon<Real>(d, e, DD(d, D_X, e), DD(d, D_Y, e), DD(d, D_P, e), d.t_elapsed[e], &u, &v);
   uv[e] = make_float2(float(u), float(v));
 }
 
@@ -303,21 +321,16 @@ k_step(DevState<Real> d, const int32_t* __restrict__ actions, float* __restrict_
     return;
   }
   BalloonState<Real> s;
-  s.x = RR(d, R_X, e); s.y = RR(d, R_Y, e); s.pressure = RR(d, R_P, e);
-  s.t_ambient = RR(d, R_TAMB, e); s.t_internal = RR(d, R_TINT, e); s.volume = RR(d, R_VOL, e);
-  s.superpressure = RR(d, R_SP, e); s.mols_air = RR(d, R_MOLS_AIR, e); s.charge = RR(d, R_CHARGE, e);
+  s.x = DD(d, D_X, e); s.y = DD(d, D_Y, e); s.pressure = DD(d, D_P, e);
+  s.t_ambient = DD(d, D_TAMB, e); s.t_internal = DD(d, D_TINT, e); s.volume = DD(d, D_VOL, e);
+  s.superpressure = DD(d, D_SP, e); s.mols_air = DD(d, D_MOLS_AIR, e); s.charge = DD(d, D_CHARGE, e);
   s.acs_power = RR(d, R_ACS_W, e); s.acs_flow = RR(d, R_ACS_FLOW, e);
   s.solar_w = RR(d, R_SOLAR_W, e); s.load_w = RR(d, R_LOAD_W, e);
   s.lat0 = RR(d, R_LAT0, e); s.lng0 = RR(d, R_LNG0, e); s.ir = RR(d, R_IR, e); s.mols_gas = RR(d, R_MOLS_GAS, e);
   s.date_time = d.l[int64_t(L_DATE_TIME) * d.n + e];
   s.time_elapsed = d.t_elapsed[e];
   s.status = kOk;
-  Atmosphere<Real> atm;
-  atm.alpha = Real(d.alpha[e]);
-  atm.l0 = RR(d, R_L0, e); atm.l1 = RR(d, R_L1, e); atm.l2 = RR(d, R_L2, e);
-  atm.t1 = RR(d, R_T1, e); atm.t2 = RR(d, R_T2, e);
-  atm.p1 = RR(d, R_P1, e); atm.p2 = RR(d, R_P2, e); atm.p3 = RR(d, R_P3, e);
-  atm.ok = true;
+  Atmosphere atm = load_atmosphere(d, e);
   SafetyState ss;
   ss.sunrise_h = d.l[int64_t(L_SUNRISE_H) * d.n + e];
   ss.sunset = d.l[int64_t(L_SUNSET) * d.n + e];
@@ -330,11 +343,11 @@ k_step(DevState<Real> d, const int32_t* __restrict__ actions, float* __restrict_
   int action = actions[e];
   action = action < 0 ? 0 : (action > 2 ? 2 : action);
   int eff;
-  const Real r = agent_step<Real>(s, atm, ss, action, u, v, &eff);
+  const Real r = agent_step<Real>(s, atm, ss, action, double(u), double(v), &eff);
 
-  RR(d, R_X, e) = s.x; RR(d, R_Y, e) = s.y; RR(d, R_P, e) = s.pressure;
-  RR(d, R_TAMB, e) = s.t_ambient; RR(d, R_TINT, e) = s.t_internal; RR(d, R_VOL, e) = s.volume;
-  RR(d, R_SP, e) = s.superpressure; RR(d, R_MOLS_AIR, e) = s.mols_air; RR(d, R_CHARGE, e) = s.charge;
+  DD(d, D_X, e) = s.x; DD(d, D_Y, e) = s.y; DD(d, D_P, e) = s.pressure;
+  DD(d, D_TAMB, e) = s.t_ambient; DD(d, D_TINT, e) = s.t_internal; DD(d, D_VOL, e) = s.volume;
+  DD(d, D_SP, e) = s.superpressure; DD(d, D_MOLS_AIR, e) = s.mols_air; DD(d, D_CHARGE, e) = s.charge;
   RR(d, R_ACS_W, e) = s.acs_power; RR(d, R_ACS_FLOW, e) = s.acs_flow;
   RR(d, R_SOLAR_W, e) = s.solar_w; RR(d, R_LOAD_W, e) = s.load_w;
   d.l[int64_t(L_DATE_TIME) * d.n + e] = s.date_time;
@@ -346,6 +359,34 @@ k_step(DevState<Real> d, const int32_t* __restrict__ actions, float* __restrict_
   reward[e] = float(r);
   done[e] = (s.status != kOk) ? 1 : 0;
   if (wind_uv != nullptr) wind_uv[e] = make_float2(float(u), float(v));
+}
+
+// Derived BalloonState properties (env/balloon/balloon.py:217-250) for the N = 1 adaptor / features.
+template <typename Real>
+__global__ void __launch_bounds__(128) k_derived(DevState<Real> d, double* __restrict__ out) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  const int64_t n = d.n;
+  const double x = DD(d, D_X, e), y = DD(d, D_Y, e), p = DD(d, D_P, e), sp = DD(d, D_SP, e);
+  Real lat, lng, el, flux;
+  latlng_from_offset<Real>(RR(d, R_LAT0, e), RR(d, R_LNG0, e), Real(x), Real(y), &lat, &lng);
+  solar_calculator<Real>(lat, lng, d.l[int64_t(L_DATE_TIME) * n + e], &el, &flux);
+  const double soc = DD(d, D_CHARGE, e) / kBatteryCapacityWh;
+  const bool excess = (solar_power<Real>(el, Real(p)) > Real(kDayLoadW)) && (soc > 0.99);
+  const uint32_t fl = d.flags[e];
+  const bool paused = ((fl >> 9) & 1u) || (((fl >> 4) & 7u) != 0u) || (((fl >> 7) & 3u) != 0u);
+  Atmosphere atm = load_atmosphere(d, e);
+  double h, t;
+  atm.at_pressure(p, &h, &t);
+  out[int64_t(BLE_D_LAT) * n + e] = double(lat);
+  out[int64_t(BLE_D_LNG) * n + e] = double(lng);
+  out[int64_t(BLE_D_SOLAR_ELEVATION) * n + e] = double(el);
+  out[int64_t(BLE_D_SOLAR_FLUX) * n + e] = double(flux);
+  out[int64_t(BLE_D_EXCESS_ENERGY) * n + e] = excess ? 1.0 : 0.0;
+  out[int64_t(BLE_D_NAVIGATION_IS_PAUSED) * n + e] = paused ? 1.0 : 0.0;
+  out[int64_t(BLE_D_PRESSURE_RATIO) * n + e] = (p + fmax(sp, 0.0)) / p;
+  out[int64_t(BLE_D_BATTERY_SOC) * n + e] = soc;
+  out[int64_t(BLE_D_ALTITUDE) * n + e] = h;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -402,8 +443,8 @@ struct Philox {          // Philox4x32-10, one stream per (seed, balloon)
 // the stable-init solve.  Always fp64 (see ble_physics.cuh).
 template <typename Real>
 __device__ void init_derived_one(DevState<Real>& d, int64_t e, bool run_stable_init) {
-  const double alpha = d.alpha[e];
-  const double x = double(RR(d, R_X, e)), y = double(RR(d, R_Y, e));
+  const double alpha = DD(d, D_ALPHA, e);
+  const double x = DD(d, D_X, e), y = DD(d, D_Y, e);
   const double lat0 = double(RR(d, R_LAT0, e)), lng0 = double(RR(d, R_LNG0, e));
   const int64_t ts = d.l[int64_t(L_DATE_TIME) * d.n + e];
   double lat, lng;
@@ -416,11 +457,11 @@ __device__ void init_derived_one(DevState<Real>& d, int64_t e, bool run_stable_i
   fl &= ~((7u << 4) | (3u << 7) | (1u << 9));     // envelope/altitude NOMINAL, not paused (balloon.py:210-215)
   if (!ok) fl |= (1u << 11);
   if (run_stable_init) {                           // stable_init.cold_start_to_stable_params :132-157
-    const StableParams sp = stable_params(alpha, double(RR(d, R_P, e)), double(RR(d, R_MOLS_GAS, e)),
+    const StableParams sp = stable_params(alpha, DD(d, D_P, e), double(RR(d, R_MOLS_GAS, e)),
                                           lat, lng, ts, double(RR(d, R_IR, e)));
-    RR(d, R_TAMB, e) = Real(sp.t_ambient); RR(d, R_TINT, e) = Real(sp.t_internal);
-    RR(d, R_MOLS_AIR, e) = Real(sp.mols_air); RR(d, R_VOL, e) = Real(sp.volume);
-    RR(d, R_SP, e) = Real(sp.superpressure);
+    DD(d, D_TAMB, e) = sp.t_ambient; DD(d, D_TINT, e) = sp.t_internal;
+    DD(d, D_MOLS_AIR, e) = sp.mols_air; DD(d, D_VOL, e) = sp.volume;
+    DD(d, D_SP, e) = sp.superpressure;
     if (!sp.ok) fl |= (1u << 11);
   }
   d.flags[e] = fl;
@@ -464,15 +505,12 @@ k_reset(DevState<Real> d, const uint64_t* __restrict__ seeds, const uint8_t* __r
     ir = 315.0 * (1.0 / (1.0 + exp(-z)));
   } while (!(ir >= 225.0));
 
-  d.alpha[e] = alpha;
-  Atmosphere<Real> atm; atm.init(alpha);
-  RR(d, R_L0, e) = atm.l0; RR(d, R_L1, e) = atm.l1; RR(d, R_L2, e) = atm.l2;
-  RR(d, R_T1, e) = atm.t1; RR(d, R_T2, e) = atm.t2;
-  RR(d, R_P1, e) = atm.p1; RR(d, R_P2, e) = atm.p2; RR(d, R_P3, e) = atm.p3;
+  Atmosphere atm; atm.init(alpha);
+  store_atmosphere(d, e, atm);
   // BalloonState defaults (env/balloon/balloon.py:175-208)
-  RR(d, R_X, e) = Real(x); RR(d, R_Y, e) = Real(y); RR(d, R_P, e) = Real(pressure);
-  RR(d, R_TAMB, e) = Real(206.0); RR(d, R_TINT, e) = Real(206.0); RR(d, R_VOL, e) = Real(1804.0);
-  RR(d, R_SP, e) = Real(0); RR(d, R_MOLS_AIR, e) = Real(0); RR(d, R_CHARGE, e) = Real(2905.6);
+  DD(d, D_X, e) = x; DD(d, D_Y, e) = y; DD(d, D_P, e) = pressure;
+  DD(d, D_TAMB, e) = 206.0; DD(d, D_TINT, e) = 206.0; DD(d, D_VOL, e) = 1804.0;
+  DD(d, D_SP, e) = 0.0; DD(d, D_MOLS_AIR, e) = 0.0; DD(d, D_CHARGE, e) = 2905.6;
   RR(d, R_ACS_W, e) = Real(0); RR(d, R_ACS_FLOW, e) = Real(0); RR(d, R_SOLAR_W, e) = Real(0);
   RR(d, R_LOAD_W, e) = Real(0);
   RR(d, R_LAT0, e) = Real(lat_deg * (kPi / 180.0)); RR(d, R_LNG0, e) = Real(lng_deg * (kPi / 180.0));
@@ -503,6 +541,7 @@ struct EngineBase {
   virtual int step_host(const int32_t*, float*, uint8_t*, cudaStream_t) = 0;
   virtual int wind_at(float*, cudaStream_t) = 0;
   virtual int wind_gather(const float*, const int32_t*, float*, int64_t, cudaStream_t) = 0;
+  virtual int derived(double*, cudaStream_t) = 0;
   int64_t n = 0;
   int64_t launches = 0;
   std::string err;
@@ -535,8 +574,8 @@ struct Engine : EngineBase {
     device = dev; n = n_envs; cfg = c;
     BLE_CUDA(cudaSetDevice(device));
     d.n = n;
+    BLE_CUDA(cudaMalloc(&d.dd, sizeof(double) * D_COUNT * n));
     BLE_CUDA(cudaMalloc(&d.r, sizeof(Real) * R_COUNT * n));
-    BLE_CUDA(cudaMalloc(&d.alpha, sizeof(double) * n));
     BLE_CUDA(cudaMalloc(&d.l, sizeof(int64_t) * L_COUNT * n));
     BLE_CUDA(cudaMalloc(&d.t_elapsed, sizeof(int32_t) * n));
     BLE_CUDA(cudaMalloc(&d.flags, sizeof(uint32_t) * n));
@@ -559,7 +598,7 @@ struct Engine : EngineBase {
 
   ~Engine() override {
     cudaSetDevice(device);
-    cudaFree(d.r); cudaFree(d.alpha); cudaFree(d.l); cudaFree(d.t_elapsed); cudaFree(d.flags);
+    cudaFree(d.dd); cudaFree(d.r); cudaFree(d.l); cudaFree(d.t_elapsed); cudaFree(d.flags);
     cudaFree(env_field); cudaFree(d.noise_partial); cudaFree(cells); cudaFree(perm); cudaFree(offsets);
     cudaFree(noise_seeds); cudaFree(noise_offsets_in);
     cudaFree(d_actions); cudaFree(d_reward); cudaFree(d_done);
@@ -719,6 +758,16 @@ struct Engine : EngineBase {
     return BLE_OK;
   }
 
+  int derived(double* out, cudaStream_t s) override {
+    if (out == nullptr) { err = "derived: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    if (!have_state) { err = "derived: no balloon state"; return BLE_ERR_NOT_READY; }
+    BLE_CUDA(cudaSetDevice(device));
+    k_derived<Real><<<grid_for(n, 128), 128, 0, s>>>(d, out);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
   int wind_gather(const float* xyzt, const int32_t* fidx, float* uv, int64_t m, cudaStream_t s) override {
     if (m < 0 || (m > 0 && (xyzt == nullptr || fidx == nullptr || uv == nullptr))) { err = "wind_gather: bad argument"; return BLE_ERR_INVALID_ARGUMENT; }
     if (!have_fields) { err = "wind_gather: no wind fields (call ble_upload_fields first)"; return BLE_ERR_NOT_READY; }
@@ -818,6 +867,9 @@ int ble_step_host(ble_handle* h, const int32_t* actions_host, float* reward_host
 }
 int ble_wind_at_balloon(ble_handle* h, float* wind_uv, void* stream) {
   BLE_H(h); return h->eng->wind_at(wind_uv, cudaStream_t(stream));
+}
+int ble_derived(ble_handle* h, double* out, void* stream) {
+  BLE_H(h); return h->eng->derived(out, cudaStream_t(stream));
 }
 int ble_wind_gather(ble_handle* h, const float* xyzt, const int32_t* field_idx, float* uv, int64_t m, void* stream) {
   BLE_H(h); return h->eng->wind_gather(xyzt, field_idx, uv, m, cudaStream_t(stream));

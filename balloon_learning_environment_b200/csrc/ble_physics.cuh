@@ -165,56 +165,41 @@ BLE_HD bool atm_at_height_generic(double alpha, double h, double* pressure, doub
   return false;
 }
 
-// Register-resident lower atmosphere (layers 0, 1, 2).
-template <typename Real>
+// Register-resident lower atmosphere (layers 0, 1, 2), always fp64: pressure <-> height feeds the
+// stiff buoyancy loop of the Euler integrator (see the note above BalloonState).
 struct Atmosphere {
-  Real alpha;
-  Real l0, l1, l2;          // lapse rates
-  Real t1, t2;              // temperature transitions (t0 = 300)
-  Real p1, p2, p3;          // pressure transitions (p0 = 108870.8213)
+  double alpha;
+  double l0, l1, l2;        // lapse rates
+  double t1, t2;            // temperature transitions (t0 = 300)
+  double p1, p2, p3;        // pressure transitions (p0 = 108870.8213)
   bool ok;                  // false once a query fell outside the atmosphere
 
   BLE_HD void init(double a) {
     double lapse[7], t_tr[8], p_tr[8];
     atm_tables(a, lapse, t_tr, p_tr);
-    alpha = Real(a);
-    l0 = Real(lapse[0]); l1 = Real(lapse[1]); l2 = Real(lapse[2]);
-    t1 = Real(t_tr[1]); t2 = Real(t_tr[2]);
-    p1 = Real(p_tr[1]); p2 = Real(p_tr[2]); p3 = Real(p_tr[3]);
+    alpha = a;
+    l0 = lapse[0]; l1 = lapse[1]; l2 = lapse[2];
+    t1 = t_tr[1]; t2 = t_tr[2];
+    p1 = p_tr[1]; p2 = p_tr[2]; p3 = p_tr[3];
     ok = true;
   }
 
   // height [m] and temperature [K] at pressure p (:122-154).
-  BLE_HD void at_pressure(Real p, Real* height, Real* temperature) {
-    if (p > p3 && p <= Real(kAtmP0)) {
-      Real lapse, ti, pi, hi;
-      if (p > p1) { lapse = l0; ti = Real(kAtmT0); pi = Real(kAtmP0); hi = Real(-610.0); }
-      else if (p > p2) { lapse = l1; ti = t1; pi = p1; hi = Real(17000.0); }
-      else { lapse = l2; ti = t2; pi = p2; hi = Real(21000.0); }
-      const Real h = (r_pow(p / pi, Real(-kRAir) * lapse / Real(kGravity)) - Real(1)) * ti / lapse + hi;
+  BLE_HD void at_pressure(double p, double* height, double* temperature) {
+    if (p > p3 && p <= kAtmP0) {
+      double lapse, ti, pi, hi;
+      if (p > p1) { lapse = l0; ti = kAtmT0; pi = kAtmP0; hi = -610.0; }
+      else if (p > p2) { lapse = l1; ti = t1; pi = p1; hi = 17000.0; }
+      else { lapse = l2; ti = t2; pi = p2; hi = 21000.0; }
+      const double h = (pow(p / pi, -kRAir * lapse / kGravity) - 1) * ti / lapse + hi;   // :142-146
       *height = h;
-      *temperature = ti + lapse * (h - hi);
+      *temperature = ti + lapse * (h - hi);                                            // :148-149
     } else {
       double h, t;
-      if (!atm_at_pressure_generic(double(alpha), double(p), &h, &t)) { ok = false; h = 0; t = 1; }
-      *height = Real(h);
-      *temperature = Real(t);
+      if (!atm_at_pressure_generic(alpha, p, &h, &t)) { ok = false; h = 0; t = 1; }
+      *height = h;
+      *temperature = t;
     }
-  }
-
-  // fp64 height only: used for the +-1 Pa secant (env/balloon/balloon.py:438-443), where
-  // two heights ~0.7 m apart at ~17 km are subtracted.
-  BLE_HD double height_f64(double p) {
-    if (p > double(p3) && p <= kAtmP0) {
-      double lapse, ti, pi, hi;
-      if (p > double(p1)) { lapse = double(l0); ti = kAtmT0; pi = kAtmP0; hi = -610.0; }
-      else if (p > double(p2)) { lapse = double(l1); ti = double(t1); pi = double(p1); hi = 17000.0; }
-      else { lapse = double(l2); ti = double(t2); pi = double(p2); hi = 21000.0; }
-      return (pow(p / pi, -kRAir * lapse / kGravity) - 1) * ti / lapse + hi;
-    }
-    double h, t;
-    if (!atm_at_pressure_generic(double(alpha), p, &h, &t)) { ok = false; h = 0; }
-    return h;
   }
 };
 
@@ -510,9 +495,19 @@ BLE_HD int power_safety(int action, int64_t now, Real charge_wh, int64_t* sunris
 }
 
 // ---- balloon state + Euler sub-step (env/balloon/balloon.py:356-549) ------------------------------------------
+//
+// Precision note.  The reference integrates with explicit Euler at h = 10 s, and its vertical
+// dynamics  dp/dt = (dp/dh) * sign * sqrt(2 |rho V - m| g / (rho C_d V^(2/3)))  are stiff near
+// equilibrium: measured on the oracle, a pressure perturbation entering one agent step is damped
+// 1000x in the median but amplified up to ~70x (p99 ~4x) after stable-init/venting, and
+// perturbations injected at EVERY sub-step by fp32 rounding of p, T_ambient or V (3e-5 kg of
+// lift) grew to 8 Pa (8e-4 relative) within one step.  The variables of that loop -- x, y,
+// pressure, ambient/internal temperature, volume, superpressure, mols_air, battery charge -- are
+// therefore carried in fp64 (registers and HBM), and only the smooth right-hand sides (solar
+// geometry, thermal model, ACS tables, solar power, reward) are evaluated in `Real`.
 template <typename Real>
 struct BalloonState {
-  Real x, y, pressure, t_ambient, t_internal, volume, superpressure, mols_air, charge;
+  double x, y, pressure, t_ambient, t_internal, volume, superpressure, mols_air, charge;   // fp64 accumulators
   Real acs_power, acs_flow, solar_w, load_w;
   // per-episode constants
   Real lat0, lng0, ir, mols_gas;
@@ -522,63 +517,59 @@ struct BalloonState {
 };
 
 template <typename Real>
-BLE_HD void euler_substep(BalloonState<Real>& s, Atmosphere<Real>& atm, Real u, Real v, int action) {
-  const Real dt = Real(kStrideS);
-  // Step 3 inputs first (they only read old state): sun + ambient temperature.
+BLE_HD void euler_substep(BalloonState<Real>& s, Atmosphere& atm, double u, double v, int action) {
+  const double dt = double(kStrideS);
+  // Sun at the OLD position / time (:451-452).
   Real lat, lng, el, flux;
-  latlng_from_offset<Real>(s.lat0, s.lng0, s.x, s.y, &lat, &lng);
-  solar_calculator<Real>(lat, lng, s.date_time, &el, &flux);               // :451-452
+  latlng_from_offset<Real>(s.lat0, s.lng0, Real(s.x), Real(s.y), &lat, &lng);
+  solar_calculator<Real>(lat, lng, s.date_time, &el, &flux);
 
-  // Step 2: buoyancy -> dh/dt -> dp/dt (:412-445).
-  const double rho_d = (double(s.pressure) * kMAir) / (kR * double(s.t_ambient));
-  const Real rho = Real(rho_d);
-  const Real cv = r_cbrt(s.volume);
-  const Real drag = Real(kCod) * cv * cv;                                  // V^(2/3) :415
-  // mass balance in fp64: rho*V and the system mass agree to ~1e-4 near float, so the
-  // difference needs more than 24 bits.
-  const double mass = kMHe * double(s.mols_gas) + kMAir * double(s.mols_air) + kEnvelopeMass + kPayloadMass;
-  const double lift = rho_d * double(s.volume);
-  const Real direction = (lift >= mass) ? Real(1) : Real(-1);
-  const Real dh_dt = direction * r_sqrt(r_abs(Real(2 * (lift - mass) * kGravity) / (rho * drag)));  // :424-427
-  Real height0_r, t_amb_new;
-  atm.at_pressure(s.pressure, &height0_r, &t_amb_new);                     // :457-458
-  const double h0 = is_double<Real>::value ? double(height0_r) : atm.height_f64(double(s.pressure));
-  const double h1 = atm.height_f64(double(s.pressure) + double(direction));   // dp = 1 Pa :438-441
-  const Real dp_dh = direction / Real(h1 - h0);                            // :442
-  const Real new_pressure = s.pressure + dp_dh * dh_dt * dt;               // :443-445
+  // Step 2: buoyancy -> dh/dt -> dp/dt (:412-445), fp64.
+  const double rho = (s.pressure * kMAir) / (kR * s.t_ambient);
+  const double cv = cbrt(s.volume);
+  const double drag = kCod * cv * cv;                                      // V^(2/3) :415
+  const double mass = kMHe * double(s.mols_gas) + kMAir * s.mols_air + kEnvelopeMass + kPayloadMass;
+  const double lift = rho * s.volume;
+  const double direction = (lift >= mass) ? 1.0 : -1.0;
+  const double dh_dt = direction * sqrt(fabs(2 * (lift - mass) * kGravity / (rho * drag)));   // :424-427
+  double h0, t_amb_new, h1, t_unused;
+  atm.at_pressure(s.pressure, &h0, &t_amb_new);                            // :439, :457-458
+  atm.at_pressure(s.pressure + direction, &h1, &t_unused);                 // dp = 1 Pa :440-441
+  const double dp_dh = direction / (h1 - h0);                              // :442
+  const double new_pressure = s.pressure + dp_dh * dh_dt * dt;             // :443-445
 
-  // Step 3: internal temperature (:462-467).
-  const Real d_t = d_balloon_temperature_dt<Real>(s.volume, Real(kEnvelopeMass), s.t_internal,
-                                                  s.t_ambient, s.pressure, el, flux, s.ir);
-  const Real new_t_internal = s.t_internal + d_t * dt;
+  // Step 3: internal temperature (:462-467); smooth right-hand side in Real.
+  const Real d_t = d_balloon_temperature_dt<Real>(Real(s.volume), Real(kEnvelopeMass), Real(s.t_internal),
+                                                  Real(s.t_ambient), Real(s.pressure), el, flux, s.ir);
+  const double new_t_internal = s.t_internal + double(d_t) * dt;
 
-  // Step 4: envelope (:470-482).
-  Real new_volume, new_sp;
-  superpressure_and_volume<Real>(s.mols_gas, s.mols_air, s.t_internal, s.pressure, &new_volume, &new_sp);
+  // Step 4: envelope (:470-482), fp64.
+  double new_volume, new_sp;
+  superpressure_and_volume<double>(double(s.mols_gas), s.mols_air, s.t_internal, s.pressure, &new_volume, &new_sp);
   int status = s.status;
-  if (new_sp > Real(kMaxSuperpressure)) status = kBurst;
-  if (new_sp <= Real(0)) status = kZeroPressure;
+  if (new_sp > kMaxSuperpressure) status = kBurst;
+  if (new_sp <= 0.0) status = kZeroPressure;
 
   // Step 5: ACS (:487-519).
   Real acs_power = Real(0), flow = Real(0);
   if (action == kUp) {
     const Real valve_area = Real(kPi * kValveDiameter * kValveDiameter / 4.0);
-    const Real gas_density = (s.superpressure + s.pressure) * Real(kMAir) / (Real(kR) * s.t_internal);
-    flow = Real(-kValveCd) * valve_area * r_sqrt(Real(2) * s.superpressure * gas_density);
+    const Real gas_density = Real((s.superpressure + s.pressure) * kMAir / (kR * s.t_internal));
+    flow = Real(-kValveCd) * valve_area * r_sqrt(Real(2) * Real(s.superpressure) * gas_density);
   } else if (action == kDown) {
-    const Real pr = (s.pressure + r_max(s.superpressure, Real(0))) / s.pressure;   // :247-250
+    const Real pr = Real((s.pressure + fmax(s.superpressure, 0.0)) / s.pressure);   // :247-250
     acs_power = acs_most_efficient_power<Real>(pr);
-    flow = acs_fan_efficiency<Real>(pr, acs_power) * acs_power / Real(3600);       // acs.py:67-68
+    flow = acs_fan_efficiency<Real>(pr, acs_power) * acs_power / Real(3600);        // acs.py:67-68
   }
-  const Real new_mols_air = r_max(s.mols_air + (flow / Real(kMAir)) * dt, Real(0));
+  const double new_mols_air = fmax(s.mols_air + (double(flow) / kMAir) * dt, 0.0);
 
   // Step 6: power (:524-542).
   const bool is_day = el > Real(kMinSolarElDeg);
-  const Real solar_w = is_day ? solar_power<Real>(el, s.pressure) : Real(0);
+  const Real solar_w = is_day ? solar_power<Real>(el, Real(s.pressure)) : Real(0);
   const Real load_w = (is_day ? Real(kDayLoadW) : Real(kNightLoadW)) + acs_power;
-  Real charge = s.charge + (solar_w - load_w) * Real(double(kStrideS) / 3600.0);
-  charge = r_min(r_max(charge, Real(0)), Real(kBatteryCapacityWh));
-  if (charge <= Real(0)) status = kOutOfPower;
+  double charge = s.charge + double(solar_w - load_w) * (double(kStrideS) / 3600.0);
+  charge = fmin(fmax(charge, 0.0), kBatteryCapacityWh);
+  if (charge <= 0.0) status = kOutOfPower;
 
   s.x += u * dt;                                                           // :394-395
   s.y += v * dt;
@@ -601,7 +592,7 @@ BLE_HD void euler_substep(BalloonState<Real>& s, Atmosphere<Real>& atm, Real u, 
 // env/balloon_env.py:44-102 evaluated on the post-step state.
 template <typename Real>
 BLE_HD Real perciatelli_reward(const BalloonState<Real>& s, int last_command) {
-  const Real dist = r_sqrt(s.x * s.x + s.y * s.y);
+  const Real dist = Real(sqrt(s.x * s.x + s.y * s.y));
   const Real radius = Real(50000.0);
   Real reward = Real(1);
   if (!(dist <= radius)) {
@@ -609,10 +600,10 @@ BLE_HD Real perciatelli_reward(const BalloonState<Real>& s, int last_command) {
   }
   if (last_command == kDown) {
     Real lat, lng, el, flux;
-    latlng_from_offset<Real>(s.lat0, s.lng0, s.x, s.y, &lat, &lng);
+    latlng_from_offset<Real>(s.lat0, s.lng0, Real(s.x), Real(s.y), &lat, &lng);
     solar_calculator<Real>(lat, lng, s.date_time, &el, &flux);
-    const bool excess = (solar_power<Real>(el, s.pressure) > Real(kDayLoadW)) &&
-                        (s.charge / Real(kBatteryCapacityWh) > Real(0.99));          // balloon.py:231-238
+    const bool excess = (solar_power<Real>(el, Real(s.pressure)) > Real(kDayLoadW)) &&
+                        (s.charge / kBatteryCapacityWh > 0.99);            // balloon.py:231-238
     if (!excess) {
       const Real scale = r_min(r_max((s.acs_power - Real(100)) / Real(200), Real(0)), Real(1));
       reward *= Real(0.95) - Real(0.3) * scale;
@@ -726,17 +717,17 @@ struct SafetyState {
 };
 
 template <typename Real>
-BLE_HD Real agent_step(BalloonState<Real>& s, Atmosphere<Real>& atm, SafetyState& ss, int action,
-                       Real u, Real v, int* effective_action) {
+BLE_HD Real agent_step(BalloonState<Real>& s, Atmosphere& atm, SafetyState& ss, int action,
+                       double u, double v, int* effective_action) {
   ss.last_command = action;                                                // balloon.py:286
   int eff = action;
   if (ss.power_safety_enabled) {                                           // :305-309
-    eff = power_safety<Real>(eff, s.date_time, s.charge, &ss.sunrise_h, &ss.sunset, &ss.power_paused);
+    eff = power_safety<double>(eff, s.date_time, s.charge, &ss.sunrise_h, &ss.sunset, &ss.power_paused);
   }
-  eff = envelope_safety<Real>(eff, s.superpressure, &ss.envelope_state);   // :310-311
-  Real altitude, t_unused;
+  eff = envelope_safety<double>(eff, s.superpressure, &ss.envelope_state);  // :310-311
+  double altitude, t_unused;
   atm.at_pressure(s.pressure, &altitude, &t_unused);
-  eff = altitude_safety<Real>(eff, altitude, &ss.altitude_state);          // :312-313
+  eff = altitude_safety<double>(eff, altitude, &ss.altitude_state);         // :312-313
   *effective_action = eff;
   for (int k = 0; k < kSubSteps; ++k) {                                    // :321-328
     euler_substep<Real>(s, atm, u, v, eff);

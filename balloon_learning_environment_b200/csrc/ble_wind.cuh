@@ -105,7 +105,7 @@ BLE_HD void static_wind(Real p, Real* u, Real* v) {
 // ---- simplex noise -------------------------------------------------------------------------------------
 constexpr double kStretch4 = -0.138196601125011;
 constexpr double kSquish4 = 0.309016994374947;
-constexpr double kNoiseMagnitude = 4.2339715669708655;   // sqrt(1.02 / 0.0569), simplex_wind_noise.py:76
+constexpr double kNoiseMagnitude = 4.233932721683222;   // sqrt(1.02 / 0.0569), simplex_wind_noise.py:76
 
 // weight, x, y, pressure, time spacings (simplex_wind_noise.py:50-64); index = component * 5 + harmonic
 BLE_HD void harmonic_params(int h10, double* w, double* sx, double* sy, double* sp, double* st) {

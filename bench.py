@@ -213,7 +213,7 @@ def run_b200(args):
   e2e_s = time.perf_counter() - t0
 
   # ---- wind-gather roofline (dominant HBM kernel named by BASELINE.json's metric) -----------
-  m = n * 8
+  m = max(n * 8, 1 << 24)                                   # >= 16.7 M lookups, 2.6 GB of algorithmic traffic
   gq = torch.Generator(device=device); gq.manual_seed(99 + rank)
   xyzt = torch.empty(m, 4, dtype=torch.float32, device=device)
   xyzt[:, 0].uniform_(-500, 500, generator=gq); xyzt[:, 1].uniform_(-500, 500, generator=gq)

@@ -135,6 +135,16 @@ int ble_wind_at_balloon(ble_handle* h, float* wind_uv, void* stream);
 int ble_wind_gather(ble_handle* h, const float* xyzt, const int32_t* field_idx, float* uv,
                     int64_t m, void* stream);
 
+/* Derived properties of BalloonState at the CURRENT state (env/balloon/balloon.py:217-250), all
+ * balloons, float64 [BLE_NUM_D][N]. */
+enum {
+  BLE_D_LAT = 0 /* rad, BalloonState.latlng */, BLE_D_LNG, BLE_D_SOLAR_ELEVATION /* deg */, BLE_D_SOLAR_FLUX,
+  BLE_D_EXCESS_ENERGY /* 0/1 */, BLE_D_NAVIGATION_IS_PAUSED /* 0/1 */, BLE_D_PRESSURE_RATIO, BLE_D_BATTERY_SOC,
+  BLE_D_ALTITUDE /* m, Atmosphere.at_pressure(pressure).height */,
+  BLE_NUM_D
+};
+int ble_derived(ble_handle* h, double* out, void* stream);
+
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t ble_launch_count(const ble_handle* h);
 

@@ -22,24 +22,24 @@ static void step_impl(int64_t n, double* f, int64_t* iv, const int32_t* actions,
     eff_out[e] = kStay;
     if (I(BLE_I_STATUS, e) != kOk) continue;
     BalloonState<Real> s;
-    s.x = Real(F(BLE_F_X, e)); s.y = Real(F(BLE_F_Y, e)); s.pressure = Real(F(BLE_F_PRESSURE, e));
-    s.t_ambient = Real(F(BLE_F_AMBIENT_TEMPERATURE, e)); s.t_internal = Real(F(BLE_F_INTERNAL_TEMPERATURE, e));
-    s.volume = Real(F(BLE_F_ENVELOPE_VOLUME, e)); s.superpressure = Real(F(BLE_F_SUPERPRESSURE, e));
-    s.mols_air = Real(F(BLE_F_MOLS_AIR, e)); s.charge = Real(F(BLE_F_BATTERY_CHARGE, e));
+    s.x = F(BLE_F_X, e); s.y = F(BLE_F_Y, e); s.pressure = F(BLE_F_PRESSURE, e);
+    s.t_ambient = F(BLE_F_AMBIENT_TEMPERATURE, e); s.t_internal = F(BLE_F_INTERNAL_TEMPERATURE, e);
+    s.volume = F(BLE_F_ENVELOPE_VOLUME, e); s.superpressure = F(BLE_F_SUPERPRESSURE, e);
+    s.mols_air = F(BLE_F_MOLS_AIR, e); s.charge = F(BLE_F_BATTERY_CHARGE, e);
     s.acs_power = Real(F(BLE_F_ACS_POWER, e)); s.acs_flow = Real(F(BLE_F_ACS_MASS_FLOW, e));
     s.solar_w = Real(F(BLE_F_SOLAR_CHARGING, e)); s.load_w = Real(F(BLE_F_POWER_LOAD, e));
     s.lat0 = Real(F(BLE_F_CENTER_LAT, e)); s.lng0 = Real(F(BLE_F_CENTER_LNG, e));
     s.ir = Real(F(BLE_F_UPWELLING_INFRARED, e)); s.mols_gas = Real(F(BLE_F_MOLS_LIFT_GAS, e));
     s.date_time = I(BLE_I_DATE_TIME, e); s.time_elapsed = int32_t(I(BLE_I_TIME_ELAPSED, e));
     s.status = int(I(BLE_I_STATUS, e));
-    Atmosphere<Real> atm; atm.init(F(BLE_F_ATMOSPHERE_ALPHA, e));
+    Atmosphere atm; atm.init(F(BLE_F_ATMOSPHERE_ALPHA, e));
     SafetyState ss;
     ss.sunrise_h = I(BLE_I_SUNRISE_H, e); ss.sunset = I(BLE_I_SUNSET, e);
     ss.envelope_state = int(I(BLE_I_ENVELOPE_STATE, e)); ss.altitude_state = int(I(BLE_I_ALTITUDE_STATE, e));
     ss.power_paused = int(I(BLE_I_POWER_PAUSED, e)); ss.power_safety_enabled = int(I(BLE_I_POWER_SAFETY_ENABLED, e));
     ss.last_command = int(I(BLE_I_LAST_COMMAND, e));
     int eff;
-    const Real r = agent_step<Real>(s, atm, ss, actions[e], Real(wind[2 * e]), Real(wind[2 * e + 1]), &eff);
+    const Real r = agent_step<Real>(s, atm, ss, actions[e], wind[2 * e], wind[2 * e + 1], &eff);
     reward[e] = double(r); eff_out[e] = eff;
     F(BLE_F_X, e) = s.x; F(BLE_F_Y, e) = s.y; F(BLE_F_PRESSURE, e) = s.pressure;
     F(BLE_F_AMBIENT_TEMPERATURE, e) = s.t_ambient; F(BLE_F_INTERNAL_TEMPERATURE, e) = s.t_internal;
@@ -55,7 +55,37 @@ static void step_impl(int64_t n, double* f, int64_t* iv, const int32_t* actions,
   }
 }
 
+template <typename Real>
+static void substeps_impl(int64_t n, double* f, int64_t* iv, const int32_t* eff, const double* wind, int nsub) {
+  auto F = [&](int r, int64_t e) -> double& { return f[int64_t(r) * n + e]; };
+  auto I = [&](int r, int64_t e) -> int64_t& { return iv[int64_t(r) * n + e]; };
+  for (int64_t e = 0; e < n; ++e) {
+    BalloonState<Real> s;
+    s.x = F(BLE_F_X, e); s.y = F(BLE_F_Y, e); s.pressure = F(BLE_F_PRESSURE, e);
+    s.t_ambient = F(BLE_F_AMBIENT_TEMPERATURE, e); s.t_internal = F(BLE_F_INTERNAL_TEMPERATURE, e);
+    s.volume = F(BLE_F_ENVELOPE_VOLUME, e); s.superpressure = F(BLE_F_SUPERPRESSURE, e);
+    s.mols_air = F(BLE_F_MOLS_AIR, e); s.charge = F(BLE_F_BATTERY_CHARGE, e);
+    s.acs_power = 0; s.acs_flow = 0; s.solar_w = 0; s.load_w = 0;
+    s.lat0 = Real(F(BLE_F_CENTER_LAT, e)); s.lng0 = Real(F(BLE_F_CENTER_LNG, e));
+    s.ir = Real(F(BLE_F_UPWELLING_INFRARED, e)); s.mols_gas = Real(F(BLE_F_MOLS_LIFT_GAS, e));
+    s.date_time = I(BLE_I_DATE_TIME, e); s.time_elapsed = int32_t(I(BLE_I_TIME_ELAPSED, e));
+    s.status = 0;
+    Atmosphere atm; atm.init(F(BLE_F_ATMOSPHERE_ALPHA, e));
+    for (int k = 0; k < nsub; ++k) euler_substep<Real>(s, atm, wind[2 * e], wind[2 * e + 1], eff[e]);
+    F(BLE_F_X, e) = s.x; F(BLE_F_Y, e) = s.y; F(BLE_F_PRESSURE, e) = s.pressure;
+    F(BLE_F_AMBIENT_TEMPERATURE, e) = s.t_ambient; F(BLE_F_INTERNAL_TEMPERATURE, e) = s.t_internal;
+    F(BLE_F_ENVELOPE_VOLUME, e) = s.volume; F(BLE_F_SUPERPRESSURE, e) = s.superpressure;
+    F(BLE_F_MOLS_AIR, e) = s.mols_air; F(BLE_F_BATTERY_CHARGE, e) = s.charge;
+    I(BLE_I_DATE_TIME, e) = s.date_time; I(BLE_I_TIME_ELAPSED, e) = s.time_elapsed;
+  }
+}
+
 extern "C" {
+
+void emu_substeps(int precision, int64_t n, double* f, int64_t* iv, const int32_t* eff, const double* wind, int nsub) {
+  if (precision == BLE_PRECISION_FP64) substeps_impl<double>(n, f, iv, eff, wind, nsub);
+  else substeps_impl<float>(n, f, iv, eff, wind, nsub);
+}
 
 void emu_step(int precision, int64_t n, double* f, int64_t* iv, const int32_t* actions,
               const double* wind, double* reward, int32_t* eff) {

@@ -170,6 +170,10 @@ def test_single_steps_fp64_device_code_tight():
 def test_single_steps_fp32_device_code_within_1e4():
   worst, mism, total, rworst = _single_step_errors(0)
   print(worst)
-  assert max(worst.values()) < 1e-4, worst
+  # north_star tolerance is 1e-4; with the stiff variables in fp64 the production arithmetic
+  # lands at <= 1e-5 (solar_charging, fp32 trig) and <= 1e-6 for the integrated state.
+  assert max(worst.values()) < 2e-5, worst
+  assert max(worst[k] for k in ('pressure', 'internal_temperature', 'envelope_volume', 'superpressure',
+                                'mols_air', 'battery_charge')) < 2e-6, worst
   assert mism == 0, (mism, total)
   assert rworst < 1e-4
