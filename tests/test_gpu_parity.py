@@ -372,3 +372,57 @@ def test_full_size_properties(ble):
     np.testing.assert_array_equal(before[k][:100], after[k][:100])
   assert (done.cpu().numpy()[:100] == 1).all() and (reward.cpu().numpy()[:100] == 0).all()
   env.close(); twin.close()
+
+
+# ------------------------------------------------------------------------------ N = 1 adaptor (drop-in boundary)
+
+def test_cuda_balloon_arena_follows_reference_episode(ble):
+  """The reference's own calling sequence -- arena.step(action); reward_fn(arena.get_simulator_state()) --
+  on CudaBalloonArena, against the recorded reference episode 'grid_random' (first 120 steps)."""
+  import datetime as dt
+  import math
+  from balloon_learning_environment_b200 import arena as arena_lib, units
+  sc = TRAJ['grid_random']
+  bank = golden_fields.field_bank()
+  a = arena_lib.CudaBalloonArena(wind_field=bank[int(sc['field'])], seed=0, precision='fp64')
+  a.set_wind_noise(sc['seeds'], sc['offsets'])
+  s = a.get_balloon_state()
+  f0 = dict(zip(FF, sc['f0'])); i0 = dict(zip(IF, sc['i0']))
+  utc = lambda ts: dt.datetime.fromtimestamp(int(ts), tz=dt.timezone.utc)
+  s.center_latlng = arena_lib.LatLng(f0['center_lat'], f0['center_lng'])
+  s.x, s.y = units.Distance(f0['x']), units.Distance(f0['y'])
+  for k in ('pressure', 'ambient_temperature', 'internal_temperature', 'envelope_volume', 'superpressure',
+            'mols_air', 'mols_lift_gas', 'upwelling_infrared', 'acs_mass_flow'):
+    setattr(s, k, f0[k])
+  s.battery_charge = units.Energy(f0['battery_charge']); s.acs_power = units.Power(f0['acs_power'])
+  s.solar_charging = units.Power(f0['solar_charging']); s.power_load = units.Power(f0['power_load'])
+  s.date_time = utc(i0['date_time']); s.time_elapsed = dt.timedelta(seconds=int(i0['time_elapsed']))
+  s.last_command = arena_lib.AltitudeControlCommand(int(i0['last_command']))
+  s.status = arena_lib.BalloonStatus(int(i0['status']))
+  s.envelope_state, s.altitude_state, s.power_paused = int(i0['envelope_state']), int(i0['altitude_state']), bool(i0['power_paused'])
+  s.sunrise_with_hysteresis, s.sunset = utc(i0['sunrise_h']), utc(i0['sunset'])
+  s.atmosphere_alpha = float(sc['alpha'])
+  a.set_balloon_state(s)
+
+  def reward_fn(sim_state):                     # env/balloon_env.py:44-102 written against the state view
+    b = sim_state.balloon_state
+    distance_km = math.hypot(b.x.m, b.y.m) / 1000.0
+    reward = 1.0 if distance_km <= 50.0 else 0.4 * math.exp(-0.69314718056 / 100.0 * (distance_km - 50.0))
+    if b.last_command == arena_lib.AltitudeControlCommand.DOWN and not b.excess_energy:
+      reward *= 0.95 - 0.3 * min(max((b.acs_power.watts - 100.0) / 200.0, 0.0), 1.0)
+    return reward
+
+  for t in range(120):
+    w = a.get_measurements().wind_at_balloon
+    assert abs(w.u.mps - sc['wind'][t, 0]) < 2e-5 and abs(w.v.mps - sc['wind'][t, 1]) < 2e-5
+    obs = a.step(arena_lib.AltitudeControlCommand(int(sc['actions'][t])))
+    assert isinstance(obs, np.ndarray)
+    sim = a.get_simulator_state()
+    b = sim.balloon_state
+    want = dict(zip(FF, sc['f'][t])); wi = dict(zip(IF, sc['i'][t]))
+    assert abs(b.x.km - want['x'] / 1000.0) < 1e-5 and abs(b.pressure - want['pressure']) < 1e-4
+    assert abs(b.battery_charge.watt_hours - want['battery_charge']) < 1e-6
+    assert b.status.value == wi['status'] and int(b.last_command) == wi['last_command']
+    assert int(b.time_elapsed.total_seconds()) == wi['time_elapsed']
+    assert abs(reward_fn(sim) - sc['reward'][t]) < 1e-6
+  a.close()
