@@ -11,7 +11,7 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
-LIB_PATH = os.path.join(PKG_DIR, 'libble_b200.so')
+LIB_PATH = os.environ.get('BLE_B200_LIB') or os.path.join(PKG_DIR, 'libble_b200.so')
 SOURCES = [os.path.join(CSRC, 'ble_engine.cu')]
 HEADERS = [os.path.join(CSRC, 'ble_physics.cuh'), os.path.join(CSRC, 'ble_wind.cuh'),
            os.path.join(PKG_DIR, '..', 'include', 'ble_b200.h')]

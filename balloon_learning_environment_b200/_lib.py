@@ -14,6 +14,7 @@ _LIB = None
 BLE_OK = 0
 PRECISION = {'fp32': 0, 'fp64': 1}
 WIND_MODEL = {'grid': 0, 'simple_static': 1}
+FIELD_LAYOUT = {'x64': 0, 'x128': 1}
 
 # Row order of the state exchange matrices (include/ble_b200.h, BLE_F_* / BLE_I_*).
 F_ROWS = ('x', 'y', 'pressure', 'ambient_temperature', 'internal_temperature', 'envelope_volume',
@@ -27,6 +28,7 @@ D_ROWS = ('lat', 'lng', 'solar_elevation', 'solar_flux', 'excess_energy', 'navig
           'pressure_ratio', 'battery_soc', 'altitude')
 
 EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_upload_fields',
+           'ble_alloc_fields', 'ble_write_fields', 'ble_set_field_map',
            'ble_set_noise', 'ble_state_upload', 'ble_state_download', 'ble_reset', 'ble_init_derived',
            'ble_step', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_derived',
            'ble_launch_count')
@@ -34,7 +36,7 @@ EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_u
 
 class BleConfig(_c.Structure):
   _fields_ = [('precision', _c.c_int32), ('wind_model', _c.c_int32), ('enable_noise', _c.c_int32),
-              ('reserved', _c.c_int32)]
+              ('field_layout', _c.c_int32)]
 
 
 class BleStateSoa(_c.Structure):
@@ -70,6 +72,9 @@ def load(build_if_missing=True):
   lib.ble_launch_count.argtypes = [vp]
   lib.ble_launch_count.restype = i64
   lib.ble_upload_fields.argtypes = [vp, vp, i64, vp, vp]
+  lib.ble_alloc_fields.argtypes = [vp, i64, vp]
+  lib.ble_write_fields.argtypes = [vp, vp, i64, i64, vp]
+  lib.ble_set_field_map.argtypes = [vp, vp, vp]
   lib.ble_set_noise.argtypes = [vp, vp, vp, vp]
   lib.ble_state_upload.argtypes = [vp, _c.POINTER(BleStateSoa), vp]
   lib.ble_state_download.argtypes = [vp, _c.POINTER(BleStateSoa), vp]

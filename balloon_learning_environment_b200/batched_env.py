@@ -42,7 +42,7 @@ class BatchedBalloonArena:
   """
 
   def __init__(self, num_envs: int, *, device: str = 'cuda:0', precision: str = 'fp32',
-               wind_model: str = 'grid', enable_noise: bool = True):
+               wind_model: str = 'grid', enable_noise: bool = True, field_layout: str = 'x64'):
     if not torch.cuda.is_available():
       raise _lib.BleError('BatchedBalloonArena needs a CUDA device (no CPU fallback exists)')
     self._lib = _lib.load()
@@ -51,7 +51,8 @@ class BatchedBalloonArena:
     self.precision = precision
     self.wind_model = wind_model
     self.enable_noise = bool(enable_noise)
-    cfg = _lib.BleConfig(_lib.PRECISION[precision], _lib.WIND_MODEL[wind_model], int(enable_noise), 0)
+    cfg = _lib.BleConfig(_lib.PRECISION[precision], _lib.WIND_MODEL[wind_model], int(enable_noise),
+                         _lib.FIELD_LAYOUT[field_layout])
     handle = ctypes.c_void_p()
     dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
     rc = self._lib.ble_create(dev_index, self.num_envs, ctypes.byref(cfg), ctypes.byref(handle))
@@ -103,6 +104,29 @@ class BatchedBalloonArena:
     rc = self._lib.ble_upload_fields(self._h, _ptr(fields), fields.shape[0], _ptr(env_to_field), self._stream())
     self._check(rc, 'ble_upload_fields')
     self._keepalive = [fields, env_to_field]
+
+  def alloc_wind_fields(self, n_fields: int):
+    """Room for n_fields grids; fill with write_wind_fields (keeps peak memory at one chunk)."""
+    self._check(self._lib.ble_alloc_fields(self._h, int(n_fields), self._stream()), 'ble_alloc_fields')
+    self._n_fields = int(n_fields)
+
+  def write_wind_fields(self, fields: torch.Tensor, first_field: int):
+    fields = fields.to(self.device, torch.float32).contiguous()
+    if tuple(fields.shape[1:]) != FIELD_SHAPE:
+      raise ValueError(f'fields must have shape [F, {FIELD_SHAPE}], got {tuple(fields.shape)}')
+    rc = self._lib.ble_write_fields(self._h, _ptr(fields), int(first_field), fields.shape[0], self._stream())
+    self._check(rc, 'ble_write_fields')
+    torch.cuda.current_stream(self.device).synchronize()
+
+  def set_field_map(self, env_to_field: torch.Tensor):
+    env_to_field = env_to_field.to(self.device, torch.int32).contiguous()
+    if env_to_field.numel() != self.num_envs:
+      raise ValueError('env_to_field must have one entry per balloon')
+    if int(env_to_field.max()) >= self._n_fields or int(env_to_field.min()) < 0:
+      raise ValueError('env_to_field refers to a field that was not allocated')
+    self._check(self._lib.ble_set_field_map(self._h, _ptr(env_to_field), self._stream()), 'ble_set_field_map')
+    torch.cuda.current_stream(self.device).synchronize()
+    self._keepalive = [None, env_to_field]
 
   def set_wind_noise(self, seeds: torch.Tensor, offsets: torch.Tensor):
     """seeds int64 [N,2,5], offsets float32 [N,2,5,4] (env/simplex_wind_noise.py:98-114)."""

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -47,7 +48,8 @@ struct DevState {
   int32_t* t_elapsed; // [n]
   uint32_t* flags;    // [n]
   // wind
-  const float* cells;        // [F][kCellFieldFloats]
+  const float* cells;        // [F][layout.field_floats], 128-byte windows (ble_wind.cuh)
+  FieldLayout layout;
   const int32_t* env_field;  // [n]
   const uint8_t* perm;       // [10][n][256], each table rotated by 4*(env%32) bytes
   const float* offsets;      // [10][4][n]
@@ -135,54 +137,82 @@ __global__ void k_state_download(DevState<Real> d, double* __restrict__ f, int64
 }
 
 // ---------------------------------------------------------------------------------------------
-// Wind field re-layout: native [F,21,21,10,9,2] -> 32-byte (pressure, time) cells
+// Wind field re-layout: native [F,21,21,10,9,2] -> 128-byte lookup windows (ble_wind.cuh)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_fields_to_cells(const float* __restrict__ native, float* __restrict__ cells, int64_t n_cells) {
-  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;   // global cell index
-  if (c >= n_cells) return;
-  const int64_t cells_per_field = int64_t(kNX) * kNY * kPC * kTC;
-  const int64_t f = c / cells_per_field;
-  int64_t r = c - f * cells_per_field;
+// One thread per 64-byte block = one grid column (ix) of one (y,p,t) cell, ordered [dy][dp][dt][uv].
+// X64: 21 blocks per row; X128: 20 windows per row, each holding block(ix) then block(ix+1).
+__global__ void k_fields_to_windows(const float* __restrict__ native, float* __restrict__ cells,
+                                    FieldLayout layout, int64_t first_field, int64_t n_fields) {
+  const int blocks_per_row = layout.row_floats / 16;
+  const int64_t per_field = int64_t(kYC) * kPC * kTC * blocks_per_row;
+  const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (t >= per_field * n_fields) return;
+  const int64_t f = t / per_field;
+  int64_t r = t - f * per_field;
+  const int b = int(r % blocks_per_row); r /= blocks_per_row;
   const int tc = int(r % kTC); r /= kTC;
-  const int pc = int(r % kPC); r /= kPC;
-  const int iy = int(r % kNY);
-  const int ix = int(r / kNY);
+  const int pc = int(r % kPC);
+  const int iy = int(r / kPC);
+  const int ix = (layout.x_stride_floats == 32) ? (b >> 1) + (b & 1) : b;   // X128: window b/2, half b&1
   const float* src = native + f * kFieldFloats;
-  float4 a, b;
-  a.x = src[native_index(ix, iy, pc, tc, 0)];     a.y = src[native_index(ix, iy, pc, tc, 1)];
-  a.z = src[native_index(ix, iy, pc, tc + 1, 0)]; a.w = src[native_index(ix, iy, pc, tc + 1, 1)];
-  b.x = src[native_index(ix, iy, pc + 1, tc, 0)];     b.y = src[native_index(ix, iy, pc + 1, tc, 1)];
-  b.z = src[native_index(ix, iy, pc + 1, tc + 1, 0)]; b.w = src[native_index(ix, iy, pc + 1, tc + 1, 1)];
-  float4* dst = reinterpret_cast<float4*>(cells + c * kCellFloats);
-  dst[0] = a;
-  dst[1] = b;
+  float4* dst = reinterpret_cast<float4*>(cells + (first_field + f) * layout.field_floats +
+                                          ((int64_t(iy) * kPC + pc) * kTC + tc) * layout.row_floats + int64_t(b) * 16);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {                       // chunk c = dy*2 + dp
+    const int y = iy + (c >> 1), p = pc + (c & 1);
+    dst[c] = make_float4(src[native_index(ix, y, p, tc, 0)], src[native_index(ix, y, p, tc, 1)],
+                         src[native_index(ix, y, p, tc + 1, 0)], src[native_index(ix, y, p, tc + 1, 1)]);
+  }
 }
 
-struct CellLoader {
-  const float* base;
-  __device__ __forceinline__ float8 operator()(int64_t idx) const {
-    const float4* p = reinterpret_cast<const float4*>(base + idx);
-    float8 c;
-    c.a = __ldg(p);
-    c.b = __ldg(p + 1);
-    return c;
-  }
+struct WindowLoader {        // per-thread path: the 8 chunks of one window
+  const float4* base;
+  __device__ __forceinline__ float4 operator()(int j) const { return __ldg(base + j); }
 };
 
 // GridBasedWindField.get_forecast for M arbitrary points (C ABI ble_wind_gather).
+// One thread locates one lookup (clip, boomerang, fp32 point, cell + weights); the 128-byte
+// windows are then loaded COOPERATIVELY: in round r, the 8 lanes of group g = lane/8 read the
+// 8 x 16 B chunks of the window owned by lane 4r + g, i.e. one warp-wide LDG.128 covers four
+// whole 128-byte lines.  Each lane weights its chunk and the group reduces with 3 xor-shuffles.
 template <typename Real>
 __global__ void __launch_bounds__(256)
-k_wind_gather(const float* __restrict__ cells, const float4* __restrict__ xyzt,
+k_wind_gather(const float* __restrict__ cells, FieldLayout layout, const float4* __restrict__ xyzt,
               const int32_t* __restrict__ field_idx, float2* __restrict__ uv, int64_t m) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (i >= m) return;
-  const float4 q4 = __ldg(xyzt + i);
-  const int32_t f = __ldg(field_idx + i);
-  const FieldPoint q = make_field_point(double(q4.x), double(q4.y), double(q4.z), double(q4.w));
-  CellLoader ld{cells + int64_t(f) * kCellFieldFloats};
-  Real u, v;
-  interp_cells<Real>(q, ld, &u, &v);
-  uv[i] = make_float2(float(u), float(v));
+  const unsigned lane = threadIdx.x & 31u;
+  const bool valid = i < m;
+  FieldCell<Real> c{};
+  int64_t base = -1;                                   // in float4 units; -1 = no lookup
+  if (valid) {
+    const float4 q4 = __ldg(xyzt + i);
+    const FieldPoint q = make_field_point(double(q4.x), double(q4.y), double(q4.z), double(q4.w));
+    c = locate<Real>(q);
+    base = (int64_t(__ldg(field_idx + i)) * layout.field_floats + window_index(layout, c.ix, c.iy, c.pc, c.tc)) >> 2;
+  }
+  const float4* cells4 = reinterpret_cast<const float4*>(cells);
+  const int j = int(lane & 7u);                        // my chunk within the group's window
+  const unsigned g = lane >> 3;
+  Real my_u = Real(0), my_v = Real(0);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int src = 4 * r + int(g);
+    const int64_t b = __shfl_sync(0xffffffffu, base, src);
+    FieldCell<Real> o;
+    o.wx = __shfl_sync(0xffffffffu, c.wx, src); o.wy = __shfl_sync(0xffffffffu, c.wy, src);
+    o.wp = __shfl_sync(0xffffffffu, c.wp, src); o.wt = __shfl_sync(0xffffffffu, c.wt, src);
+    const float4 v4 = (b >= 0) ? __ldg(cells4 + b + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    Real pu, pv;
+    chunk_contribution<Real>(o, j, v4, &pu, &pv);
+    pu += __shfl_xor_sync(0xffffffffu, pu, 1); pv += __shfl_xor_sync(0xffffffffu, pv, 1);
+    pu += __shfl_xor_sync(0xffffffffu, pu, 2); pv += __shfl_xor_sync(0xffffffffu, pv, 2);
+    pu += __shfl_xor_sync(0xffffffffu, pu, 4); pv += __shfl_xor_sync(0xffffffffu, pv, 4);
+    // the sum for lookup `src` now sits in group g; its owner (lane src) picks it up
+    const Real ru = __shfl_sync(0xffffffffu, pu, int(lane & 3u) * 8);
+    const Real rv = __shfl_sync(0xffffffffu, pv, int(lane & 3u) * 8);
+    if (int(lane >> 2) == r) { my_u = ru; my_v = rv; }
+  }
+  if (valid) uv[i] = make_float2(float(my_u), float(my_v));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,8 +302,10 @@ __device__ __forceinline__ void wind_at_balloon(const DevState<Real>& d, int64_t
     static_wind<Real>(Real(p), u, v);
   } else {
     const FieldPoint q = make_field_point(x / 1000.0, y / 1000.0, p, double(t_elapsed) / 3600.0);
-    CellLoader ld{d.cells + int64_t(d.env_field[e]) * kCellFieldFloats};
-    interp_cells<Real>(q, ld, u, v);
+    const FieldCell<Real> c = locate<Real>(q);
+    WindowLoader ld{reinterpret_cast<const float4*>(d.cells + int64_t(d.env_field[e]) * d.layout.field_floats +
+                                                    window_index(d.layout, c.ix, c.iy, c.pc, c.tc))};
+    interp_window<Real>(c, ld, u, v);
   }
   if (d.enable_noise) {
     // NoisyWindComponent.get_noise (:180-211): weighted mean of 5 harmonics, variance-rescaled
@@ -307,8 +339,11 @@ k_wind_at_balloon(DevState<Real> d, float2* __restrict__ uv) {
 // ---------------------------------------------------------------------------------------------
 // The fused physics step: wind at balloon -> safety layers -> 18 Euler sub-steps -> reward/done
 // ---------------------------------------------------------------------------------------------
+#ifndef BLE_STEP_MIN_BLOCKS
+#define BLE_STEP_MIN_BLOCKS 4     // 128 registers: measured 0.225 ms/step vs 0.310 ms at 184 registers (N = 65,536)
+#endif
 template <typename Real>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BLE_STEP_MIN_BLOCKS)
 k_step(DevState<Real> d, const int32_t* __restrict__ actions, float* __restrict__ reward,
        uint8_t* __restrict__ done, float2* __restrict__ wind_uv) {
   const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -532,6 +567,9 @@ k_reset(DevState<Real> d, const uint64_t* __restrict__ seeds, const uint8_t* __r
 struct EngineBase {
   virtual ~EngineBase() {}
   virtual int upload_fields(const float*, int64_t, const int32_t*, cudaStream_t) = 0;
+  virtual int alloc_fields(int64_t, cudaStream_t) = 0;
+  virtual int write_fields(const float*, int64_t, int64_t, cudaStream_t) = 0;
+  virtual int set_field_map(const int32_t*, cudaStream_t) = 0;
   virtual int set_noise(const int64_t*, const float*, const uint8_t*, cudaStream_t) = 0;
   virtual int state_upload(const ble_state_soa*, cudaStream_t) = 0;
   virtual int state_download(ble_state_soa*, cudaStream_t) = 0;
@@ -573,6 +611,9 @@ struct Engine : EngineBase {
   int create(int dev, int64_t n_envs, const ble_config& c) {
     device = dev; n = n_envs; cfg = c;
     BLE_CUDA(cudaSetDevice(device));
+    if (const char* g = std::getenv("BLE_L2_FETCH_GRANULARITY")) {     // experiment knob: 32 / 64 / 128
+      BLE_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(std::atoi(g))));
+    }
     d.n = n;
     BLE_CUDA(cudaMalloc(&d.dd, sizeof(double) * D_COUNT * n));
     BLE_CUDA(cudaMalloc(&d.r, sizeof(Real) * R_COUNT * n));
@@ -591,6 +632,7 @@ struct Engine : EngineBase {
     BLE_CUDA(cudaMallocHost(&h_done, sizeof(uint8_t) * n));
     d.env_field = env_field;
     d.wind_model = cfg.wind_model;
+    d.layout = make_layout(cfg.field_layout);
     d.enable_noise = 0;
     BLE_CUDA(cudaFuncSetAttribute(k_noise<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseBlock * 256));
     return BLE_OK;
@@ -607,23 +649,47 @@ struct Engine : EngineBase {
 
   static unsigned grid_for(int64_t items, int block) { return unsigned((items + block - 1) / block); }
 
-  int upload_fields(const float* fields, int64_t nf, const int32_t* map, cudaStream_t s) override {
-    if (fields == nullptr || nf <= 0) { err = "upload_fields: fields must be non-null, n_fields > 0"; return BLE_ERR_INVALID_ARGUMENT; }
+  int alloc_fields(int64_t nf, cudaStream_t s) override {
+    if (nf <= 0) { err = "alloc_fields: n_fields must be > 0"; return BLE_ERR_INVALID_ARGUMENT; }
     BLE_CUDA(cudaSetDevice(device));
     if (nf != n_fields) {
       BLE_CUDA(cudaStreamSynchronize(s));
-      cudaFree(cells); cells = nullptr;
-      BLE_CUDA(cudaMalloc(&cells, sizeof(float) * kCellFieldFloats * nf));
+      cudaFree(cells); cells = nullptr; n_fields = 0; have_fields = false;
+      BLE_CUDA(cudaMalloc(&cells, sizeof(float) * size_t(d.layout.field_floats) * size_t(nf)));
       n_fields = nf;
     }
-    const int64_t n_cells = nf * int64_t(kNX) * kNY * kPC * kTC;
-    k_fields_to_cells<<<grid_for(n_cells, 256), 256, 0, s>>>(fields, cells, n_cells);
+    d.cells = cells;
+    return BLE_OK;
+  }
+
+  int write_fields(const float* fields, int64_t first, int64_t count, cudaStream_t s) override {
+    if (fields == nullptr || first < 0 || count <= 0 || first + count > n_fields) {
+      err = "write_fields: range outside the allocated fields (call ble_alloc_fields first)";
+      return BLE_ERR_INVALID_ARGUMENT;
+    }
+    BLE_CUDA(cudaSetDevice(device));
+    const int64_t threads = count * int64_t(kYC) * kPC * kTC * (d.layout.row_floats / 16);
+    k_fields_to_windows<<<grid_for(threads, 256), 256, 0, s>>>(fields, cells, d.layout, first, count);
     ++launches;
     BLE_CUDA(cudaGetLastError());
-    if (map != nullptr) BLE_CUDA(cudaMemcpyAsync(env_field, map, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
-    d.cells = cells;
     have_fields = true;
     return BLE_OK;
+  }
+
+  int set_field_map(const int32_t* map, cudaStream_t s) override {
+    if (map == nullptr) { err = "set_field_map: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    BLE_CUDA(cudaSetDevice(device));
+    BLE_CUDA(cudaMemcpyAsync(env_field, map, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
+    return BLE_OK;
+  }
+
+  int upload_fields(const float* fields, int64_t nf, const int32_t* map, cudaStream_t s) override {
+    if (fields == nullptr || nf <= 0) { err = "upload_fields: fields must be non-null, n_fields > 0"; return BLE_ERR_INVALID_ARGUMENT; }
+    int rc = alloc_fields(nf, s);
+    if (rc != BLE_OK) return rc;
+    rc = write_fields(fields, 0, nf, s);
+    if (rc != BLE_OK) return rc;
+    return map != nullptr ? set_field_map(map, s) : BLE_OK;
   }
 
   int ensure_noise_buffers() {
@@ -773,7 +839,7 @@ struct Engine : EngineBase {
     if (!have_fields) { err = "wind_gather: no wind fields (call ble_upload_fields first)"; return BLE_ERR_NOT_READY; }
     if (m == 0) return BLE_OK;
     BLE_CUDA(cudaSetDevice(device));
-    k_wind_gather<Real><<<grid_for(m, 256), 256, 0, s>>>(cells, reinterpret_cast<const float4*>(xyzt), fidx,
+    k_wind_gather<Real><<<grid_for(m, 256), 256, 0, s>>>(cells, d.layout, reinterpret_cast<const float4*>(xyzt), fidx,
                                                        reinterpret_cast<float2*>(uv), m);
     ++launches;
     BLE_CUDA(cudaGetLastError());
@@ -801,6 +867,9 @@ int ble_create(int device, int64_t n_envs, const ble_config* config, ble_handle*
   }
   if (config->precision != BLE_PRECISION_FP32 && config->precision != BLE_PRECISION_FP64) {
     g_create_error = "ble_create: unknown precision"; return BLE_ERR_INVALID_ARGUMENT;
+  }
+  if (config->field_layout != BLE_LAYOUT_X64 && config->field_layout != BLE_LAYOUT_X128) {
+    g_create_error = "ble_create: unknown field_layout"; return BLE_ERR_INVALID_ARGUMENT;
   }
   if (config->wind_model != BLE_WIND_GRID && config->wind_model != BLE_WIND_SIMPLE_STATIC) {
     g_create_error = "ble_create: unknown wind_model"; return BLE_ERR_INVALID_ARGUMENT;
@@ -843,6 +912,15 @@ int64_t ble_launch_count(const ble_handle* h) { return h == nullptr ? 0 : h->eng
 
 int ble_upload_fields(ble_handle* h, const float* fields, int64_t n_fields, const int32_t* env_to_field, void* stream) {
   BLE_H(h); return h->eng->upload_fields(fields, n_fields, env_to_field, cudaStream_t(stream));
+}
+int ble_alloc_fields(ble_handle* h, int64_t n_fields, void* stream) {
+  BLE_H(h); return h->eng->alloc_fields(n_fields, cudaStream_t(stream));
+}
+int ble_write_fields(ble_handle* h, const float* fields, int64_t first_field, int64_t count, void* stream) {
+  BLE_H(h); return h->eng->write_fields(fields, first_field, count, cudaStream_t(stream));
+}
+int ble_set_field_map(ble_handle* h, const int32_t* env_to_field, void* stream) {
+  BLE_H(h); return h->eng->set_field_map(env_to_field, cudaStream_t(stream));
 }
 int ble_set_noise(ble_handle* h, const int64_t* seeds, const float* offsets, void* stream) {
   BLE_H(h); return h->eng->set_noise(seeds, offsets, nullptr, cudaStream_t(stream));

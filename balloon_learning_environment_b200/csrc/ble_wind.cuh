@@ -16,19 +16,36 @@ namespace ble {
 // ---- field geometry (generative/vae.py:26-51) ----------------------------------------------------
 constexpr int kNX = 21, kNY = 21, kNP = 10, kNT = 9;
 constexpr int kFieldFloats = kNX * kNY * kNP * kNT * 2;        // 79,380 (native layout)
-// "cell" layout: for every (x, y) column and every (pressure, time) cell the 2x2x2 corner
-// block {p, p+1} x {t, t+1} x {u, v} is stored contiguously = 8 floats = one 32-byte sector.
-// A lookup then touches exactly 4 aligned sectors (one per (x, y) corner).
-constexpr int kPC = kNP - 1, kTC = kNT - 1;                    // 9 x 8 cells per column
-constexpr int kCellFloats = 8;
-constexpr int64_t kColumnFloats = int64_t(kPC) * kTC * kCellFloats;           // 576
-constexpr int64_t kCellFieldFloats = int64_t(kNX) * kNY * kColumnFloats;      // 254,016 floats = 1,016,064 B
+constexpr int kYC = kNY - 1, kPC = kNP - 1, kTC = kNT - 1;     // 20 x 9 x 8 (y, pressure, time) cells
 
 BLE_HD int64_t native_index(int ix, int iy, int ip, int it, int c) {
   return ((((int64_t(ix) * kNY + iy) * kNP + ip) * kNT + it) * 2 + c);
 }
-BLE_HD int64_t cell_index(int ix, int iy, int pc, int tc) {
-  return ((int64_t(ix) * kNY + iy) * kPC + pc) * (kTC * kCellFloats) + int64_t(tc) * kCellFloats;
+
+// Device layout ("windows").  A lookup needs the 16 corners {x,x+1}x{y,y+1}x{p,p+1}x{t,t+1} x {u,v}
+// = 32 floats = 128 bytes.  B200's L2 fills whole 128-byte lines from HBM (measured: 16.3 DRAM
+// sectors per lookup with four scattered 32-byte cells), so the layout makes those 128 bytes
+// CONTIGUOUS: for every (y, p, t) cell a row of per-x blocks, block(ix) = corners of column ix,
+// ordered [dy][dp][dt][uv] (16 floats = 64 B).  The window of a lookup = block(ix) + block(ix+1).
+//   BLE_LAYOUT_X64  : blocks packed every 64 B (21 per row): windows overlap, a window straddles two
+//                     lines half of the time -> 1.5 lines / lookup, 1,935,360 B per field (6.1x).
+//   BLE_LAYOUT_X128 : every window stored separately, 128 B aligned (20 per row): exactly 1 line /
+//                     lookup, 3,686,400 B per field (11.6x).
+// Within a window, 16-byte chunk j = dx*4 + dy*2 + dp holds (t0.u, t0.v, t1.u, t1.v).
+struct FieldLayout {
+  int32_t x_stride_floats;     // 16 (X64) or 32 (X128)
+  int32_t row_floats;          // floats per (y,p,t) row: 21*16 = 336 or 20*32 = 640
+  int64_t field_floats;        // kYC*kPC*kTC rows
+};
+BLE_HD FieldLayout make_layout(int kind) {
+  FieldLayout l;
+  if (kind == 1) { l.x_stride_floats = 32; l.row_floats = (kNX - 1) * 32; }
+  else { l.x_stride_floats = 16; l.row_floats = kNX * 16; }
+  l.field_floats = int64_t(kYC) * kPC * kTC * l.row_floats;
+  return l;
+}
+BLE_HD int64_t window_index(const FieldLayout& l, int ix, int iy, int pc, int tc) {
+  return ((int64_t(iy) * kPC + pc) * kTC + tc) * l.row_floats + int64_t(ix) * l.x_stride_floats;
 }
 
 // Query point as the reference builds it (_prepare_get_forecast_inputs, :145-187): clip x, y
@@ -64,33 +81,45 @@ BLE_HD void axis_cell(float v, float g0, float step, int ncell, int* idx, Real* 
   *w = (Real(v) - g) / Real(step);
 }
 
-struct float8 { float4 a, b; };
+// Cell of the lookup and the four interpolation weights.
+template <typename Real>
+struct FieldCell { int ix, iy, pc, tc; Real wx, wy, wp, wt; };
 
-// 16-corner multilinear interpolation from the cell layout.  `ldcell` loads one 32-byte cell.
-template <typename Real, typename LoadCell>
-BLE_HD void interp_cells(const FieldPoint& q, LoadCell ldcell, Real* u, Real* v) {
-  int ix, iy, pc, tc;
-  Real wx, wy, wp, wt;
-  axis_cell<Real>(q.x_km, -500.f, 50.f, kNX - 1, &ix, &wx);
-  axis_cell<Real>(q.y_km, -500.f, 50.f, kNY - 1, &iy, &wy);
-  axis_cell<Real>(q.p, 5000.f, 1000.f, kPC, &pc, &wp);
-  axis_cell<Real>(q.t_h, 0.f, 6.f, kTC, &tc, &wt);
-  const float8 c00 = ldcell(cell_index(ix, iy, pc, tc));
-  const float8 c01 = ldcell(cell_index(ix, iy + 1, pc, tc));
-  const float8 c10 = ldcell(cell_index(ix + 1, iy, pc, tc));
-  const float8 c11 = ldcell(cell_index(ix + 1, iy + 1, pc, tc));
+template <typename Real>
+BLE_HD FieldCell<Real> locate(const FieldPoint& q) {
+  FieldCell<Real> c;
+  axis_cell<Real>(q.x_km, -500.f, 50.f, kNX - 1, &c.ix, &c.wx);
+  axis_cell<Real>(q.y_km, -500.f, 50.f, kYC, &c.iy, &c.wy);
+  axis_cell<Real>(q.p, 5000.f, 1000.f, kPC, &c.pc, &c.wp);
+  axis_cell<Real>(q.t_h, 0.f, 6.f, kTC, &c.tc, &c.wt);
+  return c;
+}
+
+// Contribution of 16-byte chunk j (= dx*4 + dy*2 + dp) of the window to (u, v).
+template <typename Real>
+BLE_HD void chunk_contribution(const FieldCell<Real>& c, int j, const float4& v4, Real* u, Real* v) {
   const Real one = Real(1);
-  // within a cell: a = {p0t0.u, p0t0.v, p0t1.u, p0t1.v}, b = {p1t0.u, p1t0.v, p1t1.u, p1t1.v}
-  const Real w00 = (one - wp) * (one - wt), w01 = (one - wp) * wt, w10 = wp * (one - wt), w11 = wp * wt;
-  auto cell_u = [&](const float8& c) {
-    return w00 * Real(c.a.x) + w01 * Real(c.a.z) + w10 * Real(c.b.x) + w11 * Real(c.b.z);
-  };
-  auto cell_v = [&](const float8& c) {
-    return w00 * Real(c.a.y) + w01 * Real(c.a.w) + w10 * Real(c.b.y) + w11 * Real(c.b.w);
-  };
-  const Real a00 = (one - wx) * (one - wy), a01 = (one - wx) * wy, a10 = wx * (one - wy), a11 = wx * wy;
-  *u = a00 * cell_u(c00) + a01 * cell_u(c01) + a10 * cell_u(c10) + a11 * cell_u(c11);
-  *v = a00 * cell_v(c00) + a01 * cell_v(c01) + a10 * cell_v(c10) + a11 * cell_v(c11);
+  const Real w = ((j & 4) ? c.wx : one - c.wx) * ((j & 2) ? c.wy : one - c.wy) * ((j & 1) ? c.wp : one - c.wp);
+  *u = w * ((one - c.wt) * Real(v4.x) + c.wt * Real(v4.z));
+  *v = w * ((one - c.wt) * Real(v4.y) + c.wt * Real(v4.w));
+}
+
+// 16-corner multilinear interpolation (== scipy interpn 'linear', grid_based_wind_field.py:91);
+// `ldchunk(j)` returns 16-byte chunk j of the lookup's 128-byte window.
+template <typename Real, typename LoadChunk>
+BLE_HD void interp_window(const FieldCell<Real>& c, LoadChunk ldchunk, Real* u, Real* v) {
+  Real su = Real(0), sv = Real(0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 8; ++j) {
+    Real pu, pv;
+    chunk_contribution<Real>(c, j, ldchunk(j), &pu, &pv);
+    su += pu;
+    sv += pv;
+  }
+  *u = su;
+  *v = sv;
 }
 
 // SimpleStaticWindField (env/wind_field.py:149-184): four 10 m/s sheets by pressure.
@@ -108,14 +137,23 @@ constexpr double kSquish4 = 0.309016994374947;
 constexpr double kNoiseMagnitude = 4.233932721683222;   // sqrt(1.02 / 0.0569), simplex_wind_noise.py:76
 
 // weight, x, y, pressure, time spacings (simplex_wind_noise.py:50-64); index = component * 5 + harmonic
+#define BLE_HARMONIC_TABLE                                                                        \
+  {{0.1445, 702.269, 2116.987, 2587.802, 245.0},   {0.2766, 1483.570, 752.124, 646.208, 16.39},   \
+   {0.2627, 276.810, 147.040, 587.702, 3.836},     {0.2137, 10214.525, 1512.216, 965.629, 41.780}, \
+   {0.1025, 181.286, 420.942, 8500.0, 245.0},      {0.2716, 1974.228, 2028.814, 713.697, 26.435}, \
+   {0.2684, 699.738, 541.845, 632.116, 9.530},     {0.2348, 217.750, 196.522, 686.825, 3.546},    \
+   {0.1186, 47.500, 43.048, 66.553, 8.424},        {0.1066, 3663.291, 232.023, 7499.741, 225.0}}
+static const double kHarmonicsHost[10][5] = BLE_HARMONIC_TABLE;
+#if defined(__CUDACC__)
+__constant__ double kHarmonicsDev[10][5] = BLE_HARMONIC_TABLE;
+#endif
 BLE_HD void harmonic_params(int h10, double* w, double* sx, double* sy, double* sp, double* st) {
-  const double t[10][5] = {
-      {0.1445, 702.269, 2116.987, 2587.802, 245.0},   {0.2766, 1483.570, 752.124, 646.208, 16.39},
-      {0.2627, 276.810, 147.040, 587.702, 3.836},     {0.2137, 10214.525, 1512.216, 965.629, 41.780},
-      {0.1025, 181.286, 420.942, 8500.0, 245.0},      {0.2716, 1974.228, 2028.814, 713.697, 26.435},
-      {0.2684, 699.738, 541.845, 632.116, 9.530},     {0.2348, 217.750, 196.522, 686.825, 3.546},
-      {0.1186, 47.500, 43.048, 66.553, 8.424},        {0.1066, 3663.291, 232.023, 7499.741, 225.0}};
-  *w = t[h10][0]; *sx = t[h10][1]; *sy = t[h10][2]; *sp = t[h10][3]; *st = t[h10][4];
+#if defined(__CUDA_ARCH__)
+  const double* t = kHarmonicsDev[h10];
+#else
+  const double* t = kHarmonicsHost[h10];
+#endif
+  *w = t[0]; *sx = t[1]; *sy = t[2]; *sp = t[3]; *st = t[4];
 }
 
 // Final blend of the 5 harmonics of one component (NoisyWindComponent.get_noise, :180-211):

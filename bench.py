@@ -134,21 +134,21 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
-def synthetic_fields(torch, n_fields, device, seed, chunk=2048):
-  """[F,21,21,10,9,2] fp32 with VAE-like magnitudes (u ~ 5.4 N(0,1), v ~ 1.5 N(0,1))."""
+def upload_synthetic_fields(torch, arena, n_fields, device, seed, chunk=2048):
+  """n_fields grids [21,21,10,9,2] fp32 with VAE-like magnitudes (u ~ 5.4 N(0,1), v ~ 1.5 N(0,1);
+  SURVEY App. B), generated and converted chunk by chunk so only one chunk is resident twice."""
   g = torch.Generator(device=device); g.manual_seed(seed)
-  out = torch.empty(n_fields, 21, 21, 10, 9, 2, dtype=torch.float32, device=device)
   scale = torch.tensor([5.4, 1.5], device=device)
+  arena.alloc_wind_fields(n_fields)
   for s in range(0, n_fields, chunk):
     e = min(n_fields, s + chunk)
-    out[s:e] = torch.randn(e - s, 21, 21, 10, 9, 2, generator=g, device=device) * scale
-  return out
+    arena.write_wind_fields(torch.randn(e - s, 21, 21, 10, 9, 2, generator=g, device=device) * scale, s)
 
 
 def run_b200(args):
   import torch
   import torch.distributed as dist
-  from balloon_learning_environment_b200 import batched_env
+  from balloon_learning_environment_b200 import batched_env, sharding
 
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
@@ -158,17 +158,14 @@ def run_b200(args):
   torch.cuda.set_device(local_rank)
   device = torch.device(f'cuda:{local_rank}')
   n_total = args.num_envs
-  n = n_total // world                                       # strong scaling: fixed total batch
-  assert n * world == n_total, 'num-envs must be divisible by the number of GPUs'
+  begin, end = sharding.shard_range(n_total, rank, world)    # strong scaling: fixed total batch
+  n = end - begin
 
-  arena = batched_env.BatchedBalloonArena(n, device=str(device), precision='fp32', wind_model='grid', enable_noise=True)
+  arena = batched_env.BatchedBalloonArena(n, device=str(device), precision='fp32', wind_model='grid', enable_noise=True,
+                                          field_layout=args.field_layout)
   n_fields = n if args.shared_fields == 0 else args.shared_fields
-  fields = synthetic_fields(torch, n_fields, device, seed=1234 + rank)
-  env_to_field = (torch.arange(n, dtype=torch.int32, device=device) % n_fields)
-  arena.set_wind_fields(fields, env_to_field)
-  torch.cuda.synchronize()
-  del fields
-  arena._keepalive = [None, env_to_field]
+  upload_synthetic_fields(torch, arena, n_fields, device, seed=1234 + rank)
+  arena.set_field_map(torch.arange(n, dtype=torch.int32, device=device) % n_fields)
   torch.cuda.empty_cache()
   g = torch.Generator(device='cpu'); g.manual_seed(2024 + rank)
   arena.reset(torch.randint(0, 2**62, (n,), dtype=torch.int64, generator=g))
@@ -232,13 +229,9 @@ def run_b200(args):
   gather_ms = g0.elapsed_time(g1) / reps
   gather_gbs = GATHER_BYTES_PER_LOOKUP * m / (gather_ms * 1e-3) / 1e9
 
-  if world > 1:
-    tmax = torch.tensor([ms, e2e_s, gather_ms], device=device, dtype=torch.float64)
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms, e2e_s, gather_ms_max = [float(v) for v in tmax]
-    lsum = torch.tensor([launches], device=device, dtype=torch.int64)
-    dist.all_reduce(lsum)
-    launches = int(lsum)
+  stats = sharding.reduce_run_stats(ms, n * args.steps, launches, device=device)
+  ms, launches = stats['elapsed_ms'], stats['launches']
+  e2e_s = sharding.reduce_run_stats(e2e_s * 1e3, 0, 0, device=device)['elapsed_ms'] * 1e-3
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -253,7 +246,7 @@ def run_b200(args):
       'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': f'batch={n_total} balloons, random agent, one synthetic wind field per balloon '
                              f'({n_fields} fields/GPU) + simplex noise, 18 sub-steps per step (BASELINE configs[2])',
-                 'num_envs': n_total, 'envs_per_gpu': n, 'fields_per_gpu': n_fields,
+                 'num_envs': n_total, 'envs_per_gpu': n, 'fields_per_gpu': n_fields, 'field_layout': args.field_layout,
                  'l2': 'inputs larger than L2 (per-balloon fields + 2.5 KB noise tables per balloon)',
                  'live_fraction_after_run': live_frac},
       'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 4 * n_total, 'd2h_bytes_per_step': 5 * n_total,
@@ -284,6 +277,7 @@ def main():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--num-envs', type=int, default=65536)
   ap.add_argument('--shared-fields', type=int, default=0, help='0 = one field per balloon; else size of a shared pool')
+  ap.add_argument('--field-layout', default='x64', choices=['x64', 'x128'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
   args = ap.parse_args()
   if args.impl == 'reference':

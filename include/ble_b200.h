@@ -50,11 +50,18 @@ typedef enum {
 #define BLE_WIND_GRID 0        /* GridBasedWindField: per-balloon [21,21,10,9,2] grids             */
 #define BLE_WIND_SIMPLE_STATIC 1  /* SimpleStaticWindField (env/wind_field.py:149-184)             */
 
+/* Device layout of the wind grids: every lookup reads one contiguous 128-byte window (its 16
+ * corners x {u,v}).  X64 packs overlapping windows every 64 B (1,935,360 B per grid, ~1.5 HBM lines
+ * per random lookup); X128 stores each window on its own 128-byte line (3,686,400 B per grid, exactly
+ * one line per lookup). */
+#define BLE_LAYOUT_X64 0
+#define BLE_LAYOUT_X128 1
+
 typedef struct {
   int32_t precision;           /* BLE_PRECISION_*                                                   */
   int32_t wind_model;          /* BLE_WIND_*                                                        */
   int32_t enable_noise;        /* 1: ground truth = forecast + simplex noise (wind_field.py:125-145) */
-  int32_t reserved;
+  int32_t field_layout;        /* BLE_LAYOUT_*                                                      */
 } ble_config;
 
 /* State exchange: two row-major device matrices, one row per field, N columns.
@@ -88,9 +95,16 @@ int64_t ble_num_envs(const ble_handle* h);
 
 /* Wind fields: F grids in the reference's native layout float32 [F,21,21,10,9,2]
  * (GridWindFieldSampler.sample_field, env/grid_wind_field_sampler.py:33-41) and the balloon ->
- * grid map int32 [N].  The handle keeps its own re-laid-out copy (32-byte (pressure,time) cells). */
+ * grid map int32 [N] (may be NULL: keep the current map).  The handle keeps its own re-laid-out copy. */
 int ble_upload_fields(ble_handle* h, const float* fields, int64_t n_fields,
                       const int32_t* env_to_field, void* stream);
+
+/* The same in pieces, so that a large bank of grids never has to be resident twice:
+ * allocate room for n_fields grids, convert `count` native-layout grids into slots
+ * [first_field, first_field + count), set the balloon -> grid map int32 [N]. */
+int ble_alloc_fields(ble_handle* h, int64_t n_fields, void* stream);
+int ble_write_fields(ble_handle* h, const float* fields, int64_t first_field, int64_t count, void* stream);
+int ble_set_field_map(ble_handle* h, const int32_t* env_to_field, void* stream);
 
 /* Simplex noise parameters, SimplexWindNoise.reset_wind_noise (env/wind_field.py:196-207,
  * env/simplex_wind_noise.py:98-114): seeds int64 [N,2,5] (component u/v, harmonic),

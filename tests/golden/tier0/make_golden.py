@@ -384,6 +384,49 @@ def run_scenario(sc, bank, rng):
               wind=np.asarray(winds, np.float64))
 
 
+def run_feature_scenario(sc, bank, rng, steps):
+  """The reference's PerciatelliFeatureConstructor (1099 features, WindGP) along an episode."""
+  from balloon_learning_environment.env import features as features_lib
+  date = units.datetime(*sc['date'])
+  atm = make_atmosphere(sc['alpha'])
+  b = test_helpers.create_balloon(
+      x=units.Distance(m=sc['x']), y=units.Distance(m=sc['y']), center_lat=sc['lat'], center_lng=sc['lng'],
+      pressure=sc['pressure'], power_percent=sc['power'], date_time=date, upwelling_infrared=sc['ir'],
+      atmosphere=atm)
+  wf = (wind_field.SimpleStaticWindField() if sc['field'] < 0 else
+        grid_based_wind_field.GridBasedWindField(_BankSampler(bank[sc['field']])))
+  wf.reset(jax.random.PRNGKey(1), date)
+  seeds = rng.integers(0, 1634753849, size=(2, 5))
+  offsets = (rng.uniform(0, 1, size=(2, 5, 4)).astype(np.float32) * np.float32(2.0) - np.float32(1.0)).astype(np.float64)
+  arena = balloon_arena.BalloonArena(features_lib.PerciatelliFeatureConstructor, wf, seed=0)
+  env = balloon_env.BalloonEnv(arena=arena, seed=0)
+  atm = make_atmosphere(sc['alpha'])
+  _inject_noise(wf, seeds, offsets)
+  if sc['field'] >= 0:
+    wf.field = bank[sc['field']]
+  arena._balloon = b
+  arena._atmosphere = atm
+  arena.feature_constructor = features_lib.PerciatelliFeatureConstructor(wf, atm)
+  arena.feature_constructor.observe(arena.get_measurements())
+  obs0 = arena.feature_constructor.get_features()
+  actions = rng.integers(0, 3, size=steps)
+  f0, i0 = snapshot(b.state)
+  obs, fl, il, rew = [obs0], [], [], []
+  for a in actions:
+    o, r, d, _ = env.step(int(a))
+    f, i = snapshot(arena.get_balloon_state())
+    obs.append(o); fl.append(f); il.append(i); rew.append(float(r))
+    assert not d
+  pr = arena.feature_constructor  # final pressure range for a direct KAT
+  from balloon_learning_environment.env.balloon import pressure_range_builder
+  rng_final = pressure_range_builder.get_pressure_range(arena.get_balloon_state(), atm)
+  return dict(alpha=sc['alpha'], field=sc['field'], power_safety=1, seeds=seeds, offsets=offsets,
+              actions=np.asarray(actions, np.int64), f0=np.asarray(f0), i0=np.asarray(i0, np.int64),
+              f=np.asarray(fl), i=np.asarray(il, np.int64), reward=np.asarray(rew),
+              obs=np.asarray(obs, np.float32),
+              final_pressure_range=np.array([rng_final.min_pressure, rng_final.max_pressure]))
+
+
 def main():
   kat = dict(atmosphere=kat_atmosphere(), solar=kat_solar(), stable_init=kat_stable_init(),
              interp=kat_interp(), safety=kat_safety(), float_fields=FLOATS, int_fields=INTS, **kat_thermal_acs_geometry())
@@ -410,6 +453,16 @@ def main():
           f"paused_steps={int(res['i'][:, 6].sum())} mean_reward={res['reward'].mean():.3f}")
   flat['names'] = np.asarray(names)
   np.savez_compressed(os.path.join(OUT, 'traj.npz'), **flat)
+  # observation surface: two episodes through the reference's PerciatelliFeatureConstructor
+  rng = np.random.default_rng(77)
+  feat = {}
+  for sc, steps in ((SCENARIOS[1], 140), (SCENARIOS[0], 40), (SCENARIOS[6], 60)):
+    res = run_feature_scenario(sc, bank, rng, steps)
+    for k, v in res.items():
+      feat[f"{sc['name']}/{k}"] = np.asarray(v)
+    print(f"features {sc['name']:20s} steps={steps} obs {res['obs'].shape} range {res['final_pressure_range']}")
+  feat['names'] = np.asarray([SCENARIOS[1]['name'], SCENARIOS[0]['name'], SCENARIOS[6]['name']])
+  np.savez_compressed(os.path.join(OUT, 'features.npz'), **feat)
   print('wrote', os.path.join(OUT, 'kat.json'), os.path.join(OUT, 'traj.npz'))
 
 

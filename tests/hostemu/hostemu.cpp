@@ -71,7 +71,13 @@ static void substeps_impl(int64_t n, double* f, int64_t* iv, const int32_t* eff,
     s.date_time = I(BLE_I_DATE_TIME, e); s.time_elapsed = int32_t(I(BLE_I_TIME_ELAPSED, e));
     s.status = 0;
     Atmosphere atm; atm.init(F(BLE_F_ATMOSPHERE_ALPHA, e));
-    for (int k = 0; k < nsub; ++k) euler_substep<Real>(s, atm, wind[2 * e], wind[2 * e + 1], eff[e]);
+    SunTrack<Real> sun; sun.init(s, wind[2 * e], wind[2 * e + 1]);
+    atm.incremental = !is_double<Real>::value;
+    const Real epa = earth_heat_per_area<Real>(s.ir);
+    for (int k = 0; k < nsub; ++k) {
+      SunAngles<Real> ang; Real flux; sun.at(s, k, &ang, &flux);
+      euler_substep<Real>(s, atm, wind[2 * e], wind[2 * e + 1], eff[e], ang, flux, epa);
+    }
     F(BLE_F_X, e) = s.x; F(BLE_F_Y, e) = s.y; F(BLE_F_PRESSURE, e) = s.pressure;
     F(BLE_F_AMBIENT_TEMPERATURE, e) = s.t_ambient; F(BLE_F_INTERNAL_TEMPERATURE, e) = s.t_internal;
     F(BLE_F_ENVELOPE_VOLUME, e) = s.volume; F(BLE_F_SUPERPRESSURE, e) = s.superpressure;
@@ -122,23 +128,18 @@ void emu_interp(int precision, int64_t m, const float* fields, const int32_t* fi
                 double* uv) {
   for (int64_t i = 0; i < m; ++i) {
     const float* base = fields + int64_t(fidx[i]) * kFieldFloats;
-    auto ld = [&](int64_t ci) {
-      // decode the cell index back to (ix, iy, pc, tc) and gather from the native layout
-      const int tc = int((ci / kCellFloats) % kTC); const int pc = int((ci / (kCellFloats * kTC)) % kPC);
-      const int iy = int((ci / kColumnFloats) % kNY); const int ix = int(ci / (kColumnFloats * kNY));
-      float8 c;
-      c.a = {base[native_index(ix, iy, pc, tc, 0)], base[native_index(ix, iy, pc, tc, 1)],
-             base[native_index(ix, iy, pc, tc + 1, 0)], base[native_index(ix, iy, pc, tc + 1, 1)]};
-      c.b = {base[native_index(ix, iy, pc + 1, tc, 0)], base[native_index(ix, iy, pc + 1, tc, 1)],
-             base[native_index(ix, iy, pc + 1, tc + 1, 0)], base[native_index(ix, iy, pc + 1, tc + 1, 1)]};
-      return c;
-    };
     const FieldPoint q = make_field_point(xyzt[4 * i], xyzt[4 * i + 1], xyzt[4 * i + 2], xyzt[4 * i + 3]);
-    if (precision == BLE_PRECISION_FP64) {
-      double u, v; interp_cells<double>(q, ld, &u, &v); uv[2 * i] = u; uv[2 * i + 1] = v;
-    } else {
-      float u, v; interp_cells<float>(q, ld, &u, &v); uv[2 * i] = u; uv[2 * i + 1] = v;
-    }
+    auto run = [&](auto tag) {
+      using R = decltype(tag);
+      const FieldCell<R> c = locate<R>(q);
+      auto ld = [&](int j) {      // chunk j = dx*4 + dy*2 + dp, gathered from the native layout
+        const int ix = c.ix + ((j >> 2) & 1), iy = c.iy + ((j >> 1) & 1), ip = c.pc + (j & 1);
+        return float4{base[native_index(ix, iy, ip, c.tc, 0)], base[native_index(ix, iy, ip, c.tc, 1)],
+                      base[native_index(ix, iy, ip, c.tc + 1, 0)], base[native_index(ix, iy, ip, c.tc + 1, 1)]};
+      };
+      R u, v; interp_window<R>(c, ld, &u, &v); uv[2 * i] = u; uv[2 * i + 1] = v;
+    };
+    if (precision == BLE_PRECISION_FP64) run(double(0)); else run(float(0));
   }
 }
 
