@@ -8,6 +8,7 @@
 #include <cstring>
 #include "../../balloon_learning_environment_b200/csrc/ble_physics.cuh"
 #include "../../balloon_learning_environment_b200/csrc/ble_wind.cuh"
+#include "../../balloon_learning_environment_b200/csrc/ble_features.cuh"
 #include "../../include/ble_b200.h"
 
 using namespace ble;
@@ -156,5 +157,34 @@ void emu_stable(int64_t n, const double* alpha, const double* p, const double* l
     out[5 * i + 3] = s.volume; out[5 * i + 4] = s.superpressure;
   }
 }
+
+// Reachable pressure range exactly as the feature kernels compute it (20 levels + min-float pressure).
+void emu_pressure_range(int64_t n, const double* alpha, const double* mols_gas, const double* lat, const double* lng,
+                        const int64_t* ts, const double* ir, double* out /*[n,2]*/, int32_t* ok) {
+  for (int64_t e = 0; e < n; ++e) {
+    double search_max, t_unused;
+    atm_at_height_generic(alpha[e], kAltMin, &search_max, &t_unused);
+    double levels[kRangeLevels], p_over_t[kRangeLevels], sp[kRangeLevels];
+    for (int j = 0; j < kRangeLevels; ++j) {
+      levels[j] = 1000.0 + (search_max - 1000.0) * double(j) / double(kRangeLevels - 1);
+      if (j == kRangeLevels - 1) levels[j] = search_max;
+      const StableParams s = stable_params(alpha[e], levels[j], mols_gas[e], lat[e], lng[e], ts[e], ir[e]);
+      p_over_t[j] = levels[j] / s.t_ambient;
+      sp[j] = s.superpressure;
+    }
+    const double pmin_sig = min_float_pressure(levels, p_over_t, mols_gas[e]);
+    const double sp_min_sig = stable_params(alpha[e], pmin_sig, mols_gas[e], lat[e], lng[e], ts[e], ir[e]).superpressure;
+    bool ok1 = search_safe_pressure(levels, sp, pmin_sig, sp_min_sig, false, &out[2 * e]);
+    bool ok2 = search_safe_pressure(levels, sp, levels[kRangeLevels - 1], sp[kRangeLevels - 1], true, &out[2 * e + 1]);
+    ok[e] = ok1 && ok2;
+  }
+}
+
+void emu_sunrise_time(int64_t n, const double* lat, const double* lng, const int64_t* ts, double* out) {
+  for (int64_t e = 0; e < n; ++e) { bool ok; out[e] = sunrise_time(lat[e], lng[e], ts[e], &ok); }
+}
+
+double emu_power_table(double pr, double soc) { return power_table_lookup(pr, soc); }
+int emu_nearest_level(double p) { return nearest_pressure_level(p); }
 
 }  // extern "C"
