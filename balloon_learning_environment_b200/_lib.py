@@ -31,12 +31,13 @@ EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_u
            'ble_alloc_fields', 'ble_write_fields', 'ble_set_field_map',
            'ble_set_noise', 'ble_state_upload', 'ble_state_download', 'ble_reset', 'ble_init_derived',
            'ble_step', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_derived',
+           'ble_features_perciatelli', 'ble_features_observe', 'ble_features_clear',
            'ble_launch_count')
 
 
 class BleConfig(_c.Structure):
   _fields_ = [('precision', _c.c_int32), ('wind_model', _c.c_int32), ('enable_noise', _c.c_int32),
-              ('field_layout', _c.c_int32)]
+              ('field_layout', _c.c_int32), ('enable_features', _c.c_int32), ('reserved', _c.c_int32 * 3)]
 
 
 class BleStateSoa(_c.Structure):
@@ -85,6 +86,9 @@ def load(build_if_missing=True):
   lib.ble_wind_at_balloon.argtypes = [vp, vp, vp]
   lib.ble_wind_gather.argtypes = [vp, vp, vp, vp, i64, vp]
   lib.ble_derived.argtypes = [vp, vp, vp]
+  lib.ble_features_perciatelli.argtypes = [vp, vp, vp]
+  lib.ble_features_observe.argtypes = [vp, vp]
+  lib.ble_features_clear.argtypes = [vp, vp]
   for name in EXPORTS:
     if name not in ('ble_last_error', 'ble_num_envs', 'ble_launch_count'):
       getattr(lib, name).restype = _c.c_int

@@ -42,7 +42,8 @@ class BatchedBalloonArena:
   """
 
   def __init__(self, num_envs: int, *, device: str = 'cuda:0', precision: str = 'fp32',
-               wind_model: str = 'grid', enable_noise: bool = True, field_layout: str = 'x64'):
+               wind_model: str = 'grid', enable_noise: bool = True, field_layout: str = 'x64',
+               enable_features: bool = False):
     if not torch.cuda.is_available():
       raise _lib.BleError('BatchedBalloonArena needs a CUDA device (no CPU fallback exists)')
     self._lib = _lib.load()
@@ -52,7 +53,8 @@ class BatchedBalloonArena:
     self.wind_model = wind_model
     self.enable_noise = bool(enable_noise)
     cfg = _lib.BleConfig(_lib.PRECISION[precision], _lib.WIND_MODEL[wind_model], int(enable_noise),
-                         _lib.FIELD_LAYOUT[field_layout])
+                         _lib.FIELD_LAYOUT[field_layout], int(enable_features))
+    self.enable_features = bool(enable_features)
     handle = ctypes.c_void_p()
     dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
     rc = self._lib.ble_create(dev_index, self.num_envs, ctypes.byref(cfg), ctypes.byref(handle))
@@ -182,6 +184,20 @@ class BatchedBalloonArena:
     out = torch.empty(len(_lib.D_ROWS), self.num_envs, dtype=torch.float64, device=self.device)
     self._check(self._lib.ble_derived(self._h, _ptr(out), self._stream()), 'ble_derived')
     return {k: out[r] for r, k in enumerate(_lib.D_ROWS)}
+
+  # -- observation surface ----------------------------------------------------------------------
+  def features(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """PerciatelliFeatureConstructor.get_features() for every balloon: float32 [N, 1099]."""
+    if out is None:
+      out = torch.empty(self.num_envs, 1099, dtype=torch.float32, device=self.device)
+    self._check(self._lib.ble_features_perciatelli(self._h, _ptr(out), self._stream()), 'ble_features_perciatelli')
+    return out
+
+  def features_observe(self):
+    self._check(self._lib.ble_features_observe(self._h, self._stream()), 'ble_features_observe')
+
+  def features_clear(self):
+    self._check(self._lib.ble_features_clear(self._h, self._stream()), 'ble_features_clear')
 
   def init_derived(self, run_stable_init: bool = True):
     """Recompute power-safety sunrise/sunset (+ stable init) from the uploaded state."""

@@ -14,6 +14,7 @@
 #include "../../include/ble_b200.h"
 #include "ble_physics.cuh"
 #include "ble_wind.cuh"
+#include "ble_features.cuh"
 
 namespace ble {
 
@@ -55,6 +56,12 @@ struct DevState {
   const float* offsets;      // [10][4][n]
   Real* noise_partial;       // [10][n]
   int wind_model, enable_noise;
+  // observation surface (WindGP history ring, env/wind_gp.py:98-119): last kGpWindow measurements
+  double* gp_obs;            // [n][kGpWindow][6] = x, y, pressure, t, error_u, error_v
+  int32_t* gp_count;         // [n] measurements seen so far (ring slot = count % kGpWindow)
+  double* gp_chol;           // [n][kGpWindow (kGpWindow + 1) / 2] packed lower Cholesky factor
+  int32_t* gp_m;             // [n] number of measurements inside the 6 h window
+  double* feat_range;        // [n][2] reachable pressure range
 };
 
 template <typename Real>
@@ -294,10 +301,10 @@ k_noise(DevState<Real> d) {
   }
 }
 
-// forecast + noise at the balloon's current state (WindField.get_ground_truth, env/wind_field.py:125-145)
-template <typename Real>
-__device__ __forceinline__ void wind_at_balloon(const DevState<Real>& d, int64_t e, double x, double y, double p,
-                                                int32_t t_elapsed, Real* u, Real* v) {
+// Forecast wind at an arbitrary point of balloon e's field (WindField.get_forecast).
+template <typename Real, typename State>
+__device__ __forceinline__ void forecast_at(const State& d, int64_t e, double x, double y, double p,
+                                            int32_t t_elapsed, Real* u, Real* v) {
   if (d.wind_model == BLE_WIND_SIMPLE_STATIC) {
     static_wind<Real>(Real(p), u, v);
   } else {
@@ -307,20 +314,34 @@ __device__ __forceinline__ void wind_at_balloon(const DevState<Real>& d, int64_t
                                                     window_index(d.layout, c.ix, c.iy, c.pc, c.tc))};
     interp_window<Real>(c, ld, u, v);
   }
-  if (d.enable_noise) {
-    // NoisyWindComponent.get_noise (:180-211): weighted mean of 5 harmonics, variance-rescaled
-    const double wu[5] = {0.1445, 0.2766, 0.2627, 0.2137, 0.1025};
-    const double wv[5] = {0.2716, 0.2684, 0.2348, 0.1186, 0.1066};
-    Real nu = Real(0), nv = Real(0);
-    double swu = 0, swu2 = 0, swv = 0, swv2 = 0;
+}
+
+// Simplex noise at balloon e's current state, from the harmonic partials written by k_noise:
+// NoisyWindComponent.get_noise (:180-211) = weighted mean of 5 harmonics, variance-rescaled.
+template <typename Real>
+__device__ __forceinline__ void noise_at(const DevState<Real>& d, int64_t e, Real* nu_out, Real* nv_out) {
+  const double wu[5] = {0.1445, 0.2766, 0.2627, 0.2137, 0.1025};
+  const double wv[5] = {0.2716, 0.2684, 0.2348, 0.1186, 0.1066};
+  Real nu = Real(0), nv = Real(0);
+  double swu = 0, swu2 = 0, swv = 0, swv2 = 0;
 #pragma unroll
-    for (int h = 0; h < 5; ++h) {
-      nu += d.noise_partial[int64_t(h) * d.n + e] * Real(wu[h]);
-      nv += d.noise_partial[int64_t(5 + h) * d.n + e] * Real(wv[h]);
-      swu += wu[h]; swu2 += wu[h] * wu[h]; swv += wv[h]; swv2 += wv[h] * wv[h];
-    }
-    nu = nu / Real(swu) * Real(sqrt(swu / swu2));
-    nv = nv / Real(swv) * Real(sqrt(swv / swv2));
+  for (int h = 0; h < 5; ++h) {
+    nu += d.noise_partial[int64_t(h) * d.n + e] * Real(wu[h]);
+    nv += d.noise_partial[int64_t(5 + h) * d.n + e] * Real(wv[h]);
+    swu += wu[h]; swu2 += wu[h] * wu[h]; swv += wv[h]; swv2 += wv[h] * wv[h];
+  }
+  *nu_out = nu / Real(swu) * Real(sqrt(swu / swu2));
+  *nv_out = nv / Real(swv) * Real(sqrt(swv / swv2));
+}
+
+// forecast + noise at the balloon's current state (WindField.get_ground_truth, env/wind_field.py:125-145)
+template <typename Real>
+__device__ __forceinline__ void wind_at_balloon(const DevState<Real>& d, int64_t e, double x, double y, double p,
+                                                int32_t t_elapsed, Real* u, Real* v) {
+  forecast_at<Real, DevState<Real>>(d, e, x, y, p, t_elapsed, u, v);
+  if (d.enable_noise) {
+    Real nu, nv;
+    noise_at<Real>(d, e, &nu, &nv);
     *u += nu;
     *v += nv;
   }
@@ -423,6 +444,8 @@ __global__ void __launch_bounds__(128) k_derived(DevState<Real> d, double* __res
   out[int64_t(BLE_D_BATTERY_SOC) * n + e] = soc;
   out[int64_t(BLE_D_ALTITUDE) * n + e] = h;
 }
+
+#include "ble_feature_kernels.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Reset (env/balloon_arena.py:161-182,228-268; utils/sampling.py:37-152)
@@ -553,6 +576,7 @@ k_reset(DevState<Real> d, const uint64_t* __restrict__ seeds, const uint8_t* __r
   d.l[int64_t(L_DATE_TIME) * d.n + e] = ts;
   d.t_elapsed[e] = 0;
   d.flags[e] = pack_flags(kOk, kStay, kEnvNominal, kAltNominal, 0, 1, 0);
+  if (d.gp_count != nullptr) d.gp_count[e] = 0;          // new FeatureConstructor (env/balloon_arena.py:179-182)
   init_derived_one<Real>(d, e, true);
   // SimplexWindNoise.reset_wind_noise (simplex_wind_noise.py:98-114)
   for (int h = 0; h < 10; ++h) {
@@ -580,6 +604,9 @@ struct EngineBase {
   virtual int wind_at(float*, cudaStream_t) = 0;
   virtual int wind_gather(const float*, const int32_t*, float*, int64_t, cudaStream_t) = 0;
   virtual int derived(double*, cudaStream_t) = 0;
+  virtual int features_observe(cudaStream_t) = 0;
+  virtual int features(float*, cudaStream_t) = 0;
+  virtual int features_clear(const uint8_t*, cudaStream_t) = 0;
   int64_t n = 0;
   int64_t launches = 0;
   std::string err;
@@ -604,6 +631,9 @@ struct Engine : EngineBase {
   uint8_t* perm = nullptr; float* offsets = nullptr;
   int64_t* noise_seeds = nullptr; float* noise_offsets_in = nullptr;
   bool have_state = false, have_fields = false, have_noise = false;
+  bool noise_valid = false;      // noise_partial matches the current state
+  double* gp_obs = nullptr; int32_t* gp_count = nullptr; double* gp_chol = nullptr; int32_t* gp_m = nullptr;
+  double* feat_range = nullptr;
   // ble_step_host staging
   int32_t* h_actions = nullptr; float* h_reward = nullptr; uint8_t* h_done = nullptr;
   int32_t* d_actions = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr;
@@ -635,6 +665,18 @@ struct Engine : EngineBase {
     d.layout = make_layout(cfg.field_layout);
     d.enable_noise = 0;
     BLE_CUDA(cudaFuncSetAttribute(k_noise<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseBlock * 256));
+    if (cfg.enable_features) {
+      BLE_CUDA(cudaMalloc(&gp_obs, sizeof(double) * size_t(kGpWindow) * 6 * n));
+      BLE_CUDA(cudaMalloc(&gp_count, sizeof(int32_t) * n));
+      BLE_CUDA(cudaMemset(gp_count, 0, sizeof(int32_t) * n));
+      BLE_CUDA(cudaMalloc(&gp_chol, sizeof(double) * size_t(kGpPacked) * n));
+      BLE_CUDA(cudaMalloc(&gp_m, sizeof(int32_t) * n));
+      BLE_CUDA(cudaMalloc(&feat_range, sizeof(double) * 2 * n));
+      d.gp_obs = gp_obs; d.gp_count = gp_count; d.gp_chol = gp_chol; d.gp_m = gp_m; d.feat_range = feat_range;
+      BLE_CUDA(cudaFuncSetAttribute(k_gp_factor<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(sizeof(double) * (kGpPacked + kGpWindow * 4))));
+      BLE_CUDA(cudaFuncSetAttribute(k_gp_column<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kColumnSmem)));
+    }
     return BLE_OK;
   }
 
@@ -643,6 +685,7 @@ struct Engine : EngineBase {
     cudaFree(d.dd); cudaFree(d.r); cudaFree(d.l); cudaFree(d.t_elapsed); cudaFree(d.flags);
     cudaFree(env_field); cudaFree(d.noise_partial); cudaFree(cells); cudaFree(perm); cudaFree(offsets);
     cudaFree(noise_seeds); cudaFree(noise_offsets_in);
+    cudaFree(gp_obs); cudaFree(gp_count); cudaFree(gp_chol); cudaFree(gp_m); cudaFree(feat_range);
     cudaFree(d_actions); cudaFree(d_reward); cudaFree(d_done);
     cudaFreeHost(h_actions); cudaFreeHost(h_reward); cudaFreeHost(h_done);
   }
@@ -711,6 +754,7 @@ struct Engine : EngineBase {
     BLE_CUDA(cudaGetLastError());
     have_noise = true;
     d.enable_noise = cfg.enable_noise ? 1 : 0;
+    noise_valid = false;
     return BLE_OK;
   }
 
@@ -721,6 +765,7 @@ struct Engine : EngineBase {
     ++launches;
     BLE_CUDA(cudaGetLastError());
     have_state = true;
+    noise_valid = false;
     return BLE_OK;
   }
 
@@ -752,6 +797,9 @@ struct Engine : EngineBase {
     BLE_CUDA(cudaGetLastError());
     have_state = true; have_noise = true;
     d.enable_noise = cfg.enable_noise ? 1 : 0;
+    noise_valid = false;
+    // arena.reset ends with feature_constructor.observe(get_measurements()) (env/balloon_arena.py:179-182)
+    if (cfg.enable_features && (cfg.wind_model != BLE_WIND_GRID || have_fields)) return features_observe(s);
     return BLE_OK;
   }
 
@@ -775,11 +823,12 @@ struct Engine : EngineBase {
   }
 
   int launch_noise(cudaStream_t s) {
-    if (!d.enable_noise) return BLE_OK;
+    if (!d.enable_noise || noise_valid) return BLE_OK;
     dim3 grid(grid_for(n, kNoiseBlock), 10);
     k_noise<Real><<<grid, kNoiseBlock, kNoiseBlock * 256, s>>>(d);
     ++launches;
     BLE_CUDA(cudaGetLastError());
+    noise_valid = true;
     return BLE_OK;
   }
 
@@ -792,6 +841,49 @@ struct Engine : EngineBase {
     if (rc != BLE_OK) return rc;
     k_step<Real><<<grid_for(n, 128), 128, 0, s>>>(d, actions, reward, done, reinterpret_cast<float2*>(wind_uv));
     ++launches;
+    BLE_CUDA(cudaGetLastError());
+    noise_valid = false;
+    // arena.step ends with feature_constructor.observe(get_measurements()) (env/balloon_arena.py:201):
+    // the noise evaluated for it at the post-step state is also next step's pre-step wind.
+    if (cfg.enable_features) return features_observe(s);
+    return BLE_OK;
+  }
+
+  int features_observe(cudaStream_t s) override {
+    if (!cfg.enable_features) { err = "features_observe: handle was created with enable_features = 0"; return BLE_ERR_UNSUPPORTED; }
+    int rc = check_ready("features_observe");
+    if (rc != BLE_OK) return rc;
+    BLE_CUDA(cudaSetDevice(device));
+    rc = launch_noise(s);
+    if (rc != BLE_OK) return rc;
+    k_feat_observe<Real><<<grid_for(n, 128), 128, 0, s>>>(d);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
+  int features_clear(const uint8_t* mask, cudaStream_t s) override {
+    if (!cfg.enable_features) { err = "features_clear: handle was created with enable_features = 0"; return BLE_ERR_UNSUPPORTED; }
+    BLE_CUDA(cudaSetDevice(device));
+    if (mask == nullptr) {
+      BLE_CUDA(cudaMemsetAsync(gp_count, 0, sizeof(int32_t) * n, s));
+    } else {
+      err = "features_clear: masked clear is done by ble_reset"; return BLE_ERR_UNSUPPORTED;
+    }
+    return BLE_OK;
+  }
+
+  int features(float* obs, cudaStream_t s) override {
+    if (obs == nullptr) { err = "features: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    if (!cfg.enable_features) { err = "features: handle was created with enable_features = 0"; return BLE_ERR_UNSUPPORTED; }
+    int rc = check_ready("features");
+    if (rc != BLE_OK) return rc;
+    BLE_CUDA(cudaSetDevice(device));
+    k_feat_ambient<Real><<<grid_for(n, 128), 128, 0, s>>>(d, obs);
+    k_feat_range<Real><<<grid_for(n, 4), 128, 0, s>>>(d);
+    k_gp_factor<Real><<<unsigned(n), kFactorThreads, sizeof(double) * (kGpPacked + kGpWindow * 4), s>>>(d);
+    k_gp_column<Real><<<unsigned(n), kColumnThreads, kColumnSmem, s>>>(d, obs);
+    launches += 4;
     BLE_CUDA(cudaGetLastError());
     return BLE_OK;
   }
@@ -945,6 +1037,15 @@ int ble_step_host(ble_handle* h, const int32_t* actions_host, float* reward_host
 }
 int ble_wind_at_balloon(ble_handle* h, float* wind_uv, void* stream) {
   BLE_H(h); return h->eng->wind_at(wind_uv, cudaStream_t(stream));
+}
+int ble_features_observe(ble_handle* h, void* stream) {
+  BLE_H(h); return h->eng->features_observe(cudaStream_t(stream));
+}
+int ble_features_perciatelli(ble_handle* h, float* obs, void* stream) {
+  BLE_H(h); return h->eng->features(obs, cudaStream_t(stream));
+}
+int ble_features_clear(ble_handle* h, void* stream) {
+  BLE_H(h); return h->eng->features_clear(nullptr, cudaStream_t(stream));
 }
 int ble_derived(ble_handle* h, double* out, void* stream) {
   BLE_H(h); return h->eng->derived(out, cudaStream_t(stream));

@@ -62,6 +62,8 @@ typedef struct {
   int32_t wind_model;          /* BLE_WIND_*                                                        */
   int32_t enable_noise;        /* 1: ground truth = forecast + simplex noise (wind_field.py:125-145) */
   int32_t field_layout;        /* BLE_LAYOUT_*                                                      */
+  int32_t enable_features;     /* 1: keep the WindGP history and allow ble_features_perciatelli      */
+  int32_t reserved[3];         /* must be 0                                                         */
 } ble_config;
 
 /* State exchange: two row-major device matrices, one row per field, N columns.
@@ -148,6 +150,18 @@ int ble_wind_at_balloon(ble_handle* h, float* wind_uv, void* stream);
  * reference, 16-corner multilinear interpolation. */
 int ble_wind_gather(ble_handle* h, const float* xyzt, const int32_t* field_idx, float* uv,
                     int64_t m, void* stream);
+
+/* Observation surface: PerciatelliFeatureConstructor (env/features.py:269-581) for all balloons.
+ * With enable_features = 1, ble_reset and ble_step end with the constructor's observe() of the new
+ * state (env/balloon_arena.py:179-182, 201), i.e. the WindGP measurement history (env/wind_gp.py:98-119,
+ * last 6 h = 120 measurements) is maintained by the handle.
+ *   ble_features_perciatelli: get_features() -> obs float32 [N, 1099] (16 ambient features + 361 x 3
+ *     wind-column features from the GP posterior, the forecast column and the reachable pressure range).
+ *   ble_features_observe: observe() of the current state (only needed after ble_state_upload).
+ *   ble_features_clear: forget every balloon's measurement history. */
+int ble_features_perciatelli(ble_handle* h, float* obs, void* stream);
+int ble_features_observe(ble_handle* h, void* stream);
+int ble_features_clear(ble_handle* h, void* stream);
 
 /* Derived properties of BalloonState at the CURRENT state (env/balloon/balloon.py:217-250), all
  * balloons, float64 [BLE_NUM_D][N]. */

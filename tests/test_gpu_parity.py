@@ -426,3 +426,85 @@ def test_cuda_balloon_arena_follows_reference_episode(ble):
     assert int(b.time_elapsed.total_seconds()) == wi['time_elapsed']
     assert abs(reward_fn(sim) - sc['reward'][t]) < 1e-6
   a.close()
+
+
+# ------------------------------------------------------------------------------ observation surface
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_perciatelli_features_match_reference(ble, precision):
+  """Three recorded reference episodes through PerciatelliFeatureConstructor (1099 float32 features,
+  WindGP window filling up to 120 measurements) replayed on the GPU.  Tolerance 1e-4 absolute on
+  every feature (north_star / SURVEY.md f-1); the (0, 1, 1) padding pattern must match exactly."""
+  import os
+  feat = np.load(os.path.join(golden_io.GOLDEN_DIR, 'features.npz'))
+  scen = lambda name: {k.split('/', 1)[1]: feat[k] for k in feat.files if k.startswith(name + '/')}
+  for model, names in (('grid', ['grid_random', 'sticky_random']), ('simple_static', ['default_static'])):
+    scs = [scen(n) for n in names]
+    n = len(scs)
+    arena = ble.BatchedBalloonArena(n, precision=precision, wind_model=model, enable_noise=True, enable_features=True)
+    if model == 'grid':
+      arena.set_wind_fields(torch.from_numpy(golden_fields.field_bank()),
+                            torch.tensor([int(sc['field']) for sc in scs], dtype=torch.int32))
+    arena.set_wind_noise(torch.from_numpy(np.stack([sc['seeds'] for sc in scs])),
+                         torch.from_numpy(np.stack([sc['offsets'] for sc in scs]).astype(np.float32)))
+    b = golden_io.batch_from_rows(FF, IF, np.stack([sc['f0'] for sc in scs]), np.stack([sc['i0'] for sc in scs]))
+    arena.set_state(*pack(b, np.array([float(sc['alpha']) for sc in scs]), 1))
+    arena.features_clear()
+    arena.features_observe()                    # a fresh constructor observes the initial state
+    horizon = max(len(sc['actions']) for sc in scs)
+    worst = 0.0
+    for t in range(horizon + 1):
+      if t > 0:
+        acts = np.array([sc['actions'][t - 1] if t - 1 < len(sc['actions']) else 1 for sc in scs], np.int32)
+        arena.step(torch.from_numpy(acts))
+      if t % 10 and t not in (1, 2, 3) and t < horizon - 2:
+        continue
+      obs = arena.features().cpu().numpy()
+      for e, sc in enumerate(scs):
+        if t > len(sc['actions']):
+          continue
+        ref = sc['obs'][t]
+        pad_ref = np.all(ref[16:].reshape(361, 3) == np.array([0, 1, 1], np.float32), axis=1)
+        pad_got = np.all(obs[e, 16:].reshape(361, 3) == np.array([0, 1, 1], np.float32), axis=1)
+        np.testing.assert_array_equal(pad_got, pad_ref, err_msg=f'{names[e]} t={t} padding')
+        err = np.abs(obs[e] - ref)
+        worst = max(worst, float(err.max()))
+        assert err.max() < 1e-4, (names[e], t, int(err.argmax()), float(obs[e][err.argmax()]), float(ref[err.argmax()]))
+    print(precision, model, 'worst feature error', worst)
+    arena.close()
+
+
+def test_features_batch_matches_oracle_after_reset(ble):
+  """Device reset -> 12 steps -> features for 48 balloons, against the oracle fed the same states
+  and the same measurement history."""
+  from oracle import features as features_lib
+  n, steps = 48, 12
+  rng = np.random.default_rng(21)
+  bank = golden_fields.field_bank()
+  fidx = rng.integers(0, 4, n).astype(np.int32)
+  arena = ble.BatchedBalloonArena(n, precision='fp32', enable_noise=True, enable_features=True)
+  arena.set_wind_fields(torch.from_numpy(bank), torch.from_numpy(fidx))
+  arena.reset(torch.arange(n, dtype=torch.int64) * 13 + 5)
+  seeds = rng.integers(0, 1634753849, (n, 2, 5)); offsets = rng.uniform(-1, 1, (n, 2, 5, 4)).astype(np.float32)
+  arena.set_wind_noise(torch.from_numpy(seeds), torch.from_numpy(offsets))
+  arena.features_clear(); arena.features_observe()
+  noise = wind_lib.SimplexWindNoise(seeds, offsets.astype(np.float64))
+  st = state_np(arena)
+  ob = balloon_lib.BalloonBatch(**{k: st[k].copy() for k in balloon_lib.FLOAT_FIELDS + balloon_lib.INT_FIELDS})
+  oarena = env_lib.OracleArena(ob, atmosphere_lib.Atmosphere(st['atmosphere_alpha']), fields=bank, field_idx=fidx, noise=noise)
+  ofeat = features_lib.PerciatelliFeatures(oarena)
+  ofeat.observe()
+  for t in range(steps):
+    acts = rng.integers(0, 3, n).astype(np.int32)
+    arena.step(torch.from_numpy(acts))
+    # keep the oracle on the GPU's trajectory: copy the state, then let it observe
+    st = state_np(arena)
+    for k in balloon_lib.FLOAT_FIELDS + balloon_lib.INT_FIELDS:
+      setattr(ob, k, st[k].copy())
+    ofeat.observe()
+  got = arena.features().cpu().numpy()
+  want = ofeat.get_features()
+  pad = lambda o: np.all(o[:, 16:].reshape(-1, 361, 3) == np.array([0, 1, 1], np.float32), axis=2)
+  np.testing.assert_array_equal(pad(got), pad(want))
+  assert np.abs(got - want).max() < 1e-4, float(np.abs(got - want).max())
+  arena.close()
