@@ -13,10 +13,12 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.environ.get('BLE_B200_LIB') or os.path.join(PKG_DIR, 'libble_b200.so')
 SOURCES = [os.path.join(CSRC, 'ble_engine.cu')]
-HEADERS = [os.path.join(CSRC, 'ble_physics.cuh'), os.path.join(CSRC, 'ble_wind.cuh'),
+HEADERS = [os.path.join(CSRC, f) for f in ('ble_physics.cuh', 'ble_wind.cuh', 'ble_features.cuh',
+                                          'ble_feature_kernels.cuh', 'ble_decoder.cuh')] + [
            os.path.join(PKG_DIR, '..', 'include', 'ble_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--shared', '-Xcompiler', '-fPIC']
+LINK_FLAGS = ['-lcublasLt', '-Xlinker', '-rpath=/usr/local/cuda/lib64']
 
 
 def find_nvcc():
@@ -37,7 +39,7 @@ def build(force=False, verbose=False):
   """Compiles csrc/*.cu -> libble_b200.so if missing or out of date.  Returns the library path."""
   if not force and not is_stale():
     return LIB_PATH
-  cmd = [find_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + SOURCES
+  cmd = [find_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + SOURCES + LINK_FLAGS
   proc = subprocess.run(cmd, capture_output=True, text=True)
   if proc.returncode != 0:
     raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)

@@ -28,7 +28,7 @@ D_ROWS = ('lat', 'lng', 'solar_elevation', 'solar_flux', 'excess_energy', 'navig
           'pressure_ratio', 'battery_soc', 'altitude')
 
 EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_upload_fields',
-           'ble_alloc_fields', 'ble_write_fields', 'ble_set_field_map',
+           'ble_alloc_fields', 'ble_write_fields', 'ble_set_field_map', 'ble_set_decoder', 'ble_decode_fields',
            'ble_set_noise', 'ble_state_upload', 'ble_state_download', 'ble_reset', 'ble_init_derived',
            'ble_step', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_derived',
            'ble_features_perciatelli', 'ble_features_observe', 'ble_features_clear',
@@ -77,6 +77,8 @@ def load(build_if_missing=True):
   lib.ble_write_fields.argtypes = [vp, vp, i64, i64, vp]
   lib.ble_set_field_map.argtypes = [vp, vp, vp]
   lib.ble_set_noise.argtypes = [vp, vp, vp, vp]
+  lib.ble_set_decoder.argtypes = [vp, _c.POINTER(vp), _c.POINTER(vp), vp]
+  lib.ble_decode_fields.argtypes = [vp, vp, i64, vp, vp]
   lib.ble_state_upload.argtypes = [vp, _c.POINTER(BleStateSoa), vp]
   lib.ble_state_download.argtypes = [vp, _c.POINTER(BleStateSoa), vp]
   lib.ble_reset.argtypes = [vp, vp, vp, vp]

@@ -121,14 +121,35 @@ class SimulatorObservation:                   # env/simulator_data.py:38-46
 
 
 class _NullFeatureConstructor:
-  """Observes nothing (the Perciatelli constructor is a later row of the scope table)."""
+  """Observes nothing: the reference's hot path with a null feature constructor."""
   observation_space = None
+
+  def __init__(self, arena):
+    del arena
 
   def observe(self, observation):
     del observation
 
   def get_features(self) -> np.ndarray:
     return np.zeros((0,), np.float32)
+
+
+class CudaPerciatelliFeatureConstructor:
+  """FeatureConstructor interface (env/features.py:106-144) over the device-side implementation.
+
+  The measurement history (WindGP) lives in the handle and is updated by reset()/step(), so
+  observe() has nothing left to do; get_features() runs the feature kernels for this balloon.
+  """
+
+  def __init__(self, arena: 'CudaBalloonArena'):
+    self._arena = arena
+    self.observation_space = batched_env.perciatelli_observation_space()
+
+  def observe(self, observation):
+    del observation
+
+  def get_features(self) -> np.ndarray:
+    return self._arena._arena.features().cpu().numpy()[0]
 
 
 def _utc(ts: int) -> dt.datetime:
@@ -141,12 +162,18 @@ class CudaBalloonArena:
   def __init__(self, feature_constructor_factory: Optional[Callable[[Any], Any]] = None,
                wind_field: Optional[np.ndarray] = None, seed: Optional[int] = None, *,
                device: str = 'cuda:0', precision: str = 'fp32', wind_model: str = 'grid',
-               enable_noise: bool = True):
+               enable_noise: bool = True, observation: Optional[str] = 'perciatelli'):
     """wind_field: float32 [21,21,10,9,2] grid (GridWindFieldSampler.sample_field layout) for the
-    'grid' model; `wind_model='simple_static'` reproduces SimpleStaticWindField."""
+    'grid' model; `wind_model='simple_static'` reproduces SimpleStaticWindField.
+    observation='perciatelli' (default, as in the reference) makes reset()/step() return the
+    1099-feature observation computed on the device; None returns an empty vector.
+    feature_constructor_factory(arena) may supply any object with observe/get_features/
+    observation_space instead."""
     self._arena = batched_env.BatchedBalloonArena(1, device=device, precision=precision,
-                                                  wind_model=wind_model, enable_noise=enable_noise)
-    self._factory = feature_constructor_factory or (lambda arena: _NullFeatureConstructor())
+                                                  wind_model=wind_model, enable_noise=enable_noise,
+                                                  enable_features=observation == 'perciatelli')
+    default_factory = CudaPerciatelliFeatureConstructor if observation == 'perciatelli' else _NullFeatureConstructor
+    self._factory = feature_constructor_factory or default_factory
     if wind_model == 'grid':
       if wind_field is None:
         raise ValueError("wind_model='grid' needs a [21,21,10,9,2] wind_field")
@@ -231,6 +258,13 @@ class CudaBalloonArena:
   def set_wind_noise(self, seeds: np.ndarray, offsets: np.ndarray) -> None:
     self._arena.set_wind_noise(torch.as_tensor(np.asarray(seeds, np.int64)).reshape(1, 2, 5),
                                torch.as_tensor(np.asarray(offsets, np.float32)).reshape(1, 2, 5, 4))
+
+  def reset_feature_history(self) -> None:
+    """A fresh FeatureConstructor that has observed only the current state (what BalloonArena.reset
+    does at env/balloon_arena.py:179-182); use after set_balloon_state when starting a new episode."""
+    if self._arena.enable_features:
+      self._arena.features_clear()
+      self._arena.features_observe()
 
   def close(self):
     self._arena.close()

@@ -130,6 +130,43 @@ class BatchedBalloonArena:
     torch.cuda.current_stream(self.device).synchronize()
     self._keepalive = [None, env_to_field]
 
+  # -- VAE wind generator (reset path) ------------------------------------------------------------
+  def set_decoder(self, params) -> None:
+    """params: {'Dense_0'..'Dense_3': {'kernel': [in, out], 'bias': [out]}} (the flax tree of
+    models/offlineskies22_decoder.msgpack['params'], numpy or torch)."""
+    ks, bs = [], []
+    for i in range(4):
+      layer = params[f'Dense_{i}']
+      ks.append(torch.as_tensor(np.asarray(layer['kernel'], np.float32)).to(self.device).contiguous())
+      bs.append(torch.as_tensor(np.asarray(layer['bias'], np.float32)).to(self.device).contiguous())
+    expected = [(64, 1000), (1000, 1000), (1000, 1000), (1000, 4410)]
+    if [tuple(k.shape) for k in ks] != expected or [b.numel() for b in bs] != [1000, 1000, 1000, 4410]:
+      raise ValueError('decoder weights do not have the vae.Decoder shapes')
+    kp = (ctypes.c_void_p * 4)(*[k.data_ptr() for k in ks])
+    bp = (ctypes.c_void_p * 4)(*[b.data_ptr() for b in bs])
+    self._check(self._lib.ble_set_decoder(self._h, kp, bp, self._stream()), 'ble_set_decoder')
+    torch.cuda.current_stream(self.device).synchronize()
+
+  def decode_wind_fields(self, latents: torch.Tensor) -> torch.Tensor:
+    """vae.Decoder().apply(params, z) for a batch: latents float32 [F, 64] -> [F,21,21,10,9,2]."""
+    latents = latents.to(self.device, torch.float32).contiguous()
+    if latents.dim() != 2 or latents.shape[1] != 64:
+      raise ValueError('latents must be [F, 64]')
+    out = torch.empty(latents.shape[0], *FIELD_SHAPE, dtype=torch.float32, device=self.device)
+    rc = self._lib.ble_decode_fields(self._h, _ptr(latents), latents.shape[0], _ptr(out), self._stream())
+    self._check(rc, 'ble_decode_fields')
+    return out
+
+  def generate_wind_fields(self, n_fields: int, seed: int, chunk: int = 2048) -> None:
+    """GenerativeWindFieldSampler.sample_field for n_fields grids: z ~ N(0, I_64) -> decoder -> field bank."""
+    g = torch.Generator(device=self.device)
+    g.manual_seed(int(seed))
+    self.alloc_wind_fields(n_fields)
+    for first in range(0, n_fields, chunk):
+      c = min(chunk, n_fields - first)
+      z = torch.randn(c, 64, generator=g, device=self.device, dtype=torch.float32)
+      self.write_wind_fields(self.decode_wind_fields(z), first)
+
   def set_wind_noise(self, seeds: torch.Tensor, offsets: torch.Tensor):
     """seeds int64 [N,2,5], offsets float32 [N,2,5,4] (env/simplex_wind_noise.py:98-114)."""
     seeds = seeds.to(self.device, torch.int64).contiguous()
@@ -232,28 +269,62 @@ class BatchedBalloonArena:
     self._check(rc, 'ble_step_host')
 
 
+class Box:
+  """Minimal stand-in for gym.spaces.Box (low / high / shape)."""
+
+  def __init__(self, low: np.ndarray, high: np.ndarray):
+    self.low, self.high, self.shape, self.dtype = low, high, low.shape, low.dtype
+
+  def __repr__(self):
+    return f'Box{self.shape}'
+
+
+def perciatelli_observation_space() -> Box:
+  """PerciatelliFeatureConstructor.observation_space (env/features.py:332-348)."""
+  low = np.zeros(1099, np.float32)
+  high = np.ones(1099, np.float32)
+  low[[3, 4, 5, 6]] = -1.0          # sin / cos features
+  low[15] = 1.0                      # ACS pressure ratio in [1, inf)
+  high[15] = np.inf
+  return Box(low, high)
+
+
 class BatchedBalloonEnv:
   """Vectorised BalloonEnv: `step(actions[N]) -> (obs, reward[N], done[N], info)`.
 
-  Reference: BalloonEnv (env/balloon_env.py:105-300).  `action_space.n == 3`.  The observation is
-  produced by `feature_constructor(arena)` when one is given (the Perciatelli 1099-feature
-  constructor is a later row of the scope table); without one `obs` is None.
+  Reference: BalloonEnv (env/balloon_env.py:105-300).  `action_space.n == 3`.
+  observation='perciatelli' returns the reference's default observation (float32 [N, 1099],
+  PerciatelliFeatureConstructor, env/features.py:269-581) computed on the device;
+  observation=None skips it (obs is None), which is the reference's hot path with a null feature
+  constructor.
   """
 
   def __init__(self, num_envs: int, *, device: str = 'cuda:0', precision: str = 'fp32',
                wind_model: str = 'grid', enable_noise: bool = True, seed: int = 0,
-               arena: Optional[BatchedBalloonArena] = None, feature_constructor=None):
+               arena: Optional[BatchedBalloonArena] = None, observation: Optional[str] = None,
+               field_layout: str = 'x64'):
+    if observation not in (None, 'perciatelli'):
+      raise ValueError("observation must be None or 'perciatelli'")
     self.arena = arena if arena is not None else BatchedBalloonArena(
-        num_envs, device=device, precision=precision, wind_model=wind_model, enable_noise=enable_noise)
+        num_envs, device=device, precision=precision, wind_model=wind_model, enable_noise=enable_noise,
+        field_layout=field_layout, enable_features=observation == 'perciatelli')
+    if observation == 'perciatelli' and not self.arena.enable_features:
+      raise ValueError("the arena was created without enable_features=True")
+    self.observation = observation
     self.num_envs = self.arena.num_envs
     self.device = self.arena.device
-    self.feature_constructor = feature_constructor
+    self._obs = (torch.empty(self.num_envs, 1099, dtype=torch.float32, device=self.device)
+                 if observation == 'perciatelli' else None)
     self._generator = torch.Generator(device='cpu')
     self.seed(seed)
 
   @property
   def action_space(self) -> Discrete:
     return Discrete(3)
+
+  @property
+  def observation_space(self) -> Optional[Box]:
+    return perciatelli_observation_space() if self.observation == 'perciatelli' else None
 
   @property
   def reward_range(self) -> Tuple[float, float]:
@@ -270,9 +341,9 @@ class BatchedBalloonEnv:
     return self._observe()
 
   def _observe(self):
-    if self.feature_constructor is None:
+    if self.observation is None:
       return None
-    return self.feature_constructor(self.arena)
+    return self.arena.features(self._obs)
 
   def step(self, actions: torch.Tensor):
     reward, done, _ = self.arena.step(actions)

@@ -2,6 +2,7 @@
 // Target: sm_100a (B200).  One handle per GPU, one thread per balloon in the physics kernel,
 // one thread per (balloon, noise harmonic) in the noise kernel with TMA bulk staging of the
 // permutation tables.
+#include <cublasLt.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -446,6 +447,7 @@ __global__ void __launch_bounds__(128) k_derived(DevState<Real> d, double* __res
 }
 
 #include "ble_feature_kernels.cuh"
+#include "ble_decoder.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Reset (env/balloon_arena.py:161-182,228-268; utils/sampling.py:37-152)
@@ -604,6 +606,8 @@ struct EngineBase {
   virtual int wind_at(float*, cudaStream_t) = 0;
   virtual int wind_gather(const float*, const int32_t*, float*, int64_t, cudaStream_t) = 0;
   virtual int derived(double*, cudaStream_t) = 0;
+  virtual int set_decoder(const float* const*, const float* const*, cudaStream_t) = 0;
+  virtual int decode(const float*, int64_t, float*, cudaStream_t) = 0;
   virtual int features_observe(cudaStream_t) = 0;
   virtual int features(float*, cudaStream_t) = 0;
   virtual int features_clear(const uint8_t*, cudaStream_t) = 0;
@@ -634,6 +638,15 @@ struct Engine : EngineBase {
   bool noise_valid = false;      // noise_partial matches the current state
   double* gp_obs = nullptr; int32_t* gp_count = nullptr; double* gp_chol = nullptr; int32_t* gp_m = nullptr;
   double* feat_range = nullptr;
+  // VAE decoder (reset path)
+  float* dec_w[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* dec_b[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* dec_act[2] = {nullptr, nullptr};
+  void* dec_workspace = nullptr;
+  cublasLtHandle_t lt = nullptr;
+  bool have_decoder = false;
+  static constexpr int64_t kDecChunk = 4096;
+  static constexpr size_t kDecWorkspace = size_t(32) << 20;
   // ble_step_host staging
   int32_t* h_actions = nullptr; float* h_reward = nullptr; uint8_t* h_done = nullptr;
   int32_t* d_actions = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr;
@@ -685,6 +698,9 @@ struct Engine : EngineBase {
     cudaFree(d.dd); cudaFree(d.r); cudaFree(d.l); cudaFree(d.t_elapsed); cudaFree(d.flags);
     cudaFree(env_field); cudaFree(d.noise_partial); cudaFree(cells); cudaFree(perm); cudaFree(offsets);
     cudaFree(noise_seeds); cudaFree(noise_offsets_in);
+    for (int i = 0; i < 4; ++i) { cudaFree(dec_w[i]); cudaFree(dec_b[i]); }
+    cudaFree(dec_act[0]); cudaFree(dec_act[1]); cudaFree(dec_workspace);
+    if (lt != nullptr) cublasLtDestroy(lt);
     cudaFree(gp_obs); cudaFree(gp_count); cudaFree(gp_chol); cudaFree(gp_m); cudaFree(feat_range);
     cudaFree(d_actions); cudaFree(d_reward); cudaFree(d_done);
     cudaFreeHost(h_actions); cudaFreeHost(h_reward); cudaFreeHost(h_done);
@@ -846,6 +862,85 @@ struct Engine : EngineBase {
     // arena.step ends with feature_constructor.observe(get_measurements()) (env/balloon_arena.py:201):
     // the noise evaluated for it at the post-step state is also next step's pre-step wind.
     if (cfg.enable_features) return features_observe(s);
+    return BLE_OK;
+  }
+
+  // ---- VAE decoder: Dense 64 -> 1000 -> 1000 -> 1000 -> 4410 (flax kernels are [in, out] row-major) ----
+  int set_decoder(const float* const* kernels, const float* const* biases, cudaStream_t s) override {
+    if (kernels == nullptr || biases == nullptr) { err = "set_decoder: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    BLE_CUDA(cudaSetDevice(device));
+    const int dims[5] = {kDecLatents, kDecHidden, kDecHidden, kDecHidden, kDecOut};
+    if (lt == nullptr && cublasLtCreate(&lt) != CUBLAS_STATUS_SUCCESS) { err = "set_decoder: cublasLtCreate failed"; return BLE_ERR_CUDA; }
+    for (int i = 0; i < 4; ++i) {
+      if (kernels[i] == nullptr || biases[i] == nullptr) { err = "set_decoder: null layer"; return BLE_ERR_INVALID_ARGUMENT; }
+      if (dec_w[i] == nullptr) {
+        BLE_CUDA(cudaMalloc(&dec_w[i], sizeof(float) * size_t(dims[i]) * dims[i + 1]));
+        BLE_CUDA(cudaMalloc(&dec_b[i], sizeof(float) * dims[i + 1]));
+      }
+      BLE_CUDA(cudaMemcpyAsync(dec_w[i], kernels[i], sizeof(float) * size_t(dims[i]) * dims[i + 1], cudaMemcpyDeviceToDevice, s));
+      BLE_CUDA(cudaMemcpyAsync(dec_b[i], biases[i], sizeof(float) * dims[i + 1], cudaMemcpyDeviceToDevice, s));
+    }
+    if (dec_act[0] == nullptr) {
+      BLE_CUDA(cudaMalloc(&dec_act[0], sizeof(float) * kDecChunk * kDecOut));
+      BLE_CUDA(cudaMalloc(&dec_act[1], sizeof(float) * kDecChunk * kDecOut));
+      BLE_CUDA(cudaMalloc(&dec_workspace, kDecWorkspace));
+    }
+    have_decoder = true;
+    return BLE_OK;
+  }
+
+  // out[F, n_out] = act(in[F, k] @ W[k, n_out] + b), row-major == column-major (n_out x F) = W^T-free GEMM
+  int dense(const float* in, float* out, int layer, int64_t f, int k, int n_out, bool relu, cudaStream_t s) {
+    cublasLtMatmulDesc_t op = nullptr;
+    cublasLtMatrixLayout_t la = nullptr, lb = nullptr, lc = nullptr;
+    cublasLtMatmulPreference_t pref = nullptr;
+    auto cleanup = [&]() {
+      if (pref) cublasLtMatmulPreferenceDestroy(pref);
+      if (la) cublasLtMatrixLayoutDestroy(la);
+      if (lb) cublasLtMatrixLayoutDestroy(lb);
+      if (lc) cublasLtMatrixLayoutDestroy(lc);
+      if (op) cublasLtMatmulDescDestroy(op);
+    };
+    bool ok = cublasLtMatmulDescCreate(&op, CUBLAS_COMPUTE_32F, CUDA_R_32F) == CUBLAS_STATUS_SUCCESS;
+    const cublasLtEpilogue_t epi = relu ? CUBLASLT_EPILOGUE_RELU_BIAS : CUBLASLT_EPILOGUE_BIAS;
+    const float* bias = dec_b[layer];
+    ok = ok && cublasLtMatmulDescSetAttribute(op, CUBLASLT_MATMUL_DESC_EPILOGUE, &epi, sizeof(epi)) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatmulDescSetAttribute(op, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bias, sizeof(bias)) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatrixLayoutCreate(&la, CUDA_R_32F, n_out, k, n_out) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatrixLayoutCreate(&lb, CUDA_R_32F, k, f, k) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatrixLayoutCreate(&lc, CUDA_R_32F, n_out, f, n_out) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatmulPreferenceCreate(&pref) == CUBLAS_STATUS_SUCCESS;
+    size_t ws = kDecWorkspace;
+    ok = ok && cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &ws, sizeof(ws)) == CUBLAS_STATUS_SUCCESS;
+    cublasLtMatmulHeuristicResult_t heur;
+    int found = 0;
+    ok = ok && cublasLtMatmulAlgoGetHeuristic(lt, op, la, lb, lc, lc, pref, 1, &heur, &found) == CUBLAS_STATUS_SUCCESS && found > 0;
+    const float one = 1.f, zero = 0.f;
+    ok = ok && cublasLtMatmul(lt, op, &one, dec_w[layer], la, in, lb, &zero, out, lc, out, lc, &heur.algo,
+                              dec_workspace, kDecWorkspace, s) == CUBLAS_STATUS_SUCCESS;
+    cleanup();
+    if (!ok) { err = "decode: cuBLASLt GEMM failed"; return BLE_ERR_CUDA; }
+    ++launches;
+    return BLE_OK;
+  }
+
+  int decode(const float* latents, int64_t f, float* fields, cudaStream_t s) override {
+    if (latents == nullptr || fields == nullptr || f <= 0) { err = "decode: bad argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    if (!have_decoder) { err = "decode: no decoder weights (call ble_set_decoder first)"; return BLE_ERR_NOT_READY; }
+    BLE_CUDA(cudaSetDevice(device));
+    const ResizeTaps taps = make_resize_taps();
+    for (int64_t first = 0; first < f; first += kDecChunk) {
+      const int64_t c = std::min<int64_t>(kDecChunk, f - first);
+      int rc = dense(latents + first * kDecLatents, dec_act[0], 0, c, kDecLatents, kDecHidden, true, s);
+      if (rc == BLE_OK) rc = dense(dec_act[0], dec_act[1], 1, c, kDecHidden, kDecHidden, true, s);
+      if (rc == BLE_OK) rc = dense(dec_act[1], dec_act[0], 2, c, kDecHidden, kDecHidden, true, s);
+      if (rc == BLE_OK) rc = dense(dec_act[0], dec_act[1], 3, c, kDecHidden, kDecOut, false, s);
+      if (rc != BLE_OK) return rc;
+      const int64_t threads = c * int64_t(kNX) * kNY * kDecFlows;
+      k_decode_epilogue<<<grid_for(threads, 256), 256, 0, s>>>(dec_act[1], fields + first * kFieldFloats, taps, c);
+      ++launches;
+      BLE_CUDA(cudaGetLastError());
+    }
     return BLE_OK;
   }
 
@@ -1037,6 +1132,12 @@ int ble_step_host(ble_handle* h, const int32_t* actions_host, float* reward_host
 }
 int ble_wind_at_balloon(ble_handle* h, float* wind_uv, void* stream) {
   BLE_H(h); return h->eng->wind_at(wind_uv, cudaStream_t(stream));
+}
+int ble_set_decoder(ble_handle* h, const float* const* kernels, const float* const* biases, void* stream) {
+  BLE_H(h); return h->eng->set_decoder(kernels, biases, cudaStream_t(stream));
+}
+int ble_decode_fields(ble_handle* h, const float* latents, int64_t n_fields, float* fields, void* stream) {
+  BLE_H(h); return h->eng->decode(latents, n_fields, fields, cudaStream_t(stream));
 }
 int ble_features_observe(ble_handle* h, void* stream) {
   BLE_H(h); return h->eng->features_observe(cudaStream_t(stream));

@@ -171,36 +171,68 @@ __global__ void __launch_bounds__(kFactorThreads) k_gp_factor(DevState<Real> d) 
     if (tid == j) L[tri(j) + j] = sqrt(s);
     __syncthreads();
     if (tid > j && tid < m) L[tri(tid) + j] = s / L[tri(j) + j];
+    __syncthreads();                             // column j is complete before iteration j + 1 reads row j + 1
   }
-  __syncthreads();
   double* out = d.gp_chol + e * int64_t(kGpPacked);
   for (int k = tid; k < total; k += kFactorThreads) out[k] = L[k];
 }
 
 // ---- predictive column + feature assembly ------------------------------------------------------------------
+// One CTA per balloon, one thread per query level (181) + one per target column (2).  Every thread
+// runs a forward substitution v = L^-1 rhs (rhs = k* for a query, the measured errors for a target):
+//   variance = sigma^2 - |v|^2,  mean = v . z  with z = L^-1 y      (sklearn GPR.predict)
+// The substitution is blocked by 8 rows (left-looking): for row block b the thread keeps 8 fp64
+// accumulators and streams v_j (own column, fp32 in shared memory) against the 8 x 1 slivers
+// L[8b..8b+7][j], which are stored contiguously (block-column-major) so that a sliver is four
+// broadcast LDS.128.  That is 14 instructions per 8 DFMA instead of 4 per DFMA.
 constexpr int kColumnThreads = 192;              // 181 query levels + 2 right-hand sides (error u, v)
-constexpr size_t kColumnSmem = sizeof(double) * (kGpPacked + kGpWindow * 4 + kGpWindow * 2) +
+constexpr int kGpBlock = 8;
+constexpr int kGpBlocks = kGpWindow / kGpBlock;  // 15
+// Lb: for block b, columns j = 0 .. 8b+7, 8 rows each -> 64 * (1 + 2 + ... + 15) doubles
+constexpr int kGpBlockedDoubles = kGpBlock * kGpBlock * (kGpBlocks * (kGpBlocks + 1) / 2);   // 7,680
+constexpr size_t kColumnSmem = sizeof(double) * (kGpBlockedDoubles + kGpWindow * 4 + kGpWindow * 2 + kGpWindow) +
                                sizeof(float) * (size_t(kGpWindow) * kColumnThreads + kNumLevels * 3);
+
+__device__ __forceinline__ int lb_offset(int b) { return kGpBlock * kGpBlock * ((b * (b + 1)) >> 1); }
+
 template <typename Real>
 __global__ void __launch_bounds__(kColumnThreads) k_gp_column(DevState<Real> d, float* __restrict__ obs) {
   extern __shared__ __align__(16) double s_mem[];
-  double* L = s_mem;                               // kGpPacked
-  double* a = L + kGpPacked;                       // [m][4]
+  double* Lb = s_mem;                              // blocked factor, kGpBlockedDoubles
+  double* a = Lb + kGpBlockedDoubles;              // [m][4] scaled measurement coordinates
   double* z = a + kGpWindow * 4;                   // [m][2] = L^-1 y
-  float* V = reinterpret_cast<float*>(z + kGpWindow * 2);      // [m][kColumnThreads]
+  double* inv_diag = z + kGpWindow * 2;            // [m] 1 / L_ii
+  float* V = reinterpret_cast<float*>(inv_diag + kGpWindow);   // [m][kColumnThreads]
   float* feat = V + size_t(kGpWindow) * kColumnThreads;          // [181][3]
   __shared__ int s_idx[kGpWindow];
   const int64_t e = blockIdx.x;
   const int tid = threadIdx.x;
   const int m = d.gp_m[e];
+  const int nb = (m + kGpBlock - 1) / kGpBlock;    // row blocks actually used
   const double* ring = d.gp_obs + e * int64_t(kGpWindow * 6);
   const double x = DD(d, D_X, e), y = DD(d, D_Y, e), p_b = DD(d, D_P, e);
   const int32_t t_elapsed = d.t_elapsed[e];
+  const double pmin = d.feat_range[2 * e], pmax = d.feat_range[2 * e + 1];
   if (m > 0) {
     if (tid == 0) gp_window_indices(ring, d.gp_count[e], double(t_elapsed), s_idx);
+    // packed row-major (global) -> block-column-major (shared); rows >= m are identity padding
     const double* src = d.gp_chol + e * int64_t(kGpPacked);
-    for (int k = tid; k < tri(m); k += kColumnThreads) L[k] = src[k];
+    for (int k = tid; k < lb_offset(nb); k += kColumnThreads) {
+      int b = 0;
+      while (lb_offset(b + 1) <= k) ++b;
+      const int rel = k - lb_offset(b);
+      const int j = rel / kGpBlock, r = rel % kGpBlock;
+      const int i = b * kGpBlock + r;
+      double v = 0.0;
+      if (i < m && j <= i) v = src[tri(i) + j];
+      else if (i >= m && j == i) v = 1.0;
+      Lb[k] = v;
+    }
     __syncthreads();
+    if (tid < nb * kGpBlock) {
+      const int b = tid / kGpBlock, r = tid % kGpBlock;
+      inv_diag[tid] = 1.0 / Lb[lb_offset(b) + tid * kGpBlock + r];
+    }
     if (tid < m) {
       const double* o = ring + s_idx[tid] * 6;
       a[tid * 4 + 0] = o[0] / kGpScaleXY; a[tid * 4 + 1] = o[1] / kGpScaleXY;
@@ -212,28 +244,46 @@ __global__ void __launch_bounds__(kColumnThreads) k_gp_column(DevState<Real> d, 
   double mean_u = 0.0, mean_v = 0.0, deviation = 0.0;
   const bool is_query = tid < kNumLevels;
   const bool is_rhs = tid == kNumLevels || tid == kNumLevels + 1;
-  if (m > 0 && (is_query || is_rhs)) {
-    double qa[4] = {x / kGpScaleXY, y / kGpScaleXY, pressure_level(tid) / kGpScaleP, double(t_elapsed) / kGpScaleT};
+  const double level_p = pressure_level(tid < kNumLevels ? tid : 0);
+  const bool reachable = is_query && !(level_p < pmin || level_p > pmax);   // unreachable levels are not encoded
+  if (m > 0 && (reachable || is_rhs)) {
+    const double qa[4] = {x / kGpScaleXY, y / kGpScaleXY, level_p / kGpScaleP, double(t_elapsed) / kGpScaleT};
     double norm2 = 0.0;
-    for (int i = 0; i < m; ++i) {
-      double s = is_query ? gp_kernel(qa, a + i * 4) : ring[s_idx[i] * 6 + 4 + (tid - kNumLevels)];
-      const double* li = L + tri(i);
-      double s0 = 0.0, s1 = 0.0;
-      int j = 0;
-      for (; j + 1 < i; j += 2) {
-        s0 += li[j] * double(V[j * kColumnThreads + tid]);
-        s1 += li[j + 1] * double(V[(j + 1) * kColumnThreads + tid]);
+    for (int b = 0; b < nb; ++b) {
+      double acc[kGpBlock];
+#pragma unroll
+      for (int r = 0; r < kGpBlock; ++r) {
+        const int i = b * kGpBlock + r;
+        acc[r] = (i >= m) ? 0.0 : (is_query ? gp_kernel(qa, a + i * 4) : ring[s_idx[i] * 6 + 4 + (tid - kNumLevels)]);
       }
-      if (j < i) s0 += li[j] * double(V[j * kColumnThreads + tid]);
-      const double v = (s - (s0 + s1)) / li[i];
-      V[i * kColumnThreads + tid] = float(v);
-      if (is_rhs) z[i * 2 + (tid - kNumLevels)] = v;
-      norm2 += v * v;
+      const double* lb = Lb + lb_offset(b);
+      const int jn = b * kGpBlock;
+      for (int j = 0; j < jn; ++j) {
+        const double vj = double(V[j * kColumnThreads + tid]);
+        const double2* col = reinterpret_cast<const double2*>(lb + j * kGpBlock);
+#pragma unroll
+        for (int r2 = 0; r2 < kGpBlock / 2; ++r2) {
+          const double2 l2 = col[r2];
+          acc[2 * r2] -= l2.x * vj;
+          acc[2 * r2 + 1] -= l2.y * vj;
+        }
+      }
+      // 8 x 8 diagonal block
+#pragma unroll
+      for (int r = 0; r < kGpBlock; ++r) {
+        const double v = acc[r] * inv_diag[jn + r];
+#pragma unroll
+        for (int r2 = r + 1; r2 < kGpBlock; ++r2) acc[r2] -= lb[(jn + r) * kGpBlock + r2] * v;
+        const int i = jn + r;
+        V[i * kColumnThreads + tid] = float(v);
+        if (is_rhs && i < m) z[i * 2 + (tid - kNumLevels)] = v;
+        norm2 += v * v;
+      }
     }
     deviation = fmax(kGpSigma2 - norm2, 0.0) / kGpSigma2;                  // wind_gp.py:186-193
   }
   __syncthreads();
-  if (is_query) {
+  if (reachable) {
     if (m > 0) {
       for (int i = 0; i < m; ++i) {                                        // mean = k*^T K^-1 y = v . z
         const double v = double(V[i * kColumnThreads + tid]);
@@ -241,13 +291,12 @@ __global__ void __launch_bounds__(kColumnThreads) k_gp_column(DevState<Real> d, 
       }
     }
     double fu, fv;
-    forecast_at<double, DevState<Real>>(d, e, x, y, pressure_level(tid), t_elapsed, &fu, &fv);
+    forecast_at<double, DevState<Real>>(d, e, x, y, level_p, t_elapsed, &fu, &fv);
     wind_level_features(mean_u + fu, mean_v + fv, deviation, x, y, &feat[tid * 3], &feat[tid * 3 + 1], &feat[tid * 3 + 2]);
   }
   __syncthreads();
   // centred, padded column (features.py:479-497, 536-556)
   const int lower = kNumLevels - nearest_pressure_level(p_b) - 1;
-  const double pmin = d.feat_range[2 * e], pmax = d.feat_range[2 * e + 1];
   float* o = obs + e * int64_t(kNumFeatures) + 16;
   for (int s = tid; s < 2 * kNumLevels - 1; s += kColumnThreads) {
     float f0 = 0.f, f1 = 1.f, f2 = 1.f;                                    // "unreachable" triple
@@ -259,4 +308,3 @@ __global__ void __launch_bounds__(kColumnThreads) k_gp_column(DevState<Real> d, 
     o[s * 3] = f0; o[s * 3 + 1] = f1; o[s * 3 + 2] = f2;
   }
 }
-

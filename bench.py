@@ -161,8 +161,10 @@ def run_b200(args):
   begin, end = sharding.shard_range(n_total, rank, world)    # strong scaling: fixed total batch
   n = end - begin
 
+  with_obs = args.observation == 'perciatelli'
   arena = batched_env.BatchedBalloonArena(n, device=str(device), precision='fp32', wind_model='grid', enable_noise=True,
-                                          field_layout=args.field_layout)
+                                          field_layout=args.field_layout, enable_features=True)
+  obs_buf = torch.empty(n, 1099, dtype=torch.float32, device=device)
   n_fields = n if args.shared_fields == 0 else args.shared_fields
   upload_synthetic_fields(torch, arena, n_fields, device, seed=1234 + rank)
   arena.set_field_map(torch.arange(n, dtype=torch.int32, device=device) % n_fields)
@@ -180,16 +182,21 @@ def run_b200(args):
       dist.barrier()
     torch.cuda.synchronize()
 
+  def one_step(t):
+    arena.step(actions[t])
+    if with_obs:
+      arena.features(obs_buf)
+
   # ---- device-resident timing -------------------------------------------------------------
   for t in range(args.warmup):
-    arena.step(actions[t])
+    one_step(t)
   barrier()
   launches0 = arena.launch_count
   sampler = ClockSampler(local_rank); sampler.start()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ev0.record()
   for t in range(args.warmup, total):
-    arena.step(actions[t])
+    one_step(t)
   ev1.record()
   barrier()
   ms = ev0.elapsed_time(ev1)
@@ -199,15 +206,37 @@ def run_b200(args):
 
   # ---- end to end through the host-buffer C ABI call ----------------------------------------
   reward_h = np.zeros(n, np.float32); done_h = np.zeros(n, np.uint8)
+  obs_h = torch.empty(n, 1099, dtype=torch.float32).pin_memory() if with_obs else None
   e2e_steps = args.steps
-  for t in range(min(3, args.warmup)):
+
+  def one_step_host(t):
     arena.step_host(actions_host[t], reward_h, done_h)
+    if with_obs:                                   # observation computed on the device, read back to the host
+      arena.features(obs_buf)
+      obs_h.copy_(obs_buf, non_blocking=True)
+      torch.cuda.current_stream().synchronize()
+
+  for t in range(min(3, args.warmup)):
+    one_step_host(t)
   barrier()
   t0 = time.perf_counter()
   for t in range(e2e_steps):
-    arena.step_host(actions_host[args.warmup + t % args.steps], reward_h, done_h)
+    one_step_host(args.warmup + t % args.steps)
   torch.cuda.synchronize()
   e2e_s = time.perf_counter() - t0
+
+  # ---- the same step WITH the Perciatelli observation (reference path A), a few steps ----------
+  obs_ms = None
+  if not with_obs and args.observation_probe > 0:
+    for _ in range(2):
+      arena.step(actions[0]); arena.features(obs_buf)
+    barrier()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    for t in range(args.observation_probe):
+      arena.step(actions[t % total]); arena.features(obs_buf)
+    o1.record(); torch.cuda.synchronize()
+    obs_ms = o0.elapsed_time(o1) / args.observation_probe
 
   # ---- wind-gather roofline (dominant HBM kernel named by BASELINE.json's metric) -----------
   m = max(n * 8, 1 << 24)                                   # >= 16.7 M lookups, 2.6 GB of algorithmic traffic
@@ -248,15 +277,22 @@ def run_b200(args):
                              f'({n_fields} fields/GPU) + simplex noise, 18 sub-steps per step (BASELINE configs[2])',
                  'num_envs': n_total, 'envs_per_gpu': n, 'fields_per_gpu': n_fields, 'field_layout': args.field_layout,
                  'l2': 'inputs larger than L2 (per-balloon fields + 2.5 KB noise tables per balloon)',
-                 'live_fraction_after_run': live_frac},
-      'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 4 * n_total, 'd2h_bytes_per_step': 5 * n_total,
-              'api': 'ble_step_host (host int32 actions in, host float32 reward + uint8 done out)'},
+                 'observation': args.observation, 'live_fraction_after_run': live_frac},
+      'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 4 * n_total,
+              'd2h_bytes_per_step': (5 + (4396 if with_obs else 0)) * n_total,
+              'api': 'ble_step_host (host int32 actions in, host float32 reward + uint8 done out)'
+                     + (' + ble_features_perciatelli read back to pinned host memory' if with_obs else '')},
       'gpu_launches': launches,
       'clocks': clocks,
       'roofline': {'kernel': 'k_wind_gather', 'bound': 'hbm', 'achieved': gather_gbs, 'peak': peak, 'unit': 'GB/s',
                    'frac': gather_gbs / peak, 'traffic': None, 'peak_source': peak_src,
                    'lookups_per_launch': m, 'bytes_per_lookup': GATHER_BYTES_PER_LOOKUP, 'ms_per_launch': gather_ms},
   }
+  if obs_ms is not None:
+    line['with_perciatelli_observation'] = {'ms_per_step': obs_ms, 'value': n_total / (obs_ms * 1e-3), 'unit': UNIT,
+                                            'steps': args.observation_probe,
+                                            'note': 'ble_step + ble_features_perciatelli (1099 float32 features per balloon, '
+                                                    'GP window still filling), device-resident; single GPU share'}
   if world == 1 and not args.no_cpu_baseline:
     t0 = time.perf_counter()
     v1 = cpu_oracle_throughput(2048, 40, 1)
@@ -278,6 +314,10 @@ def main():
   ap.add_argument('--num-envs', type=int, default=65536)
   ap.add_argument('--shared-fields', type=int, default=0, help='0 = one field per balloon; else size of a shared pool')
   ap.add_argument('--field-layout', default='x64', choices=['x64', 'x128'])
+  ap.add_argument('--observation', default='none', choices=['none', 'perciatelli'],
+                  help="'perciatelli': every step also computes the 1099-feature observation")
+  ap.add_argument('--observation-probe', type=int, default=10,
+                  help='extra steps timed WITH the observation when --observation none (0 = skip)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   args = ap.parse_args()
   if args.impl == 'reference':

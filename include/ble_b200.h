@@ -108,6 +108,17 @@ int ble_alloc_fields(ble_handle* h, int64_t n_fields, void* stream);
 int ble_write_fields(ble_handle* h, const float* fields, int64_t first_field, int64_t count, void* stream);
 int ble_set_field_map(ble_handle* h, const int32_t* env_to_field, void* stream);
 
+/* VAE wind-field generator, reset path (generative/vae.py:134-186, env/generative_wind_field.py:52-62).
+ * ble_set_decoder: the four Dense layers of vae.Decoder in flax layout -- kernels[i] float32 [in, out]
+ *   row-major with (in, out) = (64,1000), (1000,1000), (1000,1000), (1000,4410); biases[i] float32 [out]
+ *   (the arrays of models/offlineskies22_decoder.msgpack).  `kernels` / `biases` are HOST arrays of four
+ *   DEVICE pointers; the handle keeps its own copy.
+ * ble_decode_fields: latents float32 [F, 64] (the reference draws jax.random.normal) -> fields float32
+ *   [F,21,21,10,9,2] in the native layout, ready for ble_write_fields.  Four cuBLASLt fp32 GEMMs with
+ *   fused bias(+ReLU) epilogues, then resize 7->23 / central differences / crop in one kernel. */
+int ble_set_decoder(ble_handle* h, const float* const* kernels, const float* const* biases, void* stream);
+int ble_decode_fields(ble_handle* h, const float* latents, int64_t n_fields, float* fields, void* stream);
+
 /* Simplex noise parameters, SimplexWindNoise.reset_wind_noise (env/wind_field.py:196-207,
  * env/simplex_wind_noise.py:98-114): seeds int64 [N,2,5] (component u/v, harmonic),
  * offsets float32 [N,2,5,4].  Builds the 256-entry permutation tables on the device. */

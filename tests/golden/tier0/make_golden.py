@@ -436,6 +436,15 @@ def main():
   pts = rng.uniform(-40, 40, (64, 4))
   kat['opensimplex_port'] = dict(seed=1234567, perm=[int(v) for v in gen._perm],
                                  points=pts.tolist(), values=[gen.noise4d(*p) for p in pts])
+  # VAE decoder: the reference's flax module (under the Tier-0 flax/jax stand-ins) on seeded
+  # random-init weights of its own architecture; a few slices are enough to pin the restatement.
+  from oracle import vae as vae_oracle
+  params = vae_oracle.synthetic_params(11)
+  zs = np.random.default_rng(12).standard_normal((2, 64)).astype(np.float32)
+  dec = [np.asarray(vae.Decoder().apply({'params': params}, z)) for z in zs]
+  kat['vae'] = dict(params_seed=11, latents=zs.tolist(),
+                    slices=[[d[:, :, 3, 4, :].tolist(), d[10, 5, :, :, :].tolist()] for d in dec],
+                    mean_abs=[float(np.abs(d).mean()) for d in dec])
   with open(os.path.join(OUT, 'kat.json'), 'w') as f:
     json.dump(kat, f)
   bank = golden_fields.field_bank()

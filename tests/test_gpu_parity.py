@@ -377,14 +377,18 @@ def test_full_size_properties(ble):
 # ------------------------------------------------------------------------------ N = 1 adaptor (drop-in boundary)
 
 def test_cuda_balloon_arena_follows_reference_episode(ble):
-  """The reference's own calling sequence -- arena.step(action); reward_fn(arena.get_simulator_state()) --
-  on CudaBalloonArena, against the recorded reference episode 'grid_random' (first 120 steps)."""
+  """The reference's own calling sequence -- obs = arena.step(action); reward_fn(arena.get_simulator_state()) --
+  on CudaBalloonArena, against the recorded reference episode 'grid_random' (state, reward AND the
+  1099-feature observation, first 60 steps)."""
   import datetime as dt
   import math
+  import os
   from balloon_learning_environment_b200 import arena as arena_lib, units
-  sc = TRAJ['grid_random']
+  feat = np.load(os.path.join(golden_io.GOLDEN_DIR, 'features.npz'))
+  sc = {k.split('/', 1)[1]: feat[k] for k in feat.files if k.startswith('grid_random/')}
   bank = golden_fields.field_bank()
   a = arena_lib.CudaBalloonArena(wind_field=bank[int(sc['field'])], seed=0, precision='fp64')
+  assert a.feature_constructor.observation_space.shape == (1099,)
   a.set_wind_noise(sc['seeds'], sc['offsets'])
   s = a.get_balloon_state()
   f0 = dict(zip(FF, sc['f0'])); i0 = dict(zip(IF, sc['i0']))
@@ -403,6 +407,8 @@ def test_cuda_balloon_arena_follows_reference_episode(ble):
   s.sunrise_with_hysteresis, s.sunset = utc(i0['sunrise_h']), utc(i0['sunset'])
   s.atmosphere_alpha = float(sc['alpha'])
   a.set_balloon_state(s)
+  a.reset_feature_history()
+  np.testing.assert_allclose(a.feature_constructor.get_features(), sc['obs'][0], rtol=0, atol=1e-5)
 
   def reward_fn(sim_state):                     # env/balloon_env.py:44-102 written against the state view
     b = sim_state.balloon_state
@@ -412,11 +418,10 @@ def test_cuda_balloon_arena_follows_reference_episode(ble):
       reward *= 0.95 - 0.3 * min(max((b.acs_power.watts - 100.0) / 200.0, 0.0), 1.0)
     return reward
 
-  for t in range(120):
-    w = a.get_measurements().wind_at_balloon
-    assert abs(w.u.mps - sc['wind'][t, 0]) < 2e-5 and abs(w.v.mps - sc['wind'][t, 1]) < 2e-5
+  for t in range(60):
     obs = a.step(arena_lib.AltitudeControlCommand(int(sc['actions'][t])))
-    assert isinstance(obs, np.ndarray)
+    assert isinstance(obs, np.ndarray) and obs.shape == (1099,) and obs.dtype == np.float32
+    np.testing.assert_allclose(obs, sc['obs'][t + 1], rtol=0, atol=1e-5)
     sim = a.get_simulator_state()
     b = sim.balloon_state
     want = dict(zip(FF, sc['f'][t])); wi = dict(zip(IF, sc['i'][t]))
@@ -507,4 +512,39 @@ def test_features_batch_matches_oracle_after_reset(ble):
   pad = lambda o: np.all(o[:, 16:].reshape(-1, 361, 3) == np.array([0, 1, 1], np.float32), axis=2)
   np.testing.assert_array_equal(pad(got), pad(want))
   assert np.abs(got - want).max() < 1e-4, float(np.abs(got - want).max())
+  arena.close()
+
+
+# ------------------------------------------------------------------------------ VAE decoder (reset path)
+
+def test_decoder_matches_oracle(ble):
+  """vae.Decoder (generative/vae.py:134-186) as cuBLASLt GEMMs + resize/curl kernel, against the
+  NumPy restatement (oracle/vae.py, itself checked against the reference's flax module under the
+  Tier-0 stubs) on seeded random-init weights of the reference architecture."""
+  from oracle import vae as vae_oracle
+  params = vae_oracle.synthetic_params(3)
+  arena = ble.BatchedBalloonArena(4, precision='fp32', enable_noise=False)
+  arena.set_decoder(params)
+  rng = np.random.default_rng(8)
+  z = rng.standard_normal((5000, 64)).astype(np.float32)           # spans two 4096-field chunks
+  got = arena.decode_wind_fields(torch.from_numpy(z)).cpu().numpy()
+  assert got.shape == (5000, 21, 21, 10, 9, 2)
+  idx = np.array([0, 1, 2, 4095, 4096, 4999])
+  want = vae_oracle.decode(params, z[idx])
+  scale = np.abs(want).max()
+  assert scale > 1.0
+  assert np.abs(got[idx] - want).max() < 2e-4 * scale               # fp32 GEMM summation order
+  # the decoded field is a discrete curl of a stream function: central-difference divergence vanishes
+  # u = D_x Psi, v = -D_y Psi with commuting central differences => D_y u + D_x v == 0
+  u, v = got[idx][..., 0].astype(np.float64), got[idx][..., 1].astype(np.float64)
+  div = (u[:, 1:-1, 2:] - u[:, 1:-1, :-2]) / 2 + (v[:, 2:, 1:-1] - v[:, :-2, 1:-1]) / 2
+  assert np.abs(div).max() < 1e-4 * scale
+  # generated bank feeds the gather: decode -> bank -> lookup at a grid node returns the node value
+  arena.generate_wind_fields(16, seed=5, chunk=8)
+  g = torch.Generator(device='cuda'); g.manual_seed(5)
+  z0 = torch.randn(8, 64, generator=g, device='cuda')
+  f0 = arena.decode_wind_fields(z0).cpu().numpy()
+  q = torch.tensor([[-500.0 + 50.0 * 3, -500.0 + 50.0 * 7, 5000.0 + 1000.0 * 4, 6.0 * 2]], dtype=torch.float32)
+  uv = arena.wind_forecast(q, torch.tensor([2], dtype=torch.int32)).cpu().numpy()[0]
+  np.testing.assert_allclose(uv, f0[2, 3, 7, 4, 2], rtol=1e-5, atol=1e-5)
   arena.close()

@@ -302,3 +302,35 @@ def test_terminal_status_precedence_and_noop_after_done():
   assert done[0] and r[0] == 0.0
   for k in FF + IF:
     np.testing.assert_array_equal(getattr(before, k), getattr(env.arena.state, k))
+
+
+# ---------------------------------------------------------------- VAE decoder (reset path)
+
+def test_vae_decoder_matches_reference_module():
+  from oracle import vae as vae_oracle
+  k = KAT['vae']
+  params = vae_oracle.synthetic_params(k['params_seed'])
+  out = vae_oracle.decode(params, np.array(k['latents'], np.float32))
+  assert out.shape == (2, 21, 21, 10, 9, 2) and out.dtype == np.float32
+  for f in range(2):
+    close(out[f][:, :, 3, 4, :], k['slices'][f][0], rtol=2e-5, atol=2e-5)
+    close(out[f][10, 5], k['slices'][f][1], rtol=2e-5, atol=2e-5)
+    close(np.abs(out[f]).mean(), k['mean_abs'][f], rtol=1e-5)
+
+
+@pytest.mark.tier0
+def test_vae_decoder_on_real_checkpoint_matches_reference_module():
+  """Only where /root/reference is mounted: the 25.9 MB offlineskies22 checkpoint cannot travel."""
+  import os
+  path = '/root/reference/balloon_learning_environment/models/offlineskies22_decoder.msgpack'
+  if not os.path.exists(path):
+    pytest.skip('reference checkpoint not available')
+  import tests.golden.tier0.boot  # noqa: F401
+  from balloon_learning_environment.generative import vae
+  from flax import serialization
+  from oracle import vae as vae_oracle
+  real = serialization.msgpack_restore(open(path, 'rb').read())
+  z = np.random.default_rng(5).standard_normal((2, 64)).astype(np.float32)
+  want = np.stack([np.asarray(vae.Decoder().apply(real, zi)) for zi in z])
+  got = vae_oracle.decode(real['params'], z)
+  assert np.abs(got - want).max() < 2e-4 and np.abs(want).max() > 5.0
