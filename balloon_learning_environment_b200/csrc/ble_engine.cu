@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 
 #include "../../include/ble_b200.h"
 #include "ble_physics.cuh"
@@ -416,6 +417,170 @@ k_step(DevState<Real> d, const int32_t* __restrict__ actions, float* __restrict_
   reward[e] = float(r);
   done[e] = (s.status != kOk) ? 1 : 0;
   if (wind_uv != nullptr) wind_uv[e] = make_float2(float(u), float(v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised physics step (production fp32 build).
+//
+// One block = 4 warps = 32 balloons; lane l of EVERY warp works on balloon 32*block + l and warp w
+// plays role w of the sub-step (ble_physics.cuh): P pressure/atmosphere, T thermal body, E envelope +
+// ACS, S sun + power.  All four keep the balloon's state in registers; per sub-step each computes
+// only its own right-hand side, publishes it in shared memory (double-buffered, ONE barrier per
+// sub-step) and then everybody applies the same update.  The dependent instruction chain per
+// sub-step drops from ~1,400 to ~300 instructions, and the kernel has 4x the warps to hide latency.
+// ---------------------------------------------------------------------------------------------
+struct WsExchange {
+  double p[2][32], tamb[2][32], vol[2][32], sp[2][32], mols[2][32], charge[2][32];
+  float dt_body[2][32], dt_solar[2][32];
+  int st_env[2][32], st_pwr[2][32];
+  int eff[32];
+  float cz[3][32], flux[2][32];
+};
+
+__global__ void __launch_bounds__(128)
+k_step_ws(DevState<float> d, const int32_t* __restrict__ actions, float* __restrict__ reward,
+          uint8_t* __restrict__ done, float2* __restrict__ wind_uv) {
+  using Real = float;
+  __shared__ WsExchange ex;
+  const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = int64_t(blockIdx.x) * 32 + lane;
+  const bool valid = e < d.n;
+  const int64_t ec = valid ? e : d.n - 1;                   // clamp: every thread stays for the barriers
+  const uint32_t fl = d.flags[ec];
+  bool live = valid && (fl & 3u) == uint32_t(kOk);
+  if (valid && !live && role == 0) {                        // finished balloon: no-op (documented divergence)
+    reward[e] = 0.f;
+    done[e] = 1;
+    if (wind_uv != nullptr) wind_uv[e] = make_float2(0.f, 0.f);
+  }
+  // state in registers (every role)
+  BalloonState<Real> s;
+  s.x = DD(d, D_X, ec); s.y = DD(d, D_Y, ec); s.pressure = DD(d, D_P, ec);
+  s.t_ambient = DD(d, D_TAMB, ec); s.t_internal = DD(d, D_TINT, ec); s.volume = DD(d, D_VOL, ec);
+  s.superpressure = DD(d, D_SP, ec); s.mols_air = DD(d, D_MOLS_AIR, ec); s.charge = DD(d, D_CHARGE, ec);
+  s.acs_power = RR(d, R_ACS_W, ec); s.acs_flow = RR(d, R_ACS_FLOW, ec);
+  s.solar_w = RR(d, R_SOLAR_W, ec); s.load_w = RR(d, R_LOAD_W, ec);
+  s.lat0 = RR(d, R_LAT0, ec); s.lng0 = RR(d, R_LNG0, ec); s.ir = RR(d, R_IR, ec); s.mols_gas = RR(d, R_MOLS_GAS, ec);
+  s.date_time = d.l[int64_t(L_DATE_TIME) * d.n + ec];
+  s.time_elapsed = d.t_elapsed[ec];
+  s.status = kOk;
+  Real uf, vf;
+  wind_at_balloon<Real>(d, ec, s.x, s.y, s.pressure, s.time_elapsed, &uf, &vf);   // PRE-step lookup (all roles)
+  const double u = double(uf), v = double(vf);
+  int action = actions[ec];
+  action = action < 0 ? 0 : (action > 2 ? 2 : action);
+
+  // ---- prologue: role 0 runs the safety layers, roles 1..3 one exact sun evaluation each ----
+  Atmosphere atm;
+  SafetyState ss;
+  if (role == 0) {
+    atm = load_atmosphere(d, ec);
+    atm.incremental = true;
+    ss.sunrise_h = d.l[int64_t(L_SUNRISE_H) * d.n + ec];
+    ss.sunset = d.l[int64_t(L_SUNSET) * d.n + ec];
+    ss.last_command = action; ss.envelope_state = int((fl >> 4) & 7);
+    ss.altitude_state = int((fl >> 7) & 3); ss.power_paused = int((fl >> 9) & 1);
+    ss.power_safety_enabled = int((fl >> 10) & 1);
+    int eff = action;
+    if (ss.power_safety_enabled) {
+      eff = power_safety<double>(eff, s.date_time, s.charge, &ss.sunrise_h, &ss.sunset, &ss.power_paused);
+    }
+    eff = envelope_safety<double>(eff, s.superpressure, &ss.envelope_state);
+    double altitude, t_unused;
+    atm.at_pressure(s.pressure, &altitude, &t_unused);
+    eff = altitude_safety<double>(eff, altitude, &ss.altitude_state);
+    ex.eff[lane] = eff;
+  } else {
+    const int point = role - 1;                             // 0, 1, 2 -> t0, t0 + 90 s, t0 + 180 s
+    const double dt_s = 90.0 * point;
+    Real cz, flux;
+    SunTrack<Real>::exact(s, s.x + u * dt_s, s.y + v * dt_s, s.date_time + int64_t(90 * point), &cz, &flux);
+    ex.cz[point][lane] = cz;
+    if (point != 1) ex.flux[point >> 1][lane] = flux;
+  }
+  __syncthreads();
+  const int eff = ex.eff[lane];
+  SunTrack<Real> sun;
+  sun.c0 = ex.cz[0][lane]; sun.c1 = ex.cz[1][lane]; sun.c2 = ex.cz[2][lane];
+  sun.f0 = ex.flux[0][lane]; sun.f2 = ex.flux[1][lane];
+  const Real earth_per_area = earth_heat_per_area<Real>(s.ir);
+
+  // ---- 18 sub-steps ----
+  int n_done = 0, status = kOk;
+  Real acs_power = s.acs_power, acs_flow = s.acs_flow, solar_w = s.solar_w, load_w = s.load_w;
+#pragma unroll 1
+  for (int k = 0; k < kSubSteps; ++k) {
+    const int b = k & 1;
+    if (live) {
+      if (role == 0) {
+        double np, nt;
+        role_pressure<Real>(atm, s.pressure, s.t_ambient, s.volume, s.mols_air, double(s.mols_gas), &np, &nt);
+        ex.p[b][lane] = np; ex.tamb[b][lane] = nt;
+      } else if (role == 1) {
+        ex.dt_body[b][lane] = role_thermal_body<Real>(s.volume, s.t_internal, s.t_ambient, s.pressure, earth_per_area);
+      } else if (role == 2) {
+        double nv, nsp, nm;
+        int st;
+        role_envelope_acs<Real>(double(s.mols_gas), s.mols_air, s.t_internal, s.pressure, s.superpressure, eff,
+                                &nv, &nsp, &nm, &acs_power, &acs_flow, &st);
+        ex.vol[b][lane] = nv; ex.sp[b][lane] = nsp; ex.mols[b][lane] = nm; ex.st_env[b][lane] = st;
+      } else {
+        SunAngles<Real> ang;
+        Real flux, dts;
+        double nc;
+        int oop;
+        sun.at(s, k, &ang, &flux);
+        role_sun_power<Real>(ang, flux, s.volume, s.pressure, s.superpressure, s.charge, eff, &dts, &solar_w, &load_w,
+                             &nc, &oop, &acs_power);
+        ex.dt_solar[b][lane] = dts; ex.charge[b][lane] = nc; ex.st_pwr[b][lane] = oop;
+      }
+    }
+    __syncthreads();
+    if (live) {
+      s.pressure = ex.p[b][lane]; s.t_ambient = ex.tamb[b][lane];
+      s.t_internal = s.t_internal + double(ex.dt_body[b][lane] + ex.dt_solar[b][lane]) * double(kStrideS);
+      s.volume = ex.vol[b][lane]; s.superpressure = ex.sp[b][lane]; s.mols_air = ex.mols[b][lane];
+      s.charge = ex.charge[b][lane];
+      ++n_done;
+      const int st_env = ex.st_env[b][lane];
+      status = ex.st_pwr[b][lane] ? int(kOutOfPower) : st_env;            // later assignment wins (:541-542)
+      if (status != kOk) live = false;                                     // break (:327-328)
+    }
+  }
+
+  // ---- epilogue: each role stores what it owns ----
+  const bool stepped = valid && (fl & 3u) == uint32_t(kOk);
+  if (!stepped) return;
+  if (role == 0) {
+    DD(d, D_X, e) = s.x + u * double(kStrideS) * double(n_done);
+    DD(d, D_Y, e) = s.y + v * double(kStrideS) * double(n_done);
+    DD(d, D_P, e) = s.pressure; DD(d, D_TAMB, e) = s.t_ambient;
+    d.l[int64_t(L_DATE_TIME) * d.n + e] = s.date_time + int64_t(kStrideS) * n_done;
+    d.l[int64_t(L_SUNRISE_H) * d.n + e] = ss.sunrise_h;
+    d.l[int64_t(L_SUNSET) * d.n + e] = ss.sunset;
+    d.t_elapsed[e] = s.time_elapsed + kStrideS * n_done;
+    d.flags[e] = pack_flags(status, ss.last_command, ss.envelope_state, ss.altitude_state, ss.power_paused,
+                            ss.power_safety_enabled, atm.ok ? 0 : 1);
+    if (wind_uv != nullptr) wind_uv[e] = make_float2(uf, vf);
+  } else if (role == 1) {
+    DD(d, D_TINT, e) = s.t_internal;
+  } else if (role == 2) {
+    DD(d, D_VOL, e) = s.volume; DD(d, D_SP, e) = s.superpressure; DD(d, D_MOLS_AIR, e) = s.mols_air;
+    RR(d, R_ACS_W, e) = acs_power; RR(d, R_ACS_FLOW, e) = acs_flow;
+  } else {
+    DD(d, D_CHARGE, e) = s.charge;
+    RR(d, R_SOLAR_W, e) = solar_w; RR(d, R_LOAD_W, e) = load_w;
+    // reward on the post-step state (env/balloon_env.py:44-102)
+    s.x += u * double(kStrideS) * double(n_done);
+    s.y += v * double(kStrideS) * double(n_done);
+    s.acs_power = acs_power;
+    SunAngles<Real> ang;
+    ang.el = Real(0);
+    Real flux;
+    if (action == kDown) sun.at(s, n_done, &ang, &flux);
+    reward[e] = perciatelli_reward<Real>(s, action, ang.el);
+    done[e] = (status != kOk) ? 1 : 0;
+  }
 }
 
 // Derived BalloonState properties (env/balloon/balloon.py:217-250) for the N = 1 adaptor / features.
@@ -855,7 +1020,7 @@ struct Engine : EngineBase {
     BLE_CUDA(cudaSetDevice(device));
     rc = launch_noise(s);
     if (rc != BLE_OK) return rc;
-    k_step<Real><<<grid_for(n, 128), 128, 0, s>>>(d, actions, reward, done, reinterpret_cast<float2*>(wind_uv));
+    launch_step(actions, reward, done, reinterpret_cast<float2*>(wind_uv), s);
     ++launches;
     BLE_CUDA(cudaGetLastError());
     noise_valid = false;
@@ -942,6 +1107,17 @@ struct Engine : EngineBase {
       BLE_CUDA(cudaGetLastError());
     }
     return BLE_OK;
+  }
+
+  void launch_step(const int32_t* actions, float* reward, uint8_t* done, float2* wind_uv, cudaStream_t s) {
+    if constexpr (std::is_same<Real, float>::value) {
+      static const bool thread_kernel = [] { const char* v = std::getenv("BLE_STEP_KERNEL"); return v != nullptr && std::string(v) == "thread"; }();
+      if (!thread_kernel) {
+        k_step_ws<<<grid_for(n, 32), 128, 0, s>>>(d, actions, reward, done, wind_uv);
+        return;
+      }
+    }
+    k_step<Real><<<grid_for(n, 128), 128, 0, s>>>(d, actions, reward, done, wind_uv);
   }
 
   int features_observe(cudaStream_t s) override {

@@ -732,71 +732,117 @@ struct SunTrack {
   }
 };
 
-// One explicit-Euler sub-step (:356-549).  `el`, `flux`: sun at the OLD state; `earth_per_area`:
-// earth_heat_per_area(upwelling IR), constant over the episode.
-template <typename Real>
-BLE_HD void euler_substep(BalloonState<Real>& s, Atmosphere& atm, double u, double v, int action,
-                          const SunAngles<Real>& sun, Real flux, Real earth_per_area) {
-  const Real el = sun.el;
-  const double dt = double(kStrideS);
+// ---- one explicit-Euler sub-step (:356-549) as four independent "roles" ---------------------------------
+// Every right-hand side reads only the OLD state, so the sub-step splits into four pieces with no
+// data dependence on each other.  The single-thread path (euler_substep) calls them in sequence;
+// k_step_ws in ble_engine.cu gives each role its own warp and exchanges the results through shared
+// memory once per sub-step, which cuts the dependent instruction chain per sub-step ~5x.
 
-  // Step 2: buoyancy -> dh/dt -> dp/dt (:412-445), fp64.
-  const double rho = (s.pressure * kMAir) / (kR * s.t_ambient);
-  const double cv = double(r_cbrt(Real(s.volume)));                        // drag enters multiplicatively
+// Role P: buoyancy -> dh/dt -> dp/dt and the ambient temperature (:412-445, :457-458), fp64.
+template <typename Real>
+BLE_HD void role_pressure(Atmosphere& atm, double pressure, double t_ambient, double volume, double mols_air,
+                          double mols_gas, double* new_pressure, double* new_t_ambient) {
+  const double dt = double(kStrideS);
+  const double rho = (pressure * kMAir) / (kR * t_ambient);
+  const double cv = double(r_cbrt(Real(volume)));                          // drag enters multiplicatively
   const double drag = kCod * cv * cv;                                      // V^(2/3) :415
-  const double mass = kMHe * double(s.mols_gas) + kMAir * s.mols_air + kEnvelopeMass + kPayloadMass;
-  const double lift = rho * s.volume;
+  const double mass = kMHe * mols_gas + kMAir * mols_air + kEnvelopeMass + kPayloadMass;
+  const double lift = rho * volume;
   const double direction = (lift >= mass) ? 1.0 : -1.0;
   const double dh_dt = direction * sqrt(fabs(2 * (lift - mass) * kGravity / (rho * drag)));   // :424-427
-  double t_amb_new, dh;
-  atm.temperature_and_secant(s.pressure, direction, &t_amb_new, &dh);      // :438-441, :457-458
+  double dh;
+  atm.temperature_and_secant(pressure, direction, new_t_ambient, &dh);     // :438-441
   const double dp_dh = direction / dh;                                     // :442
-  const double new_pressure = s.pressure + dp_dh * dh_dt * dt;             // :443-445
+  *new_pressure = pressure + dp_dh * dh_dt * dt;                           // :443-445
+}
 
-  // Step 3: internal temperature (:462-467); smooth right-hand side in Real.
-  const Real p_r = Real(s.pressure);
-  const Real att = solar_attenuation_s<Real>(el, sun.sin_el, p_r);         // shared with solar_power below
-  const Real d_t = d_temperature_dt_core<Real>(Real(s.volume), Real(kEnvelopeMass), Real(s.t_internal),
-                                               Real(s.t_ambient), p_r, flux * att, earth_per_area);
-  const double new_t_internal = s.t_internal + double(d_t) * dt;
+// Role T: the sun-independent part of d_balloon_temperature_dt (thermal.py:175-230):
+// (q_earth + q_convective - q_emitted) / (c m).
+template <typename Real>
+BLE_HD Real role_thermal_body(double volume, double t_internal, double t_ambient, double pressure, Real earth_per_area) {
+  return d_temperature_dt_core<Real>(Real(volume), Real(kEnvelopeMass), Real(t_internal), Real(t_ambient),
+                                     Real(pressure), Real(0), earth_per_area);
+}
 
-  // Step 4: envelope (:470-482), fp64.
-  double new_volume, new_sp;
-  superpressure_and_volume<double>(double(s.mols_gas), s.mols_air, s.t_internal, s.pressure, &new_volume, &new_sp);
-  int status = s.status;
-  if (new_sp > kMaxSuperpressure) status = kBurst;
-  if (new_sp <= 0.0) status = kZeroPressure;
-
-  // Step 5: ACS (:487-519).
+// Role E: envelope volume / superpressure (:470-482) and the ACS (:487-519).
+template <typename Real>
+BLE_HD void role_envelope_acs(double mols_gas, double mols_air, double t_internal, double pressure, double superpressure,
+                              int action, double* new_volume, double* new_sp, double* new_mols_air,
+                              Real* acs_power_out, Real* flow_out, int* status_env) {
+  const double dt = double(kStrideS);
+  superpressure_and_volume<double>(mols_gas, mols_air, t_internal, pressure, new_volume, new_sp);
+  int status = kOk;
+  if (*new_sp > kMaxSuperpressure) status = kBurst;
+  if (*new_sp <= 0.0) status = kZeroPressure;
+  *status_env = status;
   Real acs_power = Real(0), flow = Real(0);
   if (action == kUp) {
     const Real valve_area = Real(kPi * kValveDiameter * kValveDiameter / 4.0);
-    const Real gas_density = Real((s.superpressure + s.pressure) * kMAir / (kR * s.t_internal));
-    flow = Real(-kValveCd) * valve_area * r_sqrt(Real(2) * Real(s.superpressure) * gas_density);
+    const Real gas_density = Real((superpressure + pressure) * kMAir / (kR * t_internal));
+    flow = Real(-kValveCd) * valve_area * r_sqrt(Real(2) * Real(superpressure) * gas_density);
   } else if (action == kDown) {
-    const Real pr = Real((s.pressure + fmax(s.superpressure, 0.0)) / s.pressure);   // :247-250
+    const Real pr = Real((pressure + fmax(superpressure, 0.0)) / pressure);   // :247-250
     acs_power = acs_most_efficient_power<Real>(pr);
-    flow = acs_fan_efficiency<Real>(pr, acs_power) * acs_power / Real(3600);        // acs.py:67-68
+    flow = acs_fan_efficiency<Real>(pr, acs_power) * acs_power / Real(3600);   // acs.py:67-68
   }
-  const double new_mols_air = fmax(s.mols_air + (double(flow) / kMAir) * dt, 0.0);
+  *new_mols_air = fmax(mols_air + (double(flow) / kMAir) * dt, 0.0);
+  *acs_power_out = acs_power;
+  *flow_out = flow;
+}
 
-  // Step 6: power (:524-542).
-  const bool is_day = el > Real(kMinSolarElDeg);
+// Role S: everything that needs the sun -- the solar part of dT/dt and the power system (:524-542).
+// `acs_power` is the power role E chose for this sub-step (a pure function of the old state, so
+// role S recomputes it instead of waiting for role E).
+template <typename Real>
+BLE_HD void role_sun_power(const SunAngles<Real>& sun, Real flux, double volume, double pressure, double superpressure,
+                           double charge, int action, Real* d_t_solar, Real* solar_w_out, Real* load_w_out,
+                           double* new_charge, int* out_of_power, Real* acs_power_out = nullptr) {
+  const Real p_r = Real(pressure);
+  const Real att = solar_attenuation_s<Real>(sun.el, sun.sin_el, p_r);
+  const Real radius = r_cbrt(Real(3) * Real(volume) / Real(4 * kPi));
+  const Real area = Real(4 * kPi) * radius * radius;
+  *d_t_solar = (flux * att) * Real(0.25) * area * total_absorptivity<Real>(Real(0.01435)) /
+               (Real(1500) * Real(kEnvelopeMass));
+  Real acs_power = Real(0);
+  if (action == kDown) acs_power = acs_most_efficient_power<Real>(Real((pressure + fmax(superpressure, 0.0)) / pressure));
+  const bool is_day = sun.el > Real(kMinSolarElDeg);
   const Real solar_w = is_day ? solar_power_sc<Real>(sun, att) : Real(0);
   const Real load_w = (is_day ? Real(kDayLoadW) : Real(kNightLoadW)) + acs_power;
-  double charge = s.charge + double(solar_w - load_w) * (double(kStrideS) / 3600.0);
-  charge = fmin(fmax(charge, 0.0), kBatteryCapacityWh);
-  if (charge <= 0.0) status = kOutOfPower;
+  double c = charge + double(solar_w - load_w) * (double(kStrideS) / 3600.0);
+  c = fmin(fmax(c, 0.0), kBatteryCapacityWh);
+  *new_charge = c;
+  *out_of_power = (c <= 0.0) ? 1 : 0;
+  *solar_w_out = solar_w;
+  *load_w_out = load_w;
+  if (acs_power_out != nullptr) *acs_power_out = acs_power;
+}
 
+// The four roles in sequence = one sub-step for one thread.
+template <typename Real>
+BLE_HD void euler_substep(BalloonState<Real>& s, Atmosphere& atm, double u, double v, int action,
+                          const SunAngles<Real>& sun, Real flux, Real earth_per_area) {
+  const double dt = double(kStrideS);
+  double new_pressure, new_t_ambient, new_volume, new_sp, new_mols_air, new_charge;
+  Real acs_power, flow, d_t_solar, solar_w, load_w;
+  int status_env, out_of_power;
+  role_pressure<Real>(atm, s.pressure, s.t_ambient, s.volume, s.mols_air, double(s.mols_gas), &new_pressure, &new_t_ambient);
+  const Real d_t_body = role_thermal_body<Real>(s.volume, s.t_internal, s.t_ambient, s.pressure, earth_per_area);
+  role_envelope_acs<Real>(double(s.mols_gas), s.mols_air, s.t_internal, s.pressure, s.superpressure, action,
+                          &new_volume, &new_sp, &new_mols_air, &acs_power, &flow, &status_env);
+  role_sun_power<Real>(sun, flux, s.volume, s.pressure, s.superpressure, s.charge, action, &d_t_solar, &solar_w,
+                       &load_w, &new_charge, &out_of_power);
+  int status = s.status;
+  if (status_env != kOk) status = status_env;
+  if (out_of_power) status = kOutOfPower;                                  // later assignment wins (:541-542)
   s.x += u * dt;                                                           // :394-395
   s.y += v * dt;
   s.pressure = new_pressure;
-  s.t_ambient = t_amb_new;
-  s.t_internal = new_t_internal;
+  s.t_ambient = new_t_ambient;
+  s.t_internal = s.t_internal + double(d_t_body + d_t_solar) * dt;         // :462-467
   s.volume = new_volume;
   s.superpressure = new_sp;
   s.mols_air = new_mols_air;
-  s.charge = charge;
+  s.charge = new_charge;
   s.acs_power = acs_power;
   s.acs_flow = flow;
   s.solar_w = solar_w;

@@ -162,10 +162,13 @@ def run_b200(args):
   n = end - begin
 
   with_obs = args.observation == 'perciatelli'
-  arena = batched_env.BatchedBalloonArena(n, device=str(device), precision='fp32', wind_model='grid', enable_noise=True,
-                                          field_layout=args.field_layout, enable_features=True)
-  obs_buf = torch.empty(n, 1099, dtype=torch.float32, device=device)
   n_fields = n if args.shared_fields == 0 else args.shared_fields
+  layout = args.field_layout
+  if layout == 'auto':      # one 128-byte line per lookup while the bank stays inside the ~64 GB TLB reach
+    layout = 'x128' if n_fields * 3686400 <= 60e9 else 'x64'
+  arena = batched_env.BatchedBalloonArena(n, device=str(device), precision='fp32', wind_model='grid', enable_noise=True,
+                                          field_layout=layout, enable_features=True)
+  obs_buf = torch.empty(n, 1099, dtype=torch.float32, device=device)
   upload_synthetic_fields(torch, arena, n_fields, device, seed=1234 + rank)
   arena.set_field_map(torch.arange(n, dtype=torch.int32, device=device) % n_fields)
   torch.cuda.empty_cache()
@@ -244,7 +247,10 @@ def run_b200(args):
   xyzt = torch.empty(m, 4, dtype=torch.float32, device=device)
   xyzt[:, 0].uniform_(-500, 500, generator=gq); xyzt[:, 1].uniform_(-500, 500, generator=gq)
   xyzt[:, 2].uniform_(5000, 14000, generator=gq); xyzt[:, 3].uniform_(0, 48, generator=gq)
-  fidx = (torch.randperm(m, device=device, generator=gq) % n_fields).to(torch.int32)
+  # lookups grouped by balloon/field (the order every caller of the path issues them in: a balloon
+  # queries its own field); the random-field order is measured separately below
+  per_field = max(1, m // n_fields)
+  fidx = torch.clamp(torch.arange(m, device=device) // per_field, max=n_fields - 1).to(torch.int32)
   for _ in range(3):
     arena.wind_forecast(xyzt, fidx)
   torch.cuda.synchronize()
@@ -257,6 +263,17 @@ def run_b200(args):
   torch.cuda.synchronize()
   gather_ms = g0.elapsed_time(g1) / reps
   gather_gbs = GATHER_BYTES_PER_LOOKUP * m / (gather_ms * 1e-3) / 1e9
+  fidx_rand = (torch.randperm(m, device=device, generator=gq) % n_fields).to(torch.int32)
+  for _ in range(2):
+    arena.wind_forecast(xyzt, fidx_rand)
+  torch.cuda.synchronize()
+  g0.record()
+  for _ in range(reps):
+    arena.wind_forecast(xyzt, fidx_rand)
+  g1.record()
+  torch.cuda.synchronize()
+  gather_rand_ms = g0.elapsed_time(g1) / reps
+  gather_rand_gbs = GATHER_BYTES_PER_LOOKUP * m / (gather_rand_ms * 1e-3) / 1e9
 
   stats = sharding.reduce_run_stats(ms, n * args.steps, launches, device=device)
   ms, launches = stats['elapsed_ms'], stats['launches']
@@ -275,7 +292,7 @@ def run_b200(args):
       'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': f'batch={n_total} balloons, random agent, one synthetic wind field per balloon '
                              f'({n_fields} fields/GPU) + simplex noise, 18 sub-steps per step (BASELINE configs[2])',
-                 'num_envs': n_total, 'envs_per_gpu': n, 'fields_per_gpu': n_fields, 'field_layout': args.field_layout,
+                 'num_envs': n_total, 'envs_per_gpu': n, 'fields_per_gpu': n_fields, 'field_layout': layout,
                  'l2': 'inputs larger than L2 (per-balloon fields + 2.5 KB noise tables per balloon)',
                  'observation': args.observation, 'live_fraction_after_run': live_frac},
       'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 4 * n_total,
@@ -286,7 +303,13 @@ def run_b200(args):
       'clocks': clocks,
       'roofline': {'kernel': 'k_wind_gather', 'bound': 'hbm', 'achieved': gather_gbs, 'peak': peak, 'unit': 'GB/s',
                    'frac': gather_gbs / peak, 'traffic': None, 'peak_source': peak_src,
-                   'lookups_per_launch': m, 'bytes_per_lookup': GATHER_BYTES_PER_LOOKUP, 'ms_per_launch': gather_ms},
+                   'lookups_per_launch': m, 'bytes_per_lookup': GATHER_BYTES_PER_LOOKUP, 'ms_per_launch': gather_ms,
+                   'access': f'{m} uniformly random (x, y, p, t) points, grouped by field ({per_field} per field, '
+                             f'{n_fields} fields, layout {layout})',
+                   'random_field_order': {'achieved': gather_rand_gbs, 'frac': gather_rand_gbs / peak,
+                                          'ms_per_launch': gather_rand_ms,
+                                          'note': 'same lookups with the field chosen at random per lookup; above a '
+                                                  '~64 GB field bank this is TLB-miss bound (DESIGN.md section 4)'}},
   }
   if obs_ms is not None:
     line['with_perciatelli_observation'] = {'ms_per_step': obs_ms, 'value': n_total / (obs_ms * 1e-3), 'unit': UNIT,
@@ -313,7 +336,7 @@ def main():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--num-envs', type=int, default=65536)
   ap.add_argument('--shared-fields', type=int, default=0, help='0 = one field per balloon; else size of a shared pool')
-  ap.add_argument('--field-layout', default='x64', choices=['x64', 'x128'])
+  ap.add_argument('--field-layout', default='auto', choices=['auto', 'x64', 'x128'])
   ap.add_argument('--observation', default='none', choices=['none', 'perciatelli'],
                   help="'perciatelli': every step also computes the 1099-feature observation")
   ap.add_argument('--observation-probe', type=int, default=10,
