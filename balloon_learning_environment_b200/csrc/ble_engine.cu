@@ -437,7 +437,7 @@ struct WsExchange {
   float cz[3][32], flux[2][32];
 };
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_step_ws(DevState<float> d, const int32_t* __restrict__ actions, float* __restrict__ reward,
           uint8_t* __restrict__ done, float2* __restrict__ wind_uv) {
   using Real = float;
@@ -1111,8 +1111,12 @@ struct Engine : EngineBase {
 
   void launch_step(const int32_t* actions, float* reward, uint8_t* done, float2* wind_uv, cudaStream_t s) {
     if constexpr (std::is_same<Real, float>::value) {
-      static const bool thread_kernel = [] { const char* v = std::getenv("BLE_STEP_KERNEL"); return v != nullptr && std::string(v) == "thread"; }();
-      if (!thread_kernel) {
+      // k_step_ws needs 4 threads per balloon: at 128 registers an SM holds 4 blocks = 128 balloons, so
+      // one wave covers 148 * 128 = 18,944 balloons.  Below that it is ~2x faster than one thread per
+      // balloon (shorter dependent chain); above it the extra waves cost more than they save.
+      static const std::string forced = [] { const char* v = std::getenv("BLE_STEP_KERNEL"); return std::string(v ? v : ""); }();
+      const bool use_ws = forced == "ws" || (forced != "thread" && n <= int64_t(148) * 128);
+      if (use_ws) {
         k_step_ws<<<grid_for(n, 32), 128, 0, s>>>(d, actions, reward, done, wind_uv);
         return;
       }
