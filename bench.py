@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 METRIC = 'env_steps_per_s'
 UNIT = 'env-steps/s'
 GATHER_BYTES_PER_LOOKUP = 156        # 16 B query + 4 B field index + 128 B corners + 8 B result
+# DRAM bytes per k_wind_gather launch from the `ncu --set full` capture of the same launch shape
+# (dram__bytes_read.sum + dram__bytes_write.sum); key = (field layout, lookups per launch).
+NCU_GATHER_TRAFFIC = {('x64', 1 << 24): 3.685e9}
 
 
 def load_peaks():
@@ -275,6 +278,30 @@ def run_b200(args):
   gather_rand_ms = g0.elapsed_time(g1) / reps
   gather_rand_gbs = GATHER_BYTES_PER_LOOKUP * m / (gather_rand_ms * 1e-3) / 1e9
 
+  # ---- reset path: per-episode cost, not part of `value` -----------
+  del xyzt, fidx, fidx_rand
+  torch.cuda.empty_cache()
+  r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  seeds2 = torch.randint(0, 2**62, (n,), dtype=torch.int64, generator=g)
+  arena.reset(seeds2); torch.cuda.synchronize()
+  r0.record(); arena.reset(seeds2); r1.record(); torch.cuda.synchronize()
+  reset_ms = r0.elapsed_time(r1)
+  gw = torch.Generator(device=device); gw.manual_seed(5 + rank)
+  dims = [64, 1000, 1000, 1000, 4410]
+  arena.set_decoder({f'Dense_{i}': {'kernel': (torch.randn(dims[i], dims[i + 1], generator=gw, device=device)
+                                               * (2.0 / dims[i]) ** 0.5).cpu().numpy(),
+                                    'bias': np.zeros(dims[i + 1], np.float32)} for i in range(4)})
+  z = torch.randn(2048, 64, generator=gw, device=device)
+  arena.decode_wind_fields(z); torch.cuda.synchronize()
+  r0.record(); arena.decode_wind_fields(z); r1.record(); torch.cuda.synchronize()
+  decode_ms = r0.elapsed_time(r1)
+  del z
+  reset_path = {'reset_ms': reset_ms, 'balloons': n,
+                'what': 'ble_reset: Philox sampling, stable init, sunrise/sunset search, 10 noise permutation tables per balloon',
+                'decoder_fields_per_s': 2048 / (decode_ms * 1e-3), 'decoder_batch': 2048,
+                'decoder': 'ble_decode_fields: 4 cuBLASLt fp32 GEMMs (64-1000-1000-1000-4410) + resize/curl epilogue, '
+                           'random-init weights'}
+
   stats = sharding.reduce_run_stats(ms, n * args.steps, launches, device=device)
   ms, launches = stats['elapsed_ms'], stats['launches']
   e2e_s = sharding.reduce_run_stats(e2e_s * 1e3, 0, 0, device=device)['elapsed_ms'] * 1e-3
@@ -302,7 +329,9 @@ def run_b200(args):
       'gpu_launches': launches,
       'clocks': clocks,
       'roofline': {'kernel': 'k_wind_gather', 'bound': 'hbm', 'achieved': gather_gbs, 'peak': peak, 'unit': 'GB/s',
-                   'frac': gather_gbs / peak, 'traffic': None, 'peak_source': peak_src,
+                   'frac': gather_gbs / peak, 'traffic': NCU_GATHER_TRAFFIC.get((layout, m)),
+                   'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, '
+                                   'profiles/r01_prof2_k_wind_gather_details.txt)', 'peak_source': peak_src,
                    'lookups_per_launch': m, 'bytes_per_lookup': GATHER_BYTES_PER_LOOKUP, 'ms_per_launch': gather_ms,
                    'access': f'{m} uniformly random (x, y, p, t) points, grouped by field ({per_field} per field, '
                              f'{n_fields} fields, layout {layout})',
@@ -311,6 +340,7 @@ def run_b200(args):
                                           'note': 'same lookups with the field chosen at random per lookup; above a '
                                                   '~64 GB field bank this is TLB-miss bound (DESIGN.md section 4)'}},
   }
+  line['reset_path'] = reset_path
   if obs_ms is not None:
     line['with_perciatelli_observation'] = {'ms_per_step': obs_ms, 'value': n_total / (obs_ms * 1e-3), 'unit': UNIT,
                                             'steps': args.observation_probe,
