@@ -27,11 +27,15 @@ I_ROWS = ('date_time', 'time_elapsed', 'last_command', 'status', 'envelope_state
 D_ROWS = ('lat', 'lng', 'solar_elevation', 'solar_flux', 'excess_energy', 'navigation_is_paused',
           'pressure_ratio', 'battery_soc', 'altitude')
 
+E_ROWS = ('cumulative_reward', 'time_within_radius', 'out_of_power', 'envelope_burst', 'zeropressure',
+          'final_timestep', 'active')           # BLE_E_* of include/ble_b200.h
 EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_upload_fields',
            'ble_alloc_fields', 'ble_write_fields', 'ble_set_field_map', 'ble_set_decoder', 'ble_decode_fields',
            'ble_set_noise', 'ble_state_upload', 'ble_state_download', 'ble_reset', 'ble_init_derived',
            'ble_step', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_derived',
            'ble_features_perciatelli', 'ble_features_observe', 'ble_features_clear',
+           'ble_generate_fields', 'ble_agent_station_seeker', 'ble_agent_random_walk',
+           'ble_eval_begin', 'ble_eval_accumulate', 'ble_eval_results',
            'ble_launch_count')
 
 
@@ -91,6 +95,12 @@ def load(build_if_missing=True):
   lib.ble_features_perciatelli.argtypes = [vp, vp, vp]
   lib.ble_features_observe.argtypes = [vp, vp]
   lib.ble_features_clear.argtypes = [vp, vp]
+  lib.ble_generate_fields.argtypes = [vp, vp, i64, i64, vp]
+  lib.ble_agent_station_seeker.argtypes = [vp, vp, vp, vp, vp]
+  lib.ble_agent_random_walk.argtypes = [vp, vp, vp, i32, vp, vp]
+  lib.ble_eval_begin.argtypes = [vp, vp]
+  lib.ble_eval_accumulate.argtypes = [vp, vp, vp, vp]
+  lib.ble_eval_results.argtypes = [vp, vp, vp]
   for name in EXPORTS:
     if name not in ('ble_last_error', 'ble_num_envs', 'ble_launch_count'):
       getattr(lib, name).restype = _c.c_int

@@ -167,6 +167,55 @@ class BatchedBalloonArena:
       z = torch.randn(c, 64, generator=g, device=self.device, dtype=torch.float32)
       self.write_wind_fields(self.decode_wind_fields(z), first)
 
+  def sample_wind_fields(self, seeds: torch.Tensor, first_field: int = 0) -> None:
+    """GenerativeWindFieldSampler.sample_field for one seed per field: Philox(seed) latents -> decoder ->
+    fields [first_field, first_field + len(seeds)) of the bank (call alloc_wind_fields first)."""
+    seeds = seeds.to(self.device, torch.int64).contiguous()
+    rc = self._lib.ble_generate_fields(self._h, _ptr(seeds), int(first_field), seeds.numel(), self._stream())
+    self._check(rc, 'ble_generate_fields')
+
+  # -- evaluation surface (eval/eval_lib.py, agents/) ----------------------------------------------
+  def station_seeker_actions(self, obs: torch.Tensor, with_level: bool = False):
+    """StationSeekerAgent.pick_action for all balloons: obs float32 [N,1099] -> int32 [N]."""
+    obs = self._check_obs(obs)
+    actions = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+    best = torch.empty(self.num_envs, dtype=torch.int32, device=self.device) if with_level else None
+    rc = self._lib.ble_agent_station_seeker(self._h, _ptr(obs), _ptr(actions), _ptr(best), self._stream())
+    self._check(rc, 'ble_agent_station_seeker')
+    return (actions, best) if with_level else actions
+
+  def random_walk_actions(self, obs: torch.Tensor, seeds: torch.Tensor, step_index: int) -> torch.Tensor:
+    """RandomWalkAgent: step_index 0 = begin_episode, k = k-th step; seeds int64 [N]."""
+    obs = self._check_obs(obs)
+    seeds = seeds.to(self.device, torch.int64).contiguous()
+    if seeds.numel() != self.num_envs:
+      raise ValueError('seeds must have one entry per balloon')
+    actions = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+    rc = self._lib.ble_agent_random_walk(self._h, _ptr(obs), _ptr(seeds), int(step_index), _ptr(actions), self._stream())
+    self._check(rc, 'ble_agent_random_walk')
+    return actions
+
+  def _check_obs(self, obs: torch.Tensor) -> torch.Tensor:
+    if obs.shape != (self.num_envs, 1099):
+      raise ValueError(f'obs must be [{self.num_envs}, 1099]')
+    return obs.to(self.device, torch.float32).contiguous()
+
+  def eval_begin(self) -> None:
+    self._check(self._lib.ble_eval_begin(self._h, self._stream()), 'ble_eval_begin')
+
+  def eval_accumulate(self, reward: torch.Tensor, flight_path: Optional[torch.Tensor] = None) -> None:
+    """One pass of eval_agent's loop body after a step; flight_path: float32 [6, N] slot or None."""
+    if flight_path is not None and (flight_path.shape != (6, self.num_envs) or flight_path.dtype != torch.float32
+                                    or not flight_path.is_contiguous()):
+      raise ValueError('flight_path must be a contiguous float32 [6, N] tensor')
+    rc = self._lib.ble_eval_accumulate(self._h, _ptr(reward), _ptr(flight_path), self._stream())
+    self._check(rc, 'ble_eval_accumulate')
+
+  def eval_results(self) -> Dict[str, torch.Tensor]:
+    out = torch.empty(len(_lib.E_ROWS), self.num_envs, dtype=torch.float64, device=self.device)
+    self._check(self._lib.ble_eval_results(self._h, _ptr(out), self._stream()), 'ble_eval_results')
+    return {k: out[i] for i, k in enumerate(_lib.E_ROWS)}
+
   def set_wind_noise(self, seeds: torch.Tensor, offsets: torch.Tensor):
     """seeds int64 [N,2,5], offsets float32 [N,2,5,4] (env/simplex_wind_noise.py:98-114)."""
     seeds = seeds.to(self.device, torch.int64).contiguous()
@@ -302,7 +351,11 @@ class BatchedBalloonEnv:
   def __init__(self, num_envs: int, *, device: str = 'cuda:0', precision: str = 'fp32',
                wind_model: str = 'grid', enable_noise: bool = True, seed: int = 0,
                arena: Optional[BatchedBalloonArena] = None, observation: Optional[str] = None,
-               field_layout: str = 'x64'):
+               field_layout: str = 'x64', decoder_params=None):
+    """decoder_params (the flax tree of offlineskies22_decoder.msgpack['params']) switches the wind source
+    to the reference's default GenerativeWindFieldSampler: every reset decodes one new field per balloon
+    from that balloon's seed (env/generative_wind_field.py:52-62).  Without it the fields are whatever was
+    loaded with arena.set_wind_fields / write_wind_fields."""
     if observation not in (None, 'perciatelli'):
       raise ValueError("observation must be None or 'perciatelli'")
     self.arena = arena if arena is not None else BatchedBalloonArena(
@@ -317,6 +370,11 @@ class BatchedBalloonEnv:
                  if observation == 'perciatelli' else None)
     self._generator = torch.Generator(device='cpu')
     self.seed(seed)
+    self._generative = decoder_params is not None
+    if self._generative:
+      self.arena.set_decoder(decoder_params)
+      self.arena.alloc_wind_fields(self.num_envs)
+      self.arena.set_field_map(torch.arange(self.num_envs, dtype=torch.int32, device=self.device))
 
   @property
   def action_space(self) -> Discrete:
@@ -333,10 +391,18 @@ class BatchedBalloonEnv:
   def seed(self, seed: int) -> None:
     self._generator.manual_seed(int(seed))
 
-  def reset(self, *, seed: Optional[int] = None):
+  def reset(self, *, seed: Optional[int] = None, seeds: Optional[torch.Tensor] = None):
+    """seed: reseeds the stream the per-balloon seeds are drawn from (BalloonEnv.seed + reset);
+    seeds: int64 [N], one explicit episode seed per balloon (an evaluation suite's seeds)."""
     if seed is not None:
       self.seed(seed)
-    seeds = torch.randint(0, 2**62, (self.num_envs,), dtype=torch.int64, generator=self._generator)
+    if seeds is None:
+      seeds = torch.randint(0, 2**62, (self.num_envs,), dtype=torch.int64, generator=self._generator)
+    seeds = torch.as_tensor(seeds, dtype=torch.int64)
+    if seeds.numel() != self.num_envs:
+      raise ValueError('seeds must have one entry per balloon')
+    if self._generative:
+      self.arena.sample_wind_fields(seeds)
     self.arena.reset(seeds)
     return self._observe()
 

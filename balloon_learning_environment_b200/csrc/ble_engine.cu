@@ -16,6 +16,7 @@
 #include "../../include/ble_b200.h"
 #include "ble_physics.cuh"
 #include "ble_wind.cuh"
+#include "ble_agents.cuh"
 #include "ble_features.cuh"
 
 namespace ble {
@@ -615,6 +616,95 @@ __global__ void __launch_bounds__(128) k_derived(DevState<Real> d, double* __res
 #include "ble_decoder.cuh"
 
 // ---------------------------------------------------------------------------------------------
+// Evaluation surface (eval/eval_lib.py:123-211, agents/station_seeker_agent.py:72-113)
+// ---------------------------------------------------------------------------------------------
+// One warp per balloon: lanes score levels lane, lane + 32, ... of the 361-level column, then the
+// warp reduces to the FIRST level holding the largest score (the reference's strict '>' scan).
+__global__ void __launch_bounds__(128)
+k_agent_station_seeker(const float* __restrict__ obs, int64_t n, int32_t* __restrict__ actions,
+                       int32_t* __restrict__ best_level) {
+  const int64_t e = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = int(threadIdx.x & 31u);
+  if (e >= n) return;
+  const float* o = obs + e * int64_t(kNumFeatures);
+  const SeekerDistanceTerms t = seeker_distance_terms(o[7]);
+  double score = 0.0;
+  int best = kColumnLevels;
+  for (int l = lane; l < kColumnLevels; l += 32) {
+    const float w0 = o[16 + 3 * l], w1 = o[17 + 3 * l], w2 = o[18 + 3 * l];
+    if (!level_is_valid(w0, w1, w2)) continue;
+    const double sc = seeker_altitude_score(t, w0, w1, w2, l);
+    if (sc > score) { score = sc; best = l; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double os = __shfl_down_sync(0xffffffffu, score, off);
+    const int ob = __shfl_down_sync(0xffffffffu, best, off);
+    if (os > score || (os == score && ob < best)) { score = os; best = ob; }
+  }
+  if (lane == 0) {
+    const bool none = best >= kColumnLevels;       // the reference asserts here (:109-110); callers check best < 0
+    actions[e] = none ? 1 : seeker_action_for_level(best);
+    if (best_level != nullptr) best_level[e] = none ? -1 : best;
+  }
+}
+
+// RandomWalkAgent (agents/random_walk_agent.py:35-94): the target pressure performs a Gaussian random
+// walk whose step grows with the time elapsed in the episode (:82-90); Philox replaces jax.random.
+struct EvalBuffers { double* reward; int32_t* within; int32_t* steps; uint8_t* active; };
+
+template <typename Real>
+__global__ void __launch_bounds__(128) k_eval_begin(DevState<Real> d, EvalBuffers ev) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  ev.reward[e] = 0.0; ev.within[e] = 0; ev.steps[e] = 0;
+  ev.active[e] = (d.flags[e] & 3u) == uint32_t(kOk) ? 1 : 0;
+}
+
+// One pass of eval_agent's loop body (:166-185) for every balloon still flying: reward sum, steps within
+// the station-keeping radius (:119-121), step count, flight-path sample (:64-80), stop at a terminal state.
+template <typename Real>
+__global__ void __launch_bounds__(128)
+k_eval_accumulate(DevState<Real> d, EvalBuffers ev, const float* __restrict__ reward, double radius_m,
+                  float* __restrict__ path /* [6][n] or nullptr */) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  const bool live = ev.active[e] != 0;
+  const double x = DD(d, D_X, e), y = DD(d, D_Y, e);
+  if (path != nullptr) {
+    const int64_t n = d.n;
+    const float nanv = __int_as_float(0x7fc00000);
+    path[0 * n + e] = live ? float(x * 1e-3) : nanv;
+    path[1 * n + e] = live ? float(y * 1e-3) : nanv;
+    path[2 * n + e] = live ? float(DD(d, D_P, e)) : nanv;
+    path[3 * n + e] = live ? float(DD(d, D_SP, e)) : nanv;
+    path[4 * n + e] = live ? float(d.t_elapsed[e]) : nanv;
+    path[5 * n + e] = live ? float(DD(d, D_CHARGE, e) / kBatteryCapacityWh) : nanv;
+  }
+  if (!live) return;
+  ev.reward[e] += double(reward[e]);
+  ev.within[e] += (sqrt(x * x + y * y) <= radius_m) ? 1 : 0;
+  ev.steps[e] += 1;
+  if ((d.flags[e] & 3u) != uint32_t(kOk)) ev.active[e] = 0;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128) k_eval_results(DevState<Real> d, EvalBuffers ev, double* __restrict__ out) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  const int64_t n = d.n;
+  const uint32_t status = d.flags[e] & 3u;
+  const int steps = ev.steps[e];
+  out[int64_t(BLE_E_CUMULATIVE_REWARD) * n + e] = ev.reward[e];
+  out[int64_t(BLE_E_TIME_WITHIN_RADIUS) * n + e] = steps > 0 ? double(ev.within[e]) / double(steps) : 0.0;
+  out[int64_t(BLE_E_OUT_OF_POWER) * n + e] = status == uint32_t(kOutOfPower) ? 1.0 : 0.0;
+  out[int64_t(BLE_E_ENVELOPE_BURST) * n + e] = status == uint32_t(kBurst) ? 1.0 : 0.0;
+  out[int64_t(BLE_E_ZEROPRESSURE) * n + e] = status == uint32_t(kZeroPressure) ? 1.0 : 0.0;
+  out[int64_t(BLE_E_FINAL_TIMESTEP) * n + e] = double(steps);
+  out[int64_t(BLE_E_ACTIVE) * n + e] = ev.active[e] ? 1.0 : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Reset (env/balloon_arena.py:161-182,228-268; utils/sampling.py:37-152)
 // ---------------------------------------------------------------------------------------------
 struct Philox {          // Philox4x32-10, one stream per (seed, balloon)
@@ -707,7 +797,7 @@ k_reset(DevState<Real> d, const uint64_t* __restrict__ seeds, const uint8_t* __r
   if (e >= d.n) return;
   if (mask != nullptr && mask[e] == 0) return;
   Philox rng;
-  rng.init(seeds[e], uint64_t(e));
+  rng.init(seeds[e], 0);            // the episode is a function of its seed alone (eval suites shard by seed)
   // Atmosphere.reset: alpha ~ U(0,1)  (standard_atmosphere.py:82)
   const double alpha = rng.uniform();
   // sampling.sample_time: uniform second in [2011-01-01, 2014-12-31)  (utils/sampling.py:65-83)
@@ -752,6 +842,33 @@ k_reset(DevState<Real> d, const uint64_t* __restrict__ seeds, const uint8_t* __r
   }
 }
 
+// GenerativeWindFieldSampler.sample_field (env/generative_wind_field.py:52-62): z ~ N(0, I_64) per seed.
+__global__ void __launch_bounds__(256)
+k_sample_latents(const uint64_t* __restrict__ seeds, int64_t count, float* __restrict__ latents /*[count,64]*/) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= count * kDecLatents) return;
+  Philox rng;
+  rng.init(seeds[i / kDecLatents], 1 + uint64_t(i % kDecLatents));        // stream 0 belongs to k_reset
+  latents[i] = float(rng.normal());
+}
+
+// RandomWalkAgent (agents/random_walk_agent.py:35-94): begin_episode draws the target pressure
+// (sampling.sample_pressure without atmosphere: U(6500, 11400), utils/sampling.py:84-111); every later
+// step adds time_elapsed_s * 0.1666 * N(0, 1) (:82-90).  Philox keyed by (seed, step) replaces jax.random.
+__global__ void __launch_bounds__(128)
+k_agent_random_walk(const float* __restrict__ obs, int64_t n, double* __restrict__ target,
+                    const uint64_t* __restrict__ seeds, int32_t step_index, int32_t* __restrict__ actions) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= n) return;
+  Philox rng;
+  rng.init(seeds[e], (uint64_t(1) << 32) + uint64_t(step_index));
+  double t;
+  if (step_index == 0) t = 6500.0 + (11400.0 - 6500.0) * rng.uniform();
+  else t = target[e] + double(step_index) * kAgentStepS * 0.1666 * rng.normal();
+  target[e] = t;
+  actions[e] = random_walk_action(obs[e * int64_t(kNumFeatures)], t);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-side engine
 // ---------------------------------------------------------------------------------------------
@@ -773,6 +890,12 @@ struct EngineBase {
   virtual int derived(double*, cudaStream_t) = 0;
   virtual int set_decoder(const float* const*, const float* const*, cudaStream_t) = 0;
   virtual int decode(const float*, int64_t, float*, cudaStream_t) = 0;
+  virtual int generate_fields(const uint64_t*, int64_t, int64_t, cudaStream_t) = 0;
+  virtual int agent_station_seeker(const float*, int32_t*, int32_t*, cudaStream_t) = 0;
+  virtual int agent_random_walk(const float*, const uint64_t*, int32_t, int32_t*, cudaStream_t) = 0;
+  virtual int eval_begin(cudaStream_t) = 0;
+  virtual int eval_accumulate(const float*, float*, cudaStream_t) = 0;
+  virtual int eval_results(double*, cudaStream_t) = 0;
   virtual int features_observe(cudaStream_t) = 0;
   virtual int features(float*, cudaStream_t) = 0;
   virtual int features_clear(const uint8_t*, cudaStream_t) = 0;
@@ -811,6 +934,11 @@ struct Engine : EngineBase {
   cublasLtHandle_t lt = nullptr;
   bool have_decoder = false;
   static constexpr int64_t kDecChunk = 4096;
+  static constexpr int64_t kGenChunk = 512;                 // fields decoded per pass of generate_fields
+  float* gen_latents = nullptr; float* gen_fields = nullptr;
+  // evaluation surface
+  EvalBuffers ev{nullptr, nullptr, nullptr, nullptr};
+  double* walk_target = nullptr;
   static constexpr size_t kDecWorkspace = size_t(32) << 20;
   // ble_step_host staging
   int32_t* h_actions = nullptr; float* h_reward = nullptr; uint8_t* h_done = nullptr;
@@ -867,6 +995,8 @@ struct Engine : EngineBase {
     cudaFree(dec_act[0]); cudaFree(dec_act[1]); cudaFree(dec_workspace);
     if (lt != nullptr) cublasLtDestroy(lt);
     cudaFree(gp_obs); cudaFree(gp_count); cudaFree(gp_chol); cudaFree(gp_m); cudaFree(feat_range);
+    cudaFree(gen_latents); cudaFree(gen_fields);
+    cudaFree(ev.reward); cudaFree(ev.within); cudaFree(ev.steps); cudaFree(ev.active); cudaFree(walk_target);
     cudaFree(d_actions); cudaFree(d_reward); cudaFree(d_done);
     cudaFreeHost(h_actions); cudaFreeHost(h_reward); cudaFreeHost(h_done);
   }
@@ -1109,6 +1239,92 @@ struct Engine : EngineBase {
     return BLE_OK;
   }
 
+  // sample_field for `count` seeds straight into the field bank: latents -> decoder -> lookup windows
+  int generate_fields(const uint64_t* seeds, int64_t first, int64_t count, cudaStream_t s) override {
+    if (seeds == nullptr || first < 0 || count <= 0 || first + count > n_fields) {
+      err = "generate_fields: range outside the allocated fields (call ble_alloc_fields first)";
+      return BLE_ERR_INVALID_ARGUMENT;
+    }
+    if (!have_decoder) { err = "generate_fields: no decoder weights (call ble_set_decoder first)"; return BLE_ERR_NOT_READY; }
+    BLE_CUDA(cudaSetDevice(device));
+    if (gen_latents == nullptr) {
+      BLE_CUDA(cudaMalloc(&gen_latents, sizeof(float) * kGenChunk * kDecLatents));
+      BLE_CUDA(cudaMalloc(&gen_fields, sizeof(float) * kGenChunk * size_t(kFieldFloats)));
+    }
+    for (int64_t done_f = 0; done_f < count; done_f += kGenChunk) {
+      const int64_t c = std::min<int64_t>(kGenChunk, count - done_f);
+      // The GEMMs always run on a full chunk (zero latents beyond c) so that cuBLASLt picks the same
+      // algorithm whatever the batch: a seed's field is then bit-identical however a suite is sharded.
+      if (c < kGenChunk) BLE_CUDA(cudaMemsetAsync(gen_latents, 0, sizeof(float) * kGenChunk * kDecLatents, s));
+      k_sample_latents<<<grid_for(c * kDecLatents, 256), 256, 0, s>>>(seeds + done_f, c, gen_latents);
+      ++launches;
+      BLE_CUDA(cudaGetLastError());
+      int rc = decode(gen_latents, kGenChunk, gen_fields, s);
+      if (rc == BLE_OK) rc = write_fields(gen_fields, first + done_f, c, s);
+      if (rc != BLE_OK) return rc;
+    }
+    return BLE_OK;
+  }
+
+  int agent_station_seeker(const float* obs, int32_t* actions, int32_t* best, cudaStream_t s) override {
+    if (obs == nullptr || actions == nullptr) { err = "agent_station_seeker: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    BLE_CUDA(cudaSetDevice(device));
+    k_agent_station_seeker<<<grid_for(n * 32, 128), 128, 0, s>>>(obs, n, actions, best);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
+  int agent_random_walk(const float* obs, const uint64_t* seeds, int32_t step_index, int32_t* actions, cudaStream_t s) override {
+    if (obs == nullptr || seeds == nullptr || actions == nullptr || step_index < 0) {
+      err = "agent_random_walk: bad argument"; return BLE_ERR_INVALID_ARGUMENT;
+    }
+    BLE_CUDA(cudaSetDevice(device));
+    if (walk_target == nullptr) {
+      if (step_index != 0) { err = "agent_random_walk: step_index 0 (begin_episode) must come first"; return BLE_ERR_NOT_READY; }
+      BLE_CUDA(cudaMalloc(&walk_target, sizeof(double) * n));
+    }
+    k_agent_random_walk<<<grid_for(n, 128), 128, 0, s>>>(obs, n, walk_target, seeds, step_index, actions);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
+  int eval_begin(cudaStream_t s) override {
+    if (!have_state) { err = "eval_begin: no balloon state"; return BLE_ERR_NOT_READY; }
+    BLE_CUDA(cudaSetDevice(device));
+    if (ev.reward == nullptr) {
+      BLE_CUDA(cudaMalloc(&ev.reward, sizeof(double) * n));
+      BLE_CUDA(cudaMalloc(&ev.within, sizeof(int32_t) * n));
+      BLE_CUDA(cudaMalloc(&ev.steps, sizeof(int32_t) * n));
+      BLE_CUDA(cudaMalloc(&ev.active, sizeof(uint8_t) * n));
+    }
+    k_eval_begin<Real><<<grid_for(n, 128), 128, 0, s>>>(d, ev);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
+  int eval_accumulate(const float* reward, float* path, cudaStream_t s) override {
+    if (reward == nullptr) { err = "eval_accumulate: null reward"; return BLE_ERR_INVALID_ARGUMENT; }
+    if (ev.reward == nullptr) { err = "eval_accumulate: call ble_eval_begin first"; return BLE_ERR_NOT_READY; }
+    BLE_CUDA(cudaSetDevice(device));
+    k_eval_accumulate<Real><<<grid_for(n, 128), 128, 0, s>>>(d, ev, reward, 50000.0, path);   // env.radius, balloon_env.py:136
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
+  int eval_results(double* out, cudaStream_t s) override {
+    if (out == nullptr) { err = "eval_results: null output"; return BLE_ERR_INVALID_ARGUMENT; }
+    if (ev.reward == nullptr) { err = "eval_results: call ble_eval_begin first"; return BLE_ERR_NOT_READY; }
+    BLE_CUDA(cudaSetDevice(device));
+    k_eval_results<Real><<<grid_for(n, 128), 128, 0, s>>>(d, ev, out);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
   void launch_step(const int32_t* actions, float* reward, uint8_t* done, float2* wind_uv, cudaStream_t s) {
     if constexpr (std::is_same<Real, float>::value) {
       // k_step_ws needs 4 threads per balloon: at 128 registers an SM holds 4 blocks = 128 balloons, so
@@ -1318,6 +1534,25 @@ int ble_set_decoder(ble_handle* h, const float* const* kernels, const float* con
 }
 int ble_decode_fields(ble_handle* h, const float* latents, int64_t n_fields, float* fields, void* stream) {
   BLE_H(h); return h->eng->decode(latents, n_fields, fields, cudaStream_t(stream));
+}
+int ble_generate_fields(ble_handle* h, const uint64_t* seeds, int64_t first_field, int64_t count, void* stream) {
+  BLE_H(h); return h->eng->generate_fields(seeds, first_field, count, cudaStream_t(stream));
+}
+int ble_agent_station_seeker(ble_handle* h, const float* obs, int32_t* actions, int32_t* best_level, void* stream) {
+  BLE_H(h); return h->eng->agent_station_seeker(obs, actions, best_level, cudaStream_t(stream));
+}
+int ble_agent_random_walk(ble_handle* h, const float* obs, const uint64_t* seeds, int32_t step_index, int32_t* actions,
+                          void* stream) {
+  BLE_H(h); return h->eng->agent_random_walk(obs, seeds, step_index, actions, cudaStream_t(stream));
+}
+int ble_eval_begin(ble_handle* h, void* stream) {
+  BLE_H(h); return h->eng->eval_begin(cudaStream_t(stream));
+}
+int ble_eval_accumulate(ble_handle* h, const float* reward, float* flight_path, void* stream) {
+  BLE_H(h); return h->eng->eval_accumulate(reward, flight_path, cudaStream_t(stream));
+}
+int ble_eval_results(ble_handle* h, double* out, void* stream) {
+  BLE_H(h); return h->eng->eval_results(out, cudaStream_t(stream));
 }
 int ble_features_observe(ble_handle* h, void* stream) {
   BLE_H(h); return h->eng->features_observe(cudaStream_t(stream));

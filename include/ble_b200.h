@@ -184,6 +184,38 @@ enum {
 };
 int ble_derived(ble_handle* h, double* out, void* stream);
 
+/* ---- evaluation surface ------------------------------------------------
+ * ble_generate_fields: GenerativeWindFieldSampler.sample_field (env/generative_wind_field.py:52-62) for
+ *   `count` seeds: z ~ N(0, I_64) from Philox(seed) -> ble_set_decoder's network -> fields
+ *   [first_field, first_field + count) of the bank allocated with ble_alloc_fields.  seeds: device
+ *   uint64 [count].
+ * ble_agent_station_seeker: StationSeekerAgent.pick_action (agents/station_seeker_agent.py:72-113) on
+ *   obs float32 [N, 1099] (device) -> actions int32 [N] (0 DOWN, 1 STAY, 2 UP) and, if best_level is not
+ *   NULL, the chosen level of the 361-level column (-1 where no level is valid; the reference asserts).
+ * ble_agent_random_walk: RandomWalkAgent (agents/random_walk_agent.py:35-94).  step_index 0 is
+ *   begin_episode (draws the target pressure), k >= 1 the k-th agent.step; the target pressures live in
+ *   the handle, the random stream is Philox(seeds[e], step_index) (jax.random in the reference; its tests
+ *   forbid depending on the stream).  seeds: device uint64 [N].
+ * ble_eval_begin / ble_eval_accumulate / ble_eval_results: eval_lib.eval_agent's bookkeeping
+ *   (eval/eval_lib.py:123-211) for N simultaneous flights.  begin: zero the sums, every balloon whose
+ *   status is OK starts flying.  accumulate (after every ble_step, with that step's reward): reward sum,
+ *   steps within the 50 km radius, step count, stop at a terminal status; flight_path (NULL or float32
+ *   [6][N]: x km, y km, pressure, superpressure, elapsed seconds, battery soc -- SimpleBalloonState,
+ *   eval_lib.py:58-80) receives this step's sample, NaN for balloons that already finished.
+ *   results: float64 [BLE_NUM_E][N], the fields of EvaluationResult (eval_lib.py:84-116). */
+enum {
+  BLE_E_CUMULATIVE_REWARD = 0, BLE_E_TIME_WITHIN_RADIUS, BLE_E_OUT_OF_POWER, BLE_E_ENVELOPE_BURST, BLE_E_ZEROPRESSURE,
+  BLE_E_FINAL_TIMESTEP, BLE_E_ACTIVE /* 1 = still flying when queried */,
+  BLE_NUM_E
+};
+int ble_generate_fields(ble_handle* h, const uint64_t* seeds, int64_t first_field, int64_t count, void* stream);
+int ble_agent_station_seeker(ble_handle* h, const float* obs, int32_t* actions, int32_t* best_level, void* stream);
+int ble_agent_random_walk(ble_handle* h, const float* obs, const uint64_t* seeds, int32_t step_index,
+                          int32_t* actions, void* stream);
+int ble_eval_begin(ble_handle* h, void* stream);
+int ble_eval_accumulate(ble_handle* h, const float* reward, float* flight_path, void* stream);
+int ble_eval_results(ble_handle* h, double* out, void* stream);
+
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t ble_launch_count(const ble_handle* h);
 

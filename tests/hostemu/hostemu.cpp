@@ -9,6 +9,7 @@
 #include "../../balloon_learning_environment_b200/csrc/ble_physics.cuh"
 #include "../../balloon_learning_environment_b200/csrc/ble_wind.cuh"
 #include "../../balloon_learning_environment_b200/csrc/ble_features.cuh"
+#include "../../balloon_learning_environment_b200/csrc/ble_agents.cuh"
 #include "../../include/ble_b200.h"
 
 using namespace ble;
@@ -186,5 +187,17 @@ void emu_sunrise_time(int64_t n, const double* lat, const double* lng, const int
 
 double emu_power_table(double pr, double soc) { return power_table_lookup(pr, soc); }
 int emu_nearest_level(double p) { return nearest_pressure_level(p); }
+
+// StationSeeker / RandomWalk action rules (ble_agents.cuh) on [n, 1099] observations.
+void emu_station_seeker(int64_t n, const float* obs, int32_t* actions, int32_t* best, double* scores /* [n,361] */) {
+  for (int64_t e = 0; e < n; ++e) {
+    const int b = seeker_best_level(obs + e * kNumFeatures, scores + e * kColumnLevels);
+    best[e] = b;
+    actions[e] = b < 0 ? 1 : seeker_action_for_level(b);
+  }
+}
+void emu_random_walk(int64_t n, const float* obs, const double* target, int32_t* actions) {
+  for (int64_t e = 0; e < n; ++e) actions[e] = random_walk_action(obs[e * kNumFeatures], target[e]);
+}
 
 }  // extern "C"

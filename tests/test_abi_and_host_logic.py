@@ -52,3 +52,29 @@ def test_product_package_does_not_import_the_oracle():
         text = open(os.path.join(dirpath, fn)).read()
         assert not re.search(r'^\s*(from|import)\s+oracle', text, re.M), fn
         assert not re.search(r'#include\s+".*hostemu', text), fn
+
+
+def test_eval_suites_and_result_schema():
+  """eval/suites.py:39-63, eval/eval.py:121-124 (sharding) and eval/eval_lib.py:33-56 (JSON schema)."""
+  import json
+  import os
+  from balloon_learning_environment_b200 import eval_lib, suites
+  assert suites.available_suites() == ['big_eval', 'medium_eval', 'small_eval', 'tiny_eval', 'micro_eval']
+  big = suites.get_eval_suite('big_eval')
+  assert len(big.seeds) == 10_000 and big.max_episode_length == 960 and big.seeds[:3] == [0, 1, 2]
+  assert suites.get_eval_suite('micro_eval').seeds == [0]
+  parts = [suites.shard(big, i, 7) for i in range(7)]
+  assert sum((p.seeds for p in parts), []) == big.seeds
+  with pytest.raises(ValueError):
+    suites.get_eval_suite('nope')
+  r = eval_lib.EvaluationResult(seed=3, cumulative_reward=1.5, time_within_radius=0.25, out_of_power=False,
+                                envelope_burst=False, zeropressure=True, final_timestep=2,
+                                flight_path=[eval_lib.SimpleBalloonState(1.0, 2.0, 9000.0, 500.0, 180.0, 0.9)] * 2)
+  mine = json.loads(eval_lib.results_to_json([r]))
+  here = os.path.dirname(os.path.abspath(__file__))
+  with open(os.path.join(here, 'golden', 'eval.json')) as f:
+    ref = json.load(f)
+  assert list(mine[0].keys()) == list(ref[0].keys())
+  assert list(mine[0]['flight_path'][0].keys()) == list(ref[0]['flight_path'][0].keys())
+  assert {k: type(v) for k, v in mine[0].items()} == {k: type(v) for k, v in ref[0].items()}
+  assert 'seed=3' in str(r)

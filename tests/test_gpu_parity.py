@@ -548,3 +548,116 @@ def test_decoder_matches_oracle(ble):
   uv = arena.wind_forecast(q, torch.tensor([2], dtype=torch.int32)).cpu().numpy()[0]
   np.testing.assert_allclose(uv, f0[2, 3, 7, 4, 2], rtol=1e-5, atol=1e-5)
   arena.close()
+
+
+# ---- evaluation surface ---------------------------------------------------
+def _agent_gold():
+  import os
+  return np.load(os.path.join(golden_io.GOLDEN_DIR, 'agents.npz'))
+
+
+def test_station_seeker_kernel_matches_reference(ble):
+  """k_agent_station_seeker on the 499 golden observations (242 recorded by the reference's feature
+  constructor, 257 synthetic with exact ties): action and chosen level bit-exact against the reference's
+  StationSeekerAgent; RandomWalk rule against the oracle."""
+  from oracle import agents as oracle_agents
+  gold = _agent_gold()
+  obs = torch.from_numpy(np.ascontiguousarray(gold['open_obs'], np.float32))
+  arena = ble.BatchedBalloonArena(len(obs), precision='fp32', wind_model='simple_static', enable_noise=False)
+  actions, best = arena.station_seeker_actions(obs, with_level=True)
+  np.testing.assert_array_equal(actions.cpu().numpy(), gold['open_actions'])
+  np.testing.assert_array_equal(best.cpu().numpy(), gold['open_best'])
+  # an all-invalid column: the reference asserts, the kernel reports level -1 and holds altitude
+  blank = obs.clone(); blank[:, 16:] = torch.tensor([0.0, 1.0, 1.0]).repeat(361)
+  a2, b2 = arena.station_seeker_actions(blank, with_level=True)
+  assert (b2 == -1).all() and (a2 == 1).all()
+  # random walk: step 0 draws targets in [6500, 11400]; the action is the band rule around the target
+  seeds = torch.arange(len(obs), dtype=torch.int64) + 7
+  a0 = arena.random_walk_actions(obs, seeds, 0).cpu().numpy()
+  a0_again = arena.random_walk_actions(obs, seeds, 0).cpu().numpy()
+  np.testing.assert_array_equal(a0, a0_again)                      # Philox(seed, step): stateless and repeatable
+  p = oracle_agents.balloon_pressure_from_obs(gold['open_obs'])
+  assert np.all(a0[p - 100 > 11400] == 2) and np.all(a0[p + 100 < 6500] == 0)
+  hist = [np.bincount(arena.random_walk_actions(obs, seeds, k).cpu().numpy(), minlength=3) for k in range(1, 40)]
+  assert np.sum(hist, axis=0).min() > 0                             # the walk visits all three commands
+  with pytest.raises(ValueError):
+    arena.station_seeker_actions(obs[:5])
+  arena.close()
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_eval_agent_closed_loop_matches_reference(ble, precision):
+  """The reference's eval_lib.eval_agent flying its StationSeekerAgent for 100 steps (two injected episodes),
+  against the CUDA closed loop: ble_step -> ble_features_perciatelli -> ble_agent_station_seeker ->
+  ble_eval_accumulate.  Actions bit-exact; cumulative reward 1e-5 relative (float32 step rewards), time
+  within radius / final step exact, flight path 1e-4 relative (north_star state tolerance)."""
+  from balloon_learning_environment_b200 import agents as agents_lib
+  gold = _agent_gold()
+  names = [str(n) for n in gold['names']]
+  scs = [{k.split('/', 1)[1]: gold[k] for k in gold.files if k.startswith(n + '/')} for n in names]
+  n = len(scs)
+  arena = ble.BatchedBalloonArena(n, precision=precision, wind_model='grid', enable_noise=True, enable_features=True)
+  arena.set_wind_fields(torch.from_numpy(golden_fields.field_bank()),
+                        torch.tensor([int(sc['field']) for sc in scs], dtype=torch.int32))
+  arena.set_wind_noise(torch.from_numpy(np.stack([sc['seeds'] for sc in scs])),
+                       torch.from_numpy(np.stack([sc['offsets'] for sc in scs]).astype(np.float32)))
+  b = golden_io.batch_from_rows(FF, IF, np.stack([sc['f0'] for sc in scs]), np.stack([sc['i0'] for sc in scs]))
+  arena.set_state(*pack(b, np.array([float(sc['alpha']) for sc in scs]), 1))
+  arena.features_clear(); arena.features_observe()
+  agent = agents_lib.StationSeekerAgent(3, (1099,), arena)
+  steps = len(scs[0]['actions'])
+  path = torch.empty(steps, 6, n, dtype=torch.float32, device=arena.device)
+  arena.eval_begin()
+  action = agent.begin_episode(arena.features())
+  taken = []
+  for t in range(steps):
+    taken.append(action.cpu().numpy().copy())
+    reward, done, _ = arena.step(action)
+    arena.eval_accumulate(reward, path[t])
+    action = agent.step(reward, arena.features())
+  taken = np.asarray(taken)
+  res = {k: v.cpu().numpy() for k, v in arena.eval_results().items()}
+  path = path.cpu().numpy()
+  for e, sc in enumerate(scs):
+    np.testing.assert_array_equal(taken[:, e], sc['actions'], err_msg=names[e])
+    np.testing.assert_allclose(res['cumulative_reward'][e], sc['cumulative_reward'], rtol=1e-5)
+    assert res['time_within_radius'][e] == sc['time_within_radius']
+    assert res['final_timestep'][e] == sc['final_timestep'] and res['active'][e] == 1
+    assert (res['out_of_power'][e], res['envelope_burst'][e], res['zeropressure'][e]) == tuple(sc['flags'])
+    np.testing.assert_allclose(path[:, :, e], sc['flight_path'], rtol=1e-4, atol=2e-3, err_msg=names[e])
+  arena.close()
+
+
+def test_vectorised_eval_driver(ble):
+  """eval_lib.eval_agent over a 24-seed suite with decoder-generated wind fields: per-seed results do not depend
+  on how the suite is sharded (seed -> field, state and noise are functions of the seed alone), the JSON has
+  the reference's schema (tests/golden/eval.json), terminated flights stop accumulating."""
+  import json
+  import os
+  from balloon_learning_environment_b200 import agents as agents_lib, eval_lib, suites
+  from oracle import vae as vae_oracle
+  params = vae_oracle.synthetic_params(3)
+  suite = suites.EvaluationSuite(list(range(100, 124)), 40)
+
+  def fly(sub):
+    env = ble.BatchedBalloonEnv(len(sub.seeds), observation='perciatelli', decoder_params=params, field_layout='x128')
+    agent = agents_lib.create_agent('station_seeker', 3, (1099,), env.arena)
+    out = eval_lib.eval_agent(agent, env, sub)
+    env.close()
+    return out
+
+  whole = fly(suite)
+  parts = fly(suites.shard(suite, 0, 2)) + fly(suites.shard(suite, 1, 2))
+  assert [r.seed for r in whole] == list(suite.seeds) == [r.seed for r in parts]
+  for a, b in zip(whole, parts):
+    assert a.cumulative_reward == b.cumulative_reward and a.time_within_radius == b.time_within_radius
+    assert a.final_timestep == b.final_timestep == 40 and len(a.flight_path) == 40
+  assert 0.0 < np.mean([r.cumulative_reward for r in whole]) <= 40.0
+  assert all(0.0 <= r.time_within_radius <= 1.0 for r in whole)
+  with open(os.path.join(golden_io.GOLDEN_DIR, 'eval.json')) as f:
+    ref = json.load(f)
+  mine = json.loads(eval_lib.results_to_json(whole))
+  assert list(mine[0].keys()) == list(ref[0].keys())
+  assert list(mine[0]['flight_path'][0].keys()) == list(ref[0]['flight_path'][0].keys())
+  merged = json.loads(eval_lib.combine_shards([eval_lib.results_to_json(parts[12:]), eval_lib.results_to_json(parts[:12])]))
+  assert [r['seed'] for r in merged] == list(suite.seeds)
