@@ -12,9 +12,9 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.environ.get('BLE_B200_LIB') or os.path.join(PKG_DIR, 'libble_b200.so')
-SOURCES = [os.path.join(CSRC, 'ble_engine.cu')]
+SOURCES = [os.path.join(CSRC, 'ble_engine.cu'), os.path.join(CSRC, 'ble_learner.cu')]
 HEADERS = [os.path.join(CSRC, f) for f in ('ble_physics.cuh', 'ble_wind.cuh', 'ble_features.cuh',
-                                          'ble_feature_kernels.cuh', 'ble_decoder.cuh')] + [
+                                          'ble_feature_kernels.cuh', 'ble_decoder.cuh', 'ble_agents.cuh', 'ble_rng.cuh')] + [
            os.path.join(PKG_DIR, '..', 'include', 'ble_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--shared', '-Xcompiler', '-fPIC']
@@ -28,23 +28,43 @@ def find_nvcc():
   raise RuntimeError('nvcc not found: cannot build libble_b200.so (set NVCC=/path/to/nvcc)')
 
 
-def is_stale():
-  if not os.path.exists(LIB_PATH):
+OBJ_DIR = os.path.join(PKG_DIR, 'build')
+
+
+def _newer_than(target, deps):
+  if not os.path.exists(target):
     return True
-  built = os.path.getmtime(LIB_PATH)
-  return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS)
+  built = os.path.getmtime(target)
+  return any(os.path.getmtime(p) > built for p in deps)
+
+
+def is_stale():
+  return _newer_than(LIB_PATH, SOURCES + HEADERS)
 
 
 def build(force=False, verbose=False):
-  """Compiles csrc/*.cu -> libble_b200.so if missing or out of date.  Returns the library path."""
+  """Compiles csrc/*.cu -> build/*.o -> libble_b200.so, redoing only what is out of date.  Returns the library path."""
   if not force and not is_stale():
     return LIB_PATH
-  cmd = [find_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + SOURCES + LINK_FLAGS
+  nvcc = find_nvcc()
+  os.makedirs(OBJ_DIR, exist_ok=True)
+  compile_flags = [f for f in NVCC_FLAGS if f != '--shared']
+  objects = []
+  for src in SOURCES:
+    obj = os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(src))[0] + '.o')
+    objects.append(obj)
+    if not force and not _newer_than(obj, [src] + HEADERS):
+      continue
+    cmd = [nvcc] + compile_flags + (['-Xptxas', '-v'] if verbose else []) + ['-c', '-o', obj, src]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+      raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
+    if verbose:
+      sys.stderr.write(proc.stderr)
+  cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '--shared', '-o', LIB_PATH] + objects + LINK_FLAGS
   proc = subprocess.run(cmd, capture_output=True, text=True)
   if proc.returncode != 0:
-    raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
-  if verbose:
-    sys.stderr.write(proc.stderr)
+    raise RuntimeError('nvcc link failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
   return LIB_PATH
 
 

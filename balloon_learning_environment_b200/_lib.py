@@ -34,14 +34,23 @@ EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_u
            'ble_set_noise', 'ble_state_upload', 'ble_state_download', 'ble_reset', 'ble_init_derived',
            'ble_step', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_derived',
            'ble_features_perciatelli', 'ble_features_observe', 'ble_features_clear',
-           'ble_generate_fields', 'ble_agent_station_seeker', 'ble_agent_random_walk',
+           'ble_generate_fields', 'ble_generate_fields_at', 'ble_agent_station_seeker', 'ble_agent_random_walk',
            'ble_eval_begin', 'ble_eval_accumulate', 'ble_eval_results',
-           'ble_launch_count')
+           'ble_launch_count',
+           'ble_qr_greedy', 'ble_qr_target', 'ble_qr_loss', 'ble_replay_sample', 'ble_adam_step',
+           'ble_marco_polo_step')
 
 
 class BleConfig(_c.Structure):
   _fields_ = [('precision', _c.c_int32), ('wind_model', _c.c_int32), ('enable_noise', _c.c_int32),
-              ('field_layout', _c.c_int32), ('enable_features', _c.c_int32), ('reserved', _c.c_int32 * 3)]
+              ('field_layout', _c.c_int32), ('enable_features', _c.c_int32), ('decoder_tf32', _c.c_int32),
+              ('reserved', _c.c_int32 * 2)]
+
+
+class BleReplayView(_c.Structure):
+  _fields_ = [('obs', _c.c_void_p), ('action', _c.c_void_p), ('reward', _c.c_void_p), ('terminal', _c.c_void_p),
+              ('truncated', _c.c_void_p), ('capacity', _c.c_int64), ('num_envs', _c.c_int64), ('count', _c.c_int64),
+              ('n_step', _c.c_int32), ('num_features', _c.c_int32), ('gamma', _c.c_float), ('reserved', _c.c_int32)]
 
 
 class BleStateSoa(_c.Structure):
@@ -96,11 +105,19 @@ def load(build_if_missing=True):
   lib.ble_features_observe.argtypes = [vp, vp]
   lib.ble_features_clear.argtypes = [vp, vp]
   lib.ble_generate_fields.argtypes = [vp, vp, i64, i64, vp]
+  lib.ble_generate_fields_at.argtypes = [vp, vp, vp, i64, vp]
   lib.ble_agent_station_seeker.argtypes = [vp, vp, vp, vp, vp]
   lib.ble_agent_random_walk.argtypes = [vp, vp, vp, i32, vp, vp]
   lib.ble_eval_begin.argtypes = [vp, vp]
   lib.ble_eval_accumulate.argtypes = [vp, vp, vp, vp]
   lib.ble_eval_results.argtypes = [vp, vp, vp]
+  f32, u64 = _c.c_float, _c.c_uint64
+  lib.ble_qr_greedy.argtypes = [vp, i64, i32, i32, vp, vp, vp]
+  lib.ble_qr_target.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
+  lib.ble_qr_loss.argtypes = [vp, vp, vp, vp, f32, i64, i32, i32, f32, vp, vp, vp]
+  lib.ble_replay_sample.argtypes = [_c.POINTER(BleReplayView), vp, u64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+  lib.ble_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, f32, vp]
+  lib.ble_marco_polo_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, f32, vp, vp]
   for name in EXPORTS:
     if name not in ('ble_last_error', 'ble_num_envs', 'ble_launch_count'):
       getattr(lib, name).restype = _c.c_int

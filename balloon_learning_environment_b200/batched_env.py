@@ -43,7 +43,7 @@ class BatchedBalloonArena:
 
   def __init__(self, num_envs: int, *, device: str = 'cuda:0', precision: str = 'fp32',
                wind_model: str = 'grid', enable_noise: bool = True, field_layout: str = 'x64',
-               enable_features: bool = False):
+               enable_features: bool = False, decoder_tf32: bool = False):
     if not torch.cuda.is_available():
       raise _lib.BleError('BatchedBalloonArena needs a CUDA device (no CPU fallback exists)')
     self._lib = _lib.load()
@@ -53,7 +53,7 @@ class BatchedBalloonArena:
     self.wind_model = wind_model
     self.enable_noise = bool(enable_noise)
     cfg = _lib.BleConfig(_lib.PRECISION[precision], _lib.WIND_MODEL[wind_model], int(enable_noise),
-                         _lib.FIELD_LAYOUT[field_layout], int(enable_features))
+                         _lib.FIELD_LAYOUT[field_layout], int(enable_features), int(decoder_tf32))
     self.enable_features = bool(enable_features)
     handle = ctypes.c_void_p()
     dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -173,6 +173,17 @@ class BatchedBalloonArena:
     seeds = seeds.to(self.device, torch.int64).contiguous()
     rc = self._lib.ble_generate_fields(self._h, _ptr(seeds), int(first_field), seeds.numel(), self._stream())
     self._check(rc, 'ble_generate_fields')
+
+  def sample_wind_fields_at(self, seeds: torch.Tensor, field_index: torch.Tensor) -> None:
+    """sample_wind_fields for a scattered set of fields: seeds int64 [K], field_index int32 [K] (distinct)."""
+    seeds = seeds.to(self.device, torch.int64).contiguous()
+    field_index = field_index.to(self.device, torch.int32).contiguous()
+    if seeds.numel() != field_index.numel():
+      raise ValueError('one seed per field index')
+    if seeds.numel() == 0:
+      return
+    rc = self._lib.ble_generate_fields_at(self._h, _ptr(seeds), _ptr(field_index), seeds.numel(), self._stream())
+    self._check(rc, 'ble_generate_fields_at')
 
   # -- evaluation surface (eval/eval_lib.py, agents/) ----------------------------------------------
   def station_seeker_actions(self, obs: torch.Tensor, with_level: bool = False):
@@ -404,6 +415,17 @@ class BatchedBalloonEnv:
     if self._generative:
       self.arena.sample_wind_fields(seeds)
     self.arena.reset(seeds)
+    return self._observe()
+
+  def reset_where(self, mask: torch.Tensor):
+    """Starts a new episode for the balloons with mask != 0 (the vectorised stand-in for the reference's
+    per-environment `env.reset()` at an episode end); the others keep flying.  Returns the observation."""
+    mask = mask.to(self.device).ne(0)
+    seeds = torch.randint(0, 2**62, (self.num_envs,), dtype=torch.int64, generator=self._generator).to(self.device)
+    if self._generative:
+      idx = mask.nonzero().flatten()
+      self.arena.sample_wind_fields_at(seeds[idx], idx.to(torch.int32))
+    self.arena.reset(seeds, mask.to(torch.uint8))
     return self._observe()
 
   def _observe(self):

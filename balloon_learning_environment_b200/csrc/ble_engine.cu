@@ -152,7 +152,8 @@ __global__ void k_state_download(DevState<Real> d, double* __restrict__ f, int64
 // One thread per 64-byte block = one grid column (ix) of one (y,p,t) cell, ordered [dy][dp][dt][uv].
 // X64: 21 blocks per row; X128: 20 windows per row, each holding block(ix) then block(ix+1).
 __global__ void k_fields_to_windows(const float* __restrict__ native, float* __restrict__ cells,
-                                    FieldLayout layout, int64_t first_field, int64_t n_fields) {
+                                    FieldLayout layout, int64_t first_field, int64_t n_fields,
+                                    const int32_t* __restrict__ dst_index /* nullptr: first_field + f */) {
   const int blocks_per_row = layout.row_floats / 16;
   const int64_t per_field = int64_t(kYC) * kPC * kTC * blocks_per_row;
   const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -165,7 +166,8 @@ __global__ void k_fields_to_windows(const float* __restrict__ native, float* __r
   const int iy = int(r / kPC);
   const int ix = (layout.x_stride_floats == 32) ? (b >> 1) + (b & 1) : b;   // X128: window b/2, half b&1
   const float* src = native + f * kFieldFloats;
-  float4* dst = reinterpret_cast<float4*>(cells + (first_field + f) * layout.field_floats +
+  const int64_t dst_field = dst_index != nullptr ? int64_t(dst_index[f]) : first_field + f;
+  float4* dst = reinterpret_cast<float4*>(cells + dst_field * layout.field_floats +
                                           ((int64_t(iy) * kPC + pc) * kTC + tc) * layout.row_floats + int64_t(b) * 16);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {                       // chunk c = dy*2 + dp
@@ -707,52 +709,7 @@ __global__ void __launch_bounds__(128) k_eval_results(DevState<Real> d, EvalBuff
 // ---------------------------------------------------------------------------------------------
 // Reset (env/balloon_arena.py:161-182,228-268; utils/sampling.py:37-152)
 // ---------------------------------------------------------------------------------------------
-struct Philox {          // Philox4x32-10, one stream per (seed, balloon)
-  uint32_t key[2], ctr[4], out[4];
-  int have;
-  __device__ void init(uint64_t seed, uint64_t stream) {
-    key[0] = uint32_t(seed); key[1] = uint32_t(seed >> 32);
-    ctr[0] = 0; ctr[1] = 0; ctr[2] = uint32_t(stream); ctr[3] = uint32_t(stream >> 32);
-    have = 0;
-  }
-  __device__ void round(uint32_t* c, const uint32_t* k) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
-    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-  }
-  __device__ uint32_t next() {
-    if (have == 0) {
-      uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
-      uint32_t k[2] = {key[0], key[1]};
-      for (int i = 0; i < 10; ++i) { round(c, k); k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
-      out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-      if (++ctr[0] == 0) ++ctr[1];
-      have = 4;
-    }
-    return out[--have];
-  }
-  __device__ double uniform() {       // [0, 1) with 53 bits
-    const uint64_t a = next(), b = next();
-    return double(((a << 32) | b) >> 11) * (1.0 / 9007199254740992.0);
-  }
-  __device__ float uniform_f32() { return float(next() >> 8) * (1.0f / 16777216.0f); }   // [0,1), 24 bits
-  __device__ double normal() {        // Box-Muller
-    const double u1 = 1.0 - uniform(), u2 = uniform();
-    return sqrt(-2.0 * log(u1)) * cos(2.0 * kPi * u2);
-  }
-  __device__ double gamma(double a) { // Marsaglia-Tsang, a >= 1
-    const double dd = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
-    for (;;) {
-      const double x = normal();
-      double v = 1.0 + c * x;
-      if (v <= 0.0) continue;
-      v = v * v * v;
-      const double u = 1.0 - uniform();
-      if (log(u) < 0.5 * x * x + dd - dd * v + dd * log(v)) return dd * v;
-    }
-  }
-};
+#include "ble_rng.cuh"
 
 // Deterministic derived state: power-safety sunrise/sunset (+30 min hysteresis) and, optionally,
 // the stable-init solve.  Always fp64 (see ble_physics.cuh).
@@ -891,6 +848,7 @@ struct EngineBase {
   virtual int set_decoder(const float* const*, const float* const*, cudaStream_t) = 0;
   virtual int decode(const float*, int64_t, float*, cudaStream_t) = 0;
   virtual int generate_fields(const uint64_t*, int64_t, int64_t, cudaStream_t) = 0;
+  virtual int generate_fields_at(const uint64_t*, int64_t, int64_t, const int32_t*, cudaStream_t) = 0;
   virtual int agent_station_seeker(const float*, int32_t*, int32_t*, cudaStream_t) = 0;
   virtual int agent_random_walk(const float*, const uint64_t*, int32_t, int32_t*, cudaStream_t) = 0;
   virtual int eval_begin(cudaStream_t) = 0;
@@ -1017,13 +975,18 @@ struct Engine : EngineBase {
   }
 
   int write_fields(const float* fields, int64_t first, int64_t count, cudaStream_t s) override {
-    if (fields == nullptr || first < 0 || count <= 0 || first + count > n_fields) {
+    return write_fields_at(fields, first, count, nullptr, s);
+  }
+
+  // dst_index (device int32 [count], every entry in [0, n_fields)) scatters the fields; nullptr = contiguous
+  int write_fields_at(const float* fields, int64_t first, int64_t count, const int32_t* dst_index, cudaStream_t s) {
+    if (fields == nullptr || first < 0 || count <= 0 || (dst_index == nullptr && first + count > n_fields) || cells == nullptr) {
       err = "write_fields: range outside the allocated fields (call ble_alloc_fields first)";
       return BLE_ERR_INVALID_ARGUMENT;
     }
     BLE_CUDA(cudaSetDevice(device));
     const int64_t threads = count * int64_t(kYC) * kPC * kTC * (d.layout.row_floats / 16);
-    k_fields_to_windows<<<grid_for(threads, 256), 256, 0, s>>>(fields, cells, d.layout, first, count);
+    k_fields_to_windows<<<grid_for(threads, 256), 256, 0, s>>>(fields, cells, d.layout, first, count, dst_index);
     ++launches;
     BLE_CUDA(cudaGetLastError());
     have_fields = true;
@@ -1196,7 +1159,8 @@ struct Engine : EngineBase {
       if (lc) cublasLtMatrixLayoutDestroy(lc);
       if (op) cublasLtMatmulDescDestroy(op);
     };
-    bool ok = cublasLtMatmulDescCreate(&op, CUBLAS_COMPUTE_32F, CUDA_R_32F) == CUBLAS_STATUS_SUCCESS;
+    bool ok = cublasLtMatmulDescCreate(&op, cfg.decoder_tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F,
+                                       CUDA_R_32F) == CUBLAS_STATUS_SUCCESS;
     const cublasLtEpilogue_t epi = relu ? CUBLASLT_EPILOGUE_RELU_BIAS : CUBLASLT_EPILOGUE_BIAS;
     const float* bias = dec_b[layer];
     ok = ok && cublasLtMatmulDescSetAttribute(op, CUBLASLT_MATMUL_DESC_EPILOGUE, &epi, sizeof(epi)) == CUBLAS_STATUS_SUCCESS;
@@ -1241,7 +1205,11 @@ struct Engine : EngineBase {
 
   // sample_field for `count` seeds straight into the field bank: latents -> decoder -> lookup windows
   int generate_fields(const uint64_t* seeds, int64_t first, int64_t count, cudaStream_t s) override {
-    if (seeds == nullptr || first < 0 || count <= 0 || first + count > n_fields) {
+    return generate_fields_at(seeds, first, count, nullptr, s);
+  }
+
+  int generate_fields_at(const uint64_t* seeds, int64_t first, int64_t count, const int32_t* dst_index, cudaStream_t s) override {
+    if (seeds == nullptr || first < 0 || count <= 0 || (dst_index == nullptr && first + count > n_fields) || count > n_fields) {
       err = "generate_fields: range outside the allocated fields (call ble_alloc_fields first)";
       return BLE_ERR_INVALID_ARGUMENT;
     }
@@ -1260,7 +1228,7 @@ struct Engine : EngineBase {
       ++launches;
       BLE_CUDA(cudaGetLastError());
       int rc = decode(gen_latents, kGenChunk, gen_fields, s);
-      if (rc == BLE_OK) rc = write_fields(gen_fields, first + done_f, c, s);
+      if (rc == BLE_OK) rc = write_fields_at(gen_fields, first + done_f, c, dst_index != nullptr ? dst_index + done_f : nullptr, s);
       if (rc != BLE_OK) return rc;
     }
     return BLE_OK;
@@ -1537,6 +1505,11 @@ int ble_decode_fields(ble_handle* h, const float* latents, int64_t n_fields, flo
 }
 int ble_generate_fields(ble_handle* h, const uint64_t* seeds, int64_t first_field, int64_t count, void* stream) {
   BLE_H(h); return h->eng->generate_fields(seeds, first_field, count, cudaStream_t(stream));
+}
+int ble_generate_fields_at(ble_handle* h, const uint64_t* seeds, const int32_t* field_index, int64_t count, void* stream) {
+  BLE_H(h);
+  if (field_index == nullptr) { h->eng->err = "generate_fields_at: null field_index"; return BLE_ERR_INVALID_ARGUMENT; }
+  return h->eng->generate_fields_at(seeds, 0, count, field_index, cudaStream_t(stream));
 }
 int ble_agent_station_seeker(ble_handle* h, const float* obs, int32_t* actions, int32_t* best_level, void* stream) {
   BLE_H(h); return h->eng->agent_station_seeker(obs, actions, best_level, cudaStream_t(stream));

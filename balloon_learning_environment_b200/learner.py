@@ -1,0 +1,406 @@
+"""QR-DQN learner surface for vectorised rollouts (BASELINE configs[4]).
+
+Mirrors what the reference assembles in `acme_utils.create_dqn` (acme_utils.py:217-277) and
+`train_acme_qrdqn.py:43-81` -- equivalently the Dopamine `QuantileAgent` of agents/quantile_agent.py with
+agents/configs/quantile.gin -- for N balloons stepping in lockstep on the device:
+
+  QuantileNetwork      agents/networks.py:63-98 (8 Dense layers x 600, 3 actions x 51 atoms)
+  DeviceReplay         the replay table (max_replay_size 2,000,000, n_step 5, discount 0.993)
+  MarcoPoloExploration agents/marco_polo_exploration.py:36-93 around RandomWalkAgent (acme_utils.py:161-214)
+  QrDqnLearner         QrDqn(num_atoms=51, huber_param=1) loss, Adam(2e-6, eps 2e-5), target period 25
+  run_training         the EnvironmentLoop of train_acme_qrdqn.py:72-81, one iteration = N env steps
+
+The dense layers are cuBLAS GEMMs through torch; everything else on the update path is a hand-written
+CUDA kernel behind the C ABI (csrc/ble_learner.cu).  Data-parallel training keeps one learner per GPU
+and sums the flat gradient buffer with ONE all-reduce per learner step (NCCL; gloo in the CPU tests
+of the host logic).  There is no CPU path for the kernels.
+"""
+import ctypes
+import dataclasses
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from balloon_learning_environment_b200 import _lib
+
+NUM_FEATURES = 1099
+
+
+def _ptr(t: Optional[torch.Tensor]):
+  return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(device):
+  return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+  if not t.is_cuda:
+    raise _lib.BleError(f'{what}: tensors must live on a CUDA device (no CPU fallback exists)')
+
+
+def _check(rc: int, what: str):
+  if rc != _lib.BLE_OK:
+    raise _lib.BleError(f'{what} failed (code {rc})')
+
+
+@dataclasses.dataclass
+class QrDqnConfig:
+  """acme_utils.create_dqn (acme_utils.py:217-246) / agents/configs/quantile.gin."""
+  num_actions: int = 3
+  num_atoms: int = 51                    # acme_utils.py:234
+  num_layers: int = 8                    # acme_utils.py:236
+  hidden_units: int = 600
+  num_features: int = NUM_FEATURES
+  discount: float = 0.993                # acme_utils.py:223
+  n_step: int = 5                        # acme_utils.py:224
+  min_replay_size: int = 500             # acme_utils.py:225 (transitions)
+  target_update_period: int = 25         # learner steps: 100 // 4, acme_utils.py:219-226
+  learning_rate: float = 2e-6            # acme_utils.py:238
+  adam_eps: float = 2e-5                 # acme_utils.py:227
+  adam_b1: float = 0.9
+  adam_b2: float = 0.999
+  huber_param: float = 1.0               # acme_utils.py:245
+  batch_size: int = 32                   # acme_utils.py:229 (per learner step, per GPU)
+  samples_per_insert: float = 8.0        # batch_size / update_period, acme_utils.py:230
+  max_replay_size: int = 2_000_000       # acme_utils.py:228 (transitions)
+  epsilon: float = 0.0                   # quantile.gin: epsilon_train = 0 (MarcoPolo explores instead)
+  exploratory_episode_probability: float = 0.8   # acme_utils.py:207
+  max_episode_length: int = 960          # train_acme_qrdqn.py:30-33
+
+
+class QuantileNetwork(nn.Module):
+  """agents/networks.py:63-98 for a batch: obs [B, F] -> logits [B, A, N]; q_values = mean over atoms."""
+
+  def __init__(self, config: QrDqnConfig = QrDqnConfig()):
+    super().__init__()
+    self.num_actions, self.num_atoms = config.num_actions, config.num_atoms
+    dims = [config.num_features] + [config.hidden_units] * (config.num_layers - 1) + [config.num_actions * config.num_atoms]
+    self.layers = nn.ModuleList(nn.Linear(i, o) for i, o in zip(dims[:-1], dims[1:]))
+    for layer in self.layers:          # variance_scaling(1/sqrt(3), 'fan_in', 'uniform'), networks.py:79-82
+      limit = math.sqrt(3.0 * (1.0 / math.sqrt(3.0)) / layer.in_features)
+      nn.init.uniform_(layer.weight, -limit, limit)
+      nn.init.zeros_(layer.bias)
+
+  def forward(self, x: torch.Tensor) -> torch.Tensor:
+    h = x.to(torch.float32)
+    for i, layer in enumerate(self.layers):
+      h = layer(h)
+      if i + 1 < len(self.layers):
+        h = torch.relu(h)
+    return h.view(-1, self.num_actions, self.num_atoms)
+
+  def load_flax_params(self, params: Dict) -> None:
+    """'Dense_i': {'kernel' [in, out], 'bias'} as produced by QuantileAgent.load_perciatelli_weights
+    (agents/quantile_agent.py:196-254) or a reference checkpoint."""
+    with torch.no_grad():
+      for i, layer in enumerate(self.layers):
+        entry = params[f'Dense_{i}']
+        layer.weight.copy_(torch.as_tensor(entry['kernel'], dtype=torch.float32).t())
+        layer.bias.copy_(torch.as_tensor(entry['bias'], dtype=torch.float32))
+
+
+def flatten_parameters(module: nn.Module, device) -> torch.Tensor:
+  """Moves every parameter of `module` into ONE contiguous fp32 buffer (returned) of which the parameters
+  become views, and gives every parameter a .grad that is a view of `module.flat_grad`: the optimiser
+  kernel and the gradient all-reduce then work on two flat buffers."""
+  params = list(module.parameters())
+  total = sum(p.numel() for p in params)
+  flat = torch.empty(total, dtype=torch.float32, device=device)
+  grad = torch.zeros(total, dtype=torch.float32, device=device)
+  offset = 0
+  for p in params:
+    n = p.numel()
+    flat[offset:offset + n].copy_(p.detach().reshape(-1))
+    p.data = flat[offset:offset + n].view(p.shape)
+    p.grad = grad[offset:offset + n].view(p.shape)
+    offset += n
+  module.flat_params, module.flat_grad = flat, grad
+  return flat
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels behind the C ABI
+# ---------------------------------------------------------------------------------------------
+def greedy_actions(logits: torch.Tensor, with_q: bool = False):
+  """argmax_a mean_j logits[b, a, j] -> int32 [B] (acme_utils.py:250-268 with epsilon = 0)."""
+  _require_cuda(logits, 'greedy_actions')
+  logits = logits.contiguous()
+  b, a, n = logits.shape
+  actions = torch.empty(b, dtype=torch.int32, device=logits.device)
+  q = torch.empty(b, a, dtype=torch.float32, device=logits.device) if with_q else None
+  _check(_lib.load().ble_qr_greedy(_ptr(logits), b, a, n, _ptr(actions), _ptr(q), _stream(logits.device)), 'ble_qr_greedy')
+  return (actions, q) if with_q else actions
+
+
+def target_distribution(next_logits: torch.Tensor, reward: torch.Tensor, discount: torch.Tensor) -> torch.Tensor:
+  """reward + discount * next_logits[greedy action] -> float32 [B, N] (dopamine target_distribution)."""
+  _require_cuda(next_logits, 'target_distribution')
+  next_logits = next_logits.contiguous()
+  b, a, n = next_logits.shape
+  target = torch.empty(b, n, dtype=torch.float32, device=next_logits.device)
+  rc = _lib.load().ble_qr_target(_ptr(next_logits), _ptr(reward.contiguous()), _ptr(discount.contiguous()), b, a, n,
+                                 _ptr(target), _stream(next_logits.device))
+  _check(rc, 'ble_qr_target')
+  return target
+
+
+class _QuantileHuberLoss(torch.autograd.Function):
+  """mean_b weight_b * loss_b with the gradient produced by the same kernel pass."""
+
+  @staticmethod
+  def forward(ctx, logits, actions, target, weight, kappa):
+    _require_cuda(logits, 'quantile_huber_loss')
+    logits = logits.contiguous()
+    b, a, n = logits.shape
+    loss = torch.empty(b, dtype=torch.float32, device=logits.device)
+    grad = torch.empty_like(logits)
+    rc = _lib.load().ble_qr_loss(_ptr(logits), _ptr(actions.contiguous()), _ptr(target.contiguous()),
+                                 _ptr(weight.contiguous() if weight is not None else None), float(kappa), b, a, n,
+                                 1.0 / b, _ptr(loss), _ptr(grad), _stream(logits.device))
+    _check(rc, 'ble_qr_loss')
+    ctx.save_for_backward(grad)
+    ctx.mark_non_differentiable(loss)
+    mean = (loss * weight).mean() if weight is not None else loss.mean()
+    return mean, loss
+
+  @staticmethod
+  def backward(ctx, grad_mean, _grad_loss):
+    (grad,) = ctx.saved_tensors
+    return grad * grad_mean, None, None, None, None
+
+
+def quantile_huber_loss(logits, actions, target, weight=None, kappa: float = 1.0):
+  """Returns (mean loss, per-sample loss [B]); differentiable w.r.t. logits only (target is a constant)."""
+  return _QuantileHuberLoss.apply(logits, actions, target, weight, kappa)
+
+
+def adam_step(params, grads, m, v, step: int, lr: float, b1=0.9, b2=0.999, eps=2e-5, grad_scale=1.0):
+  """optax.adam on flat fp32 buffers, in place; step counts from 1."""
+  _require_cuda(params, 'adam_step')
+  rc = _lib.load().ble_adam_step(_ptr(params), _ptr(grads), _ptr(m), _ptr(v), params.numel(), float(lr), float(b1),
+                                 float(b2), float(eps), int(step), float(grad_scale), _stream(params.device))
+  _check(rc, 'ble_adam_step')
+
+
+# ---------------------------------------------------------------------------------------------
+# replay
+# ---------------------------------------------------------------------------------------------
+class DeviceReplay:
+  """Time-major ring of whole N-balloon steps kept in HBM; n-step transitions are assembled at sampling
+  time by k_replay_sample.  capacity_steps * N transitions (the reference keeps 2,000,000)."""
+
+  def __init__(self, num_envs: int, capacity_steps: int, *, num_features: int = NUM_FEATURES, n_step: int = 5,
+               gamma: float = 0.993, device='cuda:0', seed: int = 0):
+    self.device = torch.device(device)
+    if self.device.type != 'cuda':
+      raise _lib.BleError('DeviceReplay lives in GPU memory (no CPU fallback exists)')
+    self.num_envs, self.capacity, self.num_features = int(num_envs), int(capacity_steps), int(num_features)
+    self.n_step, self.gamma = int(n_step), float(gamma)
+    self.obs = torch.zeros(self.capacity, self.num_envs, self.num_features, dtype=torch.float32, device=self.device)
+    self.action = torch.zeros(self.capacity, self.num_envs, dtype=torch.int32, device=self.device)
+    self.reward = torch.zeros(self.capacity, self.num_envs, dtype=torch.float32, device=self.device)
+    self.terminal = torch.zeros(self.capacity, self.num_envs, dtype=torch.uint8, device=self.device)
+    self.truncated = torch.zeros(self.capacity, self.num_envs, dtype=torch.uint8, device=self.device)
+    self.count = 0
+    self._seed = int(seed)
+    self._draws = 0
+
+  @property
+  def num_transitions(self) -> int:
+    return min(self.count, self.capacity) * self.num_envs
+
+  def add(self, obs, action, reward, terminal, truncated) -> None:
+    """One lockstep environment step: obs [N, F] the actions were chosen on, and what the step returned."""
+    slot = self.count % self.capacity
+    self.obs[slot].copy_(obs)
+    self.action[slot].copy_(action)
+    self.reward[slot].copy_(reward)
+    self.terminal[slot].copy_(terminal)
+    self.truncated[slot].copy_(truncated)
+    self.count += 1
+
+  def view(self) -> _lib.BleReplayView:
+    return _lib.BleReplayView(self.obs.data_ptr(), self.action.data_ptr(), self.reward.data_ptr(),
+                              self.terminal.data_ptr(), self.truncated.data_ptr(), self.capacity, self.num_envs,
+                              self.count, self.n_step, self.num_features, self.gamma, 0)
+
+  def sample(self, batch_size: int, indices: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """batch_size n-step transitions; indices (int64 [B, 2] = absolute step, balloon) forces the picks."""
+    b, dev = int(batch_size), self.device
+    out = {'state': torch.empty(b, self.num_features, dtype=torch.float32, device=dev),
+           'next_state': torch.empty(b, self.num_features, dtype=torch.float32, device=dev),
+           'action': torch.empty(b, dtype=torch.int32, device=dev),
+           'return': torch.empty(b, dtype=torch.float32, device=dev),
+           'discount': torch.empty(b, dtype=torch.float32, device=dev),
+           'valid': torch.empty(b, dtype=torch.uint8, device=dev),
+           'indices': torch.empty(b, 2, dtype=torch.int64, device=dev)}
+    if indices is not None:
+      indices = indices.to(dev, torch.int64).contiguous()
+    view = self.view()
+    self._draws += 1
+    seed = (self._seed * 0x9E3779B97F4A7C15 + self._draws) & 0xFFFFFFFFFFFFFFFF
+    rc = _lib.load().ble_replay_sample(ctypes.byref(view), _ptr(indices), seed, b, _ptr(out['state']),
+                                       _ptr(out['next_state']), _ptr(out['action']), _ptr(out['return']),
+                                       _ptr(out['discount']), _ptr(out['valid']), _ptr(out['indices']), _stream(dev))
+    _check(rc, 'ble_replay_sample')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# exploration
+# ---------------------------------------------------------------------------------------------
+class MarcoPoloExploration:
+  """agents/marco_polo_exploration.py:36-93 for N balloons, wrapped around RandomWalkAgent the way
+  acme_utils.CombinedActor does (acme_utils.py:161-183)."""
+
+  def __init__(self, num_envs: int, *, exploratory_episode_probability: float = 0.8, seed: int = 0, device='cuda:0'):
+    self.device = torch.device(device)
+    if self.device.type != 'cuda':
+      raise _lib.BleError('MarcoPoloExploration runs on the GPU (no CPU fallback exists)')
+    self.num_envs = int(num_envs)
+    self.probability = float(exploratory_episode_probability)
+    self.state = torch.zeros(4, self.num_envs, dtype=torch.int32, device=self.device)
+    self.walk_target = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+    g = torch.Generator(device='cpu'); g.manual_seed(int(seed))
+    self.seeds = torch.randint(0, 2**62, (self.num_envs,), dtype=torch.int64, generator=g).to(self.device)
+    self._k = 0
+
+  def step(self, obs: torch.Tensor, rl_actions: torch.Tensor, begin: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """obs [N, 1099], the learner's actions int32 [N], begin uint8 [N] (1 = first observation of an episode)."""
+    actions = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+    if begin is not None:
+      begin = begin.to(self.device, torch.uint8).contiguous()
+    rc = _lib.load().ble_marco_polo_step(_ptr(obs.contiguous()), _ptr(rl_actions.to(torch.int32).contiguous()),
+                                         _ptr(begin), self.num_envs, _ptr(self.state), _ptr(self.walk_target),
+                                         _ptr(self.seeds), self._k, self.probability, _ptr(actions), _stream(self.device))
+    _check(rc, 'ble_marco_polo_step')
+    self._k += 1
+    return actions
+
+  @property
+  def exploratory_phase(self) -> torch.Tensor:
+    return self.state[1].bool()
+
+
+# ---------------------------------------------------------------------------------------------
+# learner
+# ---------------------------------------------------------------------------------------------
+def allreduce_sum_(flat: torch.Tensor) -> int:
+  """Sums a flat gradient buffer over the data-parallel group in place; returns the group size."""
+  if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return dist.get_world_size()
+  return 1
+
+
+class QrDqnLearner:
+  """One data-parallel replica of the QR-DQN learner (acme dqn learner with the QrDqn loss)."""
+
+  def __init__(self, config: QrDqnConfig = QrDqnConfig(), *, device='cuda:0', seed: int = 0):
+    self.config = config
+    self.device = torch.device(device)
+    if self.device.type != 'cuda':
+      raise _lib.BleError('QrDqnLearner needs a CUDA device (no CPU fallback exists)')
+    torch.manual_seed(int(seed))                       # same seed on every rank -> identical initial replicas
+    self.online = QuantileNetwork(config).to(self.device)
+    self.target = QuantileNetwork(config).to(self.device)
+    self.flat = flatten_parameters(self.online, self.device)
+    self.flat_target = flatten_parameters(self.target, self.device)
+    self.flat_target.copy_(self.flat)
+    for p in self.target.parameters():
+      p.requires_grad_(False)
+    self.m = torch.zeros_like(self.flat)
+    self.v = torch.zeros_like(self.flat)
+    self.steps = 0
+    self.kernel_launches = 0
+
+  @torch.no_grad()
+  def act(self, obs: torch.Tensor, epsilon: Optional[float] = None, generator: Optional[torch.Generator] = None):
+    """Behaviour policy (acme_utils.py:250-258): epsilon-greedy on the mean over atoms."""
+    actions = greedy_actions(self.online(obs))
+    self.kernel_launches += 1
+    eps = self.config.epsilon if epsilon is None else epsilon
+    if eps > 0.0:
+      n = actions.numel()
+      explore = torch.rand(n, device=self.device, generator=generator) < eps
+      random_actions = torch.randint(0, self.config.num_actions, (n,), dtype=torch.int32, device=self.device, generator=generator)
+      actions = torch.where(explore, random_actions, actions)
+    return actions
+
+  def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """One SGD step on a sampled batch; returns the mean loss (device scalar)."""
+    cfg = self.config
+    with torch.no_grad():
+      target = target_distribution(self.target(batch['next_state']), batch['return'], batch['discount'])
+    logits = self.online(batch['state'])
+    weight = batch['valid'].to(torch.float32) if 'valid' in batch else None
+    self.online.flat_grad.zero_()
+    mean_loss, _ = quantile_huber_loss(logits, batch['action'], target, weight, cfg.huber_param)
+    mean_loss.backward()
+    world = allreduce_sum_(self.online.flat_grad)
+    self.steps += 1
+    adam_step(self.flat, self.online.flat_grad, self.m, self.v, self.steps, cfg.learning_rate, cfg.adam_b1, cfg.adam_b2,
+              cfg.adam_eps, 1.0 / world)
+    self.kernel_launches += 3
+    if self.steps % cfg.target_update_period == 0:     # optax.periodically_update in acme's dqn learner
+      self.flat_target.copy_(self.flat)
+    return mean_loss.detach()
+
+  def state_dict(self) -> Dict[str, torch.Tensor]:
+    return {'params': self.flat.clone(), 'target': self.flat_target.clone(), 'm': self.m.clone(), 'v': self.v.clone(),
+            'steps': torch.tensor(self.steps)}
+
+  def load_state_dict(self, state: Dict[str, torch.Tensor]) -> None:
+    self.flat.copy_(state['params']); self.flat_target.copy_(state['target'])
+    self.m.copy_(state['m']); self.v.copy_(state['v'])
+    self.steps = int(state['steps'])
+
+
+def run_training(env, learner: QrDqnLearner, *, num_iterations: int, replay: Optional[DeviceReplay] = None,
+                 exploration: Optional[MarcoPoloExploration] = None, learner_steps_per_iteration: Optional[int] = None,
+                 seed: int = 0, log=None) -> Dict[str, float]:
+  """train_acme_qrdqn.py:72-81 for a BatchedBalloonEnv(observation='perciatelli'): every iteration steps all N
+  balloons once, appends the step to the replay ring, restarts the balloons whose episode ended (terminal
+  status or max_episode_length) and runs the learner.  learner_steps_per_iteration defaults to the
+  reference's ratio (samples_per_insert = 8): N * 8 / batch_size SGD steps per N inserted transitions."""
+  cfg = learner.config
+  n, dev = env.num_envs, env.device
+  replay = replay if replay is not None else DeviceReplay(
+      n, max(cfg.n_step + 2, cfg.max_replay_size // n), num_features=cfg.num_features, n_step=cfg.n_step,
+      gamma=cfg.discount, device=dev, seed=seed)
+  if learner_steps_per_iteration is None:
+    learner_steps_per_iteration = max(1, round(n * cfg.samples_per_insert / cfg.batch_size))
+  obs = env.reset(seed=seed)
+  begin = torch.ones(n, dtype=torch.uint8, device=dev)
+  episode_steps = torch.zeros(n, dtype=torch.int32, device=dev)
+  reward_sum = torch.zeros((), dtype=torch.float64, device=dev)
+  episodes = torch.zeros((), dtype=torch.int64, device=dev)
+  last_loss = torch.zeros((), device=dev)
+  for it in range(num_iterations):
+    actions = learner.act(obs)
+    if exploration is not None:
+      actions = exploration.step(obs, actions, begin)
+    acted_on = obs.clone()                       # env.step overwrites its observation buffer
+    obs, reward, done, _ = env.step(actions)
+    episode_steps += 1
+    terminal = done.ne(0)
+    truncated = (episode_steps >= cfg.max_episode_length) & ~terminal     # StepLimitWrapper, acme_utils.py:72-73
+    replay.add(acted_on, actions, reward, terminal.to(torch.uint8), truncated.to(torch.uint8))
+    reward_sum += reward.sum(dtype=torch.float64)
+    ended = terminal | truncated
+    episodes += ended.sum()
+    if bool(ended.any()):
+      obs = env.reset_where(ended)
+      episode_steps.masked_fill_(ended, 0)
+    begin = ended.to(torch.uint8)
+    if replay.num_transitions >= cfg.min_replay_size and replay.count > cfg.n_step:
+      for _ in range(learner_steps_per_iteration):
+        last_loss = learner.step(replay.sample(cfg.batch_size))
+    if log is not None:
+      log(it, last_loss)
+  return {'env_steps': num_iterations * n, 'learner_steps': learner.steps, 'episodes': int(episodes),
+          'mean_reward': float(reward_sum) / max(1, num_iterations * n), 'last_loss': float(last_loss)}

@@ -6,7 +6,11 @@
 One "step" = one BalloonEnv.step (wind lookup + safety layers + 18 physics sub-steps + reward)
 for every balloon of the batch.  Default workload = BASELINE.json configs[2]: 65,536 balloons,
 random agent, one wind field per balloon (synthetic fields: the VAE decoder is reset-time only).
-N > 1 (torchrun) shards the balloons across ranks with no data-path collective: strong scaling.
+N > 1 (torchrun): balloons are sharded across ranks with no data-path collective.  Default is weak
+scaling (65,536 balloons PER GPU, the single-GPU workload replicated; `value` = all balloons of all
+ranks / max-over-ranks time); the same run then also times the strong-scaling split of ONE 65,536
+batch (65,536 / N per GPU) and reports it under "strong_scaling".  `--scaling strong` makes the
+fixed-total batch the headline instead.
 
 `--impl reference` times the CPU oracle port (oracle/, the restated reference algorithm) on the
 host cores on a bounded sample of the same workload.
@@ -124,7 +128,7 @@ def run_reference(args):
   line = {
       'metric': METRIC, 'value': value, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps,
       'warmup': args.warmup, 'ms_per_step': 1e3 * args.num_envs / value, 'higher_is_better': True,
-      'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+      'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
       'config': {'workload': f'batch={args.num_envs} balloons, random agent, per-balloon wind field + simplex noise '
                              '(BASELINE configs[2]); CPU arm runs a bounded sample'},
       'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
@@ -160,8 +164,9 @@ def run_b200(args):
     dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
   torch.cuda.set_device(local_rank)
   device = torch.device(f'cuda:{local_rank}')
-  n_total = args.num_envs
-  begin, end = sharding.shard_range(n_total, rank, world)    # strong scaling: fixed total batch
+  weak = args.scaling == 'weak'
+  n_total = args.num_envs * world if weak else args.num_envs
+  begin, end = sharding.shard_range(n_total, rank, world)    # contiguous balloon range of this rank
   n = end - begin
 
   with_obs = args.observation == 'perciatelli'
@@ -302,6 +307,35 @@ def run_b200(args):
                 'decoder': 'ble_decode_fields: 4 cuBLASLt fp32 GEMMs (64-1000-1000-1000-4410) + resize/curl epilogue, '
                            'random-init weights'}
 
+  # ---- N > 1, weak run: also time the strong-scaling split of ONE --num-envs batch ----------------
+  strong = None
+  if world > 1 and weak:
+    arena.close()
+    del obs_buf
+    torch.cuda.empty_cache()
+    sb, se = sharding.shard_range(args.num_envs, rank, world)
+    ns = se - sb
+    s_layout = 'x128' if ns * 3686400 <= 60e9 else 'x64'
+    arena = batched_env.BatchedBalloonArena(ns, device=str(device), precision='fp32', wind_model='grid',
+                                            enable_noise=True, field_layout=s_layout)
+    upload_synthetic_fields(torch, arena, ns, device, seed=4321 + rank)
+    arena.set_field_map(torch.arange(ns, dtype=torch.int32, device=device))
+    arena.reset(torch.randint(0, 2**62, (ns,), dtype=torch.int64, generator=g))
+    s_actions = actions[:, :ns].contiguous()
+    for t in range(args.warmup):
+      arena.step(s_actions[t])
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for t in range(args.warmup, total):
+      arena.step(s_actions[t])
+    s1.record()
+    barrier()
+    s_ms = sharding.reduce_run_stats(s0.elapsed_time(s1), 0, 0, device=device)['elapsed_ms']
+    strong = {'num_envs': args.num_envs, 'envs_per_gpu': ns, 'field_layout': s_layout, 'ms_per_step': s_ms / args.steps,
+              'value': args.num_envs * args.steps / (s_ms * 1e-3), 'unit': UNIT,
+              'note': 'one --num-envs batch split over the GPUs (fixed total work), device-resident, max over ranks'}
+
   stats = sharding.reduce_run_stats(ms, n * args.steps, launches, device=device)
   ms, launches = stats['elapsed_ms'], stats['launches']
   e2e_s = sharding.reduce_run_stats(e2e_s * 1e3, 0, 0, device=device)['elapsed_ms'] * 1e-3
@@ -315,7 +349,7 @@ def run_b200(args):
   e2e_value = n_total * e2e_steps / e2e_s
   line = {
       'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-      'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+      'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
       'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': f'batch={n_total} balloons, random agent, one synthetic wind field per balloon '
                              f'({n_fields} fields/GPU) + simplex noise, 18 sub-steps per step (BASELINE configs[2])',
@@ -346,6 +380,8 @@ def run_b200(args):
                                             'steps': args.observation_probe,
                                             'note': 'ble_step + ble_features_perciatelli (1099 float32 features per balloon, '
                                                     'GP window still filling), device-resident; single GPU share'}
+  if strong is not None:
+    line['strong_scaling'] = strong
   if world == 1 and not args.no_cpu_baseline:
     t0 = time.perf_counter()
     v1 = cpu_oracle_throughput(2048, 40, 1)
@@ -364,7 +400,10 @@ def main():
   ap.add_argument('--steps', type=int, default=50)
   ap.add_argument('--warmup', type=int, default=5)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-  ap.add_argument('--num-envs', type=int, default=65536)
+  ap.add_argument('--num-envs', type=int, default=65536,
+                  help='balloons per GPU (--scaling weak) or in total (--scaling strong)')
+  ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                  help='N > 1: weak = --num-envs balloons per GPU; strong = --num-envs balloons split over the GPUs')
   ap.add_argument('--shared-fields', type=int, default=0, help='0 = one field per balloon; else size of a shared pool')
   ap.add_argument('--field-layout', default='auto', choices=['auto', 'x64', 'x128'])
   ap.add_argument('--observation', default='none', choices=['none', 'perciatelli'],

@@ -63,7 +63,9 @@ typedef struct {
   int32_t enable_noise;        /* 1: ground truth = forecast + simplex noise (wind_field.py:125-145) */
   int32_t field_layout;        /* BLE_LAYOUT_*                                                      */
   int32_t enable_features;     /* 1: keep the WindGP history and allow ble_features_perciatelli      */
-  int32_t reserved[3];         /* must be 0                                                         */
+  int32_t decoder_tf32;        /* 1: the decoder GEMMs run on the tensor cores (TF32 inputs, fp32
+                                * accumulate); 0 (default): fp32 FMA, used by the parity tests        */
+  int32_t reserved[2];         /* must be 0                                                         */
 } ble_config;
 
 /* State exchange: two row-major device matrices, one row per field, N columns.
@@ -209,12 +211,73 @@ enum {
   BLE_NUM_E
 };
 int ble_generate_fields(ble_handle* h, const uint64_t* seeds, int64_t first_field, int64_t count, void* stream);
+/* Same for a scattered set of fields (the balloons whose episode just ended): field_index is device
+ * int32 [count], each entry in [0, n_fields) and distinct. */
+int ble_generate_fields_at(ble_handle* h, const uint64_t* seeds, const int32_t* field_index, int64_t count,
+                           void* stream);
 int ble_agent_station_seeker(ble_handle* h, const float* obs, int32_t* actions, int32_t* best_level, void* stream);
 int ble_agent_random_walk(ble_handle* h, const float* obs, const uint64_t* seeds, int32_t step_index,
                           int32_t* actions, void* stream);
 int ble_eval_begin(ble_handle* h, void* stream);
 int ble_eval_accumulate(ble_handle* h, const float* reward, float* flight_path, void* stream);
 int ble_eval_results(ble_handle* h, double* out, void* stream);
+
+/* ---- QR-DQN learner surface (BASELINE configs[4]) ----------------------
+ * Stateless kernels around the quantile network the reference trains with Acme's DQN builder
+ * (acme_utils.py:217-277: 8 layers x 600 units, 3 actions x 51 atoms, QrDqn(huber_param=1), n_step 5,
+ * discount 0.993, Adam 2e-6 / eps 2e-5, target period 25 learner steps) or Dopamine's JaxQuantileAgent
+ * (agents/quantile_agent.py:37-160, agents/configs/quantile.gin).  Every pointer is caller-owned DEVICE
+ * memory; no handle is needed.  The dense layers are library GEMMs on the caller's side.
+ *   ble_qr_greedy: actions[b] = argmax_a mean_j logits[b, a, j] (first maximum), the epsilon = 0
+ *     behaviour / eval policy of acme_utils.py:250-268; q_values float32 [B, A] or NULL.
+ *   ble_qr_target: target[b, j] = reward[b] + discount[b] * next_logits[b, a*, j] with a* the greedy action
+ *     of next_logits (dopamine quantile_agent.target_distribution; discount = gamma^n * (1 - terminal)).
+ *   ble_qr_loss: loss[b] = (1/N) sum_i sum_j |tau_i - 1{d_ij < 0}| huber_kappa(d_ij), d_ij = target[b, j] -
+ *     logits[b, actions[b], i], tau_i = (i + 0.5) / N (dopamine quantile_agent.train == rlax
+ *     quantile_q_learning for kappa = 1).  If grad_logits is not NULL it receives
+ *     grad_scale * weight[b] * d loss[b] / d logits[b, :, :] (zero rows for the other actions); weight may be
+ *     NULL (= 1).  num_atoms <= 64.
+ *   ble_replay_sample: draws `batch` n-step transitions from a time-major ring of N-balloon steps.
+ *     A window that reaches a terminal step is cut there (discount 0); one that crosses a step-limit
+ *     truncation, the write cursor or the ring's oldest step is redrawn (up to 32 times; valid[b] = 0 if
+ *     none was found).  forced_indices (int64 [B, 2] = absolute step, balloon) replaces the random draw
+ *     when not NULL; picked (int64 [B, 2] or NULL) reports the indices used.
+ *   ble_adam_step: optax.adam on a flat buffer: m, v moments, step counted from 1, grads multiplied by
+ *     grad_scale first (1 / world_size after a summing all-reduce).
+ *   ble_marco_polo_step: MarcoPoloExploration (agents/marco_polo_exploration.py:36-93) wrapped around
+ *     RandomWalkAgent (agents/random_walk_agent.py:35-94) the way acme_utils.CombinedActor does
+ *     (acme_utils.py:161-183): begin[e] != 0 marks the first observation of an episode.  state: int32
+ *     [4][N] (exploratory_episode, exploratory_phase, phase_elapsed_s, walk_elapsed_s); walk_target:
+ *     float64 [N]; random stream Philox(seeds[e], step_index). */
+typedef struct ble_replay_view {
+  const float* obs;            /* [capacity][N][num_features] observation the action was chosen on */
+  const int32_t* action;       /* [capacity][N] */
+  const float* reward;         /* [capacity][N] */
+  const uint8_t* terminal;     /* [capacity][N] 1: the environment ended the episode after this step */
+  const uint8_t* truncated;    /* [capacity][N] 1: the step limit ended the episode after this step  */
+  int64_t capacity;            /* ring length in steps                                               */
+  int64_t num_envs;            /* N                                                                  */
+  int64_t count;               /* steps written so far (monotonic; slot = step % capacity)           */
+  int32_t n_step;              /* update horizon (5)                                                 */
+  int32_t num_features;        /* 1099                                                               */
+  float gamma;                 /* 0.993                                                              */
+  int32_t reserved;
+} ble_replay_view;
+int ble_qr_greedy(const float* logits, int64_t batch, int32_t num_actions, int32_t num_atoms, int32_t* actions,
+                  float* q_values, void* stream);
+int ble_qr_target(const float* next_logits, const float* reward, const float* discount, int64_t batch,
+                  int32_t num_actions, int32_t num_atoms, float* target, void* stream);
+int ble_qr_loss(const float* logits, const int32_t* actions, const float* target, const float* weight, float kappa,
+                int64_t batch, int32_t num_actions, int32_t num_atoms, float grad_scale, float* loss,
+                float* grad_logits, void* stream);
+int ble_replay_sample(const ble_replay_view* view, const int64_t* forced_indices, uint64_t seed, int64_t batch,
+                      float* state, float* next_state, int32_t* action, float* n_step_return, float* discount,
+                      uint8_t* valid, int64_t* picked, void* stream);
+int ble_adam_step(float* params, const float* grads, float* m, float* v, int64_t count, float learning_rate,
+                  float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
+int ble_marco_polo_step(const float* obs, const int32_t* rl_actions, const uint8_t* begin, int64_t num_envs,
+                        int32_t* state, double* walk_target, const uint64_t* seeds, int64_t step_index,
+                        float exploratory_episode_probability, int32_t* actions, void* stream);
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t ble_launch_count(const ble_handle* h);
