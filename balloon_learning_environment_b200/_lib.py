@@ -111,12 +111,12 @@ def load(build_if_missing=True):
   lib.ble_eval_begin.argtypes = [vp, vp]
   lib.ble_eval_accumulate.argtypes = [vp, vp, vp, vp]
   lib.ble_eval_results.argtypes = [vp, vp, vp]
-  f32, u64 = _c.c_float, _c.c_uint64
+  f32, f64, u64 = _c.c_float, _c.c_double, _c.c_uint64
   lib.ble_qr_greedy.argtypes = [vp, i64, i32, i32, vp, vp, vp]
   lib.ble_qr_target.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
   lib.ble_qr_loss.argtypes = [vp, vp, vp, vp, f32, i64, i32, i32, f32, vp, vp, vp]
   lib.ble_replay_sample.argtypes = [_c.POINTER(BleReplayView), vp, u64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
-  lib.ble_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, f32, vp]
+  lib.ble_adam_step.argtypes = [vp, vp, vp, vp, i64, f64, f64, f64, f64, i64, f32, vp]
   lib.ble_marco_polo_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, f32, vp, vp]
   for name in EXPORTS:
     if name not in ('ble_last_error', 'ble_num_envs', 'ble_launch_count'):

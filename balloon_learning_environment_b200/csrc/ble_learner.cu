@@ -207,12 +207,12 @@ k_replay_sample(ReplayView r, const int64_t* __restrict__ forced /*[B,2] (t, e) 
 // ---- optimiser -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t count,
-       float lr, float b1, float b2, float eps, float inv_c1, float inv_c2, float grad_scale) {
+       float lr, float b1, float b2, float omb1, float omb2, float eps, float inv_c1, float inv_c2, float grad_scale) {
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += stride) {
     const float gi = g[i] * grad_scale;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float mi = b1 * m[i] + omb1 * gi;            // 1 - beta formed in double on the host (1.f - 0.999f is 4.7e-5 off)
+    const float vi = b2 * v[i] + omb2 * gi * gi;
     m[i] = mi; v[i] = vi;
     p[i] -= lr * (mi * inv_c1) / (sqrtf(vi * inv_c2) + eps);
   }
@@ -310,14 +310,15 @@ int ble_replay_sample(const ble_replay_view* view, const int64_t* forced_indices
   return ble::finish();
 }
 
-int ble_adam_step(float* params, const float* grads, float* m, float* v, int64_t count, float learning_rate, float beta1,
-                  float beta2, float eps, int64_t step, float grad_scale, void* stream) {
+int ble_adam_step(float* params, const float* grads, float* m, float* v, int64_t count, double learning_rate, double beta1,
+                  double beta2, double eps, int64_t step, float grad_scale, void* stream) {
   if (params == nullptr || grads == nullptr || m == nullptr || v == nullptr || count < 0 || step < 1) return BLE_ERR_INVALID_ARGUMENT;
   if (count == 0) return BLE_OK;
-  const double c1 = std::pow(double(beta1), double(step)), c2 = std::pow(double(beta2), double(step));
+  const double c1 = std::pow(beta1, double(step)), c2 = std::pow(beta2, double(step));
   const float inv_c1 = float(1.0 / (1.0 - c1)), inv_c2 = float(1.0 / (1.0 - c2));
   const unsigned grid = unsigned(std::min<int64_t>((count + 255) / 256, 148 * 8));
-  ble::k_adam<<<grid, 256, 0, cudaStream_t(stream)>>>(params, grads, m, v, count, learning_rate, beta1, beta2, eps,
+  ble::k_adam<<<grid, 256, 0, cudaStream_t(stream)>>>(params, grads, m, v, count, float(learning_rate), float(beta1), float(beta2),
+                                                      float(1.0 - beta1), float(1.0 - beta2), float(eps),
                                                       inv_c1, inv_c2, grad_scale);
   return ble::finish();
 }

@@ -86,7 +86,7 @@ class QuantileNetwork(nn.Module):
       nn.init.zeros_(layer.bias)
 
   def forward(self, x: torch.Tensor) -> torch.Tensor:
-    h = x.to(torch.float32)
+    h = x.to(self.layers[0].weight.dtype)           # float32 in production (networks.py:83)
     for i, layer in enumerate(self.layers):
       h = layer(h)
       if i + 1 < len(self.layers):

@@ -273,8 +273,8 @@ int ble_qr_loss(const float* logits, const int32_t* actions, const float* target
 int ble_replay_sample(const ble_replay_view* view, const int64_t* forced_indices, uint64_t seed, int64_t batch,
                       float* state, float* next_state, int32_t* action, float* n_step_return, float* discount,
                       uint8_t* valid, int64_t* picked, void* stream);
-int ble_adam_step(float* params, const float* grads, float* m, float* v, int64_t count, float learning_rate,
-                  float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
+int ble_adam_step(float* params, const float* grads, float* m, float* v, int64_t count, double learning_rate,
+                  double beta1, double beta2, double eps, int64_t step, float grad_scale, void* stream);
 int ble_marco_polo_step(const float* obs, const int32_t* rl_actions, const uint8_t* begin, int64_t num_envs,
                         int32_t* state, double* walk_target, const uint64_t* seeds, int64_t step_index,
                         float exploratory_episode_probability, int32_t* actions, void* stream);
