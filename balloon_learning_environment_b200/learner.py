@@ -8,7 +8,7 @@ agents/configs/quantile.gin -- for N balloons stepping in lockstep on the device
   DeviceReplay         the replay table (max_replay_size 2,000,000, n_step 5, discount 0.993)
   MarcoPoloExploration agents/marco_polo_exploration.py:36-93 around RandomWalkAgent (acme_utils.py:161-214)
   QrDqnLearner         QrDqn(num_atoms=51, huber_param=1) loss, Adam(2e-6, eps 2e-5), target period 25
-  run_training         the EnvironmentLoop of train_acme_qrdqn.py:72-81, one iteration = N env steps
+  TrainingLoop         the EnvironmentLoop of train_acme_qrdqn.py:72-81, one iteration = N env steps
 
 The dense layers are cuBLAS GEMMs through torch; everything else on the update path is a hand-written
 CUDA kernel behind the C ABI (csrc/ble_learner.cu).  Data-parallel training keeps one learner per GPU
@@ -70,6 +70,8 @@ class QrDqnConfig:
   epsilon: float = 0.0                   # quantile.gin: epsilon_train = 0 (MarcoPolo explores instead)
   exploratory_episode_probability: float = 0.8   # acme_utils.py:207
   max_episode_length: int = 960          # train_acme_qrdqn.py:30-33
+  tf32_matmul: bool = True               # dense layers on the tensor cores (TF32 in, fp32 accumulate): what
+                                         # jax's default matmul precision does on an Ampere+ GPU
 
 
 class QuantileNetwork(nn.Module):
@@ -305,6 +307,7 @@ class QrDqnLearner:
     self.device = torch.device(device)
     if self.device.type != 'cuda':
       raise _lib.BleError('QrDqnLearner needs a CUDA device (no CPU fallback exists)')
+    torch.backends.cuda.matmul.allow_tf32 = bool(config.tf32_matmul)
     torch.manual_seed(int(seed))                       # same seed on every rank -> identical initial replicas
     self.online = QuantileNetwork(config).to(self.device)
     self.target = QuantileNetwork(config).to(self.device)
@@ -360,47 +363,88 @@ class QrDqnLearner:
     self.steps = int(state['steps'])
 
 
-def run_training(env, learner: QrDqnLearner, *, num_iterations: int, replay: Optional[DeviceReplay] = None,
-                 exploration: Optional[MarcoPoloExploration] = None, learner_steps_per_iteration: Optional[int] = None,
-                 seed: int = 0, log=None) -> Dict[str, float]:
+class TrainingLoop:
   """train_acme_qrdqn.py:72-81 for a BatchedBalloonEnv(observation='perciatelli'): every iteration steps all N
   balloons once, appends the step to the replay ring, restarts the balloons whose episode ended (terminal
   status or max_episode_length) and runs the learner.  learner_steps_per_iteration defaults to the
   reference's ratio (samples_per_insert = 8): N * 8 / batch_size SGD steps per N inserted transitions."""
-  cfg = learner.config
-  n, dev = env.num_envs, env.device
-  replay = replay if replay is not None else DeviceReplay(
-      n, max(cfg.n_step + 2, cfg.max_replay_size // n), num_features=cfg.num_features, n_step=cfg.n_step,
-      gamma=cfg.discount, device=dev, seed=seed)
-  if learner_steps_per_iteration is None:
-    learner_steps_per_iteration = max(1, round(n * cfg.samples_per_insert / cfg.batch_size))
-  obs = env.reset(seed=seed)
-  begin = torch.ones(n, dtype=torch.uint8, device=dev)
-  episode_steps = torch.zeros(n, dtype=torch.int32, device=dev)
-  reward_sum = torch.zeros((), dtype=torch.float64, device=dev)
-  episodes = torch.zeros((), dtype=torch.int64, device=dev)
-  last_loss = torch.zeros((), device=dev)
-  for it in range(num_iterations):
-    actions = learner.act(obs)
-    if exploration is not None:
-      actions = exploration.step(obs, actions, begin)
-    acted_on = obs.clone()                       # env.step overwrites its observation buffer
-    obs, reward, done, _ = env.step(actions)
-    episode_steps += 1
-    terminal = done.ne(0)
-    truncated = (episode_steps >= cfg.max_episode_length) & ~terminal     # StepLimitWrapper, acme_utils.py:72-73
-    replay.add(acted_on, actions, reward, terminal.to(torch.uint8), truncated.to(torch.uint8))
-    reward_sum += reward.sum(dtype=torch.float64)
-    ended = terminal | truncated
-    episodes += ended.sum()
-    if bool(ended.any()):
-      obs = env.reset_where(ended)
-      episode_steps.masked_fill_(ended, 0)
-    begin = ended.to(torch.uint8)
-    if replay.num_transitions >= cfg.min_replay_size and replay.count > cfg.n_step:
-      for _ in range(learner_steps_per_iteration):
-        last_loss = learner.step(replay.sample(cfg.batch_size))
-    if log is not None:
-      log(it, last_loss)
-  return {'env_steps': num_iterations * n, 'learner_steps': learner.steps, 'episodes': int(episodes),
-          'mean_reward': float(reward_sum) / max(1, num_iterations * n), 'last_loss': float(last_loss)}
+
+  def __init__(self, env, learner: QrDqnLearner, *, replay: Optional[DeviceReplay] = None,
+               exploration: Optional[MarcoPoloExploration] = None, learner_steps_per_iteration: Optional[int] = None,
+               seed: int = 0):
+    cfg = learner.config
+    self.env, self.learner, self.exploration = env, learner, exploration
+    n, dev = env.num_envs, env.device
+    self.replay = replay if replay is not None else DeviceReplay(
+        n, max(cfg.n_step + 2, cfg.max_replay_size // n), num_features=cfg.num_features, n_step=cfg.n_step,
+        gamma=cfg.discount, device=dev, seed=seed)
+    if learner_steps_per_iteration is None:
+      learner_steps_per_iteration = max(1, round(n * cfg.samples_per_insert / cfg.batch_size))
+    self.learner_steps_per_iteration = int(learner_steps_per_iteration)
+    self.obs = env.reset(seed=seed)
+    self.begin = torch.ones(n, dtype=torch.uint8, device=dev)
+    self.episode_steps = torch.zeros(n, dtype=torch.int32, device=dev)
+    self.last_loss = torch.zeros((), device=dev)
+    self.iterations = 0
+    self.phase_ms: Dict[str, float] = {}           # filled by run(profile=True)
+
+  def run(self, num_iterations: int, log=None, profile: bool = False) -> Dict[str, float]:
+    """profile=True brackets the phases of every iteration with CUDA events (sums land in self.phase_ms)."""
+    env, learner, replay, cfg = self.env, self.learner, self.replay, self.learner.config
+    n, dev = env.num_envs, env.device
+    marks = []
+
+    def mark(name):
+      if profile:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append((name, ev))
+    reward_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    episodes = torch.zeros((), dtype=torch.int64, device=dev)
+    steps_before = learner.steps
+    for _ in range(num_iterations):
+      mark('start')
+      actions = learner.act(self.obs)
+      if self.exploration is not None:
+        actions = self.exploration.step(self.obs, actions, self.begin)
+      acted_on = self.obs.clone()                  # env.step overwrites its observation buffer
+      mark('act')
+      obs, reward, done, _ = env.step(actions)
+      mark('env_step_and_observation')
+      self.episode_steps += 1
+      terminal = done.ne(0)
+      truncated = (self.episode_steps >= cfg.max_episode_length) & ~terminal     # StepLimitWrapper, acme_utils.py:72-73
+      replay.add(acted_on, actions, reward, terminal.to(torch.uint8), truncated.to(torch.uint8))
+      reward_sum += reward.sum(dtype=torch.float64)
+      ended = terminal | truncated
+      episodes += ended.sum()
+      if bool(ended.any()):
+        obs = env.reset_where(ended)
+        self.episode_steps.masked_fill_(ended, 0)
+      self.obs, self.begin = obs, ended.to(torch.uint8)
+      mark('replay_add_and_resets')
+      if replay.num_transitions >= cfg.min_replay_size and replay.count > cfg.n_step:
+        for _ in range(self.learner_steps_per_iteration):
+          batch = replay.sample(cfg.batch_size)
+          mark('replay_sample')
+          self.last_loss = learner.step(batch)
+          mark('learner_step')
+      self.iterations += 1
+      if log is not None:
+        log(self.iterations, self.last_loss)
+    if profile:
+      torch.cuda.synchronize(dev)
+      for (_, prev), (name, ev) in zip(marks[:-1], marks[1:]):
+        if name != 'start':
+          self.phase_ms[name] = self.phase_ms.get(name, 0.0) + prev.elapsed_time(ev)
+    return {'env_steps': num_iterations * n, 'learner_steps': learner.steps - steps_before, 'episodes': int(episodes),
+            'mean_reward': float(reward_sum) / max(1, num_iterations * n), 'last_loss': float(self.last_loss)}
+
+
+def run_training(env, learner: QrDqnLearner, *, num_iterations: int, replay: Optional[DeviceReplay] = None,
+                 exploration: Optional[MarcoPoloExploration] = None, learner_steps_per_iteration: Optional[int] = None,
+                 seed: int = 0, log=None) -> Dict[str, float]:
+  """One-shot form of TrainingLoop: reset, then num_iterations iterations."""
+  loop = TrainingLoop(env, learner, replay=replay, exploration=exploration,
+                      learner_steps_per_iteration=learner_steps_per_iteration, seed=seed)
+  return loop.run(num_iterations, log=log)

@@ -192,7 +192,8 @@ def test_marco_polo_matches_oracle(lrn):
 def test_learner_step_matches_torch_fp64(lrn):
   """One full learner update (target net -> target distribution -> loss -> backward -> Adam) against the
   same computation in fp64 torch on the CPU with the oracle's loss gradient."""
-  cfg = lrn.QrDqnConfig(num_layers=3, hidden_units=32, num_features=19, learning_rate=1e-3, target_update_period=2)
+  cfg = lrn.QrDqnConfig(num_layers=3, hidden_units=32, num_features=19, learning_rate=1e-3, target_update_period=2,
+                        tf32_matmul=False)
   learner = lrn.QrDqnLearner(cfg, seed=1)
   ref = lrn.QuantileNetwork(cfg).double()
   ref_t = lrn.QuantileNetwork(cfg).double()
