@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.environ.get('BLE_B200_LIB') or os.path.join(PKG_DIR, 'libble_b200.so')
 SOURCES = [os.path.join(CSRC, 'ble_engine.cu'), os.path.join(CSRC, 'ble_learner.cu')]
 HEADERS = [os.path.join(CSRC, f) for f in ('ble_physics.cuh', 'ble_wind.cuh', 'ble_features.cuh',
-                                          'ble_feature_kernels.cuh', 'ble_decoder.cuh', 'ble_agents.cuh', 'ble_rng.cuh')] + [
+                                          'ble_feature_kernels.cuh', 'ble_decoder.cuh', 'ble_agents.cuh', 'ble_rng.cuh', 'ble_gp_kernels.cuh')] + [
            os.path.join(PKG_DIR, '..', 'include', 'ble_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--shared', '-Xcompiler', '-fPIC']

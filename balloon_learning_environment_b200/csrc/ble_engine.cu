@@ -62,8 +62,10 @@ struct DevState {
   // observation surface (WindGP history ring, env/wind_gp.py:98-119): last kGpWindow measurements
   double* gp_obs;            // [n][kGpWindow][6] = x, y, pressure, t, error_u, error_v
   int32_t* gp_count;         // [n] measurements seen so far (ring slot = count % kGpWindow)
-  double* gp_chol;           // [n][kGpWindow (kGpWindow + 1) / 2] packed lower Cholesky factor
-  int32_t* gp_m;             // [n] number of measurements inside the 6 h window
+  double* gp_chol;           // [n][7,680] lower Cholesky factor of the window, 8 x 8 blocked (ble_gp_kernels.cuh)
+  int32_t* gp_m;             // [n] number of measurements the factor was computed for (0 = none)
+  int32_t* gp_first;         // [n] index (in measurements seen) of the factor's first point; -1 = not a suffix
+  double* gp_z;              // [n][kGpWindow][2] L^-1 (error_u, error_v)
   double* feat_range;        // [n][2] reachable pressure range
 };
 
@@ -615,6 +617,7 @@ __global__ void __launch_bounds__(128) k_derived(DevState<Real> d, double* __res
 }
 
 #include "ble_feature_kernels.cuh"
+#include "ble_gp_kernels.cuh"
 #include "ble_decoder.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -790,7 +793,7 @@ k_reset(DevState<Real> d, const uint64_t* __restrict__ seeds, const uint8_t* __r
   d.l[int64_t(L_DATE_TIME) * d.n + e] = ts;
   d.t_elapsed[e] = 0;
   d.flags[e] = pack_flags(kOk, kStay, kEnvNominal, kAltNominal, 0, 1, 0);
-  if (d.gp_count != nullptr) d.gp_count[e] = 0;          // new FeatureConstructor (env/balloon_arena.py:179-182)
+  if (d.gp_count != nullptr) { d.gp_count[e] = 0; d.gp_m[e] = 0; d.gp_first[e] = 0; }   // new FeatureConstructor (env/balloon_arena.py:179-182)
   init_derived_one<Real>(d, e, true);
   // SimplexWindNoise.reset_wind_noise (simplex_wind_noise.py:98-114)
   for (int h = 0; h < 10; ++h) {
@@ -883,6 +886,8 @@ struct Engine : EngineBase {
   bool have_state = false, have_fields = false, have_noise = false;
   bool noise_valid = false;      // noise_partial matches the current state
   double* gp_obs = nullptr; int32_t* gp_count = nullptr; double* gp_chol = nullptr; int32_t* gp_m = nullptr;
+  int32_t* gp_first = nullptr; double* gp_z = nullptr;
+  bool gp_refit_every_step = false;      // BLE_GP_REFIT=1: the first-generation kernels (full refit per call), kept for A/B checks
   double* feat_range = nullptr;
   // VAE decoder (reset path)
   float* dec_w[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -933,8 +938,16 @@ struct Engine : EngineBase {
       BLE_CUDA(cudaMalloc(&gp_obs, sizeof(double) * size_t(kGpWindow) * 6 * n));
       BLE_CUDA(cudaMalloc(&gp_count, sizeof(int32_t) * n));
       BLE_CUDA(cudaMemset(gp_count, 0, sizeof(int32_t) * n));
-      BLE_CUDA(cudaMalloc(&gp_chol, sizeof(double) * size_t(kGpPacked) * n));
+      BLE_CUDA(cudaMalloc(&gp_chol, sizeof(double) * size_t(kGpFactorDoubles) * n));
       BLE_CUDA(cudaMalloc(&gp_m, sizeof(int32_t) * n));
+      BLE_CUDA(cudaMemset(gp_m, 0, sizeof(int32_t) * n));
+      BLE_CUDA(cudaMalloc(&gp_first, sizeof(int32_t) * n));
+      BLE_CUDA(cudaMemset(gp_first, 0, sizeof(int32_t) * n));
+      BLE_CUDA(cudaMalloc(&gp_z, sizeof(double) * size_t(kGpWindow) * 2 * n));
+      d.gp_first = gp_first; d.gp_z = gp_z;
+      if (const char* g = std::getenv("BLE_GP_REFIT")) gp_refit_every_step = std::atoi(g) != 0;
+      BLE_CUDA(cudaFuncSetAttribute(k_gp_update<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUpdateSmem)));
+      BLE_CUDA(cudaFuncSetAttribute(k_gp_column2<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(ColumnSmem))));
       BLE_CUDA(cudaMalloc(&feat_range, sizeof(double) * 2 * n));
       d.gp_obs = gp_obs; d.gp_count = gp_count; d.gp_chol = gp_chol; d.gp_m = gp_m; d.feat_range = feat_range;
       BLE_CUDA(cudaFuncSetAttribute(k_gp_factor<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -953,6 +966,7 @@ struct Engine : EngineBase {
     cudaFree(dec_act[0]); cudaFree(dec_act[1]); cudaFree(dec_workspace);
     if (lt != nullptr) cublasLtDestroy(lt);
     cudaFree(gp_obs); cudaFree(gp_count); cudaFree(gp_chol); cudaFree(gp_m); cudaFree(feat_range);
+    cudaFree(gp_first); cudaFree(gp_z);
     cudaFree(gen_latents); cudaFree(gen_fields);
     cudaFree(ev.reward); cudaFree(ev.within); cudaFree(ev.steps); cudaFree(ev.active); cudaFree(walk_target);
     cudaFree(d_actions); cudaFree(d_reward); cudaFree(d_done);
@@ -1326,6 +1340,7 @@ struct Engine : EngineBase {
     BLE_CUDA(cudaSetDevice(device));
     if (mask == nullptr) {
       BLE_CUDA(cudaMemsetAsync(gp_count, 0, sizeof(int32_t) * n, s));
+      BLE_CUDA(cudaMemsetAsync(gp_m, 0, sizeof(int32_t) * n, s));
     } else {
       err = "features_clear: masked clear is done by ble_reset"; return BLE_ERR_UNSUPPORTED;
     }
@@ -1340,8 +1355,13 @@ struct Engine : EngineBase {
     BLE_CUDA(cudaSetDevice(device));
     k_feat_ambient<Real><<<grid_for(n, 128), 128, 0, s>>>(d, obs);
     k_feat_range<Real><<<grid_for(n, 4), 128, 0, s>>>(d);
-    k_gp_factor<Real><<<unsigned(n), kFactorThreads, sizeof(double) * (kGpPacked + kGpWindow * 4), s>>>(d);
-    k_gp_column<Real><<<unsigned(n), kColumnThreads, kColumnSmem, s>>>(d, obs);
+    if (gp_refit_every_step) {
+      k_gp_factor<Real><<<unsigned(n), kFactorThreads, sizeof(double) * (kGpPacked + kGpWindow * 4), s>>>(d);
+      k_gp_column<Real><<<unsigned(n), kColumnThreads, kColumnSmem, s>>>(d, obs);
+    } else {
+      k_gp_update<Real><<<unsigned(n), kUpdateThreads, kUpdateSmem, s>>>(d);
+      k_gp_column2<Real><<<unsigned(n), kColThreads, sizeof(ColumnSmem), s>>>(d, obs);
+    }
     launches += 4;
     BLE_CUDA(cudaGetLastError());
     return BLE_OK;

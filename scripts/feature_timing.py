@@ -41,9 +41,16 @@ def main():
     arena.features(obs)
   e1.record(); torch.cuda.synchronize()
   ms = e0.elapsed_time(e1) / reps
+  # sliding window: every step drops the oldest measurement and appends a new one
+  slide = []
+  for t in range(6):
+    arena.step(torch.randint(0, 3, (n,), dtype=torch.int32, device=dev, generator=g))
+    e0.record(); arena.features(obs); e1.record(); torch.cuda.synchronize()
+    slide.append(e0.elapsed_time(e1))
   live = float((arena.get_state_dict()['status'] == 0).float().mean())
   print(json.dumps({'num_envs': n, 'gp_window': min(args.fill_steps + 1, 120), 'features_ms': ms,
                     'features_per_s': n / ms * 1e3, 'live_fraction': live,
+                    'features_ms_after_a_step': sorted(slide)[len(slide) // 2],
                     'obs_checksum': float(obs.double().sum())}), flush=True)
   arena.close()
 

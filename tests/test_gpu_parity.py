@@ -479,11 +479,13 @@ def test_perciatelli_features_match_reference(ble, precision):
     arena.close()
 
 
-def test_features_batch_matches_oracle_after_reset(ble):
-  """Device reset -> 12 steps -> features for 48 balloons, against the oracle fed the same states
-  and the same measurement history."""
+@pytest.mark.parametrize('steps,every_step', [(12, False), (131, True)])
+def test_features_batch_matches_oracle_after_reset(ble, steps, every_step):
+  """Device reset -> `steps` steps -> features for 48 balloons, against the oracle fed the same states
+  and the same measurement history.  every_step: features() after every step, so that the Cholesky factor
+  is carried through 120 appends and then 11 drop + append pairs before the final comparison."""
   from oracle import features as features_lib
-  n, steps = 48, 12
+  n = 48
   rng = np.random.default_rng(21)
   bank = golden_fields.field_bank()
   fidx = rng.integers(0, 4, n).astype(np.int32)
@@ -507,12 +509,54 @@ def test_features_batch_matches_oracle_after_reset(ble):
     for k in balloon_lib.FLOAT_FIELDS + balloon_lib.INT_FIELDS:
       setattr(ob, k, st[k].copy())
     ofeat.observe()
+    if every_step:
+      arena.features()
   got = arena.features().cpu().numpy()
   want = ofeat.get_features()
   pad = lambda o: np.all(o[:, 16:].reshape(-1, 361, 3) == np.array([0, 1, 1], np.float32), axis=2)
   np.testing.assert_array_equal(pad(got), pad(want))
   assert np.abs(got - want).max() < 1e-4, float(np.abs(got - want).max())
   arena.close()
+
+
+def test_incremental_gp_matches_full_refit(ble, monkeypatch):
+  """The carried Cholesky factor (drop oldest = rank-1 update, append newest = one forward substitution) against
+  the full refit of every call, over 150 steps: window filling, then sliding (1 drop + 1 append per step),
+  features skipped for a few steps (several drops/appends at once), a masked reset in the middle."""
+  n, steps = 40, 150
+  bank = golden_fields.field_bank()
+  rng = np.random.default_rng(33)
+  fidx = torch.from_numpy(rng.integers(0, 4, n).astype(np.int32))
+  seeds = torch.arange(n, dtype=torch.int64) * 7 + 3
+  arenas = []
+  for refit in ('0', '1'):
+    monkeypatch.setenv('BLE_GP_REFIT', refit)
+    a = ble.BatchedBalloonArena(n, precision='fp32', enable_noise=True, enable_features=True)
+    a.set_wind_fields(torch.from_numpy(bank), fidx)
+    a.reset(seeds)
+    arenas.append(a)
+  monkeypatch.delenv('BLE_GP_REFIT')
+  worst = 0.0
+  skip = set(range(60, 66)) | set(range(131, 141))          # 6 and 10 steps without a features() call
+  for t in range(steps):
+    acts = torch.from_numpy(rng.integers(0, 3, n).astype(np.int32))
+    for a in arenas:
+      a.step(acts)
+    if t == 100:                                             # a third of the balloons start a new episode
+      mask = torch.from_numpy((np.arange(n) % 3 == 0).astype(np.uint8))
+      for a in arenas:
+        a.reset(seeds + 1000, mask)
+    if t in skip:
+      continue
+    got, want = (a.features().cpu().numpy() for a in arenas)
+    err = float(np.abs(got - want).max())
+    worst = max(worst, err)
+    assert err < 1e-5, (t, err, int(np.abs(got - want).max(axis=1).argmax()))   # the refit kernels keep V in fp32
+  st = arenas[0].get_state_dict()
+  assert int((st['status'] == 0).sum()) > n // 2             # most balloons flew the whole test
+  print('incremental vs refit: worst feature difference', worst)
+  for a in arenas:
+    a.close()
 
 
 # ------------------------------------------------------------------------------ VAE decoder (reset path)
