@@ -947,7 +947,8 @@ struct Engine : EngineBase {
       d.gp_first = gp_first; d.gp_z = gp_z;
       if (const char* g = std::getenv("BLE_GP_REFIT")) gp_refit_every_step = std::atoi(g) != 0;
       BLE_CUDA(cudaFuncSetAttribute(k_gp_update<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUpdateSmem)));
-      BLE_CUDA(cudaFuncSetAttribute(k_gp_column2<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(ColumnSmem))));
+      BLE_CUDA(cudaFuncSetAttribute(k_gp_column3<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(Column3Smem))));
+
       BLE_CUDA(cudaMalloc(&feat_range, sizeof(double) * 2 * n));
       d.gp_obs = gp_obs; d.gp_count = gp_count; d.gp_chol = gp_chol; d.gp_m = gp_m; d.feat_range = feat_range;
       BLE_CUDA(cudaFuncSetAttribute(k_gp_factor<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1360,7 +1361,7 @@ struct Engine : EngineBase {
       k_gp_column<Real><<<unsigned(n), kColumnThreads, kColumnSmem, s>>>(d, obs);
     } else {
       k_gp_update<Real><<<unsigned(n), kUpdateThreads, kUpdateSmem, s>>>(d);
-      k_gp_column2<Real><<<unsigned(n), kColThreads, sizeof(ColumnSmem), s>>>(d, obs);
+      k_gp_column3<Real><<<unsigned(n), kC3Threads, sizeof(Column3Smem), s>>>(d, obs);
     }
     launches += 4;
     BLE_CUDA(cudaGetLastError());

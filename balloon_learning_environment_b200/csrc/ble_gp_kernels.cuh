@@ -13,12 +13,9 @@
 //                 both O(m^2); falls back to the full left-looking factorisation when the windows do not
 //                 chain (first call, history cleared, irregular use).  Also solves z = L^-1 y for the two
 //                 error components.  Everything fp64, in shared memory.
-//   k_gp_column2  CTA (15 warps) per balloon: V = L^-1 K*^T for the reachable pressure levels as a blocked
-//                 right-looking triangular solve.  Warp b owns the 8-row block b of every column, a lane
-//                 owns two columns, accumulators live in registers; the only shared traffic per step is the
-//                 8 freshly solved entries of each column.  The owner of block j + 1 solves it inside step j
-//                 (look-ahead), so the barrier never waits for a diagonal solve.  The factor arrives with ONE
-//                 TMA bulk copy.
+//   k_gp_column3  CTA (8 warps) per balloon: V = L^-1 K*^T for the reachable pressure levels as a blocked
+//                 right-looking triangular solve on the fp64 tensor cores (see the kernel's own header).
+//                 The factor arrives with ONE TMA bulk copy.
 //
 // Factor layout in HBM ("blocked lower"): 8 x 8 blocks (b, j), j <= b, at ((b (b + 1) / 2 + j) * 64 doubles,
 // COLUMN-major inside a block (element (r, c) at c * 8 + r, so that the 8 rows of one column are two
@@ -298,39 +295,17 @@ __global__ void __launch_bounds__(kUpdateThreads) k_gp_update(DevState<Real> d) 
 }
 #undef GP_L
 
-// ---------------------------------------------------------------------------------------------------------
-// k_gp_column2
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kColWarps = kGpNumBlk;                  // 15: warp b owns the 8-row block b of every column
-constexpr int kColThreads = 32 * kColWarps;
-constexpr int kColPerPass = 64;                       // two columns per lane
-struct ColumnSmem {
-  double L[kGpBlockedLower];                          // 61,440 B, filled by one TMA bulk copy
-  double xbuf[2][kGpBlk][kColPerPass];                // freshly solved 8 entries of every column, double-buffered
-  double cxy[kGpWindow];                              // level-independent part of the squared distance
-  double pz[kGpWindow];                               // scaled pressure of the measurements
-  double z[kGpWindow][2];                             // L^-1 y
-  double inv_diag[kGpWindow];                         // 1 / L_ii
-  double red[kColWarps][kColPerPass][3];              // per-warp partial |v|^2, v.z_u, v.z_v
-  float feat[kNumLevels * 3];
-  int act[kNumLevels + 3];
-  int n_act;
-  unsigned long long bar;
-};
-
 // sigma^2 exp(-sqrt(d2)) for d2 in [0, ~1e3] to ~2 ulp, without the range checks of the library calls:
-// sqrt by one float-seeded Newton step pair, exp by 2^n * p(r), |r| <= ln2 / 2, degree-11 Taylor/Horner.
+// sqrt by one float-seeded Newton step, exp by 2^n * p(r), |r| <= ln2 / 2, degree-10 Taylor/Horner (|r|^11 / 11! < 3e-13).
 __device__ __forceinline__ double gp_kernel_from_d2(double d2) {
   d2 = fmax(d2, 1e-30);                              // keeps the float seed finite; sqrt(1e-30) ~ 0
   double yr = double(rsqrtf(float(d2)));             // ~2^-22 relative
-  yr = yr * (1.5 - 0.5 * d2 * yr * yr);              // ~2^-43
-  yr = yr * (1.5 - 0.5 * d2 * yr * yr);              // full double
+  yr = yr * (1.5 - 0.5 * d2 * yr * yr);              // ~2^-43: |error of dist| < 4e-12, far below what the features need
   const double dist = d2 * yr;
   const double t = -dist * 1.4426950408889634;       // log2(e)
   const double n = rint(t);
   const double r = fma(n, -1.9082149292705877e-10, fma(n, -0.6931471803691238, -dist));   // -dist - n ln2 (hi + lo)
-  double p = 2.505210838544172e-08;                  // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);
+  double p = 2.755731922398589e-07;                  // 1/10!
   p = fma(p, r, 2.7557319223985893e-06);
   p = fma(p, r, 2.48015873015873e-05);
   p = fma(p, r, 1.984126984126984e-04);
@@ -345,45 +320,103 @@ __device__ __forceinline__ double gp_kernel_from_d2(double d2) {
   return kGpSigma2 * __longlong_as_double(__double_as_longlong(p) + (static_cast<long long>(ni) << 52));
 }
 
-// acc[r] -= sum_c L[r][c] v[c] for one 8 x 8 block (column-major in shared memory) and two columns.
-__device__ __forceinline__ void gp_block_update(double (&a0)[kGpBlk], double (&a1)[kGpBlk], const double* __restrict__ Lb,
-                                                const double* __restrict__ xb, int lane) {
+
+// ---------------------------------------------------------------------------------------------------------
+// k_gp_column3: the same blocked right-looking solve on the fp64 tensor cores (mma.sync.m8n8k4.f64)
+// ---------------------------------------------------------------------------------------------------------
+// Measured on B200: DMMA runs at the DFMA rate (37 TFLOP/s, scripts/probes/dmma_probe.cu) but one instruction
+// does the work of eight DFMA warp instructions and its operands are 256-byte shared-memory fragments, so
+// the instruction stream and the shared-memory traffic of the update shrink ~6x.
+//   * a pass handles 64 columns = 8 n-tiles; warp w owns the row blocks w and 14 - w, their 8 x 64
+//     accumulator tiles live in registers in the C-fragment layout (row = lane / 4, cols 2 (lane % 4), +1);
+//   * trailing update of block b at step j:  C_b -= L_bj V_j  = 16 DMMA (8 n-tiles x 2 k-halves), A fragments
+//     from the column-major 8 x 8 blocks of the factor, B fragments from the published V_j;
+//   * diagonal solve: V_j = inv(L_jj) C_j, also 16 DMMA, with the 15 inverted diagonal blocks prepared once
+//     per CTA (no dependent chain of divisions in the sweep); done by the owner of block j + 1 inside step j;
+//   * |v|^2 and v . z are accumulated per column by two reducer warps straight from the published V_j.
+constexpr int kC3Warps = 8;
+constexpr int kC3Threads = 32 * kC3Warps;
+constexpr int kC3Cols = 64;
+constexpr int kC3Stride = 72;                          // doubles per row of a published tile (64 + 8: fragment
+                                                       // loads of 4 rows x 8 columns then touch every bank once)
+struct Column3Smem {
+  double L[kGpBlockedLower];                           // filled by one TMA bulk copy
+  double Linv[kGpNumBlk][kGpBlk * kGpBlk];             // inverses of the diagonal blocks, column-major
+  double xbuf[2][kGpBlk * kC3Stride];                  // V_j, double-buffered
+  double cxy[kGpWindow], pz[kGpWindow];
+  double z[kGpWindow][2];
+  double pq[kC3Cols];                                  // scaled pressure of this pass's levels
+  float feat[kNumLevels * 3];
+  int act[kNumLevels + 3];
+  int n_act;
+  unsigned long long bar;
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C (8 x 64, registers) -= Lblk (8 x 8, shared, column-major) * X (8 x 64, shared, row stride kC3Stride)
+__device__ __forceinline__ void c3_update(double (&c)[8][2], const double* __restrict__ Lblk, const double* __restrict__ X,
+                                          int g, int tq) {
 #pragma unroll
-  for (int c = 0; c < kGpBlk; ++c) {
-    const double v0 = xb[c * kColPerPass + lane], v1 = xb[c * kColPerPass + lane + 32];
-    const double2* col = reinterpret_cast<const double2*>(Lb + c * kGpBlk);
+  for (int h = 0; h < 2; ++h) {
+    const double a = -Lblk[(4 * h + tq) * kGpBlk + g];
+    const double* xr = X + (4 * h + tq) * kC3Stride + g;
 #pragma unroll
-    for (int h = 0; h < kGpBlk / 2; ++h) {
-      const double2 l = col[h];
-      a0[2 * h] -= l.x * v0; a0[2 * h + 1] -= l.y * v0;
-      a1[2 * h] -= l.x * v1; a1[2 * h + 1] -= l.y * v1;
+    for (int nt = 0; nt < 8; ++nt) dmma884(c[nt][0], c[nt][1], a, xr[nt * 8]);
+  }
+}
+
+// two owned blocks share the B fragments
+__device__ __forceinline__ void c3_update2(double (&c0)[8][2], double (&c1)[8][2], const double* __restrict__ L0,
+                                           const double* __restrict__ L1, const double* __restrict__ X, int g, int tq) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const double a0 = -L0[(4 * h + tq) * kGpBlk + g], a1 = -L1[(4 * h + tq) * kGpBlk + g];
+    const double* xr = X + (4 * h + tq) * kC3Stride + g;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const double b = xr[nt * 8];
+      dmma884(c0[nt][0], c0[nt][1], a0, b);
+      dmma884(c1[nt][0], c1[nt][1], a1, b);
     }
   }
 }
 
-// 8 x 8 lower-triangular solve of one column's block; the 8 results go to xout[r * kColPerPass].
-__device__ __forceinline__ void gp_diag_solve(double (&ac)[kGpBlk], const double* __restrict__ Ld,
-                                              const double* __restrict__ inv, const double* __restrict__ zj,
-                                              double* __restrict__ xout, double* n2, double* mu, double* mv) {
+// V = inv(L_jj) C, published into X (which also serves as the staging tile for the C -> B re-layout)
+__device__ __forceinline__ void c3_solve_publish(double (&c)[8][2], const double* __restrict__ Linv, double* __restrict__ X,
+                                                 int g, int tq) {
 #pragma unroll
-  for (int r = 0; r < kGpBlk; ++r) {
-    const double v = ac[r] * inv[r];
+  for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(X + g * kC3Stride + nt * 8 + 2 * tq) = make_double2(c[nt][0], c[nt][1]);
+  __syncwarp();
+  double b[2][8];
 #pragma unroll
-    for (int r2 = r + 1; r2 < kGpBlk; ++r2) ac[r2] -= Ld[r * kGpBlk + r2] * v;
-    xout[r * kColPerPass] = v;
-    *n2 += v * v;
-    *mu += v * zj[r * 2];
-    *mv += v * zj[r * 2 + 1];
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) b[h][nt] = X[(4 * h + tq) * kC3Stride + nt * 8 + g];
   }
+  __syncwarp();
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { c[nt][0] = 0.0; c[nt][1] = 0.0; }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const double a = Linv[(4 * h + tq) * kGpBlk + g];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) dmma884(c[nt][0], c[nt][1], a, b[h][nt]);
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(X + g * kC3Stride + nt * 8 + 2 * tq) = make_double2(c[nt][0], c[nt][1]);
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(kColThreads, 1) k_gp_column2(DevState<Real> d, float* __restrict__ obs) {
+__global__ void __launch_bounds__(kC3Threads, 2) k_gp_column3(DevState<Real> d, float* __restrict__ obs) {
   extern __shared__ __align__(128) unsigned char s_raw[];
-  ColumnSmem& S = *reinterpret_cast<ColumnSmem*>(s_raw);
+  Column3Smem& S = *reinterpret_cast<Column3Smem*>(s_raw);
   __shared__ int s_idx[kGpWindow];
   const int64_t e = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
   const int m = d.gp_m[e];
   const int nb = (m + kGpBlk - 1) / kGpBlk;
   const double* ring = d.gp_obs + e * int64_t(kGpWindow * 6);
@@ -436,74 +469,99 @@ __global__ void __launch_bounds__(kColThreads, 1) k_gp_column2(DevState<Real> d,
   }
   __syncthreads();
   const int n_act = S.n_act;
-  const int b0 = warp;                               // the block this warp owns
-  bool factor_ready = (m == 0);
-
-  for (int first = 0; first < n_act && m > 0; first += kColPerPass) {
-    const int c0 = first + lane, c1 = first + lane + 32;
-    const bool on0 = c0 < n_act, on1 = c1 < n_act;
-    const double pq0 = pressure_level(on0 ? S.act[c0] : 0) / kGpScaleP;
-    const double pq1 = pressure_level(on1 ? S.act[c1] : 0) / kGpScaleP;
-    double a0[kGpBlk], a1[kGpBlk];                   // rows of the owned block, two columns
+  const int b0 = warp, b1 = (kGpNumBlk - 1 - warp) != warp ? kGpNumBlk - 1 - warp : -1;
+  const bool own0 = b0 < nb, own1 = b1 >= 0 && b1 < nb;
+  if (m > 0) {
+    asm volatile(                                     // wait for the TMA transaction (phase 0)
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar) : "memory");
+    if (tid < nb * kGpBlk) {                          // column c of inv(L_jj): forward substitution on e_c
+      const int j = tid >> 3, c = tid & 7;
+      const double* Ld = S.L + blk_offset(j, j);
+      double xv[kGpBlk];
 #pragma unroll
-    for (int r = 0; r < kGpBlk; ++r) {
-      const int i0 = b0 * kGpBlk + r;
-      a0[r] = a1[r] = 0.0;
-      if (b0 < nb && i0 < m) {
-        const double cx = S.cxy[i0], pi = S.pz[i0];
-        if (on0) a0[r] = gp_kernel_from_d2(cx + (pq0 - pi) * (pq0 - pi));
-        if (on1) a1[r] = gp_kernel_from_d2(cx + (pq1 - pi) * (pq1 - pi));
+      for (int r = 0; r < kGpBlk; ++r) {
+        double acc = r == c ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < r; ++k) acc -= Ld[k * kGpBlk + r] * xv[k];
+        xv[r] = acc / Ld[r * kGpBlk + r];
+      }
+#pragma unroll
+      for (int r = 0; r < kGpBlk; ++r) S.Linv[j][c * kGpBlk + r] = xv[r];
+    }
+  }
+  __syncthreads();
+
+  for (int first = 0; first < n_act && m > 0; first += kC3Cols) {
+    if (tid < kC3Cols) S.pq[tid] = pressure_level(first + tid < n_act ? S.act[first + tid] : 0) / kGpScaleP;
+    __syncthreads();
+    double c0[8][2], c1[8][2];                        // accumulators of the two owned blocks (C-fragment layout)
+    {
+      const int i0 = b0 * kGpBlk + g, i1 = b1 * kGpBlk + g;
+      const bool r0 = own0 && i0 < m, r1 = own1 && i1 < m;
+      const double cx0 = r0 ? S.cxy[i0] : 0.0, pz0 = r0 ? S.pz[i0] : 0.0;
+      const double cx1 = r1 ? S.cxy[i1] : 0.0, pz1 = r1 ? S.pz[i1] : 0.0;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int col = nt * 8 + 2 * tq + i;
+          const bool on = first + col < n_act;
+          const double pq = S.pq[col];
+          c0[nt][i] = (r0 && on) ? gp_kernel_from_d2(cx0 + (pq - pz0) * (pq - pz0)) : 0.0;
+          c1[nt][i] = (r1 && on) ? gp_kernel_from_d2(cx1 + (pq - pz1) * (pq - pz1)) : 0.0;
+        }
       }
     }
-    if (!factor_ready) {                             // wait for the TMA transaction (phase 0), once
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
-          "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar) : "memory");
-      factor_ready = true;
-      if (tid < nb * kGpBlk) S.inv_diag[tid] = 1.0 / S.L[blocked_index(tid, tid)];
-      __syncthreads();
-    }
-    double n2[2] = {0.0, 0.0}, mu[2] = {0.0, 0.0}, mv[2] = {0.0, 0.0};
     // block 0 is solved up front; afterwards the owner of block j + 1 updates and solves it INSIDE step j
-    // (look-ahead), so that nobody waits at the barrier for a diagonal solve
-    if (warp == 0) {
-      gp_diag_solve(a0, S.L + blk_offset(0, 0), S.inv_diag, &S.z[0][0], &S.xbuf[0][0][lane], &n2[0], &mu[0], &mv[0]);
-      gp_diag_solve(a1, S.L + blk_offset(0, 0), S.inv_diag, &S.z[0][0], &S.xbuf[0][0][lane + 32], &n2[1], &mu[1], &mv[1]);
-    }
+    if (warp == 0) c3_solve_publish(c0, S.Linv[0], S.xbuf[0], g, tq);
     __syncthreads();
-    for (int j = 0; j + 1 < nb; ++j) {
-      if (b0 > j && b0 < nb) {
-        gp_block_update(a0, a1, S.L + blk_offset(b0, j), &S.xbuf[j & 1][0][0], lane);
-        if (b0 == j + 1) {
-          const double* Ld = S.L + blk_offset(b0, b0);
-          double* xo = &S.xbuf[b0 & 1][0][0];
-          gp_diag_solve(a0, Ld, S.inv_diag + b0 * kGpBlk, &S.z[b0 * kGpBlk][0], xo + lane, &n2[0], &mu[0], &mv[0]);
-          gp_diag_solve(a1, Ld, S.inv_diag + b0 * kGpBlk, &S.z[b0 * kGpBlk][0], xo + lane + 32, &n2[1], &mu[1], &mv[1]);
+    double n2 = 0.0, mu = 0.0, mv = 0.0;              // reducer warps 6 (columns 32..63) and 7 (columns 0..31)
+    for (int j = 0; j < nb; ++j) {
+      const double* X = S.xbuf[j & 1];
+      const int nx = j + 1;
+      if (nx < nb) {
+        const bool need0 = own0 && b0 > j, need1 = own1 && b1 > j;
+        if (need0 && b0 == nx) {
+          c3_update(c0, S.L + blk_offset(b0, j), X, g, tq);
+          c3_solve_publish(c0, S.Linv[nx], S.xbuf[nx & 1], g, tq);
+          if (need1) c3_update(c1, S.L + blk_offset(b1, j), X, g, tq);
+        } else if (need1 && b1 == nx) {
+          c3_update(c1, S.L + blk_offset(b1, j), X, g, tq);
+          c3_solve_publish(c1, S.Linv[nx], S.xbuf[nx & 1], g, tq);
+        } else if (need0 && need1) {
+          c3_update2(c0, c1, S.L + blk_offset(b0, j), S.L + blk_offset(b1, j), X, g, tq);
+        } else if (need0) {
+          c3_update(c0, S.L + blk_offset(b0, j), X, g, tq);
+        } else if (need1) {
+          c3_update(c1, S.L + blk_offset(b1, j), X, g, tq);
+        }
+      }
+      if (warp >= 6) {
+        const int col = (warp == 7 ? 0 : 32) + lane;
+#pragma unroll
+        for (int r = 0; r < kGpBlk; ++r) {
+          const double v = X[r * kC3Stride + col];
+          n2 += v * v; mu += v * S.z[j * kGpBlk + r][0]; mv += v * S.z[j * kGpBlk + r][1];
         }
       }
       __syncthreads();
     }
-    // reduce the per-warp partials of every column, then the features of this pass's levels
-#pragma unroll
-    for (int col = 0; col < 2; ++col) {
-      S.red[warp][lane + 32 * col][0] = n2[col]; S.red[warp][lane + 32 * col][1] = mu[col]; S.red[warp][lane + 32 * col][2] = mv[col];
-    }
-    __syncthreads();
-    if (tid < kColPerPass && first + tid < n_act) {
-      double norm2 = 0.0, mean_u = 0.0, mean_v = 0.0;
-#pragma unroll
-      for (int w = 0; w < kColWarps; ++w) { norm2 += S.red[w][tid][0]; mean_u += S.red[w][tid][1]; mean_v += S.red[w][tid][2]; }
-      const int l = S.act[first + tid];
-      const double deviation = fmax(kGpSigma2 - norm2, 0.0) / kGpSigma2;           // wind_gp.py:186-193
-      double fu, fv;
-      forecast_at<double, DevState<Real>>(d, e, x, y, pressure_level(l), t_elapsed, &fu, &fv);
-      wind_level_features(mean_u + fu, mean_v + fv, deviation, x, y, &S.feat[l * 3], &S.feat[l * 3 + 1], &S.feat[l * 3 + 2]);
+    if (warp >= 6) {
+      const int col = (warp == 7 ? 0 : 32) + lane;
+      if (first + col < n_act) {
+        const int l = S.act[first + col];
+        const double deviation = fmax(kGpSigma2 - n2, 0.0) / kGpSigma2;            // wind_gp.py:186-193
+        double fu, fv;
+        forecast_at<double, DevState<Real>>(d, e, x, y, pressure_level(l), t_elapsed, &fu, &fv);
+        wind_level_features(mu + fu, mv + fv, deviation, x, y, &S.feat[l * 3], &S.feat[l * 3 + 1], &S.feat[l * 3 + 2]);
+      }
     }
     __syncthreads();
   }
   if (m == 0) {                                       // no measurement yet: zero mean and deviation (wind_gp.py:161-163)
-    for (int k = tid; k < n_act; k += kColThreads) {
+    for (int k = tid; k < n_act; k += kC3Threads) {
       const int l = S.act[k];
       double fu, fv;
       forecast_at<double, DevState<Real>>(d, e, x, y, pressure_level(l), t_elapsed, &fu, &fv);
@@ -514,7 +572,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_gp_column2(DevState<Real> d,
   // centred, padded column (features.py:479-497, 536-556)
   const int lower = kNumLevels - nearest_pressure_level(p_b) - 1;
   float* o = obs + e * int64_t(kNumFeatures) + 16;
-  for (int s = tid; s < 2 * kNumLevels - 1; s += kColThreads) {
+  for (int s = tid; s < 2 * kNumLevels - 1; s += kC3Threads) {
     float f0 = 0.f, f1 = 1.f, f2 = 1.f;                                            // "unreachable" triple
     const int l = s - lower;
     if (l >= 0 && l < kNumLevels) {
