@@ -217,7 +217,6 @@ def run_b200(args):
   ev1.record()
   barrier()
   ms = ev0.elapsed_time(ev1)
-  clocks = sampler.stop()
   launches = arena.launch_count - launches0
   live_frac = float((arena.get_state_dict()['status'] == 0).float().mean())
 
@@ -241,6 +240,7 @@ def run_b200(args):
     one_step_host(args.warmup + t % args.steps)
   torch.cuda.synchronize()
   e2e_s = time.perf_counter() - t0
+  clocks = sampler.stop()          # sampled across both timed regions (device-resident and end-to-end)
 
   # ---- the same step WITH the Perciatelli observation (reference path A), a few steps ----------
   obs_ms = None

@@ -275,3 +275,36 @@ class PerciatelliFeatures:
       return u, v
     return wind.get_forecast(a.fields, np.full(NUM_LEVELS, np.asarray(a.field_idx)[e]), one(s.x), one(s.y),
                              PRESSURE_LEVELS, one(s.time_elapsed))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The step-to-step update of the WindGP Cholesky factor used by csrc/ble_gp_kernels.cuh (k_gp_update),
+# restated for the CPU tests: dropping the OLDEST measurement is a rank-1 update of the trailing factor with
+# the factor's first column, appending the NEWEST is one forward substitution.  Mathematically identical to
+# sklearn's refit on the new window (wind_gp.py:172-190).
+# ---------------------------------------------------------------------------------------------------------
+def cholesky_drop_first(l_factor):
+  """Lower factor of K[1:, 1:] from the lower factor of K (K22 = L22 L22^T + l21 l21^T)."""
+  m = l_factor.shape[0]
+  x = l_factor[1:, 0].copy()
+  out = l_factor[1:, 1:].copy()
+  for k in range(m - 1):
+    r = np.hypot(out[k, k], x[k])
+    c, s = r / out[k, k], x[k] / out[k, k]
+    out[k, k] = r
+    out[k + 1:, k] = (out[k + 1:, k] + s * x[k + 1:]) / c
+    x[k + 1:] = c * x[k + 1:] - s * out[k + 1:, k]
+  return out
+
+
+def cholesky_append(l_factor, k_new, k_diag):
+  """Lower factor of [[K, k_new], [k_new^T, k_diag]] from the lower factor of K."""
+  m = l_factor.shape[0]
+  r = np.zeros(m)
+  for j in range(m):
+    r[j] = (k_new[j] - l_factor[j, :j] @ r[:j]) / l_factor[j, j]
+  out = np.zeros((m + 1, m + 1))
+  out[:m, :m] = l_factor
+  out[m, :m] = r
+  out[m, m] = np.sqrt(k_diag - r @ r)
+  return out

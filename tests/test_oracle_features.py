@@ -96,3 +96,29 @@ def test_device_scalar_helpers_match_oracle():
   st = np.zeros(n)
   lib.emu_sunrise_time(ctypes.c_int64(n), P(lat), P(lng), P(b.date_time), P(st))
   np.testing.assert_allclose(st, F.compute_sunrise_time(lat, lng, b.date_time), rtol=1e-12)
+
+
+def test_incremental_cholesky_matches_refit():
+  """The drop-oldest / append-newest factor update (k_gp_update's algorithm) against a fresh Cholesky of the
+  Matern-1/2 Gram matrix of the shifted window, over 300 consecutive shifts of a 120-point window."""
+  from oracle import features as features_lib
+  rng = np.random.default_rng(7)
+  n_pts, m = 420, 120
+  pts = np.cumsum(rng.normal(0, 0.05, (n_pts, 4)), axis=0)          # a wandering balloon in scaled coordinates
+  pts[:, 3] = np.arange(n_pts) * (180.0 / 34560.0)
+
+  def gram(p):
+    d = np.sqrt(((p[:, None, :] - p[None, :, :]) ** 2).sum(-1))
+    return 3.6 ** 2 * np.exp(-d) + 0.05 * np.eye(len(p))
+
+  factor = np.linalg.cholesky(gram(pts[:m]))
+  worst = 0.0
+  for first in range(1, 301):
+    window = pts[first:first + m]
+    factor = features_lib.cholesky_drop_first(factor)
+    k_new = 3.6 ** 2 * np.exp(-np.sqrt(((window[:-1] - window[-1]) ** 2).sum(-1)))
+    factor = features_lib.cholesky_append(factor, k_new, 3.6 ** 2 + 0.05)
+    if first % 50 == 0 or first < 3:
+      want = np.linalg.cholesky(gram(window))
+      worst = max(worst, np.abs(factor - want).max())
+  assert worst < 1e-11, worst                                        # no drift over 300 carried steps
