@@ -886,7 +886,7 @@ struct Engine : EngineBase {
   bool have_state = false, have_fields = false, have_noise = false;
   bool noise_valid = false;      // noise_partial matches the current state
   double* gp_obs = nullptr; int32_t* gp_count = nullptr; double* gp_chol = nullptr; int32_t* gp_m = nullptr;
-  int32_t* gp_first = nullptr; double* gp_z = nullptr;
+  int32_t* gp_first = nullptr; double* gp_z = nullptr; double* range_scratch = nullptr;
   bool gp_refit_every_step = false;      // BLE_GP_REFIT=1: the first-generation kernels (full refit per call), kept for A/B checks
   double* feat_range = nullptr;
   // VAE decoder (reset path)
@@ -944,6 +944,7 @@ struct Engine : EngineBase {
       BLE_CUDA(cudaMalloc(&gp_first, sizeof(int32_t) * n));
       BLE_CUDA(cudaMemset(gp_first, 0, sizeof(int32_t) * n));
       BLE_CUDA(cudaMalloc(&gp_z, sizeof(double) * size_t(kGpWindow) * 2 * n));
+      BLE_CUDA(cudaMalloc(&range_scratch, sizeof(double) * size_t(kRangeLevels) * 2 * n));
       d.gp_first = gp_first; d.gp_z = gp_z;
       if (const char* g = std::getenv("BLE_GP_REFIT")) gp_refit_every_step = std::atoi(g) != 0;
       BLE_CUDA(cudaFuncSetAttribute(k_gp_update<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUpdateSmem)));
@@ -967,7 +968,7 @@ struct Engine : EngineBase {
     cudaFree(dec_act[0]); cudaFree(dec_act[1]); cudaFree(dec_workspace);
     if (lt != nullptr) cublasLtDestroy(lt);
     cudaFree(gp_obs); cudaFree(gp_count); cudaFree(gp_chol); cudaFree(gp_m); cudaFree(feat_range);
-    cudaFree(gp_first); cudaFree(gp_z);
+    cudaFree(gp_first); cudaFree(gp_z); cudaFree(range_scratch);
     cudaFree(gen_latents); cudaFree(gen_fields);
     cudaFree(ev.reward); cudaFree(ev.within); cudaFree(ev.steps); cudaFree(ev.active); cudaFree(walk_target);
     cudaFree(d_actions); cudaFree(d_reward); cudaFree(d_done);
@@ -1355,7 +1356,8 @@ struct Engine : EngineBase {
     if (rc != BLE_OK) return rc;
     BLE_CUDA(cudaSetDevice(device));
     k_feat_ambient<Real><<<grid_for(n, 128), 128, 0, s>>>(d, obs);
-    k_feat_range<Real><<<grid_for(n, 4), 128, 0, s>>>(d);
+    k_feat_range_levels<Real><<<grid_for(n * kRangeLevels, 128), 128, 0, s>>>(d, range_scratch);
+    k_feat_range<Real><<<grid_for(n, 128), 128, 0, s>>>(d, range_scratch);
     if (gp_refit_every_step) {
       k_gp_factor<Real><<<unsigned(n), kFactorThreads, sizeof(double) * (kGpPacked + kGpWindow * 4), s>>>(d);
       k_gp_column<Real><<<unsigned(n), kColumnThreads, kColumnSmem, s>>>(d, obs);
@@ -1363,7 +1365,7 @@ struct Engine : EngineBase {
       k_gp_update<Real><<<unsigned(n), kUpdateThreads, kUpdateSmem, s>>>(d);
       k_gp_column3<Real><<<unsigned(n), kC3Threads, sizeof(Column3Smem), s>>>(d, obs);
     }
-    launches += 4;
+    launches += 5;
     BLE_CUDA(cudaGetLastError());
     return BLE_OK;
   }

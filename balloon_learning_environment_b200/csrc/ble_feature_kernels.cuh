@@ -71,44 +71,57 @@ __global__ void __launch_bounds__(128) k_feat_ambient(DevState<Real> d, float* _
 }
 
 // ---- reachable pressure range --------------------------------------------------------------------------
+// get_pressure_range (env/balloon/pressure_range_builder.py:203-275) in two launches so that every lane works:
+//   k_feat_range_levels  one thread per (balloon, scan level): the 20 stable-init solves of the scan (:231-233)
+//   k_feat_range         one thread per balloon: the fully-vented pressure (:234-245), its own solve, and the
+//                        two safe-pressure searches (:247-275)
 template <typename Real>
-__global__ void __launch_bounds__(128) k_feat_range(DevState<Real> d) {
-  __shared__ double s_levels[4][kRangeLevels], s_pt[4][kRangeLevels], s_sp[4][kRangeLevels + 1], s_sig[4];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t e = int64_t(blockIdx.x) * 4 + w;
-  if (e >= d.n) return;
+__global__ void __launch_bounds__(128) k_feat_range_levels(DevState<Real> d, double* __restrict__ scratch /*[n][20][2]*/) {
+  const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (t >= d.n * kRangeLevels) return;
+  const int64_t e = t / kRangeLevels;
+  const int lv = int(t - e * kRangeLevels);
   const double alpha = DD(d, D_ALPHA, e), mols_gas = double(RR(d, R_MOLS_GAS, e)), ir = double(RR(d, R_IR, e));
   const int64_t ts = d.l[int64_t(L_DATE_TIME) * d.n + e];
   double lat, lng;
   latlng_from_offset<double>(double(RR(d, R_LAT0, e)), double(RR(d, R_LNG0, e)), DD(d, D_X, e), DD(d, D_Y, e), &lat, &lng);
   double search_max, t_unused;
   atm_at_height_generic(alpha, kAltMin, &search_max, &t_unused);           // :230
-  if (lane < kRangeLevels) {
-    const double step = (search_max - 1000.0) / double(kRangeLevels - 1);  // np.linspace(1000, search_max, 20)
-    const double level = (lane == kRangeLevels - 1) ? search_max : double(lane) * step + 1000.0;
-    const StableParams s = stable_params(alpha, level, mols_gas, lat, lng, ts, ir);
-    s_levels[w][lane] = level;
-    s_pt[w][lane] = level / s.t_ambient;
-    s_sp[w][lane] = s.superpressure;
+  const double step = (search_max - 1000.0) / double(kRangeLevels - 1);    // np.linspace(1000, search_max, 20)
+  const double level = (lv == kRangeLevels - 1) ? search_max : double(lv) * step + 1000.0;
+  const StableParams sp = stable_params(alpha, level, mols_gas, lat, lng, ts, ir);
+  scratch[t * 2] = level / sp.t_ambient;
+  scratch[t * 2 + 1] = sp.superpressure;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128) k_feat_range(DevState<Real> d, const double* __restrict__ scratch) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  const double alpha = DD(d, D_ALPHA, e), mols_gas = double(RR(d, R_MOLS_GAS, e)), ir = double(RR(d, R_IR, e));
+  const int64_t ts = d.l[int64_t(L_DATE_TIME) * d.n + e];
+  double lat, lng;
+  latlng_from_offset<double>(double(RR(d, R_LAT0, e)), double(RR(d, R_LNG0, e)), DD(d, D_X, e), DD(d, D_Y, e), &lat, &lng);
+  double search_max, t_unused;
+  atm_at_height_generic(alpha, kAltMin, &search_max, &t_unused);
+  const double step = (search_max - 1000.0) / double(kRangeLevels - 1);
+  double levels[kRangeLevels], pt[kRangeLevels], sp[kRangeLevels + 1];
+#pragma unroll
+  for (int lv = 0; lv < kRangeLevels; ++lv) {
+    levels[lv] = (lv == kRangeLevels - 1) ? search_max : double(lv) * step + 1000.0;
+    pt[lv] = scratch[(e * kRangeLevels + lv) * 2];
+    sp[lv] = scratch[(e * kRangeLevels + lv) * 2 + 1];
   }
-  __syncwarp();
-  if (lane == kRangeLevels) {
-    const double sig = min_float_pressure(s_levels[w], s_pt[w], mols_gas);
-    s_sig[w] = sig;
-    s_sp[w][kRangeLevels] = stable_params(alpha, sig, mols_gas, lat, lng, ts, ir).superpressure;
-  }
-  __syncwarp();
-  if (lane == 0) {
-    double pmin = 0.0, pmax = 0.0;
-    const bool ok1 = search_safe_pressure(s_levels[w], s_sp[w], s_sig[w], s_sp[w][kRangeLevels], false, &pmin);
-    const bool ok2 = search_safe_pressure(s_levels[w], s_sp[w], s_levels[w][kRangeLevels - 1],
-                                          s_sp[w][kRangeLevels - 1], true, &pmax);
-    d.feat_range[2 * e] = pmin;
-    d.feat_range[2 * e + 1] = pmax;
-    if (!(ok1 && ok2)) {                         // the reference raises ValueError here; flag it and mark all unreachable
-      d.feat_range[2 * e] = 1.0; d.feat_range[2 * e + 1] = 0.0;
-      atomicOr(&d.flags[e], 1u << 11);
-    }
+  const double sig = min_float_pressure(levels, pt, mols_gas);
+  sp[kRangeLevels] = stable_params(alpha, sig, mols_gas, lat, lng, ts, ir).superpressure;
+  double pmin = 0.0, pmax = 0.0;
+  const bool ok1 = search_safe_pressure(levels, sp, sig, sp[kRangeLevels], false, &pmin);
+  const bool ok2 = search_safe_pressure(levels, sp, levels[kRangeLevels - 1], sp[kRangeLevels - 1], true, &pmax);
+  d.feat_range[2 * e] = pmin;
+  d.feat_range[2 * e + 1] = pmax;
+  if (!(ok1 && ok2)) {                           // the reference raises ValueError here; flag it and mark all unreachable
+    d.feat_range[2 * e] = 1.0; d.feat_range[2 * e + 1] = 0.0;
+    atomicOr(&d.flags[e], 1u << 11);
   }
 }
 
