@@ -310,8 +310,19 @@ def run_b200(args):
   r0.record(); arena.decode_wind_fields(z); r1.record(); torch.cuda.synchronize()
   decode_ms = r0.elapsed_time(r1)
   del z
+  # BASELINE configs[2] draws a new VAE field for every balloon at every reset: all n fields through
+  # ble_generate_fields (latents -> 4 GEMMs -> resize / curl -> 128-byte windows in the bank)
+  gen_seeds = torch.randint(0, 2**62, (n_fields,), dtype=torch.int64, generator=g)
+  arena.sample_wind_fields(gen_seeds[:2048]); torch.cuda.synchronize()
+  r0.record(); arena.sample_wind_fields(gen_seeds); r1.record(); torch.cuda.synchronize()
+  generate_ms = r0.elapsed_time(r1)
   reset_path = {'reset_ms': reset_ms, 'balloons': n,
                 'what': 'ble_reset: Philox sampling, stable init, sunrise/sunset search, 10 noise permutation tables per balloon',
+                'generate_fields_ms': generate_ms, 'generated_fields': n_fields,
+                'episode_steps': 960,
+                'amortised_env_steps_per_s': n * 960 / ((960 * ms / args.steps + reset_ms + generate_ms) * 1e-3),
+                'amortised_note': 'this rank: 960-step episodes with ble_generate_fields (one new field per balloon) + '
+                                  'ble_reset charged once per episode',
                 'decoder_fields_per_s': 2048 / (decode_ms * 1e-3), 'decoder_batch': 2048,
                 'decoder': 'ble_decode_fields: 4 cuBLASLt fp32 GEMMs (64-1000-1000-1000-4410) + resize/curl epilogue, '
                            'random-init weights'}

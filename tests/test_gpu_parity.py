@@ -594,6 +594,48 @@ def test_decoder_matches_oracle(ble):
   arena.close()
 
 
+@pytest.mark.parametrize('layout', ['x64', 'x128'])
+def test_fused_field_generation_fills_the_same_windows(ble, layout):
+  """ble_generate_fields writes the gather's windows straight from the decoder output (k_decode_windows).  Reading
+  the bank back at every grid node gives the native field; loading THAT field through the two-pass path
+  (ble_write_fields) must give bit-identical lookups everywhere, and the field must be a discrete curl."""
+  from oracle import vae as vae_oracle
+  params = vae_oracle.synthetic_params(4)
+  n = 6
+  arena = ble.BatchedBalloonArena(n, precision='fp32', enable_noise=False, field_layout=layout)
+  arena.set_decoder(params)
+  arena.alloc_wind_fields(n)
+  seeds = torch.tensor([11, 22, 33, 44, 55, 66], dtype=torch.int64)
+  arena.sample_wind_fields(seeds)
+  # scattered regeneration of two fields leaves the others untouched and is reproducible per seed
+  ix, iy, ip, it = np.meshgrid(np.arange(21), np.arange(21), np.arange(10), np.arange(9), indexing='ij')
+  nodes = np.stack([-500.0 + 50.0 * ix, -500.0 + 50.0 * iy, 5000.0 + 1000.0 * ip, 6.0 * it], -1).reshape(-1, 4).astype(np.float32)
+  q = torch.from_numpy(nodes)
+
+  def read_back(a, f):
+    return a.wind_forecast(q, torch.full((len(nodes),), f, dtype=torch.int32)).cpu().numpy().reshape(21, 21, 10, 9, 2)
+
+  fields = np.stack([read_back(arena, f) for f in range(n)])
+  assert np.abs(fields).max() > 0.5
+  u, v = fields[..., 0].astype(np.float64), fields[..., 1].astype(np.float64)
+  div = (u[:, 1:-1, 2:] - u[:, 1:-1, :-2]) / 2 + (v[:, 2:, 1:-1] - v[:, :-2, 1:-1]) / 2
+  assert np.abs(div).max() < 1e-4 * np.abs(fields).max()
+  other = ble.BatchedBalloonArena(n, precision='fp32', enable_noise=False, field_layout=layout)
+  other.set_wind_fields(torch.from_numpy(fields))
+  rng = np.random.default_rng(3)
+  pts = np.stack([rng.uniform(-520, 520, 20000), rng.uniform(-520, 520, 20000), rng.uniform(4000, 15000, 20000),
+                  rng.uniform(0, 100, 20000)], -1).astype(np.float32)
+  fidx = torch.from_numpy(rng.integers(0, n, 20000).astype(np.int32))
+  got = arena.wind_forecast(torch.from_numpy(pts), fidx).cpu().numpy()
+  want = other.wind_forecast(torch.from_numpy(pts), fidx).cpu().numpy()
+  np.testing.assert_array_equal(got, want)
+  arena.sample_wind_fields_at(torch.tensor([33, 11], dtype=torch.int64), torch.tensor([4, 1], dtype=torch.int32))
+  np.testing.assert_array_equal(read_back(arena, 4), fields[2])      # seed 33 again, now in slot 4
+  np.testing.assert_array_equal(read_back(arena, 1), fields[0])
+  np.testing.assert_array_equal(read_back(arena, 3), fields[3])      # untouched
+  arena.close(); other.close()
+
+
 # ---- evaluation surface (SURVEY.md section 8 row f3) ---------------------------------------------------
 def _agent_gold():
   import os
