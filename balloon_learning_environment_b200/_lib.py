@@ -33,7 +33,7 @@ EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_u
            'ble_alloc_fields', 'ble_write_fields', 'ble_set_field_map', 'ble_set_decoder', 'ble_decode_fields',
            'ble_set_noise', 'ble_state_upload', 'ble_state_download', 'ble_reset', 'ble_init_derived',
            'ble_step', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_derived',
-           'ble_features_perciatelli', 'ble_features_observe', 'ble_features_clear',
+           'ble_features_perciatelli', 'ble_features_observe', 'ble_features_clear', 'ble_features_track',
            'ble_generate_fields', 'ble_generate_fields_at', 'ble_agent_station_seeker', 'ble_agent_random_walk',
            'ble_eval_begin', 'ble_eval_accumulate', 'ble_eval_results',
            'ble_launch_count',
@@ -104,6 +104,7 @@ def load(build_if_missing=True):
   lib.ble_features_perciatelli.argtypes = [vp, vp, vp]
   lib.ble_features_observe.argtypes = [vp, vp]
   lib.ble_features_clear.argtypes = [vp, vp]
+  lib.ble_features_track.argtypes = [vp, i32]
   lib.ble_generate_fields.argtypes = [vp, vp, i64, i64, vp]
   lib.ble_generate_fields_at.argtypes = [vp, vp, vp, i64, vp]
   lib.ble_agent_station_seeker.argtypes = [vp, vp, vp, vp, vp]

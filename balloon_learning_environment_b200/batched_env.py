@@ -293,6 +293,10 @@ class BatchedBalloonArena:
   def features_observe(self):
     self._check(self._lib.ble_features_observe(self._h, self._stream()), 'ble_features_observe')
 
+  def features_track(self, on: bool) -> None:
+    """on=False: reset / step stop appending WindGP measurements (rollouts that never read the observation)."""
+    self._check(self._lib.ble_features_track(self._h, int(bool(on))), 'ble_features_track')
+
   def features_clear(self):
     self._check(self._lib.ble_features_clear(self._h, self._stream()), 'ble_features_clear')
 

@@ -860,6 +860,7 @@ struct EngineBase {
   virtual int features_observe(cudaStream_t) = 0;
   virtual int features(float*, cudaStream_t) = 0;
   virtual int features_clear(const uint8_t*, cudaStream_t) = 0;
+  virtual int features_track(int) = 0;
   int64_t n = 0;
   int64_t launches = 0;
   std::string err;
@@ -887,6 +888,7 @@ struct Engine : EngineBase {
   bool noise_valid = false;      // noise_partial matches the current state
   double* gp_obs = nullptr; int32_t* gp_count = nullptr; double* gp_chol = nullptr; int32_t* gp_m = nullptr;
   int32_t* gp_first = nullptr; double* gp_z = nullptr; double* range_scratch = nullptr;
+  bool track_measurements = true;        // ble_features_track: append a WindGP measurement after every reset / step
   bool gp_refit_every_step = false;      // BLE_GP_REFIT=1: the first-generation kernels (full refit per call), kept for A/B checks
   double* feat_range = nullptr;
   // VAE decoder (reset path)
@@ -924,11 +926,11 @@ struct Engine : EngineBase {
     BLE_CUDA(cudaMalloc(&d.noise_partial, sizeof(Real) * 10 * n));
     BLE_CUDA(cudaMemset(d.noise_partial, 0, sizeof(Real) * 10 * n));
     BLE_CUDA(cudaMalloc(&d_actions, sizeof(int32_t) * n));
-    BLE_CUDA(cudaMalloc(&d_reward, sizeof(float) * n));
-    BLE_CUDA(cudaMalloc(&d_done, sizeof(uint8_t) * n));
+    BLE_CUDA(cudaMalloc(&d_reward, sizeof(float) * n + sizeof(uint8_t) * n));      // reward [n] then done [n]: one D2H copy
+    d_done = reinterpret_cast<uint8_t*>(d_reward + n);
     BLE_CUDA(cudaMallocHost(&h_actions, sizeof(int32_t) * n));
-    BLE_CUDA(cudaMallocHost(&h_reward, sizeof(float) * n));
-    BLE_CUDA(cudaMallocHost(&h_done, sizeof(uint8_t) * n));
+    BLE_CUDA(cudaMallocHost(&h_reward, sizeof(float) * n + sizeof(uint8_t) * n));
+    h_done = reinterpret_cast<uint8_t*>(h_reward + n);
     d.env_field = env_field;
     d.wind_model = cfg.wind_model;
     d.layout = make_layout(cfg.field_layout);
@@ -971,8 +973,8 @@ struct Engine : EngineBase {
     cudaFree(gp_first); cudaFree(gp_z); cudaFree(range_scratch);
     cudaFree(gen_latents); cudaFree(gen_fields);
     cudaFree(ev.reward); cudaFree(ev.within); cudaFree(ev.steps); cudaFree(ev.active); cudaFree(walk_target);
-    cudaFree(d_actions); cudaFree(d_reward); cudaFree(d_done);
-    cudaFreeHost(h_actions); cudaFreeHost(h_reward); cudaFreeHost(h_done);
+    cudaFree(d_actions); cudaFree(d_reward);
+    cudaFreeHost(h_actions); cudaFreeHost(h_reward);
   }
 
   static unsigned grid_for(int64_t items, int block) { return unsigned((items + block - 1) / block); }
@@ -1089,7 +1091,7 @@ struct Engine : EngineBase {
     d.enable_noise = cfg.enable_noise ? 1 : 0;
     noise_valid = false;
     // arena.reset ends with feature_constructor.observe(get_measurements()) (env/balloon_arena.py:179-182)
-    if (cfg.enable_features && (cfg.wind_model != BLE_WIND_GRID || have_fields)) return features_observe(s);
+    if (cfg.enable_features && track_measurements && (cfg.wind_model != BLE_WIND_GRID || have_fields)) return features_observe(s);
     return BLE_OK;
   }
 
@@ -1135,7 +1137,7 @@ struct Engine : EngineBase {
     noise_valid = false;
     // arena.step ends with feature_constructor.observe(get_measurements()) (env/balloon_arena.py:201):
     // the noise evaluated for it at the post-step state is also next step's pre-step wind.
-    if (cfg.enable_features) return features_observe(s);
+    if (cfg.enable_features && track_measurements) return features_observe(s);
     return BLE_OK;
   }
 
@@ -1349,6 +1351,12 @@ struct Engine : EngineBase {
     return BLE_OK;
   }
 
+  int features_track(int on) override {
+    if (!cfg.enable_features) { err = "features_track: handle was created with enable_features = 0"; return BLE_ERR_UNSUPPORTED; }
+    track_measurements = on != 0;
+    return BLE_OK;
+  }
+
   int features(float* obs, cudaStream_t s) override {
     if (obs == nullptr) { err = "features: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
     if (!cfg.enable_features) { err = "features: handle was created with enable_features = 0"; return BLE_ERR_UNSUPPORTED; }
@@ -1377,8 +1385,7 @@ struct Engine : EngineBase {
     BLE_CUDA(cudaMemcpyAsync(d_actions, h_actions, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     int rc = step(d_actions, d_reward, d_done, nullptr, s);
     if (rc != BLE_OK) return rc;
-    BLE_CUDA(cudaMemcpyAsync(h_reward, d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
-    BLE_CUDA(cudaMemcpyAsync(h_done, d_done, sizeof(uint8_t) * n, cudaMemcpyDeviceToHost, s));
+    BLE_CUDA(cudaMemcpyAsync(h_reward, d_reward, (sizeof(float) + sizeof(uint8_t)) * n, cudaMemcpyDeviceToHost, s));
     BLE_CUDA(cudaStreamSynchronize(s));
     std::memcpy(reward_host, h_reward, sizeof(float) * n);
     std::memcpy(done_host, h_done, sizeof(uint8_t) * n);
@@ -1555,6 +1562,9 @@ int ble_features_observe(ble_handle* h, void* stream) {
 }
 int ble_features_perciatelli(ble_handle* h, float* obs, void* stream) {
   BLE_H(h); return h->eng->features(obs, cudaStream_t(stream));
+}
+int ble_features_track(ble_handle* h, int32_t on) {
+  BLE_H(h); return h->eng->features_track(on);
 }
 int ble_features_clear(ble_handle* h, void* stream) {
   BLE_H(h); return h->eng->features_clear(nullptr, cudaStream_t(stream));

@@ -183,6 +183,7 @@ def run_b200(args):
   g = torch.Generator(device='cpu'); g.manual_seed(2024 + rank)
   arena.reset(torch.randint(0, 2**62, (n,), dtype=torch.int64, generator=g))
 
+  arena.features_track(with_obs)         # the plain rollout does not read the observation: no measurement kernel
   total = args.warmup + args.steps
   gd = torch.Generator(device=device); gd.manual_seed(7 + rank)
   actions = torch.randint(0, 3, (total, n), dtype=torch.int32, device=device, generator=gd)   # RandomAgent
@@ -245,7 +246,8 @@ def run_b200(args):
   # ---- the same step WITH the Perciatelli observation (reference path A), a few steps ----------
   obs_ms = None
   if not with_obs and args.observation_probe > 0:
-    for t in range(max(0, args.observation_prefill - 2 * total)):      # fill the 6 h WindGP window first
+    arena.features_clear(); arena.features_track(True); arena.features_observe()
+    for t in range(args.observation_prefill):                          # fill the 6 h WindGP window first
       arena.step(actions[t % total])
     for _ in range(2):
       arena.step(actions[0]); arena.features(obs_buf)

@@ -171,10 +171,14 @@ int ble_wind_gather(ble_handle* h, const float* xyzt, const int32_t* field_idx, 
  *   ble_features_perciatelli: get_features() -> obs float32 [N, 1099] (16 ambient features + 361 x 3
  *     wind-column features from the GP posterior, the forecast column and the reachable pressure range).
  *   ble_features_observe: observe() of the current state (only needed after ble_state_upload).
- *   ble_features_clear: forget every balloon's measurement history. */
+ *   ble_features_clear: forget every balloon's measurement history.
+ *   ble_features_track: on = 0 stops ble_reset / ble_step from appending measurements (a rollout that does not
+ *     read the observation then skips that kernel); on = 1 (default) resumes.  The history is only meaningful
+ *     if tracking was on for every step since the last reset or clear. */
 int ble_features_perciatelli(ble_handle* h, float* obs, void* stream);
 int ble_features_observe(ble_handle* h, void* stream);
 int ble_features_clear(ble_handle* h, void* stream);
+int ble_features_track(ble_handle* h, int32_t on);
 
 /* Derived properties of BalloonState at the CURRENT state (env/balloon/balloon.py:217-250), all
  * balloons, float64 [BLE_NUM_D][N]. */
