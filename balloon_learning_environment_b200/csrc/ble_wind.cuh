@@ -198,25 +198,40 @@ BLE_HD Real simplex_noise4(const Perm& perm, double x, double y, double z, doubl
   const int xb = int(int64_t(fx) & 255), yb = int(int64_t(fy) & 255);
   const int zb = int(int64_t(fz) & 255), wb = int(int64_t(fw) & 255);
 
-  // pass 1: in-range mask over the 80 candidates
+  // pass 1: in-range mask over the 80 candidates.  With e_a = d0_a - o_a and T = tot * squish,
+  //   |d|^2 = sum_a (e_a - T)^2 = sum e_a^2 - 2 T sum e_a + 4 T^2,
+  // so a corner costs two 4-term sums and one FMA, and each "one step further" neighbour two more adds.
   uint64_t mask_lo = 0;   // candidates 0..63
   uint32_t mask_hi = 0;   // candidates 64..79
   const Real sq = Real(kSquish4);
+  const Real d0[4] = {dx0, dy0, dz0, dw0};
+  Real e1[4][2], q1[4][2], dq[4][2];                 // e, e^2 at offsets 0 / 1; e^2 change when stepping to -1 / 2
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    e1[a][0] = d0[a]; e1[a][1] = d0[a] - Real(1);
+    q1[a][0] = e1[a][0] * e1[a][0]; q1[a][1] = e1[a][1] * e1[a][1];
+    const Real em = d0[a] + Real(1), ep = d0[a] - Real(2);
+    dq[a][0] = em * em - q1[a][0];                   // offset 0 -> -1
+    dq[a][1] = ep * ep - q1[a][1];                   // offset 1 ->  2
+  }
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
-    const int i = m & 1, j = (m >> 1) & 1, k = (m >> 2) & 1, l = (m >> 3) & 1;
-    const int pc = i + j + k + l;
+    const int bit[4] = {m & 1, (m >> 1) & 1, (m >> 2) & 1, (m >> 3) & 1};
+    const int pc = bit[0] + bit[1] + bit[2] + bit[3];
+    const Real s1 = (e1[0][bit[0]] + e1[1][bit[1]]) + (e1[2][bit[2]] + e1[3][bit[3]]);
+    const Real s2 = (q1[0][bit[0]] + q1[1][bit[1]]) + (q1[2][bit[2]] + q1[3][bit[3]]);
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
-      int oi = i, oj = j, ok = k, ol = l, tot = pc;
-      if (e == 1) { oi = i ? 2 : -1; tot += i ? 1 : -1; }
-      if (e == 2) { oj = j ? 2 : -1; tot += j ? 1 : -1; }
-      if (e == 3) { ok = k ? 2 : -1; tot += k ? 1 : -1; }
-      if (e == 4) { ol = l ? 2 : -1; tot += l ? 1 : -1; }
-      const Real t = Real(tot) * sq;
-      const Real dx = dx0 - Real(oi) - t, dy = dy0 - Real(oj) - t;
-      const Real dz = dz0 - Real(ok) - t, dw = dw0 - Real(ol) - t;
-      const Real attn = Real(2) - dx * dx - dy * dy - dz * dz - dw * dw;
+      int tot = pc;
+      Real t1 = s1, t2 = s2;
+      if (e > 0) {
+        const int a = e - 1;
+        tot += bit[a] ? 1 : -1;
+        t1 += bit[a] ? Real(-1) : Real(1);           // e_a changes by -(o' - o)
+        t2 += dq[a][bit[a]];
+      }
+      const Real tt = Real(tot) * sq;
+      const Real attn = (Real(2) - Real(4) * tt * tt) - t2 + Real(2) * tt * t1;
       const int c = m * 5 + e;
       if (attn > Real(0)) {
         if (c < 64) mask_lo |= (uint64_t(1) << c); else mask_hi |= (1u << (c - 64));
@@ -255,6 +270,7 @@ BLE_HD Real simplex_noise4(const Perm& perm, double x, double y, double z, doubl
     const Real dx = dx0 - Real(oi) - t, dy = dy0 - Real(oj) - t;
     const Real dz = dz0 - Real(ok) - t, dw = dw0 - Real(ol) - t;
     Real attn = Real(2) - dx * dx - dy * dy - dz * dz - dw * dw;
+    attn = attn > Real(0) ? attn : Real(0);          // pass 1 decides the mask with a differently rounded sum
     int h = perm[(xb + oi) & 255];
     h = perm[(h + yb + oj) & 255];
     h = perm[(h + zb + ok) & 255];
