@@ -18,8 +18,8 @@
 //                 The factor arrives with ONE TMA bulk copy.
 //
 // Factor layout in HBM ("blocked lower"): 8 x 8 blocks (b, j), j <= b, at ((b (b + 1) / 2 + j) * 64 doubles,
-// COLUMN-major inside a block (element (r, c) at c * 8 + r, so that the 8 rows of one column are two
-// LDS.128 pairs); rows >= m are identity padding up to the next multiple of 8.
+// inside a block the elements are in mma A-fragment order (blk_inner); rows >= m are identity padding up to the
+// next multiple of 8.
 // NOTE: included from inside `namespace ble` of ble_engine.cu after ble_feature_kernels.cuh.
 #pragma once
 
@@ -29,8 +29,12 @@ constexpr int kGpBlockedLower = kGpBlk * kGpBlk * (kGpNumBlk * (kGpNumBlk + 1) /
 constexpr int kGpFactorDoubles = kGpBlockedLower;                              // per balloon in d.gp_chol
 
 __device__ __forceinline__ int blk_offset(int b, int j) { return (((b * (b + 1)) >> 1) + j) * (kGpBlk * kGpBlk); }
+// inside a block: "A-fragment order" of mma.m8n8k4 -- element (r, c) at (c / 4) * 32 + r * 4 + (c % 4), i.e. for
+// each half of the columns the 32 values sit in lane order (lane = 4 r + c % 4): a fragment load is 32 consecutive
+// doubles, free of bank conflicts in both half-warps.
+__device__ __forceinline__ int blk_inner(int r, int c) { return ((c >> 2) << 5) + (r << 2) + (c & 3); }
 __device__ __forceinline__ int blocked_index(int i, int j) {
-  return blk_offset(i >> 3, j >> 3) + (j & 7) * kGpBlk + (i & 7);
+  return blk_offset(i >> 3, j >> 3) + blk_inner(i & 7, j & 7);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(kUpdateThreads) k_gp_update(DevState<Real> d) 
   } else {
     // ---- full factorisation (left-looking, thread i owns row i) ------------------------------------
     for (int k = tid; k < blk_offset(nb_new, 0); k += kUpdateThreads) {      // K + alpha I, identity padding
-      const int blk = k >> 6, c = (k >> 3) & 7, r = k & 7;
+      const int blk = k >> 6, r = (k >> 2) & 7, c = ((k >> 5) & 1) * 4 + (k & 3);   // inverse of blk_inner
       int b = int((sqrtf(8.f * float(blk) + 1.f) - 1.f) * 0.5f);
       while (((b * (b + 1)) >> 1) > blk) --b;
       while ((((b + 1) * (b + 2)) >> 1) <= blk) ++b;
@@ -337,11 +341,11 @@ __device__ __forceinline__ double gp_kernel_from_d2(double d2) {
 constexpr int kC3Warps = 8;
 constexpr int kC3Threads = 32 * kC3Warps;
 constexpr int kC3Cols = 64;
-constexpr int kC3Stride = 72;                          // doubles per row of a published tile (64 + 8: fragment
-                                                       // loads of 4 rows x 8 columns then touch every bank once)
+constexpr int kC3Stride = 68;                          // doubles per row of a published tile: 64 + 4, so that the 4 rows x
+                                                       // 4 columns a half-warp reads for a B fragment fall into 16 distinct banks
 struct Column3Smem {
   double L[kGpBlockedLower];                           // filled by one TMA bulk copy
-  double Linv[kGpNumBlk][kGpBlk * kGpBlk];             // inverses of the diagonal blocks, column-major
+  double Linv[kGpNumBlk][kGpBlk * kGpBlk];             // inverses of the diagonal blocks, A-fragment order
   double xbuf[2][kGpBlk * kC3Stride];                  // V_j, double-buffered
   double cxy[kGpWindow], pz[kGpWindow];
   double z[kGpWindow][2];
@@ -357,12 +361,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// C (8 x 64, registers) -= Lblk (8 x 8, shared, column-major) * X (8 x 64, shared, row stride kC3Stride)
+// C (8 x 64, registers) -= Lblk (8 x 8, shared, A-fragment order) * X (8 x 64, shared, row stride kC3Stride)
 __device__ __forceinline__ void c3_update(double (&c)[8][2], const double* __restrict__ Lblk, const double* __restrict__ X,
                                           int g, int tq) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const double a = -Lblk[(4 * h + tq) * kGpBlk + g];
+    const double a = -Lblk[h * 32 + g * 4 + tq];
     const double* xr = X + (4 * h + tq) * kC3Stride + g;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) dmma884(c[nt][0], c[nt][1], a, xr[nt * 8]);
@@ -374,7 +378,7 @@ __device__ __forceinline__ void c3_update2(double (&c0)[8][2], double (&c1)[8][2
                                            const double* __restrict__ L1, const double* __restrict__ X, int g, int tq) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const double a0 = -L0[(4 * h + tq) * kGpBlk + g], a1 = -L1[(4 * h + tq) * kGpBlk + g];
+    const double a0 = -L0[h * 32 + g * 4 + tq], a1 = -L1[h * 32 + g * 4 + tq];
     const double* xr = X + (4 * h + tq) * kC3Stride + g;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -402,7 +406,7 @@ __device__ __forceinline__ void c3_solve_publish(double (&c)[8][2], const double
   for (int nt = 0; nt < 8; ++nt) { c[nt][0] = 0.0; c[nt][1] = 0.0; }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const double a = Linv[(4 * h + tq) * kGpBlk + g];
+    const double a = Linv[h * 32 + g * 4 + tq];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) dmma884(c[nt][0], c[nt][1], a, b[h][nt]);
   }
@@ -484,11 +488,11 @@ __global__ void __launch_bounds__(kC3Threads, 2) k_gp_column3(DevState<Real> d, 
       for (int r = 0; r < kGpBlk; ++r) {
         double acc = r == c ? 1.0 : 0.0;
 #pragma unroll
-        for (int k = 0; k < r; ++k) acc -= Ld[k * kGpBlk + r] * xv[k];
-        xv[r] = acc / Ld[r * kGpBlk + r];
+        for (int k = 0; k < r; ++k) acc -= Ld[blk_inner(r, k)] * xv[k];
+        xv[r] = acc / Ld[blk_inner(r, r)];
       }
 #pragma unroll
-      for (int r = 0; r < kGpBlk; ++r) S.Linv[j][c * kGpBlk + r] = xv[r];
+      for (int r = 0; r < kGpBlk; ++r) S.Linv[j][blk_inner(r, c)] = xv[r];
     }
   }
   __syncthreads();
