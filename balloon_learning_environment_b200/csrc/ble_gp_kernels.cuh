@@ -586,3 +586,229 @@ __global__ void __launch_bounds__(kC3Threads, 2) k_gp_column3(DevState<Real> d, 
     o[s * 3] = f0; o[s * 3 + 1] = f1; o[s * 3 + 2] = f2;
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// k_gp_column4: one warp per 8 columns, no dependency between warps
+// ---------------------------------------------------------------------------------------------------------
+// The columns of V = L^-1 K*^T are independent, and with DMMA an 8-column tile is exactly one n-tile: a warp
+// keeps the whole 120 x 8 tile of its columns in registers (15 C fragments = 30 doubles per lane) and runs the
+// complete blocked substitution alone --
+//   step j:  V_j = inv(L_jj) C_j            2 DMMA (the C -> B re-layout goes through a 768-byte private tile)
+//            C_b -= L_bj V_j,  b > j        2 DMMA per block, all independent
+// -- so the sweep needs no CTA barrier, no published tiles and is perfectly balanced; the dependent chain per step
+// is two DMMA pairs instead of a 16 + 16 DMMA update-and-solve by one owner warp while seven others wait
+// (k_gp_column3, kept above for reference until this one has replaced it everywhere).  A fragments of the factor
+// are read by every warp (8 x the shared-memory reads of column3, still < 25 % of the LSU).
+constexpr int kC4Warps = 8;
+constexpr int kC4Threads = 32 * kC4Warps;
+constexpr int kC4Stage = 12;                           // doubles per row of the private re-layout tile (conflict-free B loads)
+struct Column4Smem {
+  double L[kGpBlockedLower];                           // filled by one TMA bulk copy
+  double Linv[kGpNumBlk][kGpBlk * kGpBlk];             // inverses of the diagonal blocks, A-fragment order
+  double stage[kC4Warps][kGpBlk * kC4Stage];
+  double cxy[kGpWindow], pz[kGpWindow];
+  double z[kGpWindow][2];
+  float feat[kNumLevels * 3];
+  int lo, hi;
+  unsigned long long bar;
+};
+
+// C-fragment tile (row g, columns 2 tq, 2 tq + 1) -> the two B fragments (k = 4 h + tq, n = g) of the same 8 x 8 matrix
+__device__ __forceinline__ void c4_c_to_b(double c0, double c1, double* __restrict__ st, int g, int tq, double* b0, double* b1) {
+  *reinterpret_cast<double2*>(st + g * kC4Stage + 2 * tq) = make_double2(c0, c1);
+  __syncwarp();
+  *b0 = st[tq * kC4Stage + g];
+  *b1 = st[(4 + tq) * kC4Stage + g];
+  __syncwarp();
+}
+
+// Compile-time recursion over the pivot block J and the updated block B: every index of the register tile is a
+// constant, so the 30 accumulators stay in registers (a `#pragma unroll` double loop was left partly rolled by
+// nvcc, which moved the tile to local memory).
+template <int J, int B>
+struct C4Update {
+  static __device__ __forceinline__ void run(double (&c)[kGpNumBlk][2], const double* __restrict__ L, int nb, int lane,
+                                             double b0, double b1) {
+    if (B < nb) {
+      // the two k halves back to back on the same accumulator: measured faster on B200 than issuing all first
+      // halves and then all second halves (10.5 vs 12.0 ms per 65,536 balloons)
+      const double* Lb = L + (((B * (B + 1)) >> 1) + J) * (kGpBlk * kGpBlk);
+      dmma884(c[B][0], c[B][1], -Lb[lane], b0);
+      dmma884(c[B][0], c[B][1], -Lb[32 + lane], b1);
+    }
+    C4Update<J, B + 1>::run(c, L, nb, lane, b0, b1);
+  }
+};
+template <int J>
+struct C4Update<J, kGpNumBlk> {
+  static __device__ __forceinline__ void run(double (&)[kGpNumBlk][2], const double*, int, int, double, double) {}
+};
+template <int J>
+struct C4Sweep {
+  static __device__ __forceinline__ void run(double (&c)[kGpNumBlk][2], const double* __restrict__ L,
+                                             const double* __restrict__ Linv, const double* __restrict__ z,
+                                             double* __restrict__ st, int nb, int lane, int g, int tq,
+                                             double (&n2)[2], double (&mu)[2], double (&mv)[2]) {
+    if (J < nb) {
+      double b0, b1, v0 = 0.0, v1 = 0.0;
+      c4_c_to_b(c[J][0], c[J][1], st, g, tq, &b0, &b1);
+      dmma884(v0, v1, Linv[J * (kGpBlk * kGpBlk) + lane], b0);           // V_J = inv(L_JJ) C_J
+      dmma884(v0, v1, Linv[J * (kGpBlk * kGpBlk) + 32 + lane], b1);
+      const double zu = z[(J * kGpBlk + g) * 2], zv = z[(J * kGpBlk + g) * 2 + 1];
+      n2[0] += v0 * v0; n2[1] += v1 * v1;
+      mu[0] += v0 * zu; mu[1] += v1 * zu;
+      mv[0] += v0 * zv; mv[1] += v1 * zv;
+      if (J + 1 < nb) {
+        c4_c_to_b(v0, v1, st, g, tq, &b0, &b1);
+        C4Update<J, J + 1>::run(c, L, nb, lane, b0, b1);
+      }
+      C4Sweep<J + 1>::run(c, L, Linv, z, st, nb, lane, g, tq, n2, mu, mv);
+    }
+  }
+};
+template <>
+struct C4Sweep<kGpNumBlk> {
+  static __device__ __forceinline__ void run(double (&)[kGpNumBlk][2], const double*, const double*, const double*, double*,
+                                             int, int, int, int, double (&)[2], double (&)[2], double (&)[2]) {}
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(kC4Threads, 2) k_gp_column4(DevState<Real> d, float* __restrict__ obs) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  Column4Smem& S = *reinterpret_cast<Column4Smem*>(s_raw);
+  __shared__ int s_idx[kGpWindow];
+  const int64_t e = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int m = d.gp_m[e];
+  const int nb = (m + kGpBlk - 1) / kGpBlk;
+  const double* ring = d.gp_obs + e * int64_t(kGpWindow * 6);
+  const double x = DD(d, D_X, e), y = DD(d, D_Y, e), p_b = DD(d, D_P, e);
+  const int32_t t_elapsed = d.t_elapsed[e];
+  const double pmin = d.feat_range[2 * e], pmax = d.feat_range[2 * e + 1];
+  const uint32_t bar = smem_u32(&S.bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    S.lo = kNumLevels; S.hi = -1;
+  }
+  __syncthreads();
+  if (tid == 0 && m > 0) {
+    const uint32_t bytes = uint32_t(blk_offset(nb, 0)) * 8u;
+    const double* src = d.gp_chol + e * int64_t(kGpFactorDoubles);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(S.L)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  }
+  // while the factor is in flight: window slots and the (contiguous) range of reachable levels
+  if (tid < kNumLevels) {
+    const double pl = pressure_level(tid);
+    if (!(pl < pmin || pl > pmax)) { atomicMin(&S.lo, tid); atomicMax(&S.hi, tid); }
+  }
+  const int first_abs = d.gp_first[e];
+  if (m > 0) {
+    if (first_abs >= 0) { if (tid < m) s_idx[tid] = (first_abs + tid) % kGpWindow; }
+    else if (tid == 0) gp_window_indices(ring, d.gp_count[e], double(t_elapsed), s_idx);   // irregular history
+  }
+  __syncthreads();
+  const double qx = x / kGpScaleXY, qy = y / kGpScaleXY, qt = double(t_elapsed) / kGpScaleT;
+  if (tid < nb * kGpBlk) {
+    double c = 0.0, pz = 0.0, zu = 0.0, zv = 0.0;
+    if (tid < m) {
+      const double* o = ring + s_idx[tid] * 6;
+      const double dx = qx - o[0] / kGpScaleXY, dy = qy - o[1] / kGpScaleXY, dt = qt - o[3] / kGpScaleT;
+      c = dx * dx + dy * dy + dt * dt;
+      pz = o[2] / kGpScaleP;
+      const double* zz = d.gp_z + e * int64_t(kGpWindow * 2) + tid * 2;
+      zu = zz[0]; zv = zz[1];
+    }
+    S.cxy[tid] = c; S.pz[tid] = pz; S.z[tid][0] = zu; S.z[tid][1] = zv;
+  }
+  const int lo = S.lo, hi = S.hi;
+  const int n_act = hi >= lo ? hi - lo + 1 : 0;          // reachable levels lo .. hi
+  if (m > 0) {
+    asm volatile(                                     // wait for the TMA transaction (phase 0)
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar) : "memory");
+    if (tid < nb * kGpBlk) {                          // column c of inv(L_jj): forward substitution on e_c
+      const int j = tid >> 3, c = tid & 7;
+      const double* Ld = S.L + blk_offset(j, j);
+      double xv[kGpBlk];
+#pragma unroll
+      for (int r = 0; r < kGpBlk; ++r) {
+        double acc = r == c ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < r; ++k) acc -= Ld[blk_inner(r, k)] * xv[k];
+        xv[r] = acc / Ld[blk_inner(r, r)];
+      }
+#pragma unroll
+      for (int r = 0; r < kGpBlk; ++r) S.Linv[j][blk_inner(r, c)] = xv[r];
+    }
+  }
+  __syncthreads();
+
+  double* st = S.stage[warp];
+  for (int tile = warp; tile * 8 < n_act && m > 0; tile += kC4Warps) {
+    const int col0 = tile * 8 + 2 * tq;                  // this lane's two columns (C-fragment layout)
+    const bool on0 = col0 < n_act, on1 = col0 + 1 < n_act;
+    const double pq0 = pressure_level(lo + (on0 ? col0 : 0)) / kGpScaleP;
+    const double pq1 = pressure_level(lo + (on1 ? col0 + 1 : 0)) / kGpScaleP;
+    double c[kGpNumBlk][2];
+#pragma unroll
+    for (int b = 0; b < kGpNumBlk; ++b) {
+      const int i = b * kGpBlk + g;
+      c[b][0] = 0.0; c[b][1] = 0.0;
+      if (b < nb && i < m) {
+        const double cx = S.cxy[i], pi = S.pz[i];
+        if (on0) c[b][0] = gp_kernel_from_d2(cx + (pq0 - pi) * (pq0 - pi));
+        if (on1) c[b][1] = gp_kernel_from_d2(cx + (pq1 - pi) * (pq1 - pi));
+      }
+    }
+    double n2[2] = {0.0, 0.0}, mu[2] = {0.0, 0.0}, mv[2] = {0.0, 0.0};
+    C4Sweep<0>::run(c, S.L, &S.Linv[0][0], &S.z[0][0], st, nb, lane, g, tq, n2, mu, mv);
+    // sum over the 8 rows of the fragment (lanes with the same tq), then lane l < 8 finishes column tile * 8 + l
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        n2[i] += __shfl_xor_sync(0xffffffffu, n2[i], o);
+        mu[i] += __shfl_xor_sync(0xffffffffu, mu[i], o);
+        mv[i] += __shfl_xor_sync(0xffffffffu, mv[i], o);
+      }
+    }
+    const int src = (lane >> 1) & 3;
+    const double a0 = __shfl_sync(0xffffffffu, n2[0], src), a1 = __shfl_sync(0xffffffffu, n2[1], src);
+    const double u0 = __shfl_sync(0xffffffffu, mu[0], src), u1 = __shfl_sync(0xffffffffu, mu[1], src);
+    const double w0 = __shfl_sync(0xffffffffu, mv[0], src), w1 = __shfl_sync(0xffffffffu, mv[1], src);
+    const int col = tile * 8 + lane;
+    if (lane < 8 && col < n_act) {
+      const double norm2 = (lane & 1) ? a1 : a0, mean_u = (lane & 1) ? u1 : u0, mean_v = (lane & 1) ? w1 : w0;
+      const int l = lo + col;
+      const double deviation = fmax(kGpSigma2 - norm2, 0.0) / kGpSigma2;             // wind_gp.py:186-193
+      double fu, fv;
+      forecast_at<double, DevState<Real>>(d, e, x, y, pressure_level(l), t_elapsed, &fu, &fv);
+      wind_level_features(mean_u + fu, mean_v + fv, deviation, x, y, &S.feat[l * 3], &S.feat[l * 3 + 1], &S.feat[l * 3 + 2]);
+    }
+  }
+  if (m == 0) {                                       // no measurement yet: zero mean and deviation (wind_gp.py:161-163)
+    for (int k = tid; k < n_act; k += kC4Threads) {
+      const int l = lo + k;
+      double fu, fv;
+      forecast_at<double, DevState<Real>>(d, e, x, y, pressure_level(l), t_elapsed, &fu, &fv);
+      wind_level_features(fu, fv, 0.0, x, y, &S.feat[l * 3], &S.feat[l * 3 + 1], &S.feat[l * 3 + 2]);
+    }
+  }
+  __syncthreads();
+  // centred, padded column (features.py:479-497, 536-556)
+  const int lower = kNumLevels - nearest_pressure_level(p_b) - 1;
+  float* o = obs + e * int64_t(kNumFeatures) + 16;
+  for (int s = tid; s < 2 * kNumLevels - 1; s += kC4Threads) {
+    float f0 = 0.f, f1 = 1.f, f2 = 1.f;                                            // "unreachable" triple
+    const int l = s - lower;
+    if (l >= 0 && l < kNumLevels) {
+      const double pl = pressure_level(l);
+      if (!(pl < pmin || pl > pmax)) { f0 = S.feat[l * 3]; f1 = S.feat[l * 3 + 1]; f2 = S.feat[l * 3 + 2]; }
+    }
+    o[s * 3] = f0; o[s * 3 + 1] = f1; o[s * 3 + 2] = f2;
+  }
+}
