@@ -889,7 +889,6 @@ struct Engine : EngineBase {
   double* gp_obs = nullptr; int32_t* gp_count = nullptr; double* gp_chol = nullptr; int32_t* gp_m = nullptr;
   int32_t* gp_first = nullptr; double* gp_z = nullptr; double* range_scratch = nullptr;
   bool track_measurements = true;        // ble_features_track: append a WindGP measurement after every reset / step
-  bool gp_column3 = false;               // BLE_GP_COLUMN3=1: the row-block-per-warp DMMA variant (A/B timing)
   bool gp_refit_every_step = false;      // BLE_GP_REFIT=1: the first-generation kernels (full refit per call), kept for A/B checks
   double* feat_range = nullptr;
   // VAE decoder (reset path)
@@ -951,9 +950,8 @@ struct Engine : EngineBase {
       d.gp_first = gp_first; d.gp_z = gp_z;
       if (const char* g = std::getenv("BLE_GP_REFIT")) gp_refit_every_step = std::atoi(g) != 0;
       BLE_CUDA(cudaFuncSetAttribute(k_gp_update<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUpdateSmem)));
-      BLE_CUDA(cudaFuncSetAttribute(k_gp_column3<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(Column3Smem))));
       BLE_CUDA(cudaFuncSetAttribute(k_gp_column4<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(Column4Smem))));
-      if (const char* g = std::getenv("BLE_GP_COLUMN3")) gp_column3 = std::atoi(g) != 0;
+
 
       BLE_CUDA(cudaMalloc(&feat_range, sizeof(double) * 2 * n));
       d.gp_obs = gp_obs; d.gp_count = gp_count; d.gp_chol = gp_chol; d.gp_m = gp_m; d.feat_range = feat_range;
@@ -1374,8 +1372,7 @@ struct Engine : EngineBase {
       k_gp_column<Real><<<unsigned(n), kColumnThreads, kColumnSmem, s>>>(d, obs);
     } else {
       k_gp_update<Real><<<unsigned(n), kUpdateThreads, kUpdateSmem, s>>>(d);
-      if (gp_column3) k_gp_column3<Real><<<unsigned(n), kC3Threads, sizeof(Column3Smem), s>>>(d, obs);
-      else k_gp_column4<Real><<<unsigned(n), kC4Threads, sizeof(Column4Smem), s>>>(d, obs);
+      k_gp_column4<Real><<<unsigned(n), kC4Threads, sizeof(Column4Smem), s>>>(d, obs);
     }
     launches += 5;
     BLE_CUDA(cudaGetLastError());

@@ -13,9 +13,9 @@
 //                 both O(m^2); falls back to the full left-looking factorisation when the windows do not
 //                 chain (first call, history cleared, irregular use).  Also solves z = L^-1 y for the two
 //                 error components.  Everything fp64, in shared memory.
-//   k_gp_column3  CTA (8 warps) per balloon: V = L^-1 K*^T for the reachable pressure levels as a blocked
-//                 right-looking triangular solve on the fp64 tensor cores (see the kernel's own header).
-//                 The factor arrives with ONE TMA bulk copy.
+//   k_gp_column4  CTA (8 warps) per balloon: V = L^-1 K*^T for the reachable pressure levels as a blocked
+//                 right-looking triangular solve on the fp64 tensor cores, one warp per 8 columns (see the
+//                 kernel's own header).  The factor arrives with ONE TMA bulk copy.
 //
 // Factor layout in HBM ("blocked lower"): 8 x 8 blocks (b, j), j <= b, at ((b (b + 1) / 2 + j) * 64 doubles,
 // inside a block the elements are in mma A-fragment order (blk_inner); rows >= m are identity padding up to the
@@ -326,268 +326,6 @@ __device__ __forceinline__ double gp_kernel_from_d2(double d2) {
 
 
 // ---------------------------------------------------------------------------------------------------------
-// k_gp_column3: the same blocked right-looking solve on the fp64 tensor cores (mma.sync.m8n8k4.f64)
-// ---------------------------------------------------------------------------------------------------------
-// Measured on B200: DMMA runs at the DFMA rate (37 TFLOP/s, scripts/probes/dmma_probe.cu) but one instruction
-// does the work of eight DFMA warp instructions and its operands are 256-byte shared-memory fragments, so
-// the instruction stream and the shared-memory traffic of the update shrink ~6x.
-//   * a pass handles 64 columns = 8 n-tiles; warp w owns the row blocks w and 14 - w, their 8 x 64
-//     accumulator tiles live in registers in the C-fragment layout (row = lane / 4, cols 2 (lane % 4), +1);
-//   * trailing update of block b at step j:  C_b -= L_bj V_j  = 16 DMMA (8 n-tiles x 2 k-halves), A fragments
-//     from the column-major 8 x 8 blocks of the factor, B fragments from the published V_j;
-//   * diagonal solve: V_j = inv(L_jj) C_j, also 16 DMMA, with the 15 inverted diagonal blocks prepared once
-//     per CTA (no dependent chain of divisions in the sweep); done by the owner of block j + 1 inside step j;
-//   * |v|^2 and v . z are accumulated per column by two reducer warps straight from the published V_j.
-constexpr int kC3Warps = 8;
-constexpr int kC3Threads = 32 * kC3Warps;
-constexpr int kC3Cols = 64;
-constexpr int kC3Stride = 68;                          // doubles per row of a published tile: 64 + 4, so that the 4 rows x
-                                                       // 4 columns a half-warp reads for a B fragment fall into 16 distinct banks
-struct Column3Smem {
-  double L[kGpBlockedLower];                           // filled by one TMA bulk copy
-  double Linv[kGpNumBlk][kGpBlk * kGpBlk];             // inverses of the diagonal blocks, A-fragment order
-  double xbuf[2][kGpBlk * kC3Stride];                  // V_j, double-buffered
-  double cxy[kGpWindow], pz[kGpWindow];
-  double z[kGpWindow][2];
-  double pq[kC3Cols];                                  // scaled pressure of this pass's levels
-  float feat[kNumLevels * 3];
-  int act[kNumLevels + 3];
-  int n_act;
-  unsigned long long bar;
-};
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// C (8 x 64, registers) -= Lblk (8 x 8, shared, A-fragment order) * X (8 x 64, shared, row stride kC3Stride)
-__device__ __forceinline__ void c3_update(double (&c)[8][2], const double* __restrict__ Lblk, const double* __restrict__ X,
-                                          int g, int tq) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const double a = -Lblk[h * 32 + g * 4 + tq];
-    const double* xr = X + (4 * h + tq) * kC3Stride + g;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) dmma884(c[nt][0], c[nt][1], a, xr[nt * 8]);
-  }
-}
-
-// two owned blocks share the B fragments
-__device__ __forceinline__ void c3_update2(double (&c0)[8][2], double (&c1)[8][2], const double* __restrict__ L0,
-                                           const double* __restrict__ L1, const double* __restrict__ X, int g, int tq) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const double a0 = -L0[h * 32 + g * 4 + tq], a1 = -L1[h * 32 + g * 4 + tq];
-    const double* xr = X + (4 * h + tq) * kC3Stride + g;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const double b = xr[nt * 8];
-      dmma884(c0[nt][0], c0[nt][1], a0, b);
-      dmma884(c1[nt][0], c1[nt][1], a1, b);
-    }
-  }
-}
-
-// V = inv(L_jj) C, published into X (which also serves as the staging tile for the C -> B re-layout)
-__device__ __forceinline__ void c3_solve_publish(double (&c)[8][2], const double* __restrict__ Linv, double* __restrict__ X,
-                                                 int g, int tq) {
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(X + g * kC3Stride + nt * 8 + 2 * tq) = make_double2(c[nt][0], c[nt][1]);
-  __syncwarp();
-  double b[2][8];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) b[h][nt] = X[(4 * h + tq) * kC3Stride + nt * 8 + g];
-  }
-  __syncwarp();
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) { c[nt][0] = 0.0; c[nt][1] = 0.0; }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const double a = Linv[h * 32 + g * 4 + tq];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) dmma884(c[nt][0], c[nt][1], a, b[h][nt]);
-  }
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(X + g * kC3Stride + nt * 8 + 2 * tq) = make_double2(c[nt][0], c[nt][1]);
-}
-
-template <typename Real>
-__global__ void __launch_bounds__(kC3Threads, 2) k_gp_column3(DevState<Real> d, float* __restrict__ obs) {
-  extern __shared__ __align__(128) unsigned char s_raw[];
-  Column3Smem& S = *reinterpret_cast<Column3Smem*>(s_raw);
-  __shared__ int s_idx[kGpWindow];
-  const int64_t e = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
-  const int m = d.gp_m[e];
-  const int nb = (m + kGpBlk - 1) / kGpBlk;
-  const double* ring = d.gp_obs + e * int64_t(kGpWindow * 6);
-  const double x = DD(d, D_X, e), y = DD(d, D_Y, e), p_b = DD(d, D_P, e);
-  const int32_t t_elapsed = d.t_elapsed[e];
-  const double pmin = d.feat_range[2 * e], pmax = d.feat_range[2 * e + 1];
-  const uint32_t bar = smem_u32(&S.bar);
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    S.n_act = 0; S.act[kNumLevels] = kNumLevels; S.act[kNumLevels + 1] = -1;
-  }
-  __syncthreads();
-  if (tid == 0 && m > 0) {
-    const uint32_t bytes = uint32_t(blk_offset(nb, 0)) * 8u;
-    const double* src = d.gp_chol + e * int64_t(kGpFactorDoubles);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(S.L)), "l"(src), "r"(bytes), "r"(bar) : "memory");
-  }
-  // while the factor is in flight: window slots and the (contiguous) range of reachable levels
-  if (tid < kNumLevels) {
-    const double pl = pressure_level(tid);
-    if (!(pl < pmin || pl > pmax)) { atomicMin(&S.act[kNumLevels], tid); atomicMax(&S.act[kNumLevels + 1], tid); }
-  }
-  const int first_abs = d.gp_first[e];
-  if (m > 0) {
-    if (first_abs >= 0) { if (tid < m) s_idx[tid] = (first_abs + tid) % kGpWindow; }
-    else if (tid == 0) gp_window_indices(ring, d.gp_count[e], double(t_elapsed), s_idx);   // irregular history
-  }
-  __syncthreads();
-  {
-    const int lo = S.act[kNumLevels], hi = S.act[kNumLevels + 1];
-    const int n = hi >= lo ? hi - lo + 1 : 0;
-    if (tid < n) S.act[tid] = lo + tid;
-    if (tid == 0) S.n_act = n;
-  }
-  const double qx = x / kGpScaleXY, qy = y / kGpScaleXY, qt = double(t_elapsed) / kGpScaleT;
-  if (tid < nb * kGpBlk) {
-    double c = 0.0, pz = 0.0, zu = 0.0, zv = 0.0;
-    if (tid < m) {
-      const double* o = ring + s_idx[tid] * 6;
-      const double dx = qx - o[0] / kGpScaleXY, dy = qy - o[1] / kGpScaleXY, dt = qt - o[3] / kGpScaleT;
-      c = dx * dx + dy * dy + dt * dt;
-      pz = o[2] / kGpScaleP;
-      const double* zz = d.gp_z + e * int64_t(kGpWindow * 2) + tid * 2;
-      zu = zz[0]; zv = zz[1];
-    }
-    S.cxy[tid] = c; S.pz[tid] = pz; S.z[tid][0] = zu; S.z[tid][1] = zv;
-  }
-  __syncthreads();
-  const int n_act = S.n_act;
-  const int b0 = warp, b1 = (kGpNumBlk - 1 - warp) != warp ? kGpNumBlk - 1 - warp : -1;
-  const bool own0 = b0 < nb, own1 = b1 >= 0 && b1 < nb;
-  if (m > 0) {
-    asm volatile(                                     // wait for the TMA transaction (phase 0)
-        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
-        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar) : "memory");
-    if (tid < nb * kGpBlk) {                          // column c of inv(L_jj): forward substitution on e_c
-      const int j = tid >> 3, c = tid & 7;
-      const double* Ld = S.L + blk_offset(j, j);
-      double xv[kGpBlk];
-#pragma unroll
-      for (int r = 0; r < kGpBlk; ++r) {
-        double acc = r == c ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < r; ++k) acc -= Ld[blk_inner(r, k)] * xv[k];
-        xv[r] = acc / Ld[blk_inner(r, r)];
-      }
-#pragma unroll
-      for (int r = 0; r < kGpBlk; ++r) S.Linv[j][blk_inner(r, c)] = xv[r];
-    }
-  }
-  __syncthreads();
-
-  for (int first = 0; first < n_act && m > 0; first += kC3Cols) {
-    if (tid < kC3Cols) S.pq[tid] = pressure_level(first + tid < n_act ? S.act[first + tid] : 0) / kGpScaleP;
-    __syncthreads();
-    double c0[8][2], c1[8][2];                        // accumulators of the two owned blocks (C-fragment layout)
-    {
-      const int i0 = b0 * kGpBlk + g, i1 = b1 * kGpBlk + g;
-      const bool r0 = own0 && i0 < m, r1 = own1 && i1 < m;
-      const double cx0 = r0 ? S.cxy[i0] : 0.0, pz0 = r0 ? S.pz[i0] : 0.0;
-      const double cx1 = r1 ? S.cxy[i1] : 0.0, pz1 = r1 ? S.pz[i1] : 0.0;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int col = nt * 8 + 2 * tq + i;
-          const bool on = first + col < n_act;
-          const double pq = S.pq[col];
-          c0[nt][i] = (r0 && on) ? gp_kernel_from_d2(cx0 + (pq - pz0) * (pq - pz0)) : 0.0;
-          c1[nt][i] = (r1 && on) ? gp_kernel_from_d2(cx1 + (pq - pz1) * (pq - pz1)) : 0.0;
-        }
-      }
-    }
-    // block 0 is solved up front; afterwards the owner of block j + 1 updates and solves it INSIDE step j
-    if (warp == 0) c3_solve_publish(c0, S.Linv[0], S.xbuf[0], g, tq);
-    __syncthreads();
-    double n2 = 0.0, mu = 0.0, mv = 0.0;              // reducer warps 6 (columns 32..63) and 7 (columns 0..31)
-    for (int j = 0; j < nb; ++j) {
-      const double* X = S.xbuf[j & 1];
-      const int nx = j + 1;
-      if (nx < nb) {
-        const bool need0 = own0 && b0 > j, need1 = own1 && b1 > j;
-        if (need0 && b0 == nx) {
-          c3_update(c0, S.L + blk_offset(b0, j), X, g, tq);
-          c3_solve_publish(c0, S.Linv[nx], S.xbuf[nx & 1], g, tq);
-          if (need1) c3_update(c1, S.L + blk_offset(b1, j), X, g, tq);
-        } else if (need1 && b1 == nx) {
-          c3_update(c1, S.L + blk_offset(b1, j), X, g, tq);
-          c3_solve_publish(c1, S.Linv[nx], S.xbuf[nx & 1], g, tq);
-        } else if (need0 && need1) {
-          c3_update2(c0, c1, S.L + blk_offset(b0, j), S.L + blk_offset(b1, j), X, g, tq);
-        } else if (need0) {
-          c3_update(c0, S.L + blk_offset(b0, j), X, g, tq);
-        } else if (need1) {
-          c3_update(c1, S.L + blk_offset(b1, j), X, g, tq);
-        }
-      }
-      if (warp >= 6) {
-        const int col = (warp == 7 ? 0 : 32) + lane;
-#pragma unroll
-        for (int r = 0; r < kGpBlk; ++r) {
-          const double v = X[r * kC3Stride + col];
-          n2 += v * v; mu += v * S.z[j * kGpBlk + r][0]; mv += v * S.z[j * kGpBlk + r][1];
-        }
-      }
-      __syncthreads();
-    }
-    if (warp >= 6) {
-      const int col = (warp == 7 ? 0 : 32) + lane;
-      if (first + col < n_act) {
-        const int l = S.act[first + col];
-        const double deviation = fmax(kGpSigma2 - n2, 0.0) / kGpSigma2;            // wind_gp.py:186-193
-        double fu, fv;
-        forecast_at<double, DevState<Real>>(d, e, x, y, pressure_level(l), t_elapsed, &fu, &fv);
-        wind_level_features(mu + fu, mv + fv, deviation, x, y, &S.feat[l * 3], &S.feat[l * 3 + 1], &S.feat[l * 3 + 2]);
-      }
-    }
-    __syncthreads();
-  }
-  if (m == 0) {                                       // no measurement yet: zero mean and deviation (wind_gp.py:161-163)
-    for (int k = tid; k < n_act; k += kC3Threads) {
-      const int l = S.act[k];
-      double fu, fv;
-      forecast_at<double, DevState<Real>>(d, e, x, y, pressure_level(l), t_elapsed, &fu, &fv);
-      wind_level_features(fu, fv, 0.0, x, y, &S.feat[l * 3], &S.feat[l * 3 + 1], &S.feat[l * 3 + 2]);
-    }
-    __syncthreads();
-  }
-  // centred, padded column (features.py:479-497, 536-556)
-  const int lower = kNumLevels - nearest_pressure_level(p_b) - 1;
-  float* o = obs + e * int64_t(kNumFeatures) + 16;
-  for (int s = tid; s < 2 * kNumLevels - 1; s += kC3Threads) {
-    float f0 = 0.f, f1 = 1.f, f2 = 1.f;                                            // "unreachable" triple
-    const int l = s - lower;
-    if (l >= 0 && l < kNumLevels) {
-      const double pl = pressure_level(l);
-      if (!(pl < pmin || pl > pmax)) { f0 = S.feat[l * 3]; f1 = S.feat[l * 3 + 1]; f2 = S.feat[l * 3 + 2]; }
-    }
-    o[s * 3] = f0; o[s * 3 + 1] = f1; o[s * 3 + 2] = f2;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // k_gp_column4: one warp per 8 columns, no dependency between warps
 // ---------------------------------------------------------------------------------------------------------
 // The columns of V = L^-1 K*^T are independent, and with DMMA an 8-column tile is exactly one n-tile: a warp
@@ -596,9 +334,16 @@ __global__ void __launch_bounds__(kC3Threads, 2) k_gp_column3(DevState<Real> d, 
 //   step j:  V_j = inv(L_jj) C_j            2 DMMA (the C -> B re-layout goes through a 768-byte private tile)
 //            C_b -= L_bj V_j,  b > j        2 DMMA per block, all independent
 // -- so the sweep needs no CTA barrier, no published tiles and is perfectly balanced; the dependent chain per step
-// is two DMMA pairs instead of a 16 + 16 DMMA update-and-solve by one owner warp while seven others wait
-// (k_gp_column3, kept above for reference until this one has replaced it everywhere).  A fragments of the factor
-// are read by every warp (8 x the shared-memory reads of column3, still < 25 % of the LSU).
+// is two DMMA pairs.  (Two earlier layouts -- row blocks owned by warps with V_j published through shared memory,
+// first with DFMA, then with DMMA -- spent a third of their time at the per-step barrier behind the one warp that
+// solved the diagonal block: 14.7 and 11.7 ms per 65,536 balloons against 9.4 ms here.)  DMMA runs at the DFMA
+// rate on B200 (37 TFLOP/s, scripts/probes/dmma_probe.cu) but one instruction does the work of eight DFMA warp
+// instructions and its operands are 256-byte conflict-free shared-memory fragments.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 constexpr int kC4Warps = 8;
 constexpr int kC4Threads = 32 * kC4Warps;
 constexpr int kC4Stage = 12;                           // doubles per row of the private re-layout tile (conflict-free B loads)
