@@ -348,8 +348,8 @@ constexpr int kC4Warps = 8;
 constexpr int kC4Threads = 32 * kC4Warps;
 constexpr int kC4Stage = 12;                           // doubles per row of the private re-layout tile (conflict-free B loads)
 struct Column4Smem {
-  double L[kGpBlockedLower];                           // filled by one TMA bulk copy
-  double Linv[kGpNumBlk][kGpBlk * kGpBlk];             // inverses of the diagonal blocks, A-fragment order
+  double L[kGpBlockedLower];                           // filled by one TMA bulk copy; the diagonal blocks are then
+                                                       // replaced IN PLACE by their inverses (the sweep never needs L_jj)
   double stage[kC4Warps][kGpBlk * kC4Stage];
   double cxy[kGpWindow], pz[kGpWindow];
   double z[kGpWindow][2];
@@ -391,14 +391,15 @@ struct C4Update<J, kGpNumBlk> {
 template <int J>
 struct C4Sweep {
   static __device__ __forceinline__ void run(double (&c)[kGpNumBlk][2], const double* __restrict__ L,
-                                             const double* __restrict__ Linv, const double* __restrict__ z,
+                                             const double* __restrict__ z,
                                              double* __restrict__ st, int nb, int lane, int g, int tq,
                                              double (&n2)[2], double (&mu)[2], double (&mv)[2]) {
     if (J < nb) {
       double b0, b1, v0 = 0.0, v1 = 0.0;
       c4_c_to_b(c[J][0], c[J][1], st, g, tq, &b0, &b1);
-      dmma884(v0, v1, Linv[J * (kGpBlk * kGpBlk) + lane], b0);           // V_J = inv(L_JJ) C_J
-      dmma884(v0, v1, Linv[J * (kGpBlk * kGpBlk) + 32 + lane], b1);
+      const double* Li = L + (((J * (J + 1)) >> 1) + J) * (kGpBlk * kGpBlk);   // inv(L_JJ), stored over L_JJ
+      dmma884(v0, v1, Li[lane], b0);                                     // V_J = inv(L_JJ) C_J
+      dmma884(v0, v1, Li[32 + lane], b1);
       const double zu = z[(J * kGpBlk + g) * 2], zv = z[(J * kGpBlk + g) * 2 + 1];
       n2[0] += v0 * v0; n2[1] += v1 * v1;
       mu[0] += v0 * zu; mu[1] += v1 * zu;
@@ -407,13 +408,13 @@ struct C4Sweep {
         c4_c_to_b(v0, v1, st, g, tq, &b0, &b1);
         C4Update<J, J + 1>::run(c, L, nb, lane, b0, b1);
       }
-      C4Sweep<J + 1>::run(c, L, Linv, z, st, nb, lane, g, tq, n2, mu, mv);
+      C4Sweep<J + 1>::run(c, L, z, st, nb, lane, g, tq, n2, mu, mv);
     }
   }
 };
 template <>
 struct C4Sweep<kGpNumBlk> {
-  static __device__ __forceinline__ void run(double (&)[kGpNumBlk][2], const double*, const double*, const double*, double*,
+  static __device__ __forceinline__ void run(double (&)[kGpNumBlk][2], const double*, const double*, double*,
                                              int, int, int, int, double (&)[2], double (&)[2], double (&)[2]) {}
 };
 
@@ -475,19 +476,22 @@ __global__ void __launch_bounds__(kC4Threads, 2) k_gp_column4(DevState<Real> d, 
         "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
         "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar) : "memory");
-    if (tid < nb * kGpBlk) {                          // column c of inv(L_jj): forward substitution on e_c
-      const int j = tid >> 3, c = tid & 7;
-      const double* Ld = S.L + blk_offset(j, j);
-      double xv[kGpBlk];
+    double xv[kGpBlk];
+    const int jd = tid >> 3, cd = tid & 7;
+    double* Ld = S.L + blk_offset(jd < nb ? jd : 0, jd < nb ? jd : 0);
+    if (tid < nb * kGpBlk) {                          // column cd of inv(L_jj): forward substitution on e_cd
 #pragma unroll
       for (int r = 0; r < kGpBlk; ++r) {
-        double acc = r == c ? 1.0 : 0.0;
+        double acc = r == cd ? 1.0 : 0.0;
 #pragma unroll
         for (int k = 0; k < r; ++k) acc -= Ld[blk_inner(r, k)] * xv[k];
         xv[r] = acc / Ld[blk_inner(r, r)];
       }
+    }
+    __syncthreads();                                  // every column of every diagonal block has been read
+    if (tid < nb * kGpBlk) {
 #pragma unroll
-      for (int r = 0; r < kGpBlk; ++r) S.Linv[j][blk_inner(r, c)] = xv[r];
+      for (int r = 0; r < kGpBlk; ++r) Ld[blk_inner(r, cd)] = xv[r];
     }
   }
   __syncthreads();
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(kC4Threads, 2) k_gp_column4(DevState<Real> d, 
       }
     }
     double n2[2] = {0.0, 0.0}, mu[2] = {0.0, 0.0}, mv[2] = {0.0, 0.0};
-    C4Sweep<0>::run(c, S.L, &S.Linv[0][0], &S.z[0][0], st, nb, lane, g, tq, n2, mu, mv);
+    C4Sweep<0>::run(c, S.L, &S.z[0][0], st, nb, lane, g, tq, n2, mu, mv);
     // sum over the 8 rows of the fragment (lanes with the same tq), then lane l < 8 finishes column tile * 8 + l
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) {
