@@ -888,6 +888,7 @@ struct Engine : EngineBase {
   bool noise_valid = false;      // noise_partial matches the current state
   double* gp_obs = nullptr; int32_t* gp_count = nullptr; double* gp_chol = nullptr; int32_t* gp_m = nullptr;
   int32_t* gp_first = nullptr; double* gp_z = nullptr; double* range_scratch = nullptr;
+  bool host_zero_copy = true;            // BLE_HOST_ZERO_COPY=0: staged copies in ble_step_host instead of mapped pinned memory
   bool track_measurements = true;        // ble_features_track: append a WindGP measurement after every reset / step
   bool gp_refit_every_step = false;      // BLE_GP_REFIT=1: the first-generation kernels (full refit per call), kept for A/B checks
   double* feat_range = nullptr;
@@ -912,6 +913,7 @@ struct Engine : EngineBase {
   int create(int dev, int64_t n_envs, const ble_config& c) {
     device = dev; n = n_envs; cfg = c;
     BLE_CUDA(cudaSetDevice(device));
+    if (const char* z = std::getenv("BLE_HOST_ZERO_COPY")) host_zero_copy = std::atoi(z) != 0;
     if (const char* g = std::getenv("BLE_L2_FETCH_GRANULARITY")) {     // experiment knob: 32 / 64 / 128
       BLE_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(std::atoi(g))));
     }
@@ -1383,10 +1385,18 @@ struct Engine : EngineBase {
     if (actions_host == nullptr || reward_host == nullptr || done_host == nullptr) { err = "step_host: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
     BLE_CUDA(cudaSetDevice(device));
     std::memcpy(h_actions, actions_host, sizeof(int32_t) * n);
-    BLE_CUDA(cudaMemcpyAsync(d_actions, h_actions, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
-    int rc = step(d_actions, d_reward, d_done, nullptr, s);
-    if (rc != BLE_OK) return rc;
-    BLE_CUDA(cudaMemcpyAsync(h_reward, d_reward, (sizeof(float) + sizeof(uint8_t)) * n, cudaMemcpyDeviceToHost, s));
+    int rc;
+    if (host_zero_copy) {
+      // pinned host memory is device-accessible under UVA: the step kernel reads the actions and writes reward /
+      // done straight over PCIe (4 + 5 bytes per balloon), which saves three copy launches and their latencies
+      rc = step(h_actions, h_reward, h_done, nullptr, s);
+      if (rc != BLE_OK) return rc;
+    } else {
+      BLE_CUDA(cudaMemcpyAsync(d_actions, h_actions, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+      rc = step(d_actions, d_reward, d_done, nullptr, s);
+      if (rc != BLE_OK) return rc;
+      BLE_CUDA(cudaMemcpyAsync(h_reward, d_reward, (sizeof(float) + sizeof(uint8_t)) * n, cudaMemcpyDeviceToHost, s));
+    }
     BLE_CUDA(cudaStreamSynchronize(s));
     std::memcpy(reward_host, h_reward, sizeof(float) * n);
     std::memcpy(done_host, h_done, sizeof(uint8_t) * n);

@@ -383,7 +383,7 @@ def run_b200(args):
                  'live_fraction_after_run': live_frac},
       'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 4 * n_total,
               'd2h_bytes_per_step': (5 + (4396 if with_obs else 0)) * n_total,
-              'api': 'ble_step_host (host int32 actions in, host float32 reward + uint8 done out)'
+              'api': 'ble_step_host (host int32 actions in, host float32 reward + uint8 done out; the step kernel reads / writes the pinned staging buffers over PCIe)'
                      + (' + ble_features_perciatelli read back to pinned host memory' if with_obs else '')},
       'gpu_launches': launches,
       'clocks': clocks,
