@@ -106,6 +106,9 @@ REGISTRY = {'random': RandomAgent, 'station_seeker': StationSeekerAgent, 'random
 
 def create_agent(name: str, num_actions: int, observation_shape, arena) -> BatchedAgent:
   """agents/agent_registry.py:40-75 for the controllers that exist here."""
+  if name == 'quantile':                 # the QR-DQN agent brings the learner kernels with it: imported on demand
+    from balloon_learning_environment_b200 import learner
+    return learner.QuantileAgent(num_actions, observation_shape, arena)
   if name not in REGISTRY:
     raise ValueError(f'Unknown agent {name}; available: {sorted(REGISTRY)}')
   return REGISTRY[name](num_actions, observation_shape, arena)

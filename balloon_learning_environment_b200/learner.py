@@ -448,3 +448,102 @@ def run_training(env, learner: QrDqnLearner, *, num_iterations: int, replay: Opt
   loop = TrainingLoop(env, learner, replay=replay, exploration=exploration,
                       learner_steps_per_iteration=learner_steps_per_iteration, seed=seed)
   return loop.run(num_iterations, log=log)
+
+
+class QuantileAgent:
+  """agents/quantile_agent.py:37-160 behind the batched Agent interface (agents.py): begin_episode / step /
+  end_episode take and return one entry per balloon.  In TRAIN mode every step appends the previous transition to
+  the replay ring, runs `learner_steps_per_step` SGD steps once `min_replay_size` transitions are stored and lets
+  MarcoPoloExploration override the greedy action (quantile.gin); in EVAL mode it is the greedy policy
+  (epsilon_eval = 0).  Balloons whose episode already ended keep being stepped by the loops that drive this
+  interface (their transitions carry reward 0 and are cut by the terminal flag recorded when they ended)."""
+
+  def __init__(self, num_actions: int, observation_shape, arena, *, config: Optional[QrDqnConfig] = None,
+               seed: Optional[int] = None, replay_steps: Optional[int] = None, learner_steps_per_step: int = 1):
+    cfg = config if config is not None else QrDqnConfig()
+    if num_actions != cfg.num_actions or tuple(observation_shape) != (cfg.num_features,):
+      raise ValueError('QuantileAgent: the network configuration does not match the environment')
+    self._arena = arena
+    self.device, n = arena.device, arena.num_envs
+    seed = 0 if seed is None else int(seed)
+    self.learner = QrDqnLearner(cfg, device=self.device, seed=seed)
+    self.exploration = MarcoPoloExploration(n, exploratory_episode_probability=cfg.exploratory_episode_probability,
+                                            seed=seed + 1, device=self.device)
+    steps = replay_steps if replay_steps is not None else max(cfg.n_step + 2, cfg.max_replay_size // n)
+    self.replay = DeviceReplay(n, steps, num_features=cfg.num_features, n_step=cfg.n_step, gamma=cfg.discount,
+                               device=self.device, seed=seed + 2)
+    self.learner_steps_per_step = int(learner_steps_per_step)
+    self.eval_mode = False
+    self._last_obs = torch.empty(n, cfg.num_features, dtype=torch.float32, device=self.device)
+    self._last_action = torch.zeros(n, dtype=torch.int32, device=self.device)
+    self._alive = torch.ones(n, dtype=torch.bool, device=self.device)
+    self.last_loss = torch.zeros((), device=self.device)
+
+  def get_name(self) -> str:
+    return self.__class__.__name__
+
+  def set_mode(self, mode) -> None:                       # quantile_agent.py:152-157
+    self.eval_mode = str(getattr(mode, 'value', mode)) == 'eval'
+
+  def _act(self, observation: torch.Tensor, begin: bool) -> torch.Tensor:
+    action = self.learner.act(observation, epsilon=0.0)
+    if not self.eval_mode:
+      flag = torch.full((self._arena.num_envs,), 1 if begin else 0, dtype=torch.uint8, device=self.device)
+      action = self.exploration.step(observation, action, flag)
+      self._last_obs.copy_(observation)
+      self._last_action.copy_(action)
+    return action
+
+  def begin_episode(self, observation: torch.Tensor) -> torch.Tensor:
+    self._alive.fill_(True)
+    return self._act(observation, begin=True)
+
+  def _store(self, reward: torch.Tensor, terminal: torch.Tensor, truncated: torch.Tensor) -> None:
+    # a balloon that already ended contributes a terminal, zero-reward transition that no window can cross
+    dead = ~self._alive
+    self.replay.add(self._last_obs, self._last_action, torch.where(dead, torch.zeros_like(reward), reward),
+                    (terminal | dead).to(torch.uint8), (truncated & ~dead).to(torch.uint8))
+    self._alive &= ~terminal
+
+  def _train(self) -> None:
+    cfg = self.learner.config
+    if self.replay.num_transitions >= cfg.min_replay_size and self.replay.count > cfg.n_step:
+      for _ in range(self.learner_steps_per_step):
+        self.last_loss = self.learner.step(self.replay.sample(cfg.batch_size))
+
+  def step(self, reward: torch.Tensor, observation: torch.Tensor, done: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """done (uint8 / bool [N], optional): balloons whose episode ended with this reward (terminal status)."""
+    if not self.eval_mode:
+      terminal = done.ne(0) if done is not None else torch.zeros_like(self._alive)
+      self._store(reward, terminal, torch.zeros_like(terminal))
+      self._train()
+    return self._act(observation, begin=False)
+
+  def end_episode(self, reward: torch.Tensor, terminal: Optional[torch.Tensor] = None) -> None:
+    """terminal False (or None) marks a step-limit truncation, as train_lib does at max_episode_length."""
+    if self.eval_mode:
+      return
+    term = terminal.ne(0) if terminal is not None else torch.zeros_like(self._alive)
+    self._store(reward, term, ~term)
+    self._train()
+
+  def save_checkpoint(self, checkpoint_dir: str, iteration_number: int) -> None:      # quantile_agent.py:159-170
+    import os
+    os.makedirs(checkpoint_dir, exist_ok=True)
+    torch.save(self.learner.state_dict(), os.path.join(checkpoint_dir, f'ckpt.{int(iteration_number)}'))
+
+  def load_checkpoint(self, checkpoint_dir: str, iteration_number: int) -> None:      # quantile_agent.py:172-176
+    import os
+    self.learner.load_state_dict(torch.load(os.path.join(checkpoint_dir, f'ckpt.{int(iteration_number)}'),
+                                            map_location=self.device))
+
+  def reload_latest_checkpoint(self, checkpoint_dir: str) -> int:                      # quantile_agent.py:178-190
+    import os
+    try:
+      found = [int(f.split('.', 1)[1]) for f in os.listdir(checkpoint_dir) if f.startswith('ckpt.')]
+    except (FileNotFoundError, ValueError):
+      return -1
+    if not found:
+      return -1
+    self.load_checkpoint(checkpoint_dir, max(found))
+    return max(found)

@@ -250,3 +250,42 @@ def test_training_loop_smoke(lrn):
   assert float((learner.flat - before).abs().max()) > 0
   assert int(replay.truncated.sum()) >= n                 # the step-limit truncations were recorded
   env.close()
+
+
+def test_quantile_agent_interface(lrn, tmp_path):
+  """QuantileAgent behind the batched Agent interface: greedy in EVAL mode through eval_lib.eval_agent, replay +
+  SGD + exploration in TRAIN mode, checkpoint round trip."""
+  from balloon_learning_environment_b200 import agents, batched_env, eval_lib, suites
+  from tests.golden import fields as golden_fields
+  n = 32
+  env = batched_env.BatchedBalloonEnv(n, observation='perciatelli', field_layout='x128', seed=1)
+  env.arena.set_wind_fields(torch.from_numpy(golden_fields.field_bank()), torch.arange(n, dtype=torch.int32) % 4)
+  cfg = lrn.QrDqnConfig(num_layers=3, hidden_units=64, batch_size=64, min_replay_size=128, learning_rate=1e-4)
+  agent = lrn.QuantileAgent(3, (1099,), env.arena, config=cfg, seed=4, replay_steps=32, learner_steps_per_step=2)
+  assert isinstance(agents.create_agent('quantile', 3, (1099,), env.arena), lrn.QuantileAgent)
+  suite = suites.EvaluationSuite(seeds=list(range(100, 100 + n)), max_episode_length=12)
+  results = eval_lib.eval_agent(agent, env, suite, calculate_flight_path=False)
+  assert len(results) == n and all(r.final_timestep == 12 for r in results)
+  assert agent.replay.count == 0 and agent.learner.steps == 0             # EVAL mode neither stores nor learns
+  # greedy and deterministic: the same observation gives the same action
+  obs = env.reset(seeds=torch.arange(n, dtype=torch.int64))
+  a1 = agent.begin_episode(obs).clone(); a2 = agent.begin_episode(obs)
+  assert torch.equal(a1, a2) and int(a1.min()) >= 0 and int(a1.max()) <= 2
+  # TRAIN mode: one lockstep episode of 10 steps
+  agent.set_mode(agents.AgentMode.TRAIN)
+  before = agent.learner.flat.clone()
+  action = agent.begin_episode(obs)
+  for t in range(10):
+    obs, reward, done, _ = env.step(action)
+    action = agent.step(reward, obs, done)
+  agent.end_episode(reward, done)
+  assert agent.replay.count == 11 and int(agent.replay.truncated[10].sum()) == n - int(done.ne(0).sum())
+  assert agent.learner.steps > 0 and float((agent.learner.flat - before).abs().max()) > 0
+  assert np.isfinite(float(agent.last_loss))
+  agent.save_checkpoint(str(tmp_path), 3)
+  saved = agent.learner.flat.clone()
+  agent.learner.flat.zero_()
+  assert agent.reload_latest_checkpoint(str(tmp_path)) == 3
+  assert torch.equal(agent.learner.flat, saved)
+  assert agent.reload_latest_checkpoint(str(tmp_path / 'missing')) == -1
+  env.close()
