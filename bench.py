@@ -33,7 +33,7 @@ UNIT = 'env-steps/s'
 GATHER_BYTES_PER_LOOKUP = 156        # 16 B query + 4 B field index + 128 B corners + 8 B result
 # DRAM bytes per k_wind_gather launch from the `ncu --set full` capture of the same launch shape
 # (dram__bytes_read.sum + dram__bytes_write.sum); key = (field layout, lookups per launch).
-NCU_GATHER_TRAFFIC = {('x64', 1 << 24): 3.685e9}
+NCU_GATHER_TRAFFIC = {('x64', 1 << 24): 3.652e9}      # 3.516 GB read + 0.136 GB written
 
 
 def load_peaks():
@@ -390,7 +390,7 @@ def run_b200(args):
       'roofline': {'kernel': 'k_wind_gather', 'bound': 'hbm', 'achieved': gather_gbs, 'peak': peak, 'unit': 'GB/s',
                    'frac': gather_gbs / peak, 'traffic': NCU_GATHER_TRAFFIC.get((layout, m)),
                    'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, '
-                                   'profiles/r01_prof2_k_wind_gather_details.txt)', 'peak_source': peak_src,
+                                   'profiles/r01c_k_wind_gather_details.txt)', 'peak_source': peak_src,
                    'lookups_per_launch': m, 'bytes_per_lookup': GATHER_BYTES_PER_LOOKUP, 'ms_per_launch': gather_ms,
                    'access': f'{m} uniformly random (x, y, p, t) points, grouped by field ({per_field} per field, '
                              f'{n_fields} fields, layout {layout})',
