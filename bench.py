@@ -125,12 +125,16 @@ def run_reference(args):
   value = cpu_oracle_throughput(n_per_worker, max(1, args.steps), cores)
   wall = time.perf_counter() - t0
   sample = f'{cores} processes x {n_per_worker} balloons x {max(1, args.steps)} steps of the oracle port (NumPy fp64)'
+  # same workload description as the GPU arm's line (the host has one set of cores whatever --gpus says)
+  n_total = args.num_envs * max(1, args.gpus) if args.scaling == 'weak' else args.num_envs
   line = {
       'metric': METRIC, 'value': value, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps,
-      'warmup': args.warmup, 'ms_per_step': 1e3 * args.num_envs / value, 'higher_is_better': True,
+      'warmup': args.warmup, 'ms_per_step': 1e3 * n_total / value, 'higher_is_better': True,
       'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-      'config': {'workload': f'batch={args.num_envs} balloons, random agent, per-balloon wind field + simplex noise '
-                             '(BASELINE configs[2]); CPU arm runs a bounded sample'},
+      'config': {'workload': f'batch={n_total} balloons, random agent, one synthetic wind field per balloon '
+                             '+ simplex noise, 18 sub-steps per step (BASELINE configs[2]); the CPU arm times a bounded '
+                             'sample of it',
+                 'num_envs': n_total, 'envs_per_gpu': n_total // max(1, args.gpus), 'observation': 'none'},
       'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
       'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'wall_s': wall,
