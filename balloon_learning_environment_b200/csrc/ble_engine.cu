@@ -1319,7 +1319,10 @@ struct Engine : EngineBase {
       // k_step_ws needs 4 threads per balloon: at 128 registers an SM holds 4 blocks = 128 balloons, so
       // one wave covers 148 * 128 = 18,944 balloons.  Below that it is ~2x faster than one thread per
       // balloon (shorter dependent chain); above it the extra waves cost more than they save.
-      static const std::string forced = [] { const char* v = std::getenv("BLE_STEP_KERNEL"); return std::string(v ? v : ""); }();
+      // BLE_STEP_KERNEL = "ws" | "thread" overrides the choice (read per call: the parity tests run both
+      // kernels on the same recorded states)
+      const char* env = std::getenv("BLE_STEP_KERNEL");
+      const std::string forced(env != nullptr ? env : "");
       const bool use_ws = forced == "ws" || (forced != "thread" && n <= int64_t(148) * 128);
       if (use_ws) {
         k_step_ws<<<grid_for(n, 32), 128, 0, s>>>(d, actions, reward, done, wind_uv);

@@ -155,9 +155,13 @@ def _all_recorded_states():
               seeds=cat(seeds), offsets=cat(offs))
 
 
-@pytest.mark.parametrize('precision,tol,wtol', [('fp64', 1e-8, 2e-6), ('fp32', 1e-4, 5e-4)])
-def test_single_step_matches_reference(ble, precision, tol, wtol):
-  """~4,400 recorded reference states advanced by ONE BalloonEnv.step on the GPU."""
+@pytest.mark.parametrize('precision,tol,wtol,kernel', [('fp64', 1e-8, 2e-6, 'thread'), ('fp32', 1e-4, 5e-4, 'thread'),
+                                                       ('fp32', 1e-4, 5e-4, 'ws')])
+def test_single_step_matches_reference(ble, monkeypatch, precision, tol, wtol, kernel):
+  """~4,400 recorded reference states advanced by ONE BalloonEnv.step on the GPU, through BOTH step kernels:
+  k_step (one thread per balloon; what runs above one wave, i.e. at the benchmark's 65,536 balloons) and
+  k_step_ws (four warps per 32 balloons; what a batch this small would get by default)."""
+  monkeypatch.setenv('BLE_STEP_KERNEL', kernel)
   rec = _all_recorded_states()
   grid = rec['field'] >= 0                      # SimpleStaticWindField scenario runs in its own arena
   for model, sel in (('grid', grid), ('simple_static', ~grid)):
@@ -337,6 +341,8 @@ def test_full_size_properties(ble):
   bank = golden_fields.field_bank()
   env.arena.set_wind_fields(torch.from_numpy(bank), torch.from_numpy(rng.integers(0, 4, n).astype(np.int32)))
   env.reset(seed=3)
+  noise_seeds = rng.integers(0, 1634753849, (n, 2, 5)); noise_offsets = rng.uniform(-1, 1, (n, 2, 5, 4)).astype(np.float32)
+  env.arena.set_wind_noise(torch.from_numpy(noise_seeds), torch.from_numpy(noise_offsets))   # known to the oracle
   s0 = state_np(env.arena)
   acts = torch.from_numpy(rng.integers(0, 3, n).astype(np.int32)).cuda()
   _, reward, done, _ = env.step(acts)
@@ -352,10 +358,26 @@ def test_full_size_properties(ble):
   r = reward.cpu().numpy()
   assert (r >= 0).all() and (r <= 1).all()
   np.testing.assert_array_equal(s1['last_command'][ok], acts.cpu().numpy()[ok])
+  # the same launch against the oracle on a sample of the batch (this size runs k_step, one thread per balloon)
+  idx = np.sort(rng.choice(n, 2048, replace=False))
+  b = balloon_lib.BalloonBatch(**{k: s0[k][idx].copy() for k in balloon_lib.FLOAT_FIELDS + balloon_lib.INT_FIELDS})
+  fidx_all = env.arena._keepalive[1].cpu().numpy()
+  oenv = env_lib.OracleEnv(env_lib.OracleArena(
+      b, atmosphere_lib.Atmosphere(s0['atmosphere_alpha'][idx]), fields=bank, field_idx=fidx_all[idx],
+      noise=wind_lib.SimplexWindNoise(noise_seeds[idx], noise_offsets[idx].astype(np.float64))))
+  want_r, want_done, _ = oenv.step(acts.cpu().numpy()[idx])
+  for k in balloon_lib.FLOAT_FIELDS:
+    assert rel_err(s1[k][idx], getattr(b, k), k) < 1e-4, k
+  for k in ('status', 'last_command', 'envelope_state', 'altitude_state', 'power_paused', 'time_elapsed',
+            'date_time', 'sunrise_h', 'sunset'):
+    np.testing.assert_array_equal(s1[k][idx], getattr(b, k), err_msg=k)
+  assert np.abs(r[idx] - want_r).max() < 2e-4
+  np.testing.assert_array_equal(done.cpu().numpy()[idx] != 0, want_done)
   # determinism: a twin env with the same seeds and actions lands in the same state, bit for bit
   twin = ble.BatchedBalloonEnv(n, precision='fp32', enable_noise=True, seed=3)
   twin.arena.set_wind_fields(torch.from_numpy(bank), env.arena._keepalive[1])
   twin.reset(seed=3)
+  twin.arena.set_wind_noise(torch.from_numpy(noise_seeds), torch.from_numpy(noise_offsets))
   twin.step(acts)
   s1b = state_np(twin.arena)
   for k in s1:
