@@ -886,9 +886,11 @@ struct Engine : EngineBase {
   int64_t* noise_seeds = nullptr; float* noise_offsets_in = nullptr;
   bool have_state = false, have_fields = false, have_noise = false;
   bool noise_valid = false;      // noise_partial matches the current state
+  cudaStream_t noise_stream = nullptr;   // stream the valid noise_partial was (or is being) produced on
   double* gp_obs = nullptr; int32_t* gp_count = nullptr; double* gp_chol = nullptr; int32_t* gp_m = nullptr;
   int32_t* gp_first = nullptr; double* gp_z = nullptr; double* range_scratch = nullptr;
   bool host_zero_copy = true;            // BLE_HOST_ZERO_COPY=0: staged copies in ble_step_host instead of mapped pinned memory
+  bool host_prefetch_noise = true;       // BLE_HOST_PREFETCH_NOISE=0: ble_step_host does not queue the next step's noise kernel
   bool track_measurements = true;        // ble_features_track: append a WindGP measurement after every reset / step
   bool gp_refit_every_step = false;      // BLE_GP_REFIT=1: the first-generation kernels (full refit per call), kept for A/B checks
   double* feat_range = nullptr;
@@ -914,6 +916,7 @@ struct Engine : EngineBase {
     device = dev; n = n_envs; cfg = c;
     BLE_CUDA(cudaSetDevice(device));
     if (const char* z = std::getenv("BLE_HOST_ZERO_COPY")) host_zero_copy = std::atoi(z) != 0;
+    if (const char* z = std::getenv("BLE_HOST_PREFETCH_NOISE")) host_prefetch_noise = std::atoi(z) != 0;
     if (const char* g = std::getenv("BLE_L2_FETCH_GRANULARITY")) {     // experiment knob: 32 / 64 / 128
       BLE_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(std::atoi(g))));
     }
@@ -1118,12 +1121,18 @@ struct Engine : EngineBase {
   }
 
   int launch_noise(cudaStream_t s) {
-    if (!d.enable_noise || noise_valid) return BLE_OK;
+    if (!d.enable_noise) return BLE_OK;
+    if (noise_valid) {
+      // produced ahead of time (features_observe, step_host's prefetch): a consumer on another stream waits for it
+      if (noise_stream != s) BLE_CUDA(cudaStreamSynchronize(noise_stream));
+      return BLE_OK;
+    }
     dim3 grid(grid_for(n, kNoiseBlock), 10);
     k_noise<Real><<<grid, kNoiseBlock, kNoiseBlock * 256, s>>>(d);
     ++launches;
     BLE_CUDA(cudaGetLastError());
     noise_valid = true;
+    noise_stream = s;
     return BLE_OK;
   }
 
@@ -1386,9 +1395,12 @@ struct Engine : EngineBase {
 
   int step_host(const int32_t* actions_host, float* reward_host, uint8_t* done_host, cudaStream_t s) override {
     if (actions_host == nullptr || reward_host == nullptr || done_host == nullptr) { err = "step_host: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    int rc = check_ready("step_host");
+    if (rc != BLE_OK) return rc;
     BLE_CUDA(cudaSetDevice(device));
+    rc = launch_noise(s);                  // needs no actions: runs while the host stages them (no-op when prefetched)
+    if (rc != BLE_OK) return rc;
     std::memcpy(h_actions, actions_host, sizeof(int32_t) * n);
-    int rc;
     if (host_zero_copy) {
       // pinned host memory is device-accessible under UVA: the step kernel reads the actions and writes reward /
       // done straight over PCIe (4 + 5 bytes per balloon), which saves three copy launches and their latencies
@@ -1401,6 +1413,13 @@ struct Engine : EngineBase {
       BLE_CUDA(cudaMemcpyAsync(h_reward, d_reward, (sizeof(float) + sizeof(uint8_t)) * n, cudaMemcpyDeviceToHost, s));
     }
     BLE_CUDA(cudaStreamSynchronize(s));
+    // The wind at the post-step state is the next step's pre-step wind (env/balloon_arena.py:184-202), so its noise
+    // kernel is queued now and runs while the host copies the results out and prepares the next actions; any call
+    // that changes the state (reset, state_upload, set_noise) invalidates it.
+    if (host_prefetch_noise) {
+      rc = launch_noise(s);
+      if (rc != BLE_OK) return rc;
+    }
     std::memcpy(reward_host, h_reward, sizeof(float) * n);
     std::memcpy(done_host, h_done, sizeof(uint8_t) * n);
     return BLE_OK;

@@ -333,6 +333,40 @@ def test_errors_and_host_step(ble):
   arena.close(); twin.close()
 
 
+def test_host_step_sequence_matches_device_steps(ble):
+  """ble_step_host queues the next step's noise kernel while the host copies results out; a sequence of host
+  steps, with a state upload in the middle (which must invalidate the queued noise), lands bit for bit where
+  the same sequence of device-resident ble_step calls does."""
+  n = 1000
+  rng = np.random.default_rng(21)
+  bank = golden_fields.field_bank()
+  fidx = torch.from_numpy(rng.integers(0, 4, n).astype(np.int32))
+  arenas = []
+  for _ in range(2):
+    a = ble.BatchedBalloonArena(n, precision='fp32', enable_noise=True)
+    a.set_wind_fields(torch.from_numpy(bank), fidx)
+    a.reset(torch.arange(n, dtype=torch.int64) + 5)
+    arenas.append(a)
+  host, dev = arenas
+  r_host = np.zeros(n, np.float32); d_host = np.zeros(n, np.uint8)
+  for t in range(6):
+    if t == 3:                                   # move every balloon: the wind queued for the old position is stale
+      for a in arenas:
+        f, i = a.get_state()
+        f = f.clone(); f[0] += 25000.0; f[1] -= 40000.0
+        a.set_state(f, i)
+    acts = rng.integers(0, 3, n).astype(np.int32)
+    host.step_host(acts, r_host, d_host)
+    r_dev, d_dev, _ = dev.step(torch.from_numpy(acts))
+    np.testing.assert_array_equal(r_host, r_dev.cpu().numpy())
+    np.testing.assert_array_equal(d_host, d_dev.cpu().numpy())
+    sh, sd = state_np(host), state_np(dev)
+    for k in sh:
+      np.testing.assert_array_equal(sh[k], sd[k], err_msg=f'{k} at step {t}')
+  assert host.launch_count <= dev.launch_count + 2     # one noise launch queued ahead + the one the upload made stale
+  host.close(); dev.close()
+
+
 def test_full_size_properties(ble):
   """BASELINE.json size (65,536 balloons): size-independent invariants of the transition."""
   n = 65536
