@@ -149,7 +149,10 @@ int ble_step(ble_handle* h, const int32_t* actions, float* reward, uint8_t* done
              void* stream);
 
 /* Same, with HOST buffers (pageable or pinned): copies actions in, steps, copies reward/done out
- * and waits.  This is the call a Python/NumPy user of the reference makes per step. */
+ * and waits.  This is the call a Python/NumPy user of the reference makes per step.  Before it
+ * returns it queues, on `stream`, the wind-noise kernel of the NEXT step (the wind at the post-step
+ * state is the next step's pre-step wind, env/balloon_arena.py:184-202); any call that changes the
+ * state discards that result.  Use one stream per handle for consecutive calls. */
 int ble_step_host(ble_handle* h, const int32_t* actions_host, float* reward_host,
                   uint8_t* done_host, void* stream);
 
