@@ -1124,7 +1124,10 @@ struct Engine : EngineBase {
     if (!d.enable_noise) return BLE_OK;
     if (noise_valid) {
       // produced ahead of time (features_observe, step_host's prefetch): a consumer on another stream waits for it
-      if (noise_stream != s) BLE_CUDA(cudaStreamSynchronize(noise_stream));
+      if (noise_stream != s && cudaStreamSynchronize(noise_stream) != cudaSuccess) {
+        cudaGetLastError();                                   // the producing stream was destroyed meanwhile
+        BLE_CUDA(cudaDeviceSynchronize());
+      }
       return BLE_OK;
     }
     dim3 grid(grid_for(n, kNoiseBlock), 10);
