@@ -1,8 +1,8 @@
-"""Known answers from the reference's own unit tests for the reward and the WindGP, replayed on the
-oracle (and, where a scalar device helper exists, on the host replay of the device headers).
+"""Known answers and properties from the reference's own unit tests, replayed on the oracle.
 
-Reference: env/balloon_env_test.py:87-206 (reward), env/wind_gp_test.py:44-54 (GP variance at a measured
-point), env/balloon_env.py:44-102.
+Reference: env/balloon_env_test.py:87-206 (reward), env/wind_gp_test.py:44-65 (GP variance at a measured
+point), env/balloon/balloon_test.py:93-212 (dynamics properties), env/balloon/stable_init_test.py:36-83
+(stable initialisation holds pressure and temperature).
 """
 import numpy as np
 
@@ -82,3 +82,64 @@ def test_gp_variance_at_a_measured_point():
   # 6 h horizon (wind_gp.py:172-178): an old measurement no longer informs the query
   stale_means, stale_var = gp.query_column(0, 0.0, 0.0, F.GP_HORIZON_S)
   assert (stale_means == 0.0).all() and (stale_var == 1.0).all()
+
+
+# ------------------------------------------------------------------ dynamics properties of the reference's unit tests
+
+def _sub_step(b, atm, action, u=10.0, v=12.0, n=1):
+  """n calls of Balloon.simulate_step(..., time_delta = 10 s) (one physics sub-step each)."""
+  for _ in range(n):
+    balloon.simulate_step(b, u, v, atm, np.full(b.n, action), time_delta=10, stride=10)
+
+
+def _default_balloon(atm, pressure=9000.0, stable=True, **kw):
+  from oracle import stable_init
+  b = balloon.make_batch(1, center_lat=0.0, center_lng=0.0, date_time=_T0, pressure=pressure, **kw)
+  if stable:
+    stable_init.cold_start_to_stable_params(b, atm)
+  return b
+
+
+def test_balloon_dynamics_properties():
+  """env/balloon/balloon_test.py:93-212 on the oracle (the solar-calculator mocks become a day / night date)."""
+  from oracle import atmosphere
+  atm = atmosphere.Atmosphere([0.5])
+  b = _default_balloon(atm)
+  _sub_step(b, atm, C.STAY)
+  assert b.x[0] == 100.0 and b.y[0] == 120.0                              # :93-105 goes in the wind direction
+  for p0, sign in [(20123.0, -1), (2345.0, +1)]:                          # :107-131 up when low, down when high
+    b = _default_balloon(atm, pressure=p0, stable=False)
+    _sub_step(b, atm, C.STAY, u=3.0, v=-4.0)
+    assert np.sign(b.pressure[0] - p0) == sign
+  day, night = _T0, _T0 + 12 * 3600                                       # 09:25 / 21:25 UTC at (0, 0)
+  half = 0.5 * C.BATTERY_CAPACITY_WH
+  b = balloon.make_batch(1, center_lat=0.0, center_lng=0.0, date_time=day, pressure=9000.0, battery_charge=half)
+  _sub_step(b, atm, C.STAY)
+  assert b.battery_charge[0] > half and b.power_load[0] == C.DAYTIME_POWER_LOAD_W      # :139-152, :184-197
+  b = balloon.make_batch(1, center_lat=0.0, center_lng=0.0, date_time=night, pressure=9000.0, battery_charge=half)
+  _sub_step(b, atm, C.STAY)
+  assert b.battery_charge[0] < half and b.power_load[0] == C.NIGHTTIME_POWER_LOAD_W    # :154-182
+  assert b.solar_charging[0] == 0.0
+  b = _default_balloon(atm)
+  _sub_step(b, atm, C.DOWN)
+  assert b.power_load[0] > C.DAYTIME_POWER_LOAD_W and b.acs_power[0] > 0.0             # :199-212
+
+
+def test_stable_init_holds_pressure_and_temperature():
+  """env/balloon/stable_init_test.py:36-83: after cold_start_to_stable_params the balloon stays within 100 Pa over
+  100 sub-steps and dT/dt < 1e-3 K/s.  Atmosphere(PRNGKey(38)) draws alpha = 0.99589407."""
+  from oracle import atmosphere, solar, stable_init, thermal
+  atm = atmosphere.Atmosphere([0.99589407])
+  midnight = 1590969600                                                    # 2020-06-01 00:00:00 UTC
+  for p0 in (9500.0, 11500.0, 6500.0):
+    b = balloon.make_batch(1, center_lat=0.0, center_lng=0.0, date_time=midnight, pressure=p0)
+    stable_init.cold_start_to_stable_params(b, atm)
+    _sub_step(b, atm, C.STAY, u=3.0, v=-4.0, n=100)
+    assert b.status[0] == C.STATUS_OK and abs(b.pressure[0] - p0) < 100.0, (p0, b.pressure[0])
+  for p0 in (9500.0, 11500.0, 5000.0):
+    b = _default_balloon(atm, pressure=p0)
+    lat, lng = b.latlng()
+    el, _, flux = solar.solar_calculator(lat, lng, b.date_time)
+    d_temp = thermal.d_balloon_temperature_dt(b.envelope_volume, C.ENVELOPE_MASS, b.internal_temperature,
+                                              b.ambient_temperature, b.pressure, el, flux, b.upwelling_infrared)
+    assert d_temp[0] < 1e-3
