@@ -20,6 +20,20 @@ def test_library_exports_every_declared_symbol():
   assert set(declared) == set(_lib.EXPORTS)
 
 
+def test_header_is_plain_c(tmp_path):
+  """The boundary is a C ABI: include/ble_b200.h must compile as C99 (no C++, CUDA or torch types)."""
+  import shutil
+  import subprocess
+  gcc = shutil.which('gcc')
+  if gcc is None:
+    pytest.skip('gcc not found')
+  src = tmp_path / 'abi.c'
+  src.write_text('#include "ble_b200.h"\nint main(void) { ble_config c; ble_state_soa s; (void)c; (void)s; return 0; }\n')
+  proc = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-fsyntax-only',
+                         '-I', os.path.join(ROOT, 'include'), str(src)], capture_output=True, text=True)
+  assert proc.returncode == 0, proc.stderr
+
+
 def test_create_without_gpu_fails_loudly():
   import torch
   if torch.cuda.is_available():
