@@ -34,6 +34,45 @@ def test_header_is_plain_c(tmp_path):
   assert proc.returncode == 0, proc.stderr
 
 
+def test_c_program_links_and_calls_the_library(tmp_path):
+  """A plain C caller (what a cgo / JNI / FFI binding boils down to): links libble_b200.so, rejects bad
+  arguments, and - without a GPU - gets BLE_ERR_CUDA with the 'no CPU fallback' message."""
+  import shutil
+  import subprocess
+  from balloon_learning_environment_b200 import _build
+  gcc = shutil.which('gcc')
+  if gcc is None:
+    pytest.skip('gcc not found')
+  lib_dir = os.path.dirname(_build.build())
+  src = tmp_path / 'caller.c'
+  src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "ble_b200.h"
+int main(void) {
+  ble_config cfg; memset(&cfg, 0, sizeof cfg);
+  cfg.precision = BLE_PRECISION_FP32; cfg.wind_model = BLE_WIND_GRID; cfg.enable_noise = 1; cfg.field_layout = BLE_LAYOUT_X64;
+  ble_handle* h = NULL;
+  if (ble_create(0, 0, &cfg, &h) != BLE_ERR_INVALID_ARGUMENT) return 10;
+  if (ble_create(0, 64, NULL, &h) != BLE_ERR_INVALID_ARGUMENT) return 11;
+  if (ble_step(NULL, NULL, NULL, NULL, NULL, NULL) != BLE_ERR_INVALID_ARGUMENT) return 12;
+  if (ble_num_envs(NULL) != 0 || ble_destroy(NULL) != BLE_ERR_INVALID_ARGUMENT) return 13;
+  int rc = ble_create(0, 64, &cfg, &h);
+  printf("%d|%s\n", rc, ble_last_error(NULL));
+  if (rc == BLE_OK) { long long n = (long long)ble_num_envs(h); ble_destroy(h); return n == 64 ? 0 : 14; }
+  return rc == BLE_ERR_CUDA ? 0 : 15;
+}
+""")
+  exe = tmp_path / 'caller'
+  proc = subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe),
+                         '-L', lib_dir, '-lble_b200', f'-Wl,-rpath,{lib_dir}'], capture_output=True, text=True)
+  assert proc.returncode == 0, proc.stderr
+  run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+  assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+  rc, msg = run.stdout.strip().split('|', 1)
+  assert int(rc) == 0 or 'no CPU fallback' in msg
+
+
 def test_create_without_gpu_fails_loudly():
   import torch
   if torch.cuda.is_available():
