@@ -12,9 +12,8 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.environ.get('BLE_B200_LIB') or os.path.join(PKG_DIR, 'libble_b200.so')
-SOURCES = [os.path.join(CSRC, 'ble_engine.cu'), os.path.join(CSRC, 'ble_learner.cu')]
-HEADERS = [os.path.join(CSRC, f) for f in ('ble_physics.cuh', 'ble_wind.cuh', 'ble_features.cuh',
-                                          'ble_feature_kernels.cuh', 'ble_decoder.cuh', 'ble_agents.cuh', 'ble_rng.cuh', 'ble_gp_kernels.cuh')] + [
+SOURCES = [os.path.join(CSRC, f) for f in ('ble_engine.cu', 'ble_step_fused.cu', 'ble_learner.cu')]
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))) + [
            os.path.join(PKG_DIR, '..', 'include', 'ble_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--shared', '-Xcompiler', '-fPIC']
@@ -49,18 +48,20 @@ def build(force=False, verbose=False):
   nvcc = find_nvcc()
   os.makedirs(OBJ_DIR, exist_ok=True)
   compile_flags = [f for f in NVCC_FLAGS if f != '--shared']
-  objects = []
+  objects, jobs = [], []
   for src in SOURCES:
     obj = os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(src))[0] + '.o')
     objects.append(obj)
     if not force and not _newer_than(obj, [src] + HEADERS):
       continue
     cmd = [nvcc] + compile_flags + (['-Xptxas', '-v'] if verbose else []) + ['-c', '-o', obj, src]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
+    jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))   # one nvcc per source, concurrently
+  for cmd, proc in jobs:
+    out, errtxt = proc.communicate()
     if proc.returncode != 0:
-      raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
+      raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + out + errtxt)
     if verbose:
-      sys.stderr.write(proc.stderr)
+      sys.stderr.write(errtxt)
   cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '--shared', '-o', LIB_PATH] + objects + LINK_FLAGS
   proc = subprocess.run(cmd, capture_output=True, text=True)
   if proc.returncode != 0:

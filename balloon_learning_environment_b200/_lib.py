@@ -32,7 +32,7 @@ E_ROWS = ('cumulative_reward', 'time_within_radius', 'out_of_power', 'envelope_b
 EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_upload_fields',
            'ble_alloc_fields', 'ble_write_fields', 'ble_set_field_map', 'ble_set_decoder', 'ble_decode_fields',
            'ble_set_noise', 'ble_state_upload', 'ble_state_download', 'ble_reset', 'ble_init_derived',
-           'ble_step', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_derived',
+           'ble_step', 'ble_step_ex', 'ble_rollout', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_derived',
            'ble_features_perciatelli', 'ble_features_observe', 'ble_features_clear', 'ble_features_track',
            'ble_generate_fields', 'ble_generate_fields_at', 'ble_agent_station_seeker', 'ble_agent_random_walk',
            'ble_eval_begin', 'ble_eval_accumulate', 'ble_eval_results',
@@ -51,6 +51,11 @@ class BleReplayView(_c.Structure):
   _fields_ = [('obs', _c.c_void_p), ('action', _c.c_void_p), ('reward', _c.c_void_p), ('terminal', _c.c_void_p),
               ('truncated', _c.c_void_p), ('capacity', _c.c_int64), ('num_envs', _c.c_int64), ('count', _c.c_int64),
               ('n_step', _c.c_int32), ('num_features', _c.c_int32), ('gamma', _c.c_float), ('reserved', _c.c_int32)]
+
+
+class BleStepOut(_c.Structure):
+  _fields_ = [('reward', _c.c_void_p), ('done', _c.c_void_p), ('wind_uv', _c.c_void_p), ('status', _c.c_void_p),
+              ('time_elapsed', _c.c_void_p), ('sim_error', _c.c_void_p), ('reserved', _c.c_void_p * 2)]
 
 
 class BleStateSoa(_c.Structure):
@@ -97,6 +102,8 @@ def load(build_if_missing=True):
   lib.ble_reset.argtypes = [vp, vp, vp, vp]
   lib.ble_init_derived.argtypes = [vp, i32, vp]
   lib.ble_step.argtypes = [vp, vp, vp, vp, vp, vp]
+  lib.ble_step_ex.argtypes = [vp, vp, _c.POINTER(BleStepOut), vp]
+  lib.ble_rollout.argtypes = [vp, vp, i32, _c.POINTER(BleStepOut), vp]
   lib.ble_step_host.argtypes = [vp, vp, vp, vp, vp]
   lib.ble_wind_at_balloon.argtypes = [vp, vp, vp]
   lib.ble_wind_gather.argtypes = [vp, vp, vp, vp, i64, vp]

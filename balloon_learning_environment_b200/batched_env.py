@@ -65,6 +65,11 @@ class BatchedBalloonArena:
       self._reward = torch.zeros(n, dtype=torch.float32, device=self.device)
       self._done = torch.zeros(n, dtype=torch.uint8, device=self.device)
       self._wind = torch.zeros(n, 2, dtype=torch.float32, device=self.device)
+      self._status = torch.zeros(n, dtype=torch.uint8, device=self.device)
+      self._time_elapsed = torch.zeros(n, dtype=torch.int32, device=self.device)
+      self._sim_error = torch.zeros(n, dtype=torch.uint8, device=self.device)
+    self._step_out = _lib.BleStepOut(self._reward.data_ptr(), self._done.data_ptr(), self._wind.data_ptr(),
+                                     self._status.data_ptr(), self._time_elapsed.data_ptr(), self._sim_error.data_ptr())
     self._keepalive = []
 
   # -- plumbing ---------------------------------------------------------------------------------
@@ -319,10 +324,32 @@ class BatchedBalloonArena:
     """actions int32 [N] -> (reward f32 [N], done u8 [N], wind_uv f32 [N,2]); stream-ordered, async."""
     if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
       actions = actions.to(self.device, torch.int32).contiguous()
-    rc = self._lib.ble_step(self._h, _ptr(actions), _ptr(self._reward), _ptr(self._done), _ptr(self._wind),
-                            self._stream())
-    self._check(rc, 'ble_step')
+    rc = self._lib.ble_step_ex(self._h, _ptr(actions), ctypes.byref(self._step_out), self._stream())
+    self._check(rc, 'ble_step_ex')
     return self._reward, self._done, self._wind
+
+  def step_info(self) -> Dict[str, torch.Tensor]:
+    """BalloonEnv.step's info (env/balloon_env.py:280-290) for the step that just ran, written by the step kernel:
+    out_of_power / envelope_burst / zeropressure bool [N], time_elapsed int32 [N] (seconds), plus sim_error bool [N]
+    (an atmosphere query or sunrise search of that balloon failed since its last reset; the reference raises)."""
+    st = self._status
+    return {'out_of_power': st == STATUS_OUT_OF_POWER, 'envelope_burst': st == STATUS_BURST,
+            'zeropressure': st == STATUS_ZEROPRESSURE, 'time_elapsed': self._time_elapsed,
+            'sim_error': self._sim_error != 0}
+
+  def rollout(self, actions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K consecutive steps in ONE launch for an open-loop action sequence: actions int32 [K, N] ->
+    (reward f32 [K, N], done u8 [K, N]).  step_info() then describes the state after the last step."""
+    if actions.dim() != 2 or actions.shape[1] != self.num_envs:
+      raise ValueError('actions must be [K, N]')
+    actions = actions.to(self.device, torch.int32).contiguous()
+    k = int(actions.shape[0])
+    reward = torch.empty(k, self.num_envs, dtype=torch.float32, device=self.device)
+    done = torch.empty(k, self.num_envs, dtype=torch.uint8, device=self.device)
+    out = _lib.BleStepOut(reward.data_ptr(), done.data_ptr(), self._wind.data_ptr(), self._status.data_ptr(),
+                          self._time_elapsed.data_ptr(), self._sim_error.data_ptr())
+    self._check(self._lib.ble_rollout(self._h, _ptr(actions), k, ctypes.byref(out), self._stream()), 'ble_rollout')
+    return reward, done
 
   def step_host(self, actions: np.ndarray, reward: np.ndarray, done: np.ndarray):
     """Host-buffer step: int32 [N] in; float32 [N] / uint8 [N] out (copies inside, blocking)."""
@@ -439,11 +466,11 @@ class BatchedBalloonEnv:
 
   def step(self, actions: torch.Tensor):
     reward, done, _ = self.arena.step(actions)
-    info = {'done': done}
-    return self._observe(), reward, done, info
+    return self._observe(), reward, done, self.arena.step_info()
 
   def get_info(self) -> Dict[str, torch.Tensor]:
-    """_get_info (env/balloon_env.py:280-290) for all balloons."""
+    """_get_info (env/balloon_env.py:280-290) for all balloons, from the CURRENT state (also valid before the first
+    step, e.g. right after reset); step() already returns the same dictionary for the state it produced."""
     st = self.arena.get_state_dict()
     status = st['status']
     return {'out_of_power': status == STATUS_OUT_OF_POWER, 'envelope_burst': status == STATUS_BURST,

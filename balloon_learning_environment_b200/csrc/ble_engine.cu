@@ -14,83 +14,12 @@
 #include <type_traits>
 
 #include "../../include/ble_b200.h"
-#include "ble_physics.cuh"
-#include "ble_wind.cuh"
+#include "ble_devstate.cuh"
+#include "ble_step_fused.h"
 #include "ble_agents.cuh"
 #include "ble_features.cuh"
 
 namespace ble {
-
-// ---------------------------------------------------------------------------------------------
-// Device-side state layout (struct of arrays, one row per field, N columns)
-// ---------------------------------------------------------------------------------------------
-enum DRow : int {     // fp64 rows: the stiff integrator variables (see ble_physics.cuh) + atmosphere
-  D_X = 0, D_Y, D_P, D_TAMB, D_TINT, D_VOL, D_SP, D_MOLS_AIR, D_CHARGE,   // 9 dynamic rows (read + written every step)
-  D_ALPHA, D_L0, D_L1, D_L2, D_T1, D_T2, D_P1, D_P2, D_P3,              // per-episode atmosphere (layers 0..2)
-  D_COUNT
-};
-enum RRow : int {     // `Real` rows (fp32 in production)
-  R_ACS_W = 0, R_ACS_FLOW, R_SOLAR_W, R_LOAD_W,      // diagnostics written every step
-  R_LAT0, R_LNG0, R_IR, R_MOLS_GAS,                  // per-episode constants
-  R_COUNT
-};
-enum LRow : int { L_DATE_TIME = 0, L_SUNRISE_H, L_SUNSET, L_COUNT };
-
-// flags word: status[0:2) last_command[2:4) envelope[4:7) altitude[7:9) paused[9] psl[10] atm_err[11]
-__host__ __device__ inline uint32_t pack_flags(int status, int last_cmd, int env, int alt, int paused,
-                                               int psl, int atm_err) {
-  return uint32_t(status) | (uint32_t(last_cmd) << 2) | (uint32_t(env) << 4) | (uint32_t(alt) << 7) |
-         (uint32_t(paused) << 9) | (uint32_t(psl) << 10) | (uint32_t(atm_err) << 11);
-}
-
-template <typename Real>
-struct DevState {
-  int64_t n;
-  double* dd;         // [D_COUNT][n]
-  Real* r;            // [R_COUNT][n]
-  int64_t* l;         // [L_COUNT][n]
-  int32_t* t_elapsed; // [n]
-  uint32_t* flags;    // [n]
-  // wind
-  const float* cells;        // [F][layout.field_floats], 128-byte windows (ble_wind.cuh)
-  FieldLayout layout;
-  const int32_t* env_field;  // [n]
-  const uint8_t* perm;       // [10][n][256], each table rotated by 4*(env%32) bytes
-  const float* offsets;      // [10][4][n]
-  Real* noise_partial;       // [10][n]
-  int wind_model, enable_noise;
-  // observation surface (WindGP history ring, env/wind_gp.py:98-119): last kGpWindow measurements
-  double* gp_obs;            // [n][kGpWindow][6] = x, y, pressure, t, error_u, error_v
-  int32_t* gp_count;         // [n] measurements seen so far (ring slot = count % kGpWindow)
-  double* gp_chol;           // [n][7,680] lower Cholesky factor of the window, 8 x 8 blocked (ble_gp_kernels.cuh)
-  int32_t* gp_m;             // [n] number of measurements the factor was computed for (0 = none)
-  int32_t* gp_first;         // [n] index (in measurements seen) of the factor's first point; -1 = not a suffix
-  double* gp_z;              // [n][kGpWindow][2] L^-1 (error_u, error_v)
-  double* feat_range;        // [n][2] reachable pressure range
-};
-
-template <typename Real>
-__device__ __forceinline__ Real& RR(const DevState<Real>& d, int row, int64_t e) { return d.r[int64_t(row) * d.n + e]; }
-template <typename Real>
-__device__ __forceinline__ double& DD(const DevState<Real>& d, int row, int64_t e) { return d.dd[int64_t(row) * d.n + e]; }
-
-template <typename Real>
-__device__ __forceinline__ void store_atmosphere(const DevState<Real>& d, int64_t e, const Atmosphere& atm) {
-  DD(d, D_ALPHA, e) = atm.alpha;
-  DD(d, D_L0, e) = atm.l0; DD(d, D_L1, e) = atm.l1; DD(d, D_L2, e) = atm.l2;
-  DD(d, D_T1, e) = atm.t1; DD(d, D_T2, e) = atm.t2;
-  DD(d, D_P1, e) = atm.p1; DD(d, D_P2, e) = atm.p2; DD(d, D_P3, e) = atm.p3;
-}
-template <typename Real>
-__device__ __forceinline__ Atmosphere load_atmosphere(const DevState<Real>& d, int64_t e) {
-  Atmosphere atm;
-  atm.alpha = DD(d, D_ALPHA, e);
-  atm.l0 = DD(d, D_L0, e); atm.l1 = DD(d, D_L1, e); atm.l2 = DD(d, D_L2, e);
-  atm.t1 = DD(d, D_T1, e); atm.t2 = DD(d, D_T2, e);
-  atm.p1 = DD(d, D_P1, e); atm.p2 = DD(d, D_P2, e); atm.p3 = DD(d, D_P3, e);
-  atm.ok = true;
-  return atm;
-}
 
 // ---------------------------------------------------------------------------------------------
 // State upload / download (get/set_balloon_state, env/balloon_arena.py:213-220)
@@ -179,11 +108,6 @@ __global__ void k_fields_to_windows(const float* __restrict__ native, float* __r
   }
 }
 
-struct WindowLoader {        // per-thread path: the 8 chunks of one window
-  const float4* base;
-  __device__ __forceinline__ float4 operator()(int j) const { return __ldg(base + j); }
-};
-
 // GridBasedWindField.get_forecast for M arbitrary points (C ABI ble_wind_gather).
 // One thread locates one lookup (clip, boomerang, fp32 point, cell + weights); the 128-byte
 // windows are then loaded COOPERATIVELY: in round r, the 8 lanes of group g = lane/8 read the
@@ -248,14 +172,6 @@ __global__ void k_make_perms(int64_t n, const int64_t* __restrict__ seeds /*[n,2
   for (int c = 0; c < 4; ++c) offsets[(int64_t(h10) * 4 + c) * n + e] = offsets_in[(e * 10 + h10) * 4 + c];
 }
 
-struct RotatedPerm {      // view of one rotated table in shared memory
-  const uint8_t* t;
-  int rot;
-  __device__ __forceinline__ int operator[](int i) const { return t[(i + rot) & 255]; }
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-
 constexpr int kNoiseBlock = 128;
 
 // One thread per (balloon, harmonic).  blockIdx.y = harmonic (0..9), blockIdx.x = block of 128
@@ -287,14 +203,12 @@ k_noise(DevState<Real> d) {
   const bool live = threadIdx.x < count;
   double X = 0, Y = 0, Z = 0, W = 0;
   if (live) {
-    double wgt, sx, sy, sp, st;
-    harmonic_params(h10, &wgt, &sx, &sy, &sp, &st);
-    const double x_km = double(DD(d, D_X, e)) / 1000.0, y_km = double(DD(d, D_Y, e)) / 1000.0;
-    const double p = double(DD(d, D_P, e)), t_h = double(d.t_elapsed[e]) / 3600.0;
-    X = x_km / sx + double(d.offsets[(int64_t(h10) * 4 + 0) * d.n + e]);
-    Y = y_km / sy + double(d.offsets[(int64_t(h10) * 4 + 1) * d.n + e]);
-    Z = p / sp + double(d.offsets[(int64_t(h10) * 4 + 2) * d.n + e]);
-    W = t_h / st + double(d.offsets[(int64_t(h10) * 4 + 3) * d.n + e]);
+    // same expression as k_step_fused's in-kernel evaluation: both paths give bit-identical noise
+    const double* hp = kHarmonicsInvDev[h10];
+    X = fma(double(DD(d, D_X, e)), hp[0], double(d.offsets[(int64_t(h10) * 4 + 0) * d.n + e]));
+    Y = fma(double(DD(d, D_Y, e)), hp[1], double(d.offsets[(int64_t(h10) * 4 + 1) * d.n + e]));
+    Z = fma(double(DD(d, D_P, e)), hp[2], double(d.offsets[(int64_t(h10) * 4 + 2) * d.n + e]));
+    W = fma(double(d.t_elapsed[e]), hp[3], double(d.offsets[(int64_t(h10) * 4 + 3) * d.n + e]));
   }
   // wait for the TMA transaction (phase 0)
   asm volatile(
@@ -305,21 +219,6 @@ k_noise(DevState<Real> d) {
     RotatedPerm perm{s_perm + threadIdx.x * 256, int(e & 31) * 4};
     const Real v = simplex_noise4<Real>(perm, X, Y, Z, W);
     d.noise_partial[int64_t(h10) * d.n + e] = Real(kNoiseMagnitude) * v;
-  }
-}
-
-// Forecast wind at an arbitrary point of balloon e's field (WindField.get_forecast).
-template <typename Real, typename State>
-__device__ __forceinline__ void forecast_at(const State& d, int64_t e, double x, double y, double p,
-                                            int32_t t_elapsed, Real* u, Real* v) {
-  if (d.wind_model == BLE_WIND_SIMPLE_STATIC) {
-    static_wind<Real>(Real(p), u, v);
-  } else {
-    const FieldPoint q = make_field_point(x / 1000.0, y / 1000.0, p, double(t_elapsed) / 3600.0);
-    const FieldCell<Real> c = locate<Real>(q);
-    WindowLoader ld{reinterpret_cast<const float4*>(d.cells + int64_t(d.env_field[e]) * d.layout.field_floats +
-                                                    window_index(d.layout, c.ix, c.iy, c.pc, c.tc))};
-    interp_window<Real>(c, ld, u, v);
   }
 }
 
@@ -418,7 +317,7 @@ k_step(DevState<Real> d, const int32_t* __restrict__ actions, float* __restrict_
   d.l[int64_t(L_SUNSET) * d.n + e] = ss.sunset;
   d.t_elapsed[e] = s.time_elapsed;
   d.flags[e] = pack_flags(s.status, ss.last_command, ss.envelope_state, ss.altitude_state, ss.power_paused,
-                          ss.power_safety_enabled, atm.ok ? 0 : 1);
+                          ss.power_safety_enabled, (atm.ok ? 0 : 1) | int((fl >> 11) & 1u));   // the error bit is sticky
   reward[e] = float(r);
   done[e] = (s.status != kOk) ? 1 : 0;
   if (wind_uv != nullptr) wind_uv[e] = make_float2(float(u), float(v));
@@ -565,7 +464,7 @@ k_step_ws(DevState<float> d, const int32_t* __restrict__ actions, float* __restr
     d.l[int64_t(L_SUNSET) * d.n + e] = ss.sunset;
     d.t_elapsed[e] = s.time_elapsed + kStrideS * n_done;
     d.flags[e] = pack_flags(status, ss.last_command, ss.envelope_state, ss.altitude_state, ss.power_paused,
-                            ss.power_safety_enabled, atm.ok ? 0 : 1);
+                            ss.power_safety_enabled, (atm.ok ? 0 : 1) | int((fl >> 11) & 1u));
     if (wind_uv != nullptr) wind_uv[e] = make_float2(uf, vf);
   } else if (role == 1) {
     DD(d, D_TINT, e) = s.t_internal;
@@ -829,9 +728,34 @@ k_agent_random_walk(const float* __restrict__ obs, int64_t n, double* __restrict
   actions[e] = random_walk_action(obs[e * int64_t(kNumFeatures)], t);
 }
 
+// info of BalloonEnv.step (env/balloon_env.py:280-290) for the first-generation kernels (k_step_fused writes it itself)
+template <typename Real>
+__global__ void __launch_bounds__(128)
+k_step_info(DevState<Real> d, uint8_t* __restrict__ status, int32_t* __restrict__ time_elapsed, uint8_t* __restrict__ sim_error) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= d.n) return;
+  const uint32_t fl = d.flags[e];
+  if (status != nullptr) status[e] = uint8_t(fl & 3u);
+  if (time_elapsed != nullptr) time_elapsed[e] = d.t_elapsed[e];
+  if (sim_error != nullptr) sim_error[e] = uint8_t((fl >> 11) & 1u);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-side engine
 // ---------------------------------------------------------------------------------------------
+// Entry points run on the handle's device and hand the calling thread's current device back on return.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 struct EngineBase {
   virtual ~EngineBase() {}
   virtual int upload_fields(const float*, int64_t, const int32_t*, cudaStream_t) = 0;
@@ -844,6 +768,7 @@ struct EngineBase {
   virtual int reset(const uint64_t*, const uint8_t*, cudaStream_t) = 0;
   virtual int init_derived(int, cudaStream_t) = 0;
   virtual int step(const int32_t*, float*, uint8_t*, float*, cudaStream_t) = 0;
+  virtual int step_ex(const int32_t*, const ble_step_out*, int, cudaStream_t) = 0;
   virtual int step_host(const int32_t*, float*, uint8_t*, cudaStream_t) = 0;
   virtual int wind_at(float*, cudaStream_t) = 0;
   virtual int wind_gather(const float*, const int32_t*, float*, int64_t, cudaStream_t) = 0;
@@ -874,6 +799,10 @@ struct EngineBase {
       return e_ == cudaErrorMemoryAllocation ? BLE_ERR_OUT_OF_MEMORY : BLE_ERR_CUDA;       \
     }                                                                                      \
   } while (0)
+
+#define BLE_DEVICE_GUARD()                                                                 \
+  DeviceGuard device_guard_(device);                                                       \
+  if (!device_guard_.ok) { err = "cudaSetDevice failed"; return BLE_ERR_CUDA; }
 
 template <typename Real>
 struct Engine : EngineBase {
@@ -914,7 +843,7 @@ struct Engine : EngineBase {
 
   int create(int dev, int64_t n_envs, const ble_config& c) {
     device = dev; n = n_envs; cfg = c;
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     if (const char* z = std::getenv("BLE_HOST_ZERO_COPY")) host_zero_copy = std::atoi(z) != 0;
     if (const char* z = std::getenv("BLE_HOST_PREFETCH_NOISE")) host_prefetch_noise = std::atoi(z) != 0;
     if (const char* g = std::getenv("BLE_L2_FETCH_GRANULARITY")) {     // experiment knob: 32 / 64 / 128
@@ -941,6 +870,8 @@ struct Engine : EngineBase {
     d.layout = make_layout(cfg.field_layout);
     d.enable_noise = 0;
     BLE_CUDA(cudaFuncSetAttribute(k_noise<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseBlock * 256));
+    BLE_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (std::is_same<Real, float>::value) BLE_CUDA(fused_setup(fused_blocks_per_sm));
     if (cfg.enable_features) {
       BLE_CUDA(cudaMalloc(&gp_obs, sizeof(double) * size_t(kGpWindow) * 6 * n));
       BLE_CUDA(cudaMalloc(&gp_count, sizeof(int32_t) * n));
@@ -968,7 +899,7 @@ struct Engine : EngineBase {
   }
 
   ~Engine() override {
-    cudaSetDevice(device);
+    DeviceGuard device_guard_(device);
     cudaFree(d.dd); cudaFree(d.r); cudaFree(d.l); cudaFree(d.t_elapsed); cudaFree(d.flags);
     cudaFree(env_field); cudaFree(d.noise_partial); cudaFree(cells); cudaFree(perm); cudaFree(offsets);
     cudaFree(noise_seeds); cudaFree(noise_offsets_in);
@@ -987,7 +918,7 @@ struct Engine : EngineBase {
 
   int alloc_fields(int64_t nf, cudaStream_t s) override {
     if (nf <= 0) { err = "alloc_fields: n_fields must be > 0"; return BLE_ERR_INVALID_ARGUMENT; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     if (nf != n_fields) {
       BLE_CUDA(cudaStreamSynchronize(s));
       cudaFree(cells); cells = nullptr; n_fields = 0; have_fields = false;
@@ -1008,7 +939,7 @@ struct Engine : EngineBase {
       err = "write_fields: range outside the allocated fields (call ble_alloc_fields first)";
       return BLE_ERR_INVALID_ARGUMENT;
     }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     const int64_t threads = count * int64_t(kYC) * kPC * kTC * (d.layout.row_floats / 16);
     k_fields_to_windows<<<grid_for(threads, 256), 256, 0, s>>>(fields, cells, d.layout, first, count, dst_index);
     ++launches;
@@ -1019,7 +950,7 @@ struct Engine : EngineBase {
 
   int set_field_map(const int32_t* map, cudaStream_t s) override {
     if (map == nullptr) { err = "set_field_map: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     BLE_CUDA(cudaMemcpyAsync(env_field, map, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
     return BLE_OK;
   }
@@ -1044,7 +975,7 @@ struct Engine : EngineBase {
 
   int set_noise(const int64_t* seeds, const float* offs, const uint8_t* mask, cudaStream_t s) override {
     if (seeds == nullptr || offs == nullptr) { err = "set_noise: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     int rc = ensure_noise_buffers();
     if (rc != BLE_OK) return rc;
     k_make_perms<<<grid_for(n * 10, 64), 64, 0, s>>>(n, seeds, offs, mask, perm, offsets);
@@ -1058,7 +989,7 @@ struct Engine : EngineBase {
 
   int state_upload(const ble_state_soa* st, cudaStream_t s) override {
     if (st == nullptr || st->f64 == nullptr || st->i64 == nullptr) { err = "state_upload: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     k_state_upload<Real><<<grid_for(n, 128), 128, 0, s>>>(d, st->f64, st->i64);
     ++launches;
     BLE_CUDA(cudaGetLastError());
@@ -1070,7 +1001,7 @@ struct Engine : EngineBase {
   int state_download(ble_state_soa* st, cudaStream_t s) override {
     if (st == nullptr || st->f64 == nullptr || st->i64 == nullptr) { err = "state_download: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
     if (!have_state) { err = "state_download: no state (call ble_reset or ble_state_upload first)"; return BLE_ERR_NOT_READY; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     k_state_download<Real><<<grid_for(n, 128), 128, 0, s>>>(d, st->f64, st->i64);
     ++launches;
     BLE_CUDA(cudaGetLastError());
@@ -1080,7 +1011,7 @@ struct Engine : EngineBase {
   int reset(const uint64_t* seeds, const uint8_t* mask, cudaStream_t s) override {
     if (seeds == nullptr) { err = "reset: seeds must be non-null"; return BLE_ERR_INVALID_ARGUMENT; }
     if (mask != nullptr && !have_state) { err = "reset: a masked reset needs an initial full reset"; return BLE_ERR_NOT_READY; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     int rc = ensure_noise_buffers();
     if (rc != BLE_OK) return rc;
     if (noise_seeds == nullptr) {
@@ -1103,7 +1034,7 @@ struct Engine : EngineBase {
 
   int init_derived(int run_stable_init, cudaStream_t s) override {
     if (!have_state) { err = "init_derived: no state uploaded"; return BLE_ERR_NOT_READY; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     k_init_derived<Real><<<grid_for(n, 128), 128, 0, s>>>(d, run_stable_init);
     ++launches;
     BLE_CUDA(cudaGetLastError());
@@ -1140,26 +1071,74 @@ struct Engine : EngineBase {
   }
 
   int step(const int32_t* actions, float* reward, uint8_t* done, float* wind_uv, cudaStream_t s) override {
-    if (actions == nullptr || reward == nullptr || done == nullptr) { err = "step: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    ble_step_out out{};
+    out.reward = reward; out.done = done; out.wind_uv = wind_uv;
+    return step_ex(actions, &out, 1, s);
+  }
+
+  // BalloonEnv.step with the info outputs (env/balloon_env.py:280-290) written by the step kernel itself;
+  // n_steps > 1 = ble_rollout: actions / reward / done are [n_steps][N] and the steps run inside ONE launch.
+  int step_ex(const int32_t* actions, const ble_step_out* o, int n_steps, cudaStream_t s) override {
+    if (actions == nullptr || o == nullptr || o->reward == nullptr || o->done == nullptr || n_steps < 1) {
+      err = "step: null argument"; return BLE_ERR_INVALID_ARGUMENT;
+    }
     int rc = check_ready("step");
     if (rc != BLE_OK) return rc;
-    BLE_CUDA(cudaSetDevice(device));
-    rc = launch_noise(s);
-    if (rc != BLE_OK) return rc;
-    launch_step(actions, reward, done, reinterpret_cast<float2*>(wind_uv), s);
-    ++launches;
-    BLE_CUDA(cudaGetLastError());
-    noise_valid = false;
+    const bool observe = cfg.enable_features && track_measurements;
+    if (n_steps > 1 && observe) {
+      err = "rollout: the WindGP measurement history cannot be tracked inside a multi-step launch (ble_features_track(0) first)";
+      return BLE_ERR_UNSUPPORTED;
+    }
+    BLE_DEVICE_GUARD();
+    FusedOut fo{o->reward, o->done, reinterpret_cast<float2*>(o->wind_uv), o->status, o->time_elapsed, o->sim_error};
+    if (use_fused()) {
+      int mode = 0;
+      if (d.enable_noise) {
+        mode = 1;
+        if (noise_valid && n_steps == 1) {      // evaluated ahead of time (features_observe, step_host's prefetch)
+          rc = launch_noise(s);                 // no launch: only orders this stream behind the producer
+          if (rc != BLE_OK) return rc;
+          mode = 2;
+        }
+      }
+      launch_fused(actions, fo, mode, n_steps, s);
+      ++launches;
+      BLE_CUDA(cudaGetLastError());
+      noise_valid = false;
+    } else {
+      for (int k = 0; k < n_steps; ++k) {
+        rc = launch_noise(s);
+        if (rc != BLE_OK) return rc;
+        launch_step(actions + int64_t(k) * n, fo.reward + int64_t(k) * n, fo.done + int64_t(k) * n,
+                    k == n_steps - 1 ? fo.wind_uv : nullptr, s);
+        ++launches;
+        BLE_CUDA(cudaGetLastError());
+        noise_valid = false;
+      }
+      if (fo.status != nullptr || fo.time_elapsed != nullptr || fo.sim_error != nullptr) {
+        k_step_info<Real><<<grid_for(n, 128), 128, 0, s>>>(d, fo.status, fo.time_elapsed, fo.sim_error);
+        ++launches;
+        BLE_CUDA(cudaGetLastError());
+      }
+    }
     // arena.step ends with feature_constructor.observe(get_measurements()) (env/balloon_arena.py:201):
     // the noise evaluated for it at the post-step state is also next step's pre-step wind.
-    if (cfg.enable_features && track_measurements) return features_observe(s);
+    if (observe) return features_observe(s);
     return BLE_OK;
+  }
+
+  // Which step kernel: the fused one-launch kernel (production fp32 build) unless BLE_STEP_KERNEL = "thread" | "ws"
+  // asks for a first-generation kernel (read per call: the parity tests run all of them on the same recorded states).
+  bool use_fused() const {
+    if constexpr (!std::is_same<Real, float>::value) return false;
+    const char* env = std::getenv("BLE_STEP_KERNEL");
+    return env == nullptr || (std::strcmp(env, "thread") != 0 && std::strcmp(env, "ws") != 0);
   }
 
   // ---- VAE decoder: Dense 64 -> 1000 -> 1000 -> 1000 -> 4410 (flax kernels are [in, out] row-major) ----
   int set_decoder(const float* const* kernels, const float* const* biases, cudaStream_t s) override {
     if (kernels == nullptr || biases == nullptr) { err = "set_decoder: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     const int dims[5] = {kDecLatents, kDecHidden, kDecHidden, kDecHidden, kDecOut};
     if (lt == nullptr && cublasLtCreate(&lt) != CUBLAS_STATUS_SUCCESS) { err = "set_decoder: cublasLtCreate failed"; return BLE_ERR_CUDA; }
     for (int i = 0; i < 4; ++i) {
@@ -1219,7 +1198,7 @@ struct Engine : EngineBase {
   int decode(const float* latents, int64_t f, float* fields, cudaStream_t s) override {
     if (latents == nullptr || fields == nullptr || f <= 0) { err = "decode: bad argument"; return BLE_ERR_INVALID_ARGUMENT; }
     if (!have_decoder) { err = "decode: no decoder weights (call ble_set_decoder first)"; return BLE_ERR_NOT_READY; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     const ResizeTaps taps = make_resize_taps();
     for (int64_t first = 0; first < f; first += kDecChunk) {
       const int64_t c = std::min<int64_t>(kDecChunk, f - first);
@@ -1247,7 +1226,7 @@ struct Engine : EngineBase {
       return BLE_ERR_INVALID_ARGUMENT;
     }
     if (!have_decoder) { err = "generate_fields: no decoder weights (call ble_set_decoder first)"; return BLE_ERR_NOT_READY; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     if (gen_latents == nullptr) {
       BLE_CUDA(cudaMalloc(&gen_latents, sizeof(float) * kGenChunk * kDecLatents));
       BLE_CUDA(cudaMalloc(&gen_fields, sizeof(float) * kGenChunk * size_t(kFieldFloats)));
@@ -1269,7 +1248,7 @@ struct Engine : EngineBase {
 
   int agent_station_seeker(const float* obs, int32_t* actions, int32_t* best, cudaStream_t s) override {
     if (obs == nullptr || actions == nullptr) { err = "agent_station_seeker: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     k_agent_station_seeker<<<grid_for(n * 32, 128), 128, 0, s>>>(obs, n, actions, best);
     ++launches;
     BLE_CUDA(cudaGetLastError());
@@ -1280,7 +1259,7 @@ struct Engine : EngineBase {
     if (obs == nullptr || seeds == nullptr || actions == nullptr || step_index < 0) {
       err = "agent_random_walk: bad argument"; return BLE_ERR_INVALID_ARGUMENT;
     }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     if (walk_target == nullptr) {
       if (step_index != 0) { err = "agent_random_walk: step_index 0 (begin_episode) must come first"; return BLE_ERR_NOT_READY; }
       BLE_CUDA(cudaMalloc(&walk_target, sizeof(double) * n));
@@ -1293,7 +1272,7 @@ struct Engine : EngineBase {
 
   int eval_begin(cudaStream_t s) override {
     if (!have_state) { err = "eval_begin: no balloon state"; return BLE_ERR_NOT_READY; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     if (ev.reward == nullptr) {
       BLE_CUDA(cudaMalloc(&ev.reward, sizeof(double) * n));
       BLE_CUDA(cudaMalloc(&ev.within, sizeof(int32_t) * n));
@@ -1309,7 +1288,7 @@ struct Engine : EngineBase {
   int eval_accumulate(const float* reward, float* path, cudaStream_t s) override {
     if (reward == nullptr) { err = "eval_accumulate: null reward"; return BLE_ERR_INVALID_ARGUMENT; }
     if (ev.reward == nullptr) { err = "eval_accumulate: call ble_eval_begin first"; return BLE_ERR_NOT_READY; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     k_eval_accumulate<Real><<<grid_for(n, 128), 128, 0, s>>>(d, ev, reward, 50000.0, path);   // env.radius, balloon_env.py:136
     ++launches;
     BLE_CUDA(cudaGetLastError());
@@ -1319,7 +1298,7 @@ struct Engine : EngineBase {
   int eval_results(double* out, cudaStream_t s) override {
     if (out == nullptr) { err = "eval_results: null output"; return BLE_ERR_INVALID_ARGUMENT; }
     if (ev.reward == nullptr) { err = "eval_results: call ble_eval_begin first"; return BLE_ERR_NOT_READY; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     k_eval_results<Real><<<grid_for(n, 128), 128, 0, s>>>(d, ev, out);
     ++launches;
     BLE_CUDA(cudaGetLastError());
@@ -1344,11 +1323,30 @@ struct Engine : EngineBase {
     k_step<Real><<<grid_for(n, 128), 128, 0, s>>>(d, actions, reward, done, wind_uv);
   }
 
+  // Warps per 32-balloon CTA of k_step_fused: the widest shape whose CTAs all fit in ONE wave (every phase-1 task on
+  // its own warp), else 4 (throughput shape).  BLE_STEP_WARPS = 4 | 8 | 10 | 14 overrides.
+  int fused_blocks_per_sm[4] = {0, 0, 0, 0};
+  int sm_count = 148;
+  int fused_warps() const {
+    if (const char* w = std::getenv("BLE_STEP_WARPS")) {
+      const int v = std::atoi(w);
+      for (int shape : kFusedShapes) if (v == shape) return v;
+    }
+    const int64_t blocks = (n + 31) / 32;
+    for (int i = 3; i >= 1; --i) {
+      if (blocks <= int64_t(fused_blocks_per_sm[i]) * sm_count) return kFusedShapes[i];
+    }
+    return 4;
+  }
+  void launch_fused(const int32_t* actions, const FusedOut& fo, int mode, int n_steps, cudaStream_t s) {
+    if constexpr (std::is_same<Real, float>::value) fused_launch(fused_warps(), d, actions, fo, mode, n_steps, s);
+  }
+
   int features_observe(cudaStream_t s) override {
     if (!cfg.enable_features) { err = "features_observe: handle was created with enable_features = 0"; return BLE_ERR_UNSUPPORTED; }
     int rc = check_ready("features_observe");
     if (rc != BLE_OK) return rc;
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     rc = launch_noise(s);
     if (rc != BLE_OK) return rc;
     k_feat_observe<Real><<<grid_for(n, 128), 128, 0, s>>>(d);
@@ -1359,7 +1357,7 @@ struct Engine : EngineBase {
 
   int features_clear(const uint8_t* mask, cudaStream_t s) override {
     if (!cfg.enable_features) { err = "features_clear: handle was created with enable_features = 0"; return BLE_ERR_UNSUPPORTED; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     if (mask == nullptr) {
       BLE_CUDA(cudaMemsetAsync(gp_count, 0, sizeof(int32_t) * n, s));
       BLE_CUDA(cudaMemsetAsync(gp_m, 0, sizeof(int32_t) * n, s));
@@ -1380,7 +1378,7 @@ struct Engine : EngineBase {
     if (!cfg.enable_features) { err = "features: handle was created with enable_features = 0"; return BLE_ERR_UNSUPPORTED; }
     int rc = check_ready("features");
     if (rc != BLE_OK) return rc;
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     k_feat_ambient<Real><<<grid_for(n, 128), 128, 0, s>>>(d, obs);
     k_feat_range_levels<Real><<<grid_for(n * kRangeLevels, 128), 128, 0, s>>>(d, range_scratch);
     k_feat_range<Real><<<grid_for(n, 128), 128, 0, s>>>(d, range_scratch);
@@ -1400,7 +1398,7 @@ struct Engine : EngineBase {
     if (actions_host == nullptr || reward_host == nullptr || done_host == nullptr) { err = "step_host: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
     int rc = check_ready("step_host");
     if (rc != BLE_OK) return rc;
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     rc = launch_noise(s);                  // needs no actions: runs while the host stages them (no-op when prefetched)
     if (rc != BLE_OK) return rc;
     std::memcpy(h_actions, actions_host, sizeof(int32_t) * n);
@@ -1432,7 +1430,7 @@ struct Engine : EngineBase {
     if (uv == nullptr) { err = "wind_at_balloon: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
     int rc = check_ready("wind_at_balloon");
     if (rc != BLE_OK) return rc;
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     rc = launch_noise(s);
     if (rc != BLE_OK) return rc;
     k_wind_at_balloon<Real><<<grid_for(n, 128), 128, 0, s>>>(d, reinterpret_cast<float2*>(uv));
@@ -1444,7 +1442,7 @@ struct Engine : EngineBase {
   int derived(double* out, cudaStream_t s) override {
     if (out == nullptr) { err = "derived: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
     if (!have_state) { err = "derived: no balloon state"; return BLE_ERR_NOT_READY; }
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     k_derived<Real><<<grid_for(n, 128), 128, 0, s>>>(d, out);
     ++launches;
     BLE_CUDA(cudaGetLastError());
@@ -1455,7 +1453,7 @@ struct Engine : EngineBase {
     if (m < 0 || (m > 0 && (xyzt == nullptr || fidx == nullptr || uv == nullptr))) { err = "wind_gather: bad argument"; return BLE_ERR_INVALID_ARGUMENT; }
     if (!have_fields) { err = "wind_gather: no wind fields (call ble_upload_fields first)"; return BLE_ERR_NOT_READY; }
     if (m == 0) return BLE_OK;
-    BLE_CUDA(cudaSetDevice(device));
+    BLE_DEVICE_GUARD();
     k_wind_gather<Real><<<grid_for(m, 256), 256, 0, s>>>(cells, d.layout, reinterpret_cast<const float4*>(xyzt), fidx,
                                                        reinterpret_cast<float2*>(uv), m);
     ++launches;
@@ -1556,6 +1554,12 @@ int ble_init_derived(ble_handle* h, int32_t run_stable_init, void* stream) {
 }
 int ble_step(ble_handle* h, const int32_t* actions, float* reward, uint8_t* done, float* wind_uv, void* stream) {
   BLE_H(h); return h->eng->step(actions, reward, done, wind_uv, cudaStream_t(stream));
+}
+int ble_step_ex(ble_handle* h, const int32_t* actions, const ble_step_out* out, void* stream) {
+  BLE_H(h); return h->eng->step_ex(actions, out, 1, cudaStream_t(stream));
+}
+int ble_rollout(ble_handle* h, const int32_t* actions, int32_t n_steps, const ble_step_out* out, void* stream) {
+  BLE_H(h); return h->eng->step_ex(actions, out, n_steps, cudaStream_t(stream));
 }
 int ble_step_host(ble_handle* h, const int32_t* actions_host, float* reward_host, uint8_t* done_host, void* stream) {
   BLE_H(h); return h->eng->step_host(actions_host, reward_host, done_host, cudaStream_t(stream));

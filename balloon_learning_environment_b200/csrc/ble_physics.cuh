@@ -15,7 +15,7 @@
 
 #if defined(__CUDACC__)
 #define BLE_HD __host__ __device__ __forceinline__
-#define BLE_HD_NOINLINE __host__ __device__ __noinline__
+#define BLE_HD_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define BLE_HD inline
 #define BLE_HD_NOINLINE inline
@@ -182,12 +182,29 @@ struct Atmosphere {
   double l0, l1, l2;        // lapse rates
   double t1, t2;            // temperature transitions (t0 = 300)
   double p1, p2, p3;        // pressure transitions (p0 = 108870.8213)
-  bool ok;                  // false once a query fell outside the atmosphere
+  bool ok = true;           // false once a query fell outside the atmosphere
   // X = (p/P_i)^k of the previous sub-step (production build only): the next X is
   // X_prev * (p/p_prev)^k with |p/p_prev - 1| ~ 1e-3, summed as a binomial series.
-  bool incremental;
-  int lcache;
-  double pcache, xcache;
+  // The cache starts EMPTY (lcache = -1) however the struct is built: the first query of an agent
+  // step always takes the exp(k log) path.
+  bool incremental = false;
+  int lcache = -1;
+  double pcache = 1.0, xcache = 1.0;
+
+  // The one way the kernels (and the host replay of tests/hostemu) rebuild the struct from the nine
+  // per-episode rows stored in HBM (DevState rows D_ALPHA .. D_P3).
+  BLE_HD static Atmosphere from_rows(double alpha, double l0, double l1, double l2, double t1, double t2,
+                                     double p1, double p2, double p3) {
+    Atmosphere a;
+    a.alpha = alpha;
+    a.l0 = l0; a.l1 = l1; a.l2 = l2;
+    a.t1 = t1; a.t2 = t2;
+    a.p1 = p1; a.p2 = p2; a.p3 = p3;
+    a.ok = true;
+    a.incremental = false;
+    a.lcache = -1; a.pcache = 1.0; a.xcache = 1.0;
+    return a;
+  }
 
   BLE_HD void init(double a) {
     double lapse[7], t_tr[8], p_tr[8];
@@ -562,7 +579,7 @@ BLE_HD Real acs_most_efficient_power(Real pr) {
    {0., 0.23, 0.23, 0.23, 0.23, 0.23, 0.20, 0.20, 0.20, 0.18, 0.16, 0.15, 0.13}}
 static const double kAcsEffHost[4][13] = BLE_ACS_EFF_TABLE;
 #if defined(__CUDACC__)
-__constant__ double kAcsEffDev[4][13] = BLE_ACS_EFF_TABLE;
+static __constant__ double kAcsEffDev[4][13] = BLE_ACS_EFF_TABLE;
 #endif
 BLE_HD double acs_eff_table(int j, int i) {
 #if defined(__CUDA_ARCH__)

@@ -145,7 +145,22 @@ constexpr double kNoiseMagnitude = 4.233932721683222;   // sqrt(1.02 / 0.0569), 
    {0.1186, 47.500, 43.048, 66.553, 8.424},        {0.1066, 3663.291, 232.023, 7499.741, 225.0}}
 static const double kHarmonicsHost[10][5] = BLE_HARMONIC_TABLE;
 #if defined(__CUDACC__)
-__constant__ double kHarmonicsDev[10][5] = BLE_HARMONIC_TABLE;
+static __constant__ double kHarmonicsDev[10][5] = BLE_HARMONIC_TABLE;
+#endif
+// Reciprocal spacings in the units of the state: (1 / (1000 sx), 1 / (1000 sy), 1 / sp, 1 / (3600 st)) so that the
+// lattice coordinate is x_m * inv + offset (production kernel; one multiply instead of two fp64 divisions).
+#define BLE_HI(sx, sy, sp, st) {1.0 / (1000.0 * (sx)), 1.0 / (1000.0 * (sy)), 1.0 / (sp), 1.0 / (3600.0 * (st))}
+#if defined(__CUDACC__)
+static __constant__ double kHarmonicsInvDev[10][4] = {
+    BLE_HI(702.269, 2116.987, 2587.802, 245.0),   BLE_HI(1483.570, 752.124, 646.208, 16.39),
+    BLE_HI(276.810, 147.040, 587.702, 3.836),     BLE_HI(10214.525, 1512.216, 965.629, 41.780),
+    BLE_HI(181.286, 420.942, 8500.0, 245.0),      BLE_HI(1974.228, 2028.814, 713.697, 26.435),
+    BLE_HI(699.738, 541.845, 632.116, 9.530),     BLE_HI(217.750, 196.522, 686.825, 3.546),
+    BLE_HI(47.500, 43.048, 66.553, 8.424),        BLE_HI(3663.291, 232.023, 7499.741, 225.0)};
+// NoisyWindComponent.get_noise (:180-211): out = (sum w_h n_h) * sqrt(sum w / sum w^2) / sum w
+static __constant__ float kBlendU[5] = {0.1445f, 0.2766f, 0.2627f, 0.2137f, 0.1025f};
+static __constant__ float kBlendV[5] = {0.2716f, 0.2684f, 0.2348f, 0.1186f, 0.1066f};
+constexpr float kBlendScaleU = 2.1196478805123253f, kBlendScaleV = 2.1018160718443704f;
 #endif
 BLE_HD void harmonic_params(int h10, double* w, double* sx, double* sy, double* sp, double* st) {
 #if defined(__CUDA_ARCH__)

@@ -148,6 +148,33 @@ int ble_init_derived(ble_handle* h, int32_t run_stable_init, void* stream);
 int ble_step(ble_handle* h, const int32_t* actions, float* reward, uint8_t* done, float* wind_uv,
              void* stream);
 
+/* ble_step with the `info` dictionary of BalloonEnv.step (env/balloon_env.py:186-190,280-290) written by the
+ * step kernel itself, so a caller never needs a second pass over the state:
+ *   status       uint8 [N]  BalloonStatus after the step: 0 OK, 1 OUT_OF_POWER, 2 BURST, 3 ZEROPRESSURE
+ *                           (info['out_of_power'], info['envelope_burst'], info['zeropressure'])
+ *   time_elapsed int32 [N]  seconds since reset (info['time_elapsed'])
+ *   sim_error    uint8 [N]  1 once an atmosphere query of this balloon fell outside the table or a sunrise /
+ *                           sunset search failed since the last reset (the reference asserts / raises there:
+ *                           env/balloon/standard_atmosphere.py:95-96,126-127, env/balloon/solar.py:318-322); sticky.
+ * reward and done are required, every other pointer may be NULL. */
+typedef struct {
+  float* reward;           /* [N]   */
+  uint8_t* done;           /* [N]   */
+  float* wind_uv;          /* [N,2] */
+  uint8_t* status;         /* [N]   */
+  int32_t* time_elapsed;   /* [N]   */
+  uint8_t* sim_error;      /* [N]   */
+  void* reserved[2];       /* must be NULL */
+} ble_step_out;
+int ble_step_ex(ble_handle* h, const int32_t* actions, const ble_step_out* out, void* stream);
+
+/* n_steps consecutive BalloonEnv.step calls in ONE kernel launch, for open-loop action sequences (a random
+ * agent, a replayed episode): actions int32 [n_steps][N]; out->reward / out->done are [n_steps][N], the other
+ * outputs describe the state after the last step.  Balloons do not interact (env/balloon_arena.py:184-202),
+ * so a CTA carries its 32 balloons through all the steps without any grid-wide synchronisation.  Not available
+ * while the WindGP measurement history is being tracked (ble_features_track). */
+int ble_rollout(ble_handle* h, const int32_t* actions, int32_t n_steps, const ble_step_out* out, void* stream);
+
 /* Same, with HOST buffers (pageable or pinned): copies actions in, steps, copies reward/done out
  * and waits.  This is the call a Python/NumPy user of the reference makes per step.  Before it
  * returns it queues, on `stream`, the wind-noise kernel of the NEXT step (the wind at the post-step

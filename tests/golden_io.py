@@ -27,6 +27,24 @@ def load_traj():
   return out
 
 
+def load_safety():
+  """tests/golden/safety.npz: single reference steps from states in every safety band
+  (tests/golden/tier0/make_safety_golden.py)."""
+  z = np.load(os.path.join(GOLDEN_DIR, 'safety.npz'))
+  return {k: z[k] for k in z.files}
+
+
+def oracle_env_for_records(rec, float_fields, int_fields, sel=slice(None)):
+  """One batched OracleEnv holding the pre-step states of single-step records (load_safety layout)."""
+  b = batch_from_rows(float_fields, int_fields, rec['f'][sel], rec['i'][sel])
+  arena = env_lib.OracleArena(
+      b, atmosphere_lib.Atmosphere(rec['alpha'][sel]), fields=golden_fields.field_bank(),
+      field_idx=np.maximum(rec['field'][sel], 0),
+      noise=wind_lib.SimplexWindNoise(rec['seeds'][sel], rec['offsets'][sel]), static_wind=rec['field'][sel] < 0,
+      power_safety_layer_enabled=rec['psl'][sel].astype(bool))
+  return env_lib.OracleEnv(arena)
+
+
 def batch_from_rows(float_fields, int_fields, f_rows, i_rows):
   """Rows [N, len(fields)] -> oracle BalloonBatch."""
   f_rows = np.atleast_2d(np.asarray(f_rows, np.float64))

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, 'libhostemu.so')
 _SRC = os.path.join(_HERE, 'hostemu.cpp')
 _HDRS = [os.path.join(_HERE, '..', '..', 'balloon_learning_environment_b200', 'csrc', f)
-         for f in ('ble_physics.cuh', 'ble_wind.cuh', 'ble_features.cuh', 'ble_agents.cuh')] + [os.path.join(_HERE, '..', '..', 'include', 'ble_b200.h')]
+         for f in ('ble_physics.cuh', 'ble_wind.cuh', 'ble_features.cuh', 'ble_agents.cuh', 'ble_step_roles.cuh', 'ble_fastmath.cuh')] + [os.path.join(_HERE, '..', '..', 'include', 'ble_b200.h')]
 
 
 def build(force=False):

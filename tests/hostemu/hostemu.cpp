@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstring>
 #include "../../balloon_learning_environment_b200/csrc/ble_physics.cuh"
+#include "../../balloon_learning_environment_b200/csrc/ble_step_roles.cuh"
 #include "../../balloon_learning_environment_b200/csrc/ble_wind.cuh"
 #include "../../balloon_learning_environment_b200/csrc/ble_features.cuh"
 #include "../../balloon_learning_environment_b200/csrc/ble_agents.cuh"
@@ -14,7 +15,16 @@
 
 using namespace ble;
 
-template <typename Real>
+// The kernels never call Atmosphere::init on the step path: k_state_upload / k_reset store the nine table rows
+// and load_atmosphere() rebuilds the struct with Atmosphere::from_rows.  The replay takes the same road.
+static Atmosphere atmosphere_as_the_kernels_load_it(double alpha) {
+  Atmosphere t; t.init(alpha);
+  return Atmosphere::from_rows(t.alpha, t.l0, t.l1, t.l2, t.t1, t.t2, t.p1, t.p2, t.p3);
+}
+
+// precision 2 = the production kernel's arithmetic: fp32 right-hand sides on the branch-free role functions
+// of ble_step_roles.cuh (what k_step_fused runs, one role per warp), replayed here in sequence.
+template <typename Real, bool kRoles = false>
 static void step_impl(int64_t n, double* f, int64_t* iv, const int32_t* actions, const double* wind,
                       double* reward, int32_t* eff_out) {
   auto F = [&](int r, int64_t e) -> double& { return f[int64_t(r) * n + e]; };
@@ -34,14 +44,16 @@ static void step_impl(int64_t n, double* f, int64_t* iv, const int32_t* actions,
     s.ir = Real(F(BLE_F_UPWELLING_INFRARED, e)); s.mols_gas = Real(F(BLE_F_MOLS_LIFT_GAS, e));
     s.date_time = I(BLE_I_DATE_TIME, e); s.time_elapsed = int32_t(I(BLE_I_TIME_ELAPSED, e));
     s.status = int(I(BLE_I_STATUS, e));
-    Atmosphere atm; atm.init(F(BLE_F_ATMOSPHERE_ALPHA, e));
+    Atmosphere atm = atmosphere_as_the_kernels_load_it(F(BLE_F_ATMOSPHERE_ALPHA, e));
     SafetyState ss;
     ss.sunrise_h = I(BLE_I_SUNRISE_H, e); ss.sunset = I(BLE_I_SUNSET, e);
     ss.envelope_state = int(I(BLE_I_ENVELOPE_STATE, e)); ss.altitude_state = int(I(BLE_I_ALTITUDE_STATE, e));
     ss.power_paused = int(I(BLE_I_POWER_PAUSED, e)); ss.power_safety_enabled = int(I(BLE_I_POWER_SAFETY_ENABLED, e));
     ss.last_command = int(I(BLE_I_LAST_COMMAND, e));
     int eff;
-    const Real r = agent_step<Real>(s, atm, ss, actions[e], wind[2 * e], wind[2 * e + 1], &eff);
+    Real r;
+    if constexpr (kRoles) r = roles::agent_step_roles(s, atm, ss, actions[e], wind[2 * e], wind[2 * e + 1], &eff);
+    else r = agent_step<Real>(s, atm, ss, actions[e], wind[2 * e], wind[2 * e + 1], &eff);
     reward[e] = double(r); eff_out[e] = eff;
     F(BLE_F_X, e) = s.x; F(BLE_F_Y, e) = s.y; F(BLE_F_PRESSURE, e) = s.pressure;
     F(BLE_F_AMBIENT_TEMPERATURE, e) = s.t_ambient; F(BLE_F_INTERNAL_TEMPERATURE, e) = s.t_internal;
@@ -72,7 +84,7 @@ static void substeps_impl(int64_t n, double* f, int64_t* iv, const int32_t* eff,
     s.ir = Real(F(BLE_F_UPWELLING_INFRARED, e)); s.mols_gas = Real(F(BLE_F_MOLS_LIFT_GAS, e));
     s.date_time = I(BLE_I_DATE_TIME, e); s.time_elapsed = int32_t(I(BLE_I_TIME_ELAPSED, e));
     s.status = 0;
-    Atmosphere atm; atm.init(F(BLE_F_ATMOSPHERE_ALPHA, e));
+    Atmosphere atm = atmosphere_as_the_kernels_load_it(F(BLE_F_ATMOSPHERE_ALPHA, e));
     SunTrack<Real> sun; sun.init(s, wind[2 * e], wind[2 * e + 1]);
     atm.incremental = !is_double<Real>::value;
     const Real epa = earth_heat_per_area<Real>(s.ir);
@@ -98,6 +110,7 @@ void emu_substeps(int precision, int64_t n, double* f, int64_t* iv, const int32_
 void emu_step(int precision, int64_t n, double* f, int64_t* iv, const int32_t* actions,
               const double* wind, double* reward, int32_t* eff) {
   if (precision == BLE_PRECISION_FP64) step_impl<double>(n, f, iv, actions, wind, reward, eff);
+  else if (precision == 2) step_impl<float, true>(n, f, iv, actions, wind, reward, eff);
   else step_impl<float>(n, f, iv, actions, wind, reward, eff);
 }
 

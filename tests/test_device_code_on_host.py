@@ -161,14 +161,44 @@ def _single_step_errors(prec):
   return worst, mism, total, rworst
 
 
+def _safety_step_errors(prec):
+  rec = golden_io.load_safety()
+  b = golden_io.batch_from_rows(FF, IF, rec['f'], rec['i'])
+  f, i = hostemu.pack_state(b, rec['alpha'], rec['psl'])
+  reward, _ = hostemu.emu_step(LIB, prec, f, i, rec['action'].astype(np.int32), rec['wind'])
+  worst, mism = {}, 0
+  floors = {'x': 1e4, 'y': 1e4, 'acs_mass_flow': 1e-2, 'superpressure': 100.0, 'solar_charging': 50.0,
+            'acs_power': 100.0, 'mols_air': 100.0}
+  for j, k in enumerate(FF):
+    ref = rec['want_f'][:, j]
+    worst[k] = float((np.abs(f[hostemu.F_ROWS.index(k)] - ref) / np.maximum(np.abs(ref), floors.get(k, 1e-30))).max())
+  for j, k in enumerate(IF):
+    bad = i[hostemu.I_ROWS.index(k)] != rec['want_i'][:, j]
+    if k in ('sunrise_h', 'sunset'):
+      bad = bad & (rec['psl'] == 1)
+    mism += int(bad.sum())
+  return worst, mism, float(np.abs(reward - rec['reward']).max())
+
+
+@pytest.mark.parametrize('prec,tol', [(1, 1e-8), (0, 1e-4), (2, 1e-4)])
+def test_safety_band_records_device_code(prec, tol):
+  """The reference's single steps from every safety band / prior machine state / terminal status through the device
+  headers: fp64 audit arithmetic, the first-generation fp32 path, and the production role functions (2)."""
+  worst, mism, rworst = _safety_step_errors(prec)
+  assert mism == 0, mism
+  assert max(worst.values()) < tol, worst
+  assert rworst < max(tol, 1e-7)
+
+
 def test_single_steps_fp64_device_code_tight():
   worst, mism, total, rworst = _single_step_errors(1)
   assert max(worst.values()) < 1e-8, worst
   assert mism == 0 and rworst < 1e-9
 
 
-def test_single_steps_fp32_device_code_within_1e4():
-  worst, mism, total, rworst = _single_step_errors(0)
+@pytest.mark.parametrize('prec', [0, 2])
+def test_single_steps_fp32_device_code_within_1e4(prec):
+  worst, mism, total, rworst = _single_step_errors(prec)
   print(worst)
   # north_star tolerance is 1e-4; with the stiff variables in fp64 the production arithmetic
   # lands at <= 1e-5 (solar_charging, fp32 trig) and <= 1e-6 for the integrated state.
