@@ -217,7 +217,7 @@ k_noise(DevState<Real> d) {
       "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar) : "memory");
   if (live) {
     RotatedPerm perm{s_perm + threadIdx.x * 256, int(e & 31) * 4};
-    const Real v = simplex_noise4<Real>(perm, X, Y, Z, W);
+    const Real v = simplex_noise4_v2<Real>(perm, X, Y, Z, W);
     d.noise_partial[int64_t(h10) * d.n + e] = Real(kNoiseMagnitude) * v;
   }
 }
@@ -1323,23 +1323,25 @@ struct Engine : EngineBase {
     k_step<Real><<<grid_for(n, 128), 128, 0, s>>>(d, actions, reward, done, wind_uv);
   }
 
-  // Warps per 32-balloon CTA of k_step_fused: the widest shape whose CTAs all fit in ONE wave (every phase-1 task on
-  // its own warp), else 4 (throughput shape).  BLE_STEP_WARPS = 4 | 8 | 10 | 14 overrides.
+  // Shape of the fused step kernel (ble_step_fused.h): the widest latency shape whose CTAs all fit in ONE wave (so that
+  // every phase-1 task has its own warp), else the throughput shape.  BLE_STEP_WARPS = 0 | 4 | 8 | 14 overrides.
   int fused_blocks_per_sm[4] = {0, 0, 0, 0};
   int sm_count = 148;
-  int fused_warps() const {
+  int fused_shape() const {
     if (const char* w = std::getenv("BLE_STEP_WARPS")) {
-      const int v = std::atoi(w);
-      for (int shape : kFusedShapes) if (v == shape) return v;
+      if (*w != 0) {
+        const int v = std::atoi(w);
+        for (int shape : kFusedShapes) if (v == shape) return v;
+      }
     }
     const int64_t blocks = (n + 31) / 32;
     for (int i = 3; i >= 1; --i) {
       if (blocks <= int64_t(fused_blocks_per_sm[i]) * sm_count) return kFusedShapes[i];
     }
-    return 4;
+    return 0;
   }
   void launch_fused(const int32_t* actions, const FusedOut& fo, int mode, int n_steps, cudaStream_t s) {
-    if constexpr (std::is_same<Real, float>::value) fused_launch(fused_warps(), d, actions, fo, mode, n_steps, s);
+    if constexpr (std::is_same<Real, float>::value) fused_launch(fused_shape(), d, actions, fo, mode, n_steps, s);
   }
 
   int features_observe(cudaStream_t s) override {

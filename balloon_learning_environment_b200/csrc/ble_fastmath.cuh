@@ -135,5 +135,35 @@ BLE_FM float cbrtf_pos(float x) {
 #endif
 }
 
+// sin and cos of |x| <~ 100 in one go: Cody-Waite reduction by pi/2 in two steps, the classic single-precision
+// minimax kernels on [-pi/4, pi/4], quadrant fix-up.  Plain arithmetic (identical on host and device); absolute
+// error < 2e-7.  libm's sinf / cosf carry a Payne-Hanek slow path that nvcc inlines at every call site.
+BLE_FM void sincosf_fast(float x, float* s, float* c) {
+  const float k = rintf(x * 0.63661977236758134308f);
+  float r = fmaf(k, -1.57079601287841796875f, x);
+  r = fmaf(k, -3.1391647326017846353e-07f, r);
+  r = fmaf(k, -5.3903025299577647655e-15f, r);
+  const float r2 = r * r;
+  const float sp = r + r * r2 * (-1.6666654611e-1f + r2 * (8.3321608736e-3f + r2 * (-1.9515295891e-4f)));
+  const float cp = 1.0f + r2 * (-0.5f + r2 * (4.166664568298827e-2f + r2 * (-1.388731625493765e-3f + r2 * 2.443315711809948e-5f)));
+  const int q = int(k) & 3;
+  const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+  *s = (q & 2) ? -ss : ss;
+  *c = ((q + 1) & 2) ? -cc : cc;
+}
+
+// x mod m for m > 0 (result in [0, m)); exact enough for fp64 angles of a few thousand degrees
+BLE_FM double mod_pos(double x, double m, double inv_m) { return fma(-m, floor(x * inv_m), x); }
+
+BLE_FM float rsqrtf_pos(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+
 }  // namespace fm
 }  // namespace ble

@@ -1,22 +1,18 @@
-// The fused one-launch step kernel of the production (fp32) build and its launcher.
-#include "ble_step_fused.h"
-
-#include "ble_step_roles.cuh"
-
-namespace ble {
-
-// k_step_fused: BalloonEnv.step for 32 balloons per CTA in ONE launch (production fp32 build).
+// The one-launch step kernels of the production (fp32) build and their launcher.
 //
 // Reference path: env/balloon_env.py:157-190 -> env/balloon_arena.py:184-202 -> WindField.get_ground_truth
 // (env/wind_field.py:125-145: grid interpolation + 10 simplex-noise harmonics) -> Balloon.simulate_step
 // (env/balloon/balloon.py:263-328: three safety layers, 18 Euler sub-steps) -> reward / terminal.
 //
-// Work decomposition (kW warps per CTA, lane l of every warp = balloon 32 * block + l):
-//   phase 1a  14 independent TASKS dealt round-robin to the kW warps:
+// Two shapes of the same computation, both one launch per BalloonEnv.step (or per ble_rollout of many steps):
+//
+// k_step_roles<kW>  LATENCY shape, for batches of at most one wave (the 8-GPU split of 65,536 balloons).
+//   32 balloons per CTA, kW warps; lane l of every warp = balloon 32 * block + l.
+//   phase 1a  13 independent TASKS dealt round-robin to the kW warps:
 //               N0..N9  one simplex-noise harmonic each; the 32 balloons' permutation tables of that harmonic
 //                       (8 KB, contiguous in HBM) arrive in the warp's staging buffer by ONE TMA bulk copy
 //                       (cp.async.bulk + mbarrier) issued before the lattice coordinates are computed;
-//               ST0..2  the time-only half of the NOAA solar calculator at t0, t0 + 90 s, t0 + 180 s;
+//               ST0..1  the time-only half of the NOAA solar calculator at t0 and t0 + 180 s;
 //               G       forecast gather (8 x LDG.128 of the lookup's 128-byte window), power / envelope /
 //                       altitude safety layers -> effective action, and X = (p/P_i)^k for role P.
 //   barrier   (whole CTA)
@@ -24,22 +20,147 @@ namespace ble {
 //             (position-dependent half: great-circle offset + hour angle), which needs the wind.
 //   barrier   (4 role warps; the other warps are done)
 //   phase 2   18 Euler sub-steps, warp w = role w (P pressure/atmosphere, T thermal body, E envelope + ACS,
-//             S sun + power) on the branch-free role functions of ble_step_roles.cuh; one named barrier and
-//             one double-buffered shared-memory exchange per sub-step.
-//   epilogue  every role stores the rows it owns; role S evaluates the reward.
-// kW = 4 is the throughput shape (65,536 balloons: 3.5 waves of 4 CTAs / SM); kW = 14 gives every task its
-// own warp and is the latency shape for batches below one wave (8,192 balloons per GPU in the 8-GPU split).
+//             S sun + power) on the branch-free role functions of ble_step_roles.cuh.  Every role runs ITS OWN
+//             loop (so the register allocation is the maximum over the roles, not their sum); one named barrier
+//             and one double-buffered shared-memory exchange per sub-step; each role stores the rows it owns.
 //
-// kSteps > 1 (ble_rollout): the same CTA runs kSteps agent steps back to back on actions[step][N]; balloons do
-// not interact, so there is no grid-wide synchronisation and no launch gap between steps.
+// k_step_warp       THROUGHPUT shape, for batches of several waves (65,536 balloons on one GPU).
+//   One WARP carries 32 balloons through the whole step: no CTA barrier, no shared-memory exchange, no duplicated
+//   work; the four roles run back to back in every thread and the compiler interleaves their independent chains.
+//   The only shared memory is the warp's 8 KB permutation-table staging buffer (same TMA bulk copy).
+//
+// n_steps > 1 (ble_rollout): the same CTA runs the steps back to back on actions[step][N]; balloons do not
+// interact, so there is no grid-wide synchronisation and no launch gap between steps.
+#include "ble_step_fused.h"
 
+#include "ble_step_roles.cuh"
+
+namespace ble {
+
+constexpr int kFusedTasks = 13;
+constexpr int kPermStageBytes = 32 * 256;
+
+__device__ __forceinline__ void role_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// One TMA bulk copy: the permutation tables of harmonic h10 for the `count` balloons starting at e0.
+__device__ __forceinline__ void stage_perm_tables(const DevState<float>& d, int h10, int64_t e0, int count, uint8_t* stage,
+                                                  uint32_t bar) {
+  const uint32_t bytes = uint32_t(count) * 256u;
+  const uint8_t* src = d.perm + (int64_t(h10) * d.n + e0) * 256;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(stage)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// NoisyWindHarmonic.get_noise (simplex_wind_noise.py:116-146) for harmonic h10 of balloon ec; the warp's staging
+// buffer must hold the tables (lane l's table at stage + 256 l, rotated by 4 l bytes).
+struct NoiseOffsets { float x, y, p, t; };
+__device__ __forceinline__ NoiseOffsets load_noise_offsets(const DevState<float>& d, int h10, int64_t ec) {
+  NoiseOffsets o;
+  o.x = d.offsets[(int64_t(h10) * 4 + 0) * d.n + ec]; o.y = d.offsets[(int64_t(h10) * 4 + 1) * d.n + ec];
+  o.p = d.offsets[(int64_t(h10) * 4 + 2) * d.n + ec]; o.t = d.offsets[(int64_t(h10) * 4 + 3) * d.n + ec];
+  return o;
+}
+__device__ __forceinline__ float noise_harmonic(int h10, const NoiseOffsets& off, int lane, double x, double y,
+                                                double p, int32_t t_elapsed, const uint8_t* stage, uint32_t bar,
+                                                uint32_t parity, bool valid) {
+  const double* hp = kHarmonicsInvDev[h10];
+  const double X = fma(x, hp[0], double(off.x));
+  const double Y = fma(y, hp[1], double(off.y));
+  const double Z = fma(p, hp[2], double(off.p));
+  const double W = fma(double(t_elapsed), hp[3], double(off.t));
+  mbar_wait(bar, parity);
+  float v = 0.f;
+  if (valid) {
+    RotatedPerm perm{stage + lane * 256, lane * 4};
+    v = simplex_noise4_v2<float>(perm, X, Y, Z, W);
+  }
+  return float(kNoiseMagnitude) * v;
+}
+
+// The three safety layers, once per agent step (balloon.py:305-313), and X = (p/P_i)^k at the pre-step pressure.
+struct SafetyOut {
+  int eff;
+  uint32_t flags_base;     // flags word without the status bits
+  double x0;               // 0 = not available (pressure outside layers 0..2)
+};
+__device__ __forceinline__ SafetyOut safety_layers(const DevState<float>& d, int64_t ec, int64_t e, bool stepped, uint32_t fl,
+                                                   int action, double p_pre, int64_t ts_pre) {
+  SafetyOut o;
+  const Atmosphere atm = load_atmosphere(d, ec);
+  int64_t sunrise_h = d.l[int64_t(L_SUNRISE_H) * d.n + ec], sunset = d.l[int64_t(L_SUNSET) * d.n + ec];
+  int env_state = int((fl >> 4) & 7), alt_state = int((fl >> 7) & 3), paused = int((fl >> 9) & 1);
+  const int psl = int((fl >> 10) & 1);
+  int eff = action;
+  if (psl) eff = power_safety<double>(eff, ts_pre, DD(d, D_CHARGE, ec), &sunrise_h, &sunset, &paused);
+  eff = envelope_safety<double>(eff, DD(d, D_SP, ec), &env_state);
+  roles::PressureRole pr;
+  pr.select_layer(atm, p_pre);
+  double altitude, x0 = 0.0;
+  bool ok = true;
+  if (pr.layer >= 0) {
+    x0 = pr.x_from_scratch(p_pre);
+    altitude = (x0 - 1.0) * pr.tl + atm_h(pr.layer);
+  } else {
+    Atmosphere a2 = atm;
+    double t_unused;
+    a2.at_pressure(p_pre, &altitude, &t_unused);
+    ok = a2.ok;
+  }
+  eff = altitude_safety<double>(eff, altitude, &alt_state);
+  o.eff = eff;
+  o.x0 = x0;
+  const uint32_t err = ((fl >> 11) & 1u) | (ok ? 0u : 1u);
+  o.flags_base = pack_flags(0, action, env_state, alt_state, paused, psl, int(err));
+  if (stepped) {
+    d.l[int64_t(L_SUNRISE_H) * d.n + e] = sunrise_h;
+    d.l[int64_t(L_SUNSET) * d.n + e] = sunset;
+  }
+  return o;
+}
+
+// info outputs of BalloonEnv.step + the flags word, written by whoever owns the balloon's discrete state
+__device__ __forceinline__ void store_discrete(const DevState<float>& d, const FusedOut& out, int64_t e, bool valid, bool stepped,
+                                               uint32_t fl, uint32_t flags_base, int status, bool atm_ok, int32_t t_new,
+                                               int64_t ts_new, bool last, float uf, float vf) {
+  if (stepped) {
+    d.l[int64_t(L_DATE_TIME) * d.n + e] = ts_new;                          // balloon.py:546-547
+    d.t_elapsed[e] = t_new;
+    const uint32_t nf = flags_base | uint32_t(status) | (atm_ok ? 0u : (1u << 11));
+    d.flags[e] = nf;
+    if (out.sim_error != nullptr) out.sim_error[e] = uint8_t((nf >> 11) & 1u);
+  } else if (valid && out.sim_error != nullptr) {
+    out.sim_error[e] = uint8_t((fl >> 11) & 1u);
+  }
+  if (valid) {
+    if (out.wind_uv != nullptr && last) out.wind_uv[e] = stepped ? make_float2(uf, vf) : make_float2(0.f, 0.f);
+    if (out.status != nullptr) out.status[e] = uint8_t(stepped ? status : int(fl & 3u));
+    if (out.time_elapsed != nullptr) out.time_elapsed[e] = t_new;
+  }
+}
+
+// =====================================================================================================================
+// Latency shape
+// =====================================================================================================================
 template <int kW>
 struct FusedSmem {
   // phase 1 results
   float noise[10][32];
   float fu[32], fv[32];
-  double fod[3][32], eqt[3][32];
-  float sdecl[3][32], cdecl[3][32], sflux[3][32];
+  double phase[2][32];                 // SolarTimeFast at t0 and t0 + 180 s
+  float sdecl[2][32], cdecl[2][32], sflux[2][32];
   float cz[3][32];
   int eff[32];
   uint32_t flags_base[32];            // flags word without the status bits, after the safety layers
@@ -51,125 +172,234 @@ struct FusedSmem {
   alignas(8) uint64_t bar[kW];
 };
 
-constexpr int kFusedTasks = 14;
-constexpr int kPermStageBytes = 32 * 256;
+// What every role needs to know about the step it is in.
+struct RoleCtx {
+  int64_t e, ec;
+  int lane;
+  bool valid, stepped, last;
+  int action, eff;
+  double x_pre, y_pre, p_pre, u, v;
+  float uf, vf;
+  int32_t t_pre;
+  int64_t ts_pre;
+  uint32_t fl;
+  int64_t o;               // index of this (step, balloon) in reward / done
+};
 
-__device__ __forceinline__ void role_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// status of sub-step b as both E (envelope) and S (power) saw it; later assignment wins (balloon.py:541-542)
+template <typename Smem>
+__device__ __forceinline__ int substep_status(const Smem& sm, int b, int lane) {
+  return sm.st_pwr[b][lane] ? int(kOutOfPower) : sm.st_env[b][lane];
+}
 
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+template <typename Smem>
+__device__ __forceinline__ void run_role_pressure(const DevState<float>& d, const FusedOut& out, Smem& sm, const RoleCtx& c) {
+  const int lane = c.lane;
+  roles::PressureRole pr;
+  pr.init(load_atmosphere(d, c.ec), double(RR(d, R_MOLS_GAS, c.ec)), c.p_pre);
+  {
+    const double x0 = sm.x0[lane];
+    if (pr.layer >= 0 && x0 > 0.0) pr.seed_x(c.p_pre, x0);
+  }
+  double p = c.p_pre, t_amb = DD(d, D_TAMB, c.ec), vol = DD(d, D_VOL, c.ec), mols = DD(d, D_MOLS_AIR, c.ec);
+  float cv = fm::cbrtf_pos(float(vol));
+  bool live = c.stepped;
+  int n_done = 0, status = kOk;
+#pragma unroll 1
+  for (int k = 0; k < kSubSteps; ++k) {
+    const int b = k & 1;
+    if (live) {
+      double np, nt;
+      pr.step(p, t_amb, vol, mols, cv, [&d, &c]() { return load_atmosphere(d, c.ec); }, &np, &nt);
+      sm.p[b][lane] = np; sm.tamb[b][lane] = nt;
+      p = np; t_amb = nt;
+    }
+    role_barrier();
+    if (live) {
+      vol = sm.vol[b][lane]; mols = sm.mols[b][lane]; cv = sm.cv[b][lane];
+      ++n_done;
+      status = substep_status(sm, b, lane);
+      if (status != kOk) live = false;                                     // break (balloon.py:327-328)
+    }
+  }
+  if (c.stepped) {
+    DD(d, D_X, c.e) = c.x_pre + c.u * double(kStrideS) * double(n_done);   // balloon.py:394-395
+    DD(d, D_Y, c.e) = c.y_pre + c.v * double(kStrideS) * double(n_done);
+    DD(d, D_P, c.e) = p; DD(d, D_TAMB, c.e) = t_amb;
+  }
+  store_discrete(d, out, c.e, c.valid, c.stepped, c.fl, sm.flags_base[lane], status, pr.atm_ok,
+                 c.t_pre + kStrideS * n_done, c.ts_pre + int64_t(kStrideS) * n_done, c.last, c.uf, c.vf);
+}
+
+template <typename Smem>
+__device__ __forceinline__ void run_role_thermal(const DevState<float>& d, Smem& sm, const RoleCtx& c) {
+  const int lane = c.lane;
+  const float earth_per_area = earth_heat_per_area<float>(RR(d, R_IR, c.ec));
+  double p = c.p_pre, t_amb = DD(d, D_TAMB, c.ec), t_int = DD(d, D_TINT, c.ec);
+  float cv = fm::cbrtf_pos(float(DD(d, D_VOL, c.ec)));
+  bool live = c.stepped;
+#pragma unroll 1
+  for (int k = 0; k < kSubSteps; ++k) {
+    const int b = k & 1;
+    float dtb = 0.f;
+    if (live) {
+      dtb = roles::thermal_body(cv, t_int, t_amb, p, earth_per_area);
+      sm.dtb[b][lane] = dtb;
+    }
+    role_barrier();
+    if (live) {
+      p = sm.p[b][lane]; t_amb = sm.tamb[b][lane]; cv = sm.cv[b][lane];
+      t_int = t_int + double(dtb + sm.dts[b][lane]) * double(kStrideS);    // balloon.py:462-467
+      if (substep_status(sm, b, lane) != kOk) live = false;
+    }
+  }
+  if (c.stepped) DD(d, D_TINT, c.e) = t_int;
+}
+
+template <typename Smem>
+__device__ __forceinline__ void run_role_envelope(const DevState<float>& d, Smem& sm, const RoleCtx& c) {
+  const int lane = c.lane;
+  const double mols_gas = double(RR(d, R_MOLS_GAS, c.ec));
+  double p = c.p_pre, t_int = DD(d, D_TINT, c.ec), sp = DD(d, D_SP, c.ec), mols = DD(d, D_MOLS_AIR, c.ec);
+  double vol = DD(d, D_VOL, c.ec);
+  float acs_power = RR(d, R_ACS_W, c.ec), acs_flow = RR(d, R_ACS_FLOW, c.ec);
+  bool live = c.stepped;
+#pragma unroll 1
+  for (int k = 0; k < kSubSteps; ++k) {
+    const int b = k & 1;
+    if (live) {
+      const roles::EnvelopeOut eo = roles::envelope_acs(mols_gas, mols, t_int, p, sp, c.eff);
+      sm.vol[b][lane] = eo.volume; sm.sp[b][lane] = eo.superpressure; sm.mols[b][lane] = eo.mols_air;
+      sm.cv[b][lane] = eo.cv; sm.st_env[b][lane] = eo.status;
+      acs_power = eo.acs_power; acs_flow = eo.flow; vol = eo.volume; sp = eo.superpressure; mols = eo.mols_air;
+    }
+    role_barrier();
+    if (live) {
+      p = sm.p[b][lane];
+      t_int = t_int + double(sm.dtb[b][lane] + sm.dts[b][lane]) * double(kStrideS);
+      if (substep_status(sm, b, lane) != kOk) live = false;
+    }
+  }
+  if (c.stepped) {
+    DD(d, D_VOL, c.e) = vol; DD(d, D_SP, c.e) = sp; DD(d, D_MOLS_AIR, c.e) = mols;
+    RR(d, R_ACS_W, c.e) = acs_power; RR(d, R_ACS_FLOW, c.e) = acs_flow;
+  }
+}
+
+template <typename Smem>
+__device__ __forceinline__ void run_role_sun(const DevState<float>& d, const FusedOut& out, Smem& sm, const RoleCtx& c) {
+  const int lane = c.lane;
+  SunTrack<float> sun;
+  sun.c0 = sm.cz[0][lane]; sun.c1 = sm.cz[1][lane]; sun.c2 = sm.cz[2][lane];
+  sun.f0 = sm.sflux[0][lane]; sun.f2 = sm.sflux[1][lane];
+  double p = c.p_pre, sp = DD(d, D_SP, c.ec), charge = DD(d, D_CHARGE, c.ec);
+  float cv = fm::cbrtf_pos(float(DD(d, D_VOL, c.ec)));
+  float solar_w = RR(d, R_SOLAR_W, c.ec), load_w = RR(d, R_LOAD_W, c.ec), acs_power = RR(d, R_ACS_W, c.ec);
+  bool live = c.stepped;
+  int n_done = 0, status = kOk;
+#pragma unroll 1
+  for (int k = 0; k < kSubSteps; ++k) {
+    const int b = k & 1;
+    if (live) {
+      float cz, flux;
+      roles::sun_track_at(sun, k, &cz, &flux);
+      const roles::SunOut so = roles::sun_power(roles::sun_angles_fast(cz), flux, cv, p, sp, charge, c.eff);
+      sm.dts[b][lane] = so.d_t_solar; sm.charge[b][lane] = so.charge; sm.st_pwr[b][lane] = so.out_of_power;
+      solar_w = so.solar_w; load_w = so.load_w; acs_power = so.acs_power; charge = so.charge;
+    }
+    role_barrier();
+    if (live) {
+      p = sm.p[b][lane]; sp = sm.sp[b][lane]; cv = sm.cv[b][lane];
+      ++n_done;
+      status = substep_status(sm, b, lane);
+      if (status != kOk) live = false;
+    }
+  }
+  if (c.stepped) {
+    DD(d, D_CHARGE, c.e) = charge;
+    RR(d, R_SOLAR_W, c.e) = solar_w; RR(d, R_LOAD_W, c.e) = load_w;
+    // reward on the post-step state (env/balloon_env.py:44-102)
+    BalloonState<float> s;
+    s.x = c.x_pre + c.u * double(kStrideS) * double(n_done);
+    s.y = c.y_pre + c.v * double(kStrideS) * double(n_done);
+    s.pressure = p; s.charge = charge; s.acs_power = acs_power;
+    float el = 0.f;
+    if (c.action == kDown) {                               // excess_energy's sun (balloon.py:231-238)
+      float cz, flux;
+      roles::sun_track_at(sun, n_done, &cz, &flux);
+      el = roles::sun_angles_fast(cz).el;
+    }
+    out.reward[c.o] = perciatelli_reward<float>(s, c.action, el);
+    out.done[c.o] = (status != kOk) ? 1 : 0;
+  } else if (c.valid) {                                    // finished balloon: no-op (documented divergence)
+    out.reward[c.o] = 0.f;
+    out.done[c.o] = 1;
+  }
 }
 
 // noise_mode: 0 = no noise, 1 = evaluate the harmonics here, 2 = read d.noise_partial (k_noise ran ahead of time:
 // the observation path needs the same values for WindGP.observe, and ble_step_host queues them behind its copies)
 template <int kW>
 __global__ void __launch_bounds__(32 * kW, (kW <= 4 ? 4 : (kW <= 8 ? 2 : 1)))
-k_step_fused(DevState<float> d, const int32_t* __restrict__ actions, FusedOut out, int noise_mode, int n_steps) {
-  using Real = float;
+k_step_roles(DevState<float> d, const int32_t* __restrict__ actions, FusedOut out, int noise_mode, int n_steps) {
   extern __shared__ __align__(128) uint8_t fused_dyn[];
   FusedSmem<kW>& sm = *reinterpret_cast<FusedSmem<kW>*>(fused_dyn);
-  uint8_t* stage = fused_dyn + ((sizeof(FusedSmem<kW>) + 127) & ~size_t(127));
+  uint8_t* stage = fused_dyn + ((sizeof(FusedSmem<kW>) + 127) & ~size_t(127)) + (threadIdx.x >> 5) * kPermStageBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t e0 = int64_t(blockIdx.x) * 32;
-  const int64_t e = e0 + lane;
-  const bool valid = e < d.n;
-  const int64_t ec = valid ? e : d.n - 1;                   // clamp: every thread stays for the barriers
+  RoleCtx c;
+  c.lane = lane;
+  c.e = e0 + lane;
+  c.valid = c.e < d.n;
+  c.ec = c.valid ? c.e : d.n - 1;                           // clamp: every thread stays for the barriers
   const int count = int(min(int64_t(32), d.n - e0));
   const uint32_t bar = smem_u32(&sm.bar[warp]);
   uint32_t bar_parity = 0;
-  if (lane == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  if (lane == 0) mbar_init(bar);
   __syncwarp();
 
   for (int step = 0; step < n_steps; ++step) {
-    const int32_t* act_row = actions + int64_t(step) * d.n;
-    const uint32_t fl = d.flags[ec];
-    const bool stepped = valid && (fl & 3u) == uint32_t(kOk);
-    const double x_pre = DD(d, D_X, ec), y_pre = DD(d, D_Y, ec), p_pre = DD(d, D_P, ec);
-    const int32_t t_pre = d.t_elapsed[ec];
-    const int64_t ts_pre = d.l[int64_t(L_DATE_TIME) * d.n + ec];
-    int action = act_row[ec];
-    action = action < 0 ? 0 : (action > 2 ? 2 : action);
+    c.fl = d.flags[c.ec];
+    c.stepped = c.valid && (c.fl & 3u) == uint32_t(kOk);
+    c.x_pre = DD(d, D_X, c.ec); c.y_pre = DD(d, D_Y, c.ec); c.p_pre = DD(d, D_P, c.ec);
+    c.t_pre = d.t_elapsed[c.ec];
+    c.ts_pre = d.l[int64_t(L_DATE_TIME) * d.n + c.ec];
+    c.last = step == n_steps - 1;
+    c.o = int64_t(step) * d.n + c.e;
+    int action = actions[int64_t(step) * d.n + c.ec];
+    c.action = action < 0 ? 0 : (action > 2 ? 2 : action);
 
     // ------------------------------------------------------------------ phase 1a: tasks
+#pragma unroll 1
     for (int task = warp; task < kFusedTasks; task += kW) {
       if (task < 10) {
         if (noise_mode == 1) {
-          const int h10 = task;
-          if (lane == 0) {
-            const uint32_t bytes = uint32_t(count) * 256u;
-            const uint8_t* src = d.perm + (int64_t(h10) * d.n + e0) * 256;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(stage + warp * kPermStageBytes)), "l"(src), "r"(bytes), "r"(bar) : "memory");
-          }
-          // lattice coordinates while the copy is in flight (NoisyWindHarmonic.get_noise, simplex_wind_noise.py:116-146)
-          const double* hp = kHarmonicsInvDev[h10];
-          const double X = fma(x_pre, hp[0], double(d.offsets[(int64_t(h10) * 4 + 0) * d.n + ec]));
-          const double Y = fma(y_pre, hp[1], double(d.offsets[(int64_t(h10) * 4 + 1) * d.n + ec]));
-          const double Z = fma(p_pre, hp[2], double(d.offsets[(int64_t(h10) * 4 + 2) * d.n + ec]));
-          const double Wc = fma(double(t_pre), hp[3], double(d.offsets[(int64_t(h10) * 4 + 3) * d.n + ec]));
-          mbar_wait(bar, bar_parity);
+          if (lane == 0) stage_perm_tables(d, task, e0, count, stage, bar);
+          sm.noise[task][lane] = noise_harmonic(task, load_noise_offsets(d, task, c.ec), lane, c.x_pre, c.y_pre, c.p_pre,
+                                                c.t_pre, stage, bar, bar_parity, c.valid);
           bar_parity ^= 1u;
-          float v = 0.f;
-          if (valid) {
-            RotatedPerm perm{stage + warp * kPermStageBytes + lane * 256, lane * 4};
-            v = simplex_noise4<Real>(perm, X, Y, Z, Wc);
-          }
-          sm.noise[h10][lane] = float(kNoiseMagnitude) * v;
           __syncwarp();                                     // every lane is done with the staging buffer
         } else {
-          sm.noise[task][lane] = noise_mode == 2 ? d.noise_partial[int64_t(task) * d.n + ec] : 0.f;
+          sm.noise[task][lane] = noise_mode == 2 ? d.noise_partial[int64_t(task) * d.n + c.ec] : 0.f;
         }
-      } else if (task < 13) {
+      } else if (task < 12) {
         const int j = task - 10;
-        const SolarTime<Real> st = solar_time<Real>(ts_pre + int64_t(90 * j));
-        sm.fod[j][lane] = st.fod; sm.eqt[j][lane] = st.eq_time_deg;
+        const roles::SolarTimeFast st = roles::solar_time_fast(c.ts_pre + int64_t(180 * j));
+        sm.phase[j][lane] = st.phase;
         sm.sdecl[j][lane] = st.sin_decl; sm.cdecl[j][lane] = st.cos_decl; sm.sflux[j][lane] = st.flux;
       } else {
         // forecast at the PRE-step state (GridBasedWindField.get_forecast, grid_based_wind_field.py:70-94)
-        Real fu, fv;
-        forecast_at<Real, DevState<Real>>(d, ec, x_pre, y_pre, p_pre, t_pre, &fu, &fv);
+        float fu, fv;
+        forecast_at<float, DevState<float>>(d, c.ec, c.x_pre, c.y_pre, c.p_pre, c.t_pre, &fu, &fv);
         sm.fu[lane] = fu; sm.fv[lane] = fv;
-        // safety layers, once per agent step (balloon.py:305-313)
-        Atmosphere atm = load_atmosphere(d, ec);
-        int64_t sunrise_h = d.l[int64_t(L_SUNRISE_H) * d.n + ec], sunset = d.l[int64_t(L_SUNSET) * d.n + ec];
-        int env_state = int((fl >> 4) & 7), alt_state = int((fl >> 7) & 3), paused = int((fl >> 9) & 1);
-        const int psl = int((fl >> 10) & 1);
-        int eff = action;
-        if (psl) eff = power_safety<double>(eff, ts_pre, DD(d, D_CHARGE, ec), &sunrise_h, &sunset, &paused);
-        eff = envelope_safety<double>(eff, DD(d, D_SP, ec), &env_state);
-        roles::PressureRole pr;
-        pr.atm = atm;
-        pr.select_layer(p_pre);
-        double altitude, x0 = 0.0;
-        if (pr.layer >= 0) {
-          x0 = pr.x_from_scratch(p_pre);
-          altitude = (x0 - 1.0) * pr.tl + atm_h(pr.layer);
-        } else {
-          double t_unused;
-          atm.at_pressure(p_pre, &altitude, &t_unused);
-        }
-        eff = altitude_safety<double>(eff, altitude, &alt_state);
-        sm.eff[lane] = eff;
-        sm.x0[lane] = x0;
-        const uint32_t err = ((fl >> 11) & 1u) | (atm.ok ? 0u : 1u);
-        sm.flags_base[lane] = pack_flags(0, action, env_state, alt_state, paused, psl, int(err));
-        if (stepped) {
-          d.l[int64_t(L_SUNRISE_H) * d.n + e] = sunrise_h;
-          d.l[int64_t(L_SUNSET) * d.n + e] = sunset;
-        }
+        const SafetyOut so = safety_layers(d, c.ec, c.e, c.stepped, c.fl, c.action, c.p_pre, c.ts_pre);
+        sm.eff[lane] = so.eff; sm.x0[lane] = so.x0; sm.flags_base[lane] = so.flags_base;
       }
     }
     __syncthreads();
 
     // ------------------------------------------------------------------ phase 1b: wind, sun track
-    float uf = sm.fu[lane], vf = sm.fv[lane];
+    c.uf = sm.fu[lane]; c.vf = sm.fv[lane];
     if (noise_mode != 0) {                                  // NoisyWindComponent.get_noise (:180-211)
       float nu = 0.f, nv = 0.f;
 #pragma unroll
@@ -177,19 +407,22 @@ k_step_fused(DevState<float> d, const int32_t* __restrict__ actions, FusedOut ou
         nu += sm.noise[h][lane] * kBlendU[h];
         nv += sm.noise[5 + h][lane] * kBlendV[h];
       }
-      uf += nu * kBlendScaleU;
-      vf += nv * kBlendScaleV;
+      c.uf += nu * kBlendScaleU;
+      c.vf += nv * kBlendScaleV;
     }
-    const double u = double(uf), v = double(vf);
-    if (warp < 3) {
+    c.u = double(c.uf); c.v = double(c.vf);
+    if (warp < 3) {                                         // one point of the quadratic sun track each (SunTrack)
       const int j = warp;
+      const roles::StationTrig stn = roles::station_trig(RR(d, R_LAT0, c.ec), RR(d, R_LNG0, c.ec));
+      const double pa = sm.phase[0][lane];
+      double pb = sm.phase[1][lane];
+      if (pb < pa - kPi) pb += 2.0 * kPi;                  // fraction_of_day wrapped at midnight
+      const double w1 = 0.5 * j, w0 = 1.0 - w1;            // the time-only terms move linearly within the step
+      const float sd = float(w0) * sm.sdecl[0][lane] + float(w1) * sm.sdecl[1][lane];
+      const float cd = float(w0) * sm.cdecl[0][lane] + float(w1) * sm.cdecl[1][lane];
       const double dt_s = 90.0 * j;
-      Real lat, lng;
-      latlng_from_offset<Real>(RR(d, R_LAT0, ec), RR(d, R_LNG0, ec), Real(x_pre + u * dt_s), Real(y_pre + v * dt_s), &lat, &lng);
-      SolarTime<Real> st;
-      st.fod = sm.fod[j][lane]; st.eq_time_deg = sm.eqt[j][lane];
-      st.sin_decl = sm.sdecl[j][lane]; st.cos_decl = sm.cdecl[j][lane]; st.flux = sm.sflux[j][lane];
-      sm.cz[j][lane] = solar_cos_zenith<Real>(st, lat, lng);
+      sm.cz[j][lane] = roles::cos_zenith_fast(stn, w0 * pa + w1 * pb, sd, cd, float(c.x_pre + c.u * dt_s),
+                                              float(c.y_pre + c.v * dt_s));
     }
     if (warp >= 4) {
       if (n_steps == 1) return;
@@ -197,161 +430,184 @@ k_step_fused(DevState<float> d, const int32_t* __restrict__ actions, FusedOut ou
       continue;
     }
     role_barrier();
+    c.eff = sm.eff[lane];
 
     // ------------------------------------------------------------------ phase 2: 18 sub-steps, one role per warp
-    const int eff = sm.eff[lane];
-    SunTrack<Real> sun;
-    sun.c0 = sm.cz[0][lane]; sun.c1 = sm.cz[1][lane]; sun.c2 = sm.cz[2][lane];
-    sun.f0 = sm.sflux[0][lane]; sun.f2 = sm.sflux[2][lane];
-    bool live = stepped;
-    int n_done = 0, status = kOk;
-    // state every role carries
-    double p = p_pre;
-    double t_int = DD(d, D_TINT, ec);
-    float cv = 0.f;
-    // role-private state
-    roles::PressureRole pr;                                  // P
-    double t_amb = 0, vol = 0, mols = 0;                     // P (t_amb also T)
-    float earth_per_area = 0.f;                              // T
-    double sp = 0, mols_gas = 0;                             // E, S (sp)
-    double charge = 0;                                       // S
-    float acs_power = 0.f, acs_flow = 0.f, solar_w = 0.f, load_w = 0.f;
-    {
-      const double vol0 = DD(d, D_VOL, ec);
-      cv = fm::cbrtf_pos(float(vol0));
-      if (warp == 0) {
-        pr.init(load_atmosphere(d, ec), double(RR(d, R_MOLS_GAS, ec)), p_pre);
-        const double x0 = sm.x0[lane];
-        if (pr.layer >= 0 && x0 > 0.0) pr.seed_x(p_pre, x0);
-        t_amb = DD(d, D_TAMB, ec); vol = vol0; mols = DD(d, D_MOLS_AIR, ec);
-      } else if (warp == 1) {
-        t_amb = DD(d, D_TAMB, ec);
-        earth_per_area = earth_heat_per_area<Real>(RR(d, R_IR, ec));
-      } else if (warp == 2) {
-        sp = DD(d, D_SP, ec); mols = DD(d, D_MOLS_AIR, ec); mols_gas = double(RR(d, R_MOLS_GAS, ec));
-        acs_power = RR(d, R_ACS_W, ec); acs_flow = RR(d, R_ACS_FLOW, ec);
-      } else {
-        sp = DD(d, D_SP, ec); charge = DD(d, D_CHARGE, ec);
-        solar_w = RR(d, R_SOLAR_W, ec); load_w = RR(d, R_LOAD_W, ec);
-      }
-    }
-#pragma unroll 1
-    for (int k = 0; k < kSubSteps; ++k) {
-      const int b = k & 1;
-      if (live) {
-        if (warp == 0) {
-          double np, nt;
-          pr.step(p, t_amb, vol, mols, cv, &np, &nt);
-          sm.p[b][lane] = np; sm.tamb[b][lane] = nt;
-        } else if (warp == 1) {
-          sm.dtb[b][lane] = roles::thermal_body(cv, t_int, t_amb, p, earth_per_area);
-        } else if (warp == 2) {
-          const roles::EnvelopeOut eo = roles::envelope_acs(mols_gas, mols, t_int, p, sp, eff);
-          sm.vol[b][lane] = eo.volume; sm.sp[b][lane] = eo.superpressure; sm.mols[b][lane] = eo.mols_air;
-          sm.cv[b][lane] = eo.cv; sm.st_env[b][lane] = eo.status;
-          acs_power = eo.acs_power; acs_flow = eo.flow; vol = eo.volume;
-        } else {
-          float cz, flux;
-          roles::sun_track_at(sun, k, &cz, &flux);
-          const roles::SunOut so = roles::sun_power(roles::sun_angles_fast(cz), flux, cv, p, sp, charge, eff);
-          sm.dts[b][lane] = so.d_t_solar; sm.charge[b][lane] = so.charge; sm.st_pwr[b][lane] = so.out_of_power;
-          solar_w = so.solar_w; load_w = so.load_w; acs_power = so.acs_power;
-        }
-      }
-      role_barrier();
-      if (live) {
-        p = sm.p[b][lane];
-        t_int = t_int + double(sm.dtb[b][lane] + sm.dts[b][lane]) * double(kStrideS);     // balloon.py:462-467
-        cv = sm.cv[b][lane];
-        if (warp == 0) { t_amb = sm.tamb[b][lane]; vol = sm.vol[b][lane]; mols = sm.mols[b][lane]; }
-        else if (warp == 1) { t_amb = sm.tamb[b][lane]; }
-        else if (warp == 2) { sp = sm.sp[b][lane]; mols = sm.mols[b][lane]; }
-        else { sp = sm.sp[b][lane]; charge = sm.charge[b][lane]; }
-        ++n_done;
-        status = sm.st_pwr[b][lane] ? int(kOutOfPower) : sm.st_env[b][lane];     // later assignment wins (:541-542)
-        if (status != kOk) live = false;                                         // break (:327-328)
-      }
-    }
-
-    // ------------------------------------------------------------------ epilogue: each role stores what it owns
-    const bool last = step == n_steps - 1;
-    const int64_t o = int64_t(step) * d.n + e;
-    if (warp == 0) {
-      if (stepped) {
-        DD(d, D_X, e) = x_pre + u * double(kStrideS) * double(n_done);     // balloon.py:394-395
-        DD(d, D_Y, e) = y_pre + v * double(kStrideS) * double(n_done);
-        DD(d, D_P, e) = p; DD(d, D_TAMB, e) = t_amb;
-        d.l[int64_t(L_DATE_TIME) * d.n + e] = ts_pre + int64_t(kStrideS) * n_done;     // :546-547
-        d.t_elapsed[e] = t_pre + kStrideS * n_done;
-        const uint32_t nf = sm.flags_base[lane] | uint32_t(status) | (pr.atm.ok ? 0u : (1u << 11));
-        d.flags[e] = nf;
-        if (out.sim_error != nullptr) out.sim_error[e] = uint8_t((nf >> 11) & 1u);
-      } else if (valid && out.sim_error != nullptr) {
-        out.sim_error[e] = uint8_t((fl >> 11) & 1u);
-      }
-      if (valid) {
-        if (out.wind_uv != nullptr && last) out.wind_uv[e] = stepped ? make_float2(uf, vf) : make_float2(0.f, 0.f);
-        if (out.status != nullptr) out.status[e] = uint8_t(stepped ? status : int(fl & 3u));
-        if (out.time_elapsed != nullptr) out.time_elapsed[e] = stepped ? t_pre + kStrideS * n_done : t_pre;
-      }
-    } else if (warp == 1) {
-      if (stepped) DD(d, D_TINT, e) = t_int;
-    } else if (warp == 2) {
-      if (stepped) {
-        DD(d, D_VOL, e) = vol;
-        DD(d, D_SP, e) = sp; DD(d, D_MOLS_AIR, e) = mols;
-        RR(d, R_ACS_W, e) = acs_power; RR(d, R_ACS_FLOW, e) = acs_flow;
-      }
-    } else {
-      if (stepped) {
-        DD(d, D_CHARGE, e) = charge;
-        RR(d, R_SOLAR_W, e) = solar_w; RR(d, R_LOAD_W, e) = load_w;
-        // reward on the post-step state (env/balloon_env.py:44-102)
-        BalloonState<Real> s;
-        s.x = x_pre + u * double(kStrideS) * double(n_done);
-        s.y = y_pre + v * double(kStrideS) * double(n_done);
-        s.pressure = p; s.charge = charge; s.acs_power = acs_power;
-        float el = 0.f;
-        if (action == kDown) {                             // excess_energy's sun (balloon.py:231-238)
-          float cz, flux;
-          roles::sun_track_at(sun, n_done, &cz, &flux);
-          el = roles::sun_angles_fast(cz).el;
-        }
-        out.reward[o] = perciatelli_reward<Real>(s, action, el);
-        out.done[o] = (status != kOk) ? 1 : 0;
-      } else if (valid) {                                  // finished balloon: no-op (documented divergence)
-        out.reward[o] = 0.f;
-        out.done[o] = 1;
-      }
-    }
+    if (warp == 0) run_role_pressure(d, out, sm, c);
+    else if (warp == 1) run_role_thermal(d, sm, c);
+    else if (warp == 2) run_role_envelope(d, sm, c);
+    else run_role_sun(d, out, sm, c);
     if (n_steps > 1) __syncthreads();
   }
 }
 
-template <int kW> static size_t fused_smem() { return ((sizeof(FusedSmem<kW>) + 127) & ~size_t(127)) + size_t(kW) * kPermStageBytes; }
+// =====================================================================================================================
+// Throughput shape
+// =====================================================================================================================
+constexpr int kWarpsPerCta = 4;
 
-template <int kW> static cudaError_t setup_one(int* blocks) {
-  cudaError_t e = cudaFuncSetAttribute(k_step_fused<kW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_smem<kW>()));
+#ifndef BLE_WARP_MIN_BLOCKS
+#define BLE_WARP_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(32 * kWarpsPerCta, BLE_WARP_MIN_BLOCKS)
+k_step_warp(DevState<float> d, const int32_t* __restrict__ actions, FusedOut out, int noise_mode, int n_steps) {
+  extern __shared__ __align__(128) uint8_t warp_dyn[];
+  __shared__ alignas(8) uint64_t s_bar[kWarpsPerCta];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* stage = warp_dyn + warp * kPermStageBytes;
+  const int64_t e0 = (int64_t(blockIdx.x) * kWarpsPerCta + warp) * 32;
+  if (e0 >= d.n) return;                                    // whole warp out of range (no CTA-wide barrier anywhere)
+  const int64_t e = e0 + lane;
+  const bool valid = e < d.n;
+  const int64_t ec = valid ? e : d.n - 1;
+  const int count = int(min(int64_t(32), d.n - e0));
+  const uint32_t bar = smem_u32(&s_bar[warp]);
+  uint32_t bar_parity = 0;
+  if (lane == 0) mbar_init(bar);
+  __syncwarp();
+
+  for (int step = 0; step < n_steps; ++step) {
+    const uint32_t fl = d.flags[ec];
+    const bool stepped = valid && (fl & 3u) == uint32_t(kOk);
+    const double x_pre = DD(d, D_X, ec), y_pre = DD(d, D_Y, ec), p_pre = DD(d, D_P, ec);
+    const int32_t t_pre = d.t_elapsed[ec];
+    const int64_t ts_pre = d.l[int64_t(L_DATE_TIME) * d.n + ec];
+    const int64_t o = int64_t(step) * d.n + e;
+    int action = actions[int64_t(step) * d.n + ec];
+    action = action < 0 ? 0 : (action > 2 ? 2 : action);
+
+    // ---- wind at the PRE-step state: forecast window + 10 noise harmonics ----
+    if (noise_mode == 1 && lane == 0) stage_perm_tables(d, 0, e0, count, stage, bar);
+    float uf, vf;
+    forecast_at<float, DevState<float>>(d, ec, x_pre, y_pre, p_pre, t_pre, &uf, &vf);
+    if (noise_mode != 0) {
+      float nu = 0.f, nv = 0.f;
+      NoiseOffsets off = load_noise_offsets(d, 0, ec);
+#pragma unroll 1
+      for (int h = 0; h < 10; ++h) {
+        float nh;
+        if (noise_mode == 1) {
+          const NoiseOffsets cur = off;
+          if (h + 1 < 10) off = load_noise_offsets(d, h + 1, ec);      // in flight while this harmonic is evaluated
+          nh = noise_harmonic(h, cur, lane, x_pre, y_pre, p_pre, t_pre, stage, bar, bar_parity, valid);
+          bar_parity ^= 1u;
+          __syncwarp();                                     // every lane is done with the staging buffer
+          if (h + 1 < 10 && lane == 0) stage_perm_tables(d, h + 1, e0, count, stage, bar);
+        } else {
+          nh = d.noise_partial[int64_t(h) * d.n + ec];
+        }
+        if (h < 5) nu += nh * kBlendU[h]; else nv += nh * kBlendV[h - 5];
+      }
+      uf += nu * kBlendScaleU;
+      vf += nv * kBlendScaleV;
+    }
+
+    // ---- safety layers, sun track ----
+    const SafetyOut so = safety_layers(d, ec, e, stepped, fl, action, p_pre, ts_pre);
+    const SunTrack<float> sun = roles::sun_track_fast(roles::solar_time_fast(ts_pre), roles::solar_time_fast(ts_pre + 180),
+                                                      RR(d, R_LAT0, ec), RR(d, R_LNG0, ec), x_pre, y_pre, double(uf), double(vf));
+
+    // ---- 18 sub-steps, the four roles back to back ----
+    roles::PressureRole pr;
+    pr.init(load_atmosphere(d, ec), double(RR(d, R_MOLS_GAS, ec)), p_pre);
+    if (pr.layer >= 0 && so.x0 > 0.0) pr.seed_x(p_pre, so.x0);
+    const double mols_gas = double(RR(d, R_MOLS_GAS, ec));
+    const float earth_per_area = earth_heat_per_area<float>(RR(d, R_IR, ec));
+    double p = p_pre, t_amb = DD(d, D_TAMB, ec), t_int = DD(d, D_TINT, ec), vol = DD(d, D_VOL, ec);
+    double sp = DD(d, D_SP, ec), mols = DD(d, D_MOLS_AIR, ec), charge = DD(d, D_CHARGE, ec);
+    float cv = fm::cbrtf_pos(float(vol));
+    float acs_power = RR(d, R_ACS_W, ec), acs_flow = RR(d, R_ACS_FLOW, ec);
+    float solar_w = RR(d, R_SOLAR_W, ec), load_w = RR(d, R_LOAD_W, ec);
+    int n_done = 0, status = kOk;
+    if (stepped) {
+#pragma unroll 1
+      for (int k = 0; k < kSubSteps; ++k) {
+        float cz, flux;
+        roles::sun_track_at(sun, k, &cz, &flux);
+        double np, nt;
+        pr.step(p, t_amb, vol, mols, cv, [&d, ec]() { return load_atmosphere(d, ec); }, &np, &nt);
+        const float dtb = roles::thermal_body(cv, t_int, t_amb, p, earth_per_area);
+        const roles::EnvelopeOut eo = roles::envelope_acs(mols_gas, mols, t_int, p, sp, so.eff);
+        const roles::SunOut po = roles::sun_power(roles::sun_angles_fast(cz), flux, cv, p, sp, charge, so.eff);
+        p = np; t_amb = nt;
+        t_int = t_int + double(dtb + po.d_t_solar) * double(kStrideS);     // balloon.py:462-467
+        vol = eo.volume; sp = eo.superpressure; mols = eo.mols_air; cv = eo.cv;
+        charge = po.charge;
+        acs_power = eo.acs_power; acs_flow = eo.flow; solar_w = po.solar_w; load_w = po.load_w;
+        ++n_done;
+        status = po.out_of_power ? int(kOutOfPower) : eo.status;           // later assignment wins (:541-542)
+        if (status != kOk) break;                                          // :327-328
+      }
+    }
+
+    // ---- epilogue ----
+    // (x, y, time are re-read here rather than kept in registers across the sub-step loop: they are L1 hits)
+    const int32_t t_old = d.t_elapsed[ec];
+    const int64_t ts_old = d.l[int64_t(L_DATE_TIME) * d.n + ec];
+    if (stepped) {
+      const double travelled = double(kStrideS) * double(n_done);
+      const double x_new = DD(d, D_X, e) + double(uf) * travelled;         // balloon.py:394-395
+      const double y_new = DD(d, D_Y, e) + double(vf) * travelled;
+      DD(d, D_X, e) = x_new; DD(d, D_Y, e) = y_new; DD(d, D_P, e) = p;
+      DD(d, D_TAMB, e) = t_amb; DD(d, D_TINT, e) = t_int; DD(d, D_VOL, e) = vol;
+      DD(d, D_SP, e) = sp; DD(d, D_MOLS_AIR, e) = mols; DD(d, D_CHARGE, e) = charge;
+      RR(d, R_ACS_W, e) = acs_power; RR(d, R_ACS_FLOW, e) = acs_flow;
+      RR(d, R_SOLAR_W, e) = solar_w; RR(d, R_LOAD_W, e) = load_w;
+      BalloonState<float> s;                                               // reward (env/balloon_env.py:44-102)
+      s.x = x_new; s.y = y_new; s.pressure = p; s.charge = charge; s.acs_power = acs_power;
+      float el = 0.f;
+      if (action == kDown) {                                               // excess_energy's sun (balloon.py:231-238)
+        float cz, flux;
+        roles::sun_track_at(sun, n_done, &cz, &flux);
+        el = roles::sun_angles_fast(cz).el;
+      }
+      out.reward[o] = perciatelli_reward<float>(s, action, el);
+      out.done[o] = (status != kOk) ? 1 : 0;
+    } else if (valid) {                                                    // finished balloon: no-op
+      out.reward[o] = 0.f;
+      out.done[o] = 1;
+    }
+    store_discrete(d, out, e, valid, stepped, fl, so.flags_base, status, pr.atm_ok, t_old + kStrideS * n_done,
+                   ts_old + int64_t(kStrideS) * n_done, step == n_steps - 1, uf, vf);
+    if (n_steps > 1) __syncwarp();
+  }
+}
+
+// =====================================================================================================================
+// Launcher
+// =====================================================================================================================
+template <int kW> static size_t roles_smem() { return ((sizeof(FusedSmem<kW>) + 127) & ~size_t(127)) + size_t(kW) * kPermStageBytes; }
+static size_t warp_smem() { return size_t(kWarpsPerCta) * kPermStageBytes; }
+
+template <typename Kernel> static cudaError_t setup_kernel(Kernel kernel, int threads, size_t smem, int* blocks) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k_step_fused<kW>, 32 * kW, fused_smem<kW>());
+  // all of the unified L1 / shared storage as shared memory: the kernels' global traffic is streaming (state rows,
+  // one 128-byte window per balloon), what they need is resident CTAs
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, int(cudaSharedmemCarveoutMaxShared));
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kernel, threads, smem);
 }
 
 cudaError_t fused_setup(int blocks_per_sm[4]) {
-  cudaError_t e = setup_one<4>(&blocks_per_sm[0]);
-  if (e == cudaSuccess) e = setup_one<8>(&blocks_per_sm[1]);
-  if (e == cudaSuccess) e = setup_one<10>(&blocks_per_sm[2]);
-  if (e == cudaSuccess) e = setup_one<14>(&blocks_per_sm[3]);
+  cudaError_t e = setup_kernel(k_step_warp, 32 * kWarpsPerCta, warp_smem(), &blocks_per_sm[0]);
+  if (e == cudaSuccess) e = setup_kernel(k_step_roles<4>, 32 * 4, roles_smem<4>(), &blocks_per_sm[1]);
+  if (e == cudaSuccess) e = setup_kernel(k_step_roles<8>, 32 * 8, roles_smem<8>(), &blocks_per_sm[2]);
+  if (e == cudaSuccess) e = setup_kernel(k_step_roles<14>, 32 * 14, roles_smem<14>(), &blocks_per_sm[3]);
   return e;
 }
 
-void fused_launch(int warps, const DevState<float>& d, const int32_t* actions, const FusedOut& out, int noise_mode,
+void fused_launch(int shape, const DevState<float>& d, const int32_t* actions, const FusedOut& out, int noise_mode,
                   int n_steps, cudaStream_t s) {
   const unsigned grid = unsigned((d.n + 31) / 32);
-  switch (warps) {
-    case 14: k_step_fused<14><<<grid, 32 * 14, fused_smem<14>(), s>>>(d, actions, out, noise_mode, n_steps); break;
-    case 10: k_step_fused<10><<<grid, 32 * 10, fused_smem<10>(), s>>>(d, actions, out, noise_mode, n_steps); break;
-    case 8: k_step_fused<8><<<grid, 32 * 8, fused_smem<8>(), s>>>(d, actions, out, noise_mode, n_steps); break;
-    default: k_step_fused<4><<<grid, 32 * 4, fused_smem<4>(), s>>>(d, actions, out, noise_mode, n_steps); break;
+  switch (shape) {
+    case 14: k_step_roles<14><<<grid, 32 * 14, roles_smem<14>(), s>>>(d, actions, out, noise_mode, n_steps); break;
+    case 8: k_step_roles<8><<<grid, 32 * 8, roles_smem<8>(), s>>>(d, actions, out, noise_mode, n_steps); break;
+    case 4: k_step_roles<4><<<grid, 32 * 4, roles_smem<4>(), s>>>(d, actions, out, noise_mode, n_steps); break;
+    default:
+      k_step_warp<<<unsigned((d.n + 32 * kWarpsPerCta - 1) / (32 * kWarpsPerCta)), 32 * kWarpsPerCta, warp_smem(), s>>>(
+          d, actions, out, noise_mode, n_steps);
+      break;
   }
 }
 

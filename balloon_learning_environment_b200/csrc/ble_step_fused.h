@@ -16,12 +16,14 @@ struct FusedOut {
   uint8_t* sim_error;       // [n] or nullptr: sticky "atmosphere query out of range / search failed" flag
 };
 
-constexpr int kFusedShapes[4] = {4, 8, 10, 14};      // warps per 32-balloon CTA the kernel is instantiated for
+// Kernel shapes: 0 = k_step_warp (throughput shape: one warp carries 32 balloons through the whole step, 4 warps / CTA);
+// 4 / 8 / 14 = k_step_roles<kW> (latency shape: kW warps share the 32 balloons of a CTA).
+constexpr int kFusedShapes[4] = {0, 4, 8, 14};
 
-// Opts every shape into its dynamic shared memory and reports how many of its CTAs one SM holds.
+// Opts every shape into its dynamic shared memory and reports how many of its CTAs one SM holds (same order).
 cudaError_t fused_setup(int blocks_per_sm[4]);
 // noise_mode: 0 = no noise, 1 = evaluate the 10 harmonics in the kernel, 2 = read d.noise_partial (k_noise ran ahead)
-void fused_launch(int warps, const DevState<float>& d, const int32_t* actions, const FusedOut& out, int noise_mode,
+void fused_launch(int shape, const DevState<float>& d, const int32_t* actions, const FusedOut& out, int noise_mode,
                   int n_steps, cudaStream_t stream);
 
 }  // namespace ble

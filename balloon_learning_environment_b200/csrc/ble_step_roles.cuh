@@ -18,9 +18,20 @@
 namespace ble {
 namespace roles {
 
+// Rare paths are kept out of line: the step kernel is instruction-cache bound if they are inlined at every use.
+BLE_HD_NOINLINE double pow_by_exp_log(double x, double k) { return exp(k * log(x)); }
+BLE_HD_NOINLINE void secant_slow_path(Atmosphere atm, double p, double direction, double* t_new, double* dh, bool* ok) {
+  atm.lcache = -1;
+  atm.incremental = false;
+  atm.temperature_and_secant(p, direction, t_new, dh);
+  *ok = atm.ok;
+}
+
 // ---- role P: buoyancy -> dh/dt -> dp/dt, ambient temperature (balloon.py:412-445,457-458) -----------
+// Holds only what the fast path reads, so that it lives in registers; the atmosphere tables themselves are fetched
+// through `load_atm()` (a callable returning an Atmosphere) on the rare paths: first use, a change of layer, a
+// pressure outside layers 0..2.
 struct PressureRole {
-  Atmosphere atm;            // tables (slow path: layer change, outside layers 0..2)
   double mass0;              // kMHe * mols_gas + envelope + payload
   // cached atmosphere layer of the balloon (standard_atmosphere.py:122-154)
   int layer;                 // 0, 1, 2; -1 = take the generic path
@@ -28,18 +39,17 @@ struct PressureRole {
   double k, ti, pi, tl;      // k = -R_air L / g, T_i, P_i, T_i / L
   double c1, c2, c3, c4, c5, c6, c7, c8;   // binomial coefficients C(k, n)
   // X = (p / P_i)^k at the pressure of the previous evaluation
-  bool have_x;
+  bool have_x, atm_ok;
   double x_prev, p_prev, inv_p_prev;
 
-  BLE_HD void select_layer(double p) {
-    double lapse = 0, hi = 0;
+  BLE_HD void select_layer(const Atmosphere& atm, double p) {
+    double lapse = 0;
     layer = -1;
     if (p > atm.p3 && p <= kAtmP0) {
       if (p > atm.p1) { layer = 0; lapse = atm.l0; ti = kAtmT0; pi = kAtmP0; p_lo = atm.p1; p_hi = kAtmP0; }
       else if (p > atm.p2) { layer = 1; lapse = atm.l1; ti = atm.t1; pi = atm.p1; p_lo = atm.p2; p_hi = atm.p1; }
       else { layer = 2; lapse = atm.l2; ti = atm.t2; pi = atm.p2; p_lo = atm.p3; p_hi = atm.p2; }
     }
-    (void)hi;
     have_x = false;
     if (layer < 0 || lapse == 0.0) { layer = -1; return; }
     k = -kRAir * lapse / kGravity;
@@ -54,16 +64,16 @@ struct PressureRole {
     c8 = c7 * (k - 7.0) * (1.0 / 8.0);
   }
 
-  BLE_HD void init(const Atmosphere& a, double mols_gas, double p) {
-    atm = a;
-    atm.incremental = false;
+  BLE_HD void init(const Atmosphere& atm, double mols_gas, double p) {
     mass0 = kMHe * mols_gas + kEnvelopeMass + kPayloadMass;
-    select_layer(p);
+    atm_ok = true;
+    x_prev = 1.0; p_prev = p; inv_p_prev = 0.0;
+    select_layer(atm, p);
   }
 
   // X = (p / P_i)^k from scratch (once per agent step; also what the altitude safety layer needs:
   // h = (X - 1) T_i / L + H_i).
-  BLE_HD double x_from_scratch(double p) const { return exp(k * log(p / pi)); }
+  BLE_HD double x_from_scratch(double p) const { return pow_by_exp_log(p / pi, k); }
 
   BLE_HD void seed_x(double p, double x) { have_x = true; p_prev = p; x_prev = x; inv_p_prev = fm::rcp(p); }
 
@@ -77,7 +87,8 @@ struct PressureRole {
 
   // One sub-step: new pressure and the ambient temperature AT THE OLD pressure (balloon.py:457-458).
   // cv = cbrt(volume).
-  BLE_HD void step(double p, double t_ambient, double volume, double mols_air, float cv,
+  template <typename LoadAtm>
+  BLE_HD void step(double p, double t_ambient, double volume, double mols_air, float cv, LoadAtm load_atm,
                    double* new_pressure, double* new_t_ambient) {
     const double dt = double(kStrideS);
     const double a = p * kMAir, b = kR * t_ambient;                        // rho = a / b
@@ -100,9 +111,11 @@ struct PressureRole {
       t_new = ti * x;                                                      // standard_atmosphere.py:148-149
       dh = tl * x * series;                                                // h(p + dir) - h(p) :438-441
     } else {
-      atm.lcache = -1;
-      atm.temperature_and_secant(p, direction, &t_new, &dh);
-      select_layer(p);
+      const Atmosphere atm = load_atm();
+      bool ok;
+      secant_slow_path(atm, p, direction, &t_new, &dh, &ok);
+      atm_ok = atm_ok && ok;
+      select_layer(atm, p);
     }
     *new_t_ambient = t_new;
     *new_pressure = fma(dh_dt_abs * dt, fm::rcp(dh), p);                   // p + (dir / dh) (dir |dh/dt|) dt :442-445
@@ -270,6 +283,119 @@ BLE_HD void sun_track_at(const SunTrack<float>& tr, int k, float* cz, float* flu
   *flux = tr.f0 + t * (tr.f2 - tr.f0);
 }
 
+// ---- the sun along one agent step (production build) ---------------------------------------------------------
+// Same quantities as solar_time<float> / latlng_from_offset<float> / solar_cos_zenith<float> (ble_physics.cuh,
+// following env/balloon/solar.py:43-174 and utils/spherical_geometry.py:44-76), reshaped so that one evaluation
+// needs 6 sincos instead of 14 libm trig calls, 2 atan2, an asin and 4 fp64 fmod:
+//   * double / triple angles by identities; cos(declination) = sqrt(1 - sin^2);
+//   * heading = atan2(x, y) only ever enters through its sine and cosine, which are x / r and y / r;
+//   * the hour angle only enters through its cosine, so the fmod(., 1440) and the +-pi wrap (solar.py:113-120) drop
+//     out: cos(ha) = -cos(2 pi fod + eq_time pi / 720 + lng), and with lng = lng0 + atan2(Y, X) the atan2 is
+//     replaced by the angle-addition formula on (X, Y) / hypot(X, Y).
+struct SolarTimeFast {
+  double phase;            // 2 pi fraction_of_day + equation_of_time [min] * pi / 720, in radians (fp64, unreduced)
+  float sin_decl, cos_decl, flux;
+};
+
+BLE_HD SolarTimeFast solar_time_fast(int64_t ts) {
+  SolarTimeFast o;
+  int64_t days = ts / 86400;
+  int64_t sod = ts - days * 86400;
+  if (sod < 0) { sod += 86400; days -= 1; }
+  const double fod = double(sod) * (1.0 / 86400.0);                        // solar.py:66-68
+  const double jc = ((2440587.5 + double(days)) + fod - 2451545.0) * (1.0 / 36525.0);   // :71-79
+  const double l0_deg = 280.46646 + jc * (36000.76983 + jc * 0.0003032);   // :82-83
+  const double m0_deg = 357.52911 + jc * (35999.05029 - 0.0001537 * jc);   // :88-89
+  const double om_deg = 125.04 - 1934.136 * jc;
+  const float l0 = float(fm::mod_pos(l0_deg, 360.0, 1.0 / 360.0) * (kPi / 180.0));
+  const float m0 = float(fm::mod_pos(m0_deg, 360.0, 1.0 / 360.0) * (kPi / 180.0));
+  const float om = float(fm::mod_pos(om_deg, 360.0, 1.0 / 360.0) * (kPi / 180.0));
+  const float jcr = float(jc);
+  float sl, cl, sm, cm, so, co;
+  fm::sincosf_fast(l0, &sl, &cl);
+  fm::sincosf_fast(m0, &sm, &cm);
+  fm::sincosf_fast(om, &so, &co);
+  const float sin2l0 = 2.0f * sl * cl, cos2l0 = 1.0f - 2.0f * sl * sl, sin4l0 = 2.0f * sin2l0 * cos2l0;
+  const float sin2m0 = 2.0f * sm * cm, sin3m0 = sm * (3.0f - 4.0f * sm * sm);
+  const float mean_obl = r_rad(23.0f + (26.0f + ((21.448f - jcr * (46.815f + jcr * (0.00059f - jcr * 0.001813f)))) *
+                               (1.0f / 60.0f)) * (1.0f / 60.0f));          // :94-97
+  const float obl = mean_obl + r_rad(0.00256f * co);                       // :99-100
+  float sh, ch;
+  fm::sincosf_fast(0.5f * obl, &sh, &ch);
+  const float ty = sh * fm::rcpf(ch);
+  const float var_y = ty * ty;                                             // :102
+  const float sin_obl = 2.0f * sh * ch;
+  const float ecc = 0.016708634f - jcr * (0.000042037f + 0.0000001267f * jcr);   // :104-105
+  const float eq_time = 4.0f * (var_y * sin2l0 - 2.0f * ecc * sm + 4.0f * ecc * var_y * sm * cos2l0 -
+                                0.5f * var_y * var_y * sin4l0 - 1.25f * ecc * ecc * sin2m0);   // :107-111
+  const float eq_center = r_rad(sm * (1.914602f - jcr * (0.004817f + 0.000014f * jcr)) +
+                                sin2m0 * (0.019993f - 0.000101f * jcr) + sin3m0 * 0.000289f);   // :122-127
+  const float app_long = l0 + eq_center - r_rad(0.00569f - 0.00478f * so);                    // :129-131
+  float sa, ca;
+  fm::sincosf_fast(app_long, &sa, &ca);
+  o.sin_decl = sin_obl * sa;                                               // :132-133
+  o.cos_decl = fm::sqrtf_pos(fmaxf(1.0f - o.sin_decl * o.sin_decl, 0.0f));
+  const float e1 = (1.0f + ecc) * fm::rcpf(1.0f - ecc);
+  o.flux = 1366.0f * (1.0f + 0.5f * (e1 * e1 - 1.0f) * cm);                // :170-172
+  // degrees(eq_time) is what the reference adds, as minutes, to the hour angle (:115): minutes * pi / 720 radians
+  o.phase = 2.0 * kPi * fod + double(r_deg(eq_time)) * (kPi / 720.0);
+  return o;
+}
+
+// Per-step constants of a balloon's station: sin / cos of the centre latitude.
+struct StationTrig { float sfl, cfl; double lng0; };
+BLE_HD StationTrig station_trig(float lat0, float lng0) {
+  StationTrig t;
+  fm::sincosf_fast(lat0, &t.sfl, &t.cfl);
+  t.lng0 = double(lng0);
+  return t;
+}
+
+// cos(zenith) at offset (x, y) [m] from the station (utils/spherical_geometry.py:61-76 + solar.py:113-138).
+BLE_HD float cos_zenith_fast(const StationTrig& st, double phase, float sin_decl, float cos_decl, float x, float y) {
+  const float r2 = x * x + y * y;
+  float ch = 1.0f, sh = 0.0f, angle = 0.0f;                                // heading = atan2(0, 0) = 0 at the station
+  if (r2 > 0.0f) {
+    const float inv_r = fm::rsqrtf_pos(r2);
+    ch = y * inv_r; sh = x * inv_r;                                        // cos / sin of atan2(x, y) :61
+    angle = (r2 * inv_r) * float(1.0 / kEarthRadiusM);                     // :62
+  }
+  float sa, ca;
+  fm::sincosf_fast(angle, &sa, &ca);
+  float sin_lat = ca * st.sfl + sa * st.cfl * ch;                          // :69-70
+  sin_lat = fminf(fmaxf(sin_lat, -1.0f), 1.0f);
+  const float X = ca - st.sfl * sin_lat, Y = sa * st.cfl * sh;             // d_lng = atan2(Y, X)
+  const float h2 = X * X + Y * Y;
+  float cosd = 1.0f, sind = 0.0f;
+  if (h2 > 1e-30f) { const float inv_h = fm::rsqrtf_pos(h2); cosd = X * inv_h; sind = Y * inv_h; }
+  const double a = phase + st.lng0;
+  const float ar = float(fma(-2.0 * kPi, rint(a * (0.5 / kPi)), a));       // reduced to [-pi, pi] in fp64
+  float sA, cA;
+  fm::sincosf_fast(ar, &sA, &cA);
+  const float cos_ha = -(cA * cosd - sA * sind);                           // cos(hour angle), solar.py:113-120
+  const float cos_lat = fm::sqrtf_pos(fmaxf(1.0f - sin_lat * sin_lat, 0.0f));
+  const float cz = sin_lat * sin_decl + cos_lat * cos_decl * cos_ha;       // :135-138
+  return fminf(fmaxf(cz, -1.0f), 1.0f);
+}
+
+// The quadratic sun track of one agent step: cos(zenith) at t0, t0 + 90 s, t0 + 180 s (SunTrack<float>, ble_physics.cuh).
+// The time-only terms are evaluated at the two ends; at the mid point they are the mean of the ends (declination and
+// equation of time move by < 1.5e-5 rad in 180 s: the interpolation error is below 1e-10).
+BLE_HD SunTrack<float> sun_track_fast(const SolarTimeFast& a, const SolarTimeFast& b, float lat0, float lng0, double x,
+                                      double y, double u, double v) {
+  SunTrack<float> tr;
+  const StationTrig st = station_trig(lat0, lng0);
+  // fraction_of_day wraps at midnight: keep the phase continuous across the step
+  double pb = b.phase;
+  if (pb < a.phase - kPi) pb += 2.0 * kPi;
+  tr.c0 = cos_zenith_fast(st, a.phase, a.sin_decl, a.cos_decl, float(x), float(y));
+  tr.c1 = cos_zenith_fast(st, 0.5 * (a.phase + pb), 0.5f * (a.sin_decl + b.sin_decl), 0.5f * (a.cos_decl + b.cos_decl),
+                          float(x + u * 90.0), float(y + v * 90.0));
+  tr.c2 = cos_zenith_fast(st, pb, b.sin_decl, b.cos_decl, float(x + u * 180.0), float(y + v * 180.0));
+  tr.f0 = a.flux; tr.f2 = b.flux;
+  return tr;
+}
+
 // ---- the four roles in sequence: one agent step for one balloon (host replay + reference for the kernel) ----
 // Same contract as agent_step<float> (ble_physics.cuh).
 BLE_HD float agent_step_roles(BalloonState<float>& s, Atmosphere& atm, SafetyState& ss, int action,
@@ -282,6 +408,7 @@ BLE_HD float agent_step_roles(BalloonState<float>& s, Atmosphere& atm, SafetySta
   eff = envelope_safety<double>(eff, s.superpressure, &ss.envelope_state);
   PressureRole pr;
   pr.init(atm, double(s.mols_gas), s.pressure);
+  auto load_atm = [&atm]() { return atm; };
   double altitude;
   if (pr.layer >= 0) {                                                     // altitude from the same X the loop starts with
     const double x0 = pr.x_from_scratch(s.pressure);
@@ -293,8 +420,8 @@ BLE_HD float agent_step_roles(BalloonState<float>& s, Atmosphere& atm, SafetySta
   }
   eff = altitude_safety<double>(eff, altitude, &ss.altitude_state);
   *effective_action = eff;
-  SunTrack<float> sun;
-  sun.init(s, u, v);
+  const SunTrack<float> sun = sun_track_fast(solar_time_fast(s.date_time), solar_time_fast(s.date_time + 180), s.lat0,
+                                             s.lng0, s.x, s.y, u, v);
   const float earth_per_area = earth_heat_per_area<float>(s.ir);
   float cv = fm::cbrtf_pos(float(s.volume));
   int k = 0;
@@ -303,7 +430,7 @@ BLE_HD float agent_step_roles(BalloonState<float>& s, Atmosphere& atm, SafetySta
     sun_track_at(sun, k, &cz, &flux);
     const SunAngles<float> ang = sun_angles_fast(cz);
     double np, nt;
-    pr.step(s.pressure, s.t_ambient, s.volume, s.mols_air, cv, &np, &nt);
+    pr.step(s.pressure, s.t_ambient, s.volume, s.mols_air, cv, load_atm, &np, &nt);
     const float dtb = thermal_body(cv, s.t_internal, s.t_ambient, s.pressure, earth_per_area);
     const EnvelopeOut eo = envelope_acs(double(s.mols_gas), s.mols_air, s.t_internal, s.pressure, s.superpressure, eff);
     const SunOut so = sun_power(ang, flux, cv, s.pressure, s.superpressure, s.charge, eff);
@@ -323,7 +450,7 @@ BLE_HD float agent_step_roles(BalloonState<float>& s, Atmosphere& atm, SafetySta
     ++k;
     if (s.status != kOk) break;
   }
-  atm.ok = atm.ok && pr.atm.ok;
+  atm.ok = atm.ok && pr.atm_ok;
   float el = 0.0f;
   if (action == kDown) {                                                   // excess_energy's sun (balloon.py:231-238)
     float cz, flux;

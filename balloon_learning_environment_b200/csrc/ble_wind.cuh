@@ -296,6 +296,146 @@ BLE_HD Real simplex_noise4(const Perm& perm, double x, double y, double z, doubl
   return value / Real(30.0);
 }
 
+// ---- second-generation evaluation of the same sum (production fp32 kernels) ---------------------------------
+// simplex_noise4 above spends ~620 instructions deciding which of the 80 candidates are in range and then loops
+// over them one at a time (a warp iterates max-over-lanes ~12 times at ~105 instructions).  Two facts make it
+// cheaper.  (1) In the skewed lattice coordinates u = x + STRETCH * sum(x) the kernel argument separates:
+//     |d|^2 = sum_a (u_a - o_a)^2 + (sum(u) - sum(o))^2,
+//   so the range test of a candidate is two table reads and two subtractions.  (2) The 16 cube corners are needed by
+//   some lane of the warp almost always (7.6 of them are in range on average), so they are evaluated unconditionally
+//   and branch-free -- compile-time offsets, the permutation look-ups shared as a binary tree (30 instead of 64) --
+//   and only the "one step further out" neighbours (1.2 in range on average, never more than one direction per axis:
+//   (u_a + 1)^2 < 2 needs u_a < 0.414, (u_a - 2)^2 < 2 needs u_a > 0.586) go through a mask + loop.
+// Same definition, different summation order: agrees with simplex_noise4 to fp32 rounding.
+template <typename Real>
+BLE_HD Real gradient_dot_fast(int hash, Real dx, Real dy, Real dz, Real dw) {
+  // hash bits: [7..4] negate component 3..0, [3..2] position of the "3"
+  const Real ax = (hash & 0x10) ? -dx : dx, ay = (hash & 0x20) ? -dy : dy;
+  const Real az = (hash & 0x40) ? -dz : dz, aw = (hash & 0x80) ? -dw : dw;
+  const int j = (hash >> 2) & 3;
+  const Real lo = (j & 1) ? ay : ax, hi = (j & 1) ? aw : az;
+  const Real pick = (j & 2) ? hi : lo;
+  return ((ax + ay) + (az + aw)) + Real(2) * pick;
+}
+
+template <typename Real, typename Perm>
+BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, double w) {
+  const double s = (x + y + z + w) * kStretch4;
+  const double xs = x + s, ys = y + s, zs = z + s, ws = w + s;
+  const double fx = floor(xs), fy = floor(ys), fz = floor(zs), fw = floor(ws);
+  const double q = (fx + fy + fz + fw) * kSquish4;
+  const Real d0[4] = {Real(x - (fx + q)), Real(y - (fy + q)), Real(z - (fz + q)), Real(w - (fw + q))};
+  const Real in[4] = {Real(xs - fx), Real(ys - fy), Real(zs - fz), Real(ws - fw)};   // inside the unit cell
+  const Real S = (in[0] + in[1]) + (in[2] + in[3]);
+  const int cb[4] = {int(int64_t(fx) & 255), int(int64_t(fy) & 255), int(int64_t(fz) & 255), int(int64_t(fw) & 255)};
+  const Real sq = Real(kSquish4);
+
+  // ---- the 16 corners, unconditionally ----
+  Real e[4][2];                                        // real-space displacement per axis at offsets 0 / 1
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int a = 0; a < 4; ++a) { e[a][0] = d0[a]; e[a][1] = d0[a] - Real(1); }
+  int h1[2], h2[4], h3[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 2; ++i) h1[i] = perm[(cb[0] + i) & 255];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 4; ++i) h2[i] = perm[(h1[i & 1] + cb[1] + (i >> 1)) & 255];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 8; ++i) h3[i] = perm[(h2[i & 3] + cb[2] + (i >> 2)) & 255];
+  Real value = Real(0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int m = 0; m < 16; ++m) {
+    const int h = perm[(h3[m & 7] + cb[3] + (m >> 3)) & 255];
+    const int pc = (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + (m >> 3);
+    const Real t = Real(pc) * sq;
+    const Real dx = e[0][m & 1] - t, dy = e[1][(m >> 1) & 1] - t, dz = e[2][(m >> 2) & 1] - t, dw = e[3][m >> 3] - t;
+    Real attn = Real(2) - dx * dx - dy * dy - dz * dz - dw * dw;
+    attn = attn > Real(0) ? attn : Real(0);
+    attn *= attn;
+    value += attn * attn * gradient_dot_fast<Real>(h, dx, dy, dz, dw);
+  }
+
+  // ---- neighbours one step further out along one axis: range test in skewed coordinates, then a loop ----
+  Real A[4][2], Ae[4];
+  int oe[4];                                           // the only feasible outward offset per axis: -1 or 2
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int a = 0; a < 4; ++a) {
+    const Real u0 = in[a], u1 = in[a] - Real(1);
+    A[a][0] = u0 * u0; A[a][1] = u1 * u1;
+    const bool low = in[a] < Real(0.5);
+    const Real ue = low ? in[a] + Real(1) : in[a] - Real(2);
+    Ae[a] = ue * ue;
+    oe[a] = low ? -1 : 2;
+  }
+  Real Q[7];                                           // 2 - (S - t)^2 for t = -1 .. 5
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int t = 0; t < 7; ++t) { const Real v = S - Real(t - 1); Q[t] = Real(2) - v * v; }
+  uint32_t mask = 0;                                   // bit a * 8 + m8, m8 = offsets (0/1) of the other three axes
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int a = 0; a < 4; ++a) {
+    const int b0 = a == 0 ? 1 : 0, b1 = a <= 1 ? 2 : 1, b2 = a <= 2 ? 3 : 2;
+    const bool low = oe[a] < 0;
+    Real QE[4];                                        // by the number of set bits among the other axes
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int n = 0; n < 4; ++n) QE[n] = (low ? Q[n] : Q[n + 3]) - Ae[a];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int m8 = 0; m8 < 8; ++m8) {
+      const int pc = (m8 & 1) + ((m8 >> 1) & 1) + (m8 >> 2);
+      const Real attn = QE[pc] - A[b0][m8 & 1] - A[b1][(m8 >> 1) & 1] - A[b2][m8 >> 2];
+      if (attn > Real(0)) mask |= 1u << (a * 8 + m8);
+    }
+  }
+  const uint32_t oe_packed = uint32_t(oe[0] & 255) | (uint32_t(oe[1] & 255) << 8) | (uint32_t(oe[2] & 255) << 16) |
+                             (uint32_t(oe[3] & 255) << 24);
+  while (mask) {
+#if defined(__CUDA_ARCH__)
+    const int c = __ffs(int(mask)) - 1;
+#else
+    const int c = __builtin_ctz(mask);
+#endif
+    mask &= mask - 1;
+    const int a = c >> 3, m8 = c & 7;
+    const int m = (m8 & ((1 << a) - 1)) | ((m8 >> a) << (a + 1));        // offsets of the other axes, bit a cleared
+    const int ext = int(int8_t((oe_packed >> (8 * a)) & 255));
+    int o[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int b = 0; b < 4; ++b) o[b] = (b == a) ? ext : ((m >> b) & 1);
+    const Real t = Real(o[0] + o[1] + o[2] + o[3]) * sq;
+    const Real dx = d0[0] - Real(o[0]) - t, dy = d0[1] - Real(o[1]) - t;
+    const Real dz = d0[2] - Real(o[2]) - t, dw = d0[3] - Real(o[3]) - t;
+    Real attn = Real(2) - dx * dx - dy * dy - dz * dz - dw * dw;
+    attn = attn > Real(0) ? attn : Real(0);            // the mask was decided with a differently rounded sum
+    int h = perm[(cb[0] + o[0]) & 255];
+    h = perm[(h + cb[1] + o[1]) & 255];
+    h = perm[(h + cb[2] + o[2]) & 255];
+    h = perm[(h + cb[3] + o[3]) & 255];
+    attn *= attn;
+    value += attn * attn * gradient_dot_fast<Real>(h, dx, dy, dz, dw);
+  }
+  return value / Real(30.0);
+}
+
 // OpenSimplex.__init__: 256-entry permutation from a 64-bit LCG (see oracle/opensimplex4.py).
 BLE_HD void simplex_make_perm(int64_t seed, uint8_t* perm /*256, may be global*/, uint8_t* source /*256 scratch*/) {
   const uint64_t A = 6364136223846793005ull, Cc = 1442695040888963407ull;

@@ -1,6 +1,6 @@
 """Times BalloonEnv.step kernels over batch sizes / CTA shapes (A/B data for DESIGN.md; not the bench).
 
-    python scripts/step_timing.py [--sizes 8192,16384,65536] [--variants fused4,fused8,fused10,fused14,thread,ws]
+    python scripts/step_timing.py [--sizes 8192,16384,65536] [--variants fused0,fused4,fused8,fused14,fusedauto,thread,ws]
 Prints one JSON line per (size, variant): ms per ble_step and ms per step inside ble_rollout (32 steps / launch).
 """
 import argparse
@@ -18,7 +18,7 @@ from balloon_learning_environment_b200 import batched_env  # noqa: E402
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--sizes', default='8192,16384,32768,65536')
-  ap.add_argument('--variants', default='fused4,fused8,fused10,fused14,thread,ws')
+  ap.add_argument('--variants', default='fused0,fused4,fused8,fused14,thread,ws')
   ap.add_argument('--fields', type=int, default=2048, help='size of the shared field pool (per-balloon fields: 0)')
   ap.add_argument('--steps', type=int, default=200)
   args = ap.parse_args()
@@ -36,7 +36,7 @@ def main():
     actions = torch.randint(0, 3, (64, n), dtype=torch.int32, device=dev, generator=g)
     for variant in args.variants.split(','):
       if variant.startswith('fused'):
-        os.environ['BLE_STEP_KERNEL'] = 'fused'; os.environ['BLE_STEP_WARPS'] = variant[5:]
+        os.environ['BLE_STEP_KERNEL'] = 'fused'; os.environ['BLE_STEP_WARPS'] = variant[5:] if variant[5:].isdigit() else ''
       else:
         os.environ['BLE_STEP_KERNEL'] = variant; os.environ.pop('BLE_STEP_WARPS', None)
       arena.reset(seeds)

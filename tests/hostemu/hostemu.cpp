@@ -136,6 +136,17 @@ void emu_noise(int precision, int64_t n, const int64_t* seeds, const double* xyz
   }
 }
 
+// second-generation evaluation (production fp32 kernels); precision as emu_noise
+void emu_noise_v2(int precision, int64_t n, const int64_t* seeds, const double* xyzw, double* out) {
+  uint8_t perm[256], scratch[256];
+  for (int64_t i = 0; i < n; ++i) {
+    simplex_make_perm(seeds[i], perm, scratch);
+    const double* p = xyzw + 4 * i;
+    out[i] = precision == BLE_PRECISION_FP64 ? simplex_noise4_v2<double>((const uint8_t*)perm, p[0], p[1], p[2], p[3])
+                                             : double(simplex_noise4_v2<float>((const uint8_t*)perm, p[0], p[1], p[2], p[3]));
+  }
+}
+
 void emu_perm(int64_t seed, uint8_t* perm) { uint8_t scratch[256]; simplex_make_perm(seed, perm, scratch); }
 
 // fields: native layout [F,21,21,10,9,2]; xyzt: (x km, y km, p, hours) float32
