@@ -517,6 +517,7 @@ __global__ void __launch_bounds__(128) k_derived(DevState<Real> d, double* __res
 
 #include "ble_feature_kernels.cuh"
 #include "ble_gp_kernels.cuh"
+#include "ble_gp_posterior.cuh"
 #include "ble_decoder.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -885,8 +886,8 @@ struct Engine : EngineBase {
       BLE_CUDA(cudaMalloc(&range_scratch, sizeof(double) * size_t(kRangeLevels) * 2 * n));
       d.gp_first = gp_first; d.gp_z = gp_z;
       if (const char* g = std::getenv("BLE_GP_REFIT")) gp_refit_every_step = std::atoi(g) != 0;
-      BLE_CUDA(cudaFuncSetAttribute(k_gp_update<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUpdateSmem)));
-      BLE_CUDA(cudaFuncSetAttribute(k_gp_column4<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(Column4Smem))));
+      BLE_CUDA(cudaFuncSetAttribute(k_gp_posterior<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(PosteriorSmem))));
+      BLE_CUDA(cudaFuncSetAttribute(k_gp_posterior<Real>, cudaFuncAttributePreferredSharedMemoryCarveout, int(cudaSharedmemCarveoutMaxShared)));
 
 
       BLE_CUDA(cudaMalloc(&feat_range, sizeof(double) * 2 * n));
@@ -1351,7 +1352,7 @@ struct Engine : EngineBase {
     BLE_DEVICE_GUARD();
     rc = launch_noise(s);
     if (rc != BLE_OK) return rc;
-    k_feat_observe<Real><<<grid_for(n, 128), 128, 0, s>>>(d);
+    k_feat_observe_k<Real><<<grid_for(n * 32, 128), 128, 0, s>>>(d);
     ++launches;
     BLE_CUDA(cudaGetLastError());
     return BLE_OK;
@@ -1388,10 +1389,9 @@ struct Engine : EngineBase {
       k_gp_factor<Real><<<unsigned(n), kFactorThreads, sizeof(double) * (kGpPacked + kGpWindow * 4), s>>>(d);
       k_gp_column<Real><<<unsigned(n), kColumnThreads, kColumnSmem, s>>>(d, obs);
     } else {
-      k_gp_update<Real><<<unsigned(n), kUpdateThreads, kUpdateSmem, s>>>(d);
-      k_gp_column4<Real><<<unsigned(n), kC4Threads, sizeof(Column4Smem), s>>>(d, obs);
+      k_gp_posterior<Real><<<unsigned(n), kGpPThreads, sizeof(PosteriorSmem), s>>>(d, obs);
     }
-    launches += 5;
+    launches += gp_refit_every_step ? 5 : 4;
     BLE_CUDA(cudaGetLastError());
     return BLE_OK;
   }

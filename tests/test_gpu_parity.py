@@ -726,14 +726,18 @@ def test_features_batch_matches_oracle_after_reset(ble, steps, every_step):
   want = ofeat.get_features()
   pad = lambda o: np.all(o[:, 16:].reshape(-1, 361, 3) == np.array([0, 1, 1], np.float32), axis=2)
   np.testing.assert_array_equal(pad(got), pad(want))
-  assert np.abs(got - want).max() < 1e-4, float(np.abs(got - want).max())
+  err = np.abs(got - want)
+  print(f'features vs fp64 oracle after {steps} steps: worst {err.max():.2e} (ambient {err[:, :16].max():.2e}, '
+        f'uncertainty {err[:, 16::3].max():.2e}, angle {err[:, 17::3].max():.2e}, magnitude {err[:, 18::3].max():.2e})')
+  assert err.max() < 1e-4, float(err.max())
   arena.close()
 
 
 def test_incremental_gp_matches_full_refit(ble, monkeypatch):
-  """The carried Cholesky factor (drop oldest = rank-1 update, append newest = one forward substitution) against
-  the full refit of every call, over 150 steps: window filling, then sliding (1 drop + 1 append per step),
-  features skipped for a few steps (several drops/appends at once), a masked reset in the middle."""
+  """k_gp_posterior (kernel matrix kept in ring-slot order in HBM, updated one row per observe; blocked fp64 Cholesky +
+  3 x TF32 column sweep per call) against the first-generation kernels that rebuild K from the measurement ring at
+  every call (BLE_GP_REFIT=1), over 150 steps: window filling, then sliding (the ring overwrites the oldest slot),
+  features skipped for a few steps, a masked reset in the middle."""
   n, steps = 40, 150
   bank = golden_fields.field_bank()
   rng = np.random.default_rng(33)
@@ -762,7 +766,9 @@ def test_incremental_gp_matches_full_refit(ble, monkeypatch):
     got, want = (a.features().cpu().numpy() for a in arenas)
     err = float(np.abs(got - want).max())
     worst = max(worst, err)
-    assert err < 1e-5, (t, err, int(np.abs(got - want).max(axis=1).argmax()))   # the refit kernels keep V in fp32
+    # two fp32-class column solves (first generation: V in fp32; k_gp_posterior: 3 x TF32), each held to 1e-4 against
+    # the reference / the fp64 oracle by the tests above
+    assert err < 1.5e-4, (t, err, int(np.abs(got - want).max(axis=1).argmax()))
   st = arenas[0].get_state_dict()
   assert int((st['status'] == 0).sum()) > n // 2             # most balloons flew the whole test
   print('incremental vs refit: worst feature difference', worst)
