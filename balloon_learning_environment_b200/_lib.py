@@ -32,7 +32,7 @@ E_ROWS = ('cumulative_reward', 'time_within_radius', 'out_of_power', 'envelope_b
 EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_upload_fields',
            'ble_alloc_fields', 'ble_write_fields', 'ble_set_field_map', 'ble_set_decoder', 'ble_decode_fields',
            'ble_set_noise', 'ble_state_upload', 'ble_state_download', 'ble_reset', 'ble_init_derived',
-           'ble_step', 'ble_step_ex', 'ble_rollout', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_derived',
+           'ble_step', 'ble_step_ex', 'ble_rollout', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_wind_query', 'ble_atmosphere_query', 'ble_derived',
            'ble_features_perciatelli', 'ble_features_observe', 'ble_features_clear', 'ble_features_track',
            'ble_generate_fields', 'ble_generate_fields_at', 'ble_agent_station_seeker', 'ble_agent_random_walk',
            'ble_eval_begin', 'ble_eval_accumulate', 'ble_eval_results',
@@ -107,6 +107,8 @@ def load(build_if_missing=True):
   lib.ble_step_host.argtypes = [vp, vp, vp, vp, vp]
   lib.ble_wind_at_balloon.argtypes = [vp, vp, vp]
   lib.ble_wind_gather.argtypes = [vp, vp, vp, vp, i64, vp]
+  lib.ble_wind_query.argtypes = [vp, vp, vp, i32, vp, i64, vp]
+  lib.ble_atmosphere_query.argtypes = [vp, i32, vp, vp, vp, i64, vp]
   lib.ble_derived.argtypes = [vp, vp, vp]
   lib.ble_features_perciatelli.argtypes = [vp, vp, vp]
   lib.ble_features_observe.argtypes = [vp, vp]

@@ -251,6 +251,28 @@ class BatchedBalloonArena:
     self._check(rc, 'ble_wind_gather')
     return uv
 
+  def wind_query(self, xyzt: torch.Tensor, env_idx: torch.Tensor, with_noise: bool) -> torch.Tensor:
+    """WindField.get_forecast (with_noise=False) / get_ground_truth (True) at M points of given balloons' own
+    fields and noise generators: xyzt float64 [M,4] (x m, y m, Pa, elapsed s), env_idx int32 [M] -> float32 [M,2]."""
+    xyzt = xyzt.to(self.device, torch.float64).contiguous()
+    env_idx = env_idx.to(self.device, torch.int32).contiguous()
+    m = xyzt.shape[0]
+    uv = torch.empty(m, 2, dtype=torch.float32, device=self.device)
+    rc = self._lib.ble_wind_query(self._h, _ptr(xyzt), _ptr(env_idx), int(bool(with_noise)), _ptr(uv), m, self._stream())
+    self._check(rc, 'ble_wind_query')
+    return uv
+
+  def atmosphere_query(self, which: str, q: torch.Tensor, env_idx: torch.Tensor) -> torch.Tensor:
+    """Atmosphere.at_pressure / at_height for given balloons' atmospheres: q float64 [M] -> float64 [M,4]
+    (height m, temperature K, pressure Pa, density kg/m^3); NaN rows where the reference asserts."""
+    q = q.to(self.device, torch.float64).contiguous()
+    env_idx = env_idx.to(self.device, torch.int32).contiguous()
+    out = torch.empty(q.shape[0], 4, dtype=torch.float64, device=self.device)
+    rc = self._lib.ble_atmosphere_query(self._h, {'pressure': 0, 'height': 1}[which], _ptr(q), _ptr(env_idx), _ptr(out),
+                                        q.shape[0], self._stream())
+    self._check(rc, 'ble_atmosphere_query')
+    return out
+
   def wind_at_balloon(self) -> torch.Tensor:
     """Ground-truth wind at the balloons' current state, float32 [N,2] (get_measurements)."""
     uv = torch.empty(self.num_envs, 2, dtype=torch.float32, device=self.device)

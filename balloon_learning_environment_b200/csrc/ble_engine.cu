@@ -263,6 +263,65 @@ k_wind_at_balloon(DevState<Real> d, float2* __restrict__ uv) {
   uv[e] = make_float2(float(u), float(v));
 }
 
+// WindField.get_forecast / get_ground_truth (env/wind_field.py:69-145) at ARBITRARY points of a balloon's own wind field
+// and noise generators -- what SimulatorState.wind_field hands to a reference consumer.  One thread per query; the
+// permutation tables are read in place (this is the N = 1 adaptor's path, not the step's).
+template <typename Real>
+__global__ void __launch_bounds__(128)
+k_wind_query(DevState<Real> d, const double* __restrict__ xyzt /*[m][4]: x m, y m, Pa, elapsed s*/,
+             const int32_t* __restrict__ env_idx, int with_noise, float2* __restrict__ uv, int64_t m) {
+  const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (q >= m) return;
+  const int64_t e = env_idx[q];
+  const double x = xyzt[4 * q], y = xyzt[4 * q + 1], p = xyzt[4 * q + 2], t_s = xyzt[4 * q + 3];
+  Real u, v;
+  if (d.wind_model == BLE_WIND_SIMPLE_STATIC) {
+    static_wind<Real>(Real(p), &u, &v);
+  } else {
+    const FieldPoint pt = make_field_point(x / 1000.0, y / 1000.0, p, t_s / 3600.0);
+    const FieldCell<Real> c = locate<Real>(pt);
+    WindowLoader ld{reinterpret_cast<const float4*>(d.cells + int64_t(d.env_field[e]) * d.layout.field_floats +
+                                                    window_index(d.layout, c.ix, c.iy, c.pc, c.tc))};
+    interp_window<Real>(c, ld, &u, &v);
+  }
+  if (with_noise && d.enable_noise) {                      // SimplexWindNoise.get_wind_noise (:209-218)
+    Real comp[2] = {Real(0), Real(0)};
+    for (int h10 = 0; h10 < 10; ++h10) {
+      const double* hp = kHarmonicsInvDev[h10];
+      const double X = fma(x, hp[0], double(d.offsets[(int64_t(h10) * 4 + 0) * d.n + e]));
+      const double Y = fma(y, hp[1], double(d.offsets[(int64_t(h10) * 4 + 1) * d.n + e]));
+      const double Z = fma(p, hp[2], double(d.offsets[(int64_t(h10) * 4 + 2) * d.n + e]));
+      const double W = fma(t_s, hp[3], double(d.offsets[(int64_t(h10) * 4 + 3) * d.n + e]));
+      RotatedPerm perm{d.perm + (int64_t(h10) * d.n + e) * 256, int(e & 31) * 4};
+      const Real nh = Real(kNoiseMagnitude) * simplex_noise4_v2<Real>(perm, X, Y, Z, W);
+      comp[h10 / 5] += nh * Real(h10 < 5 ? kBlendU[h10] : kBlendV[h10 - 5]);
+    }
+    u += comp[0] * Real(kBlendScaleU);
+    v += comp[1] * Real(kBlendScaleV);
+  }
+  uv[q] = make_float2(float(u), float(v));
+}
+
+// Atmosphere.at_pressure / at_height (env/balloon/standard_atmosphere.py:89-154) of a balloon's atmosphere.
+// out[q] = (height m, temperature K, pressure Pa, density kg/m^3); NaN where the reference asserts (:95-96, :126-127).
+template <typename Real>
+__global__ void __launch_bounds__(128)
+k_atmosphere_query(DevState<Real> d, int which, const double* __restrict__ q, const int32_t* __restrict__ env_idx,
+                   double* __restrict__ out, int64_t m) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= m) return;
+  const double alpha = DD(d, D_ALPHA, env_idx[i]);
+  double height, pressure, temperature;
+  bool ok;
+  if (which == 0) { pressure = q[i]; ok = atm_at_pressure_generic(alpha, pressure, &height, &temperature); }
+  else { height = q[i]; ok = atm_at_height_generic(alpha, height, &pressure, &temperature); }
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  out[4 * i] = ok ? height : nan;
+  out[4 * i + 1] = ok ? temperature : nan;
+  out[4 * i + 2] = ok ? pressure : nan;
+  out[4 * i + 3] = ok ? pressure * kMAir / (kR * temperature) : nan;      // :150-153
+}
+
 // ---------------------------------------------------------------------------------------------
 // The fused physics step: wind at balloon -> safety layers -> 18 Euler sub-steps -> reward/done
 // ---------------------------------------------------------------------------------------------
@@ -774,6 +833,8 @@ struct EngineBase {
   virtual int wind_at(float*, cudaStream_t) = 0;
   virtual int wind_gather(const float*, const int32_t*, float*, int64_t, cudaStream_t) = 0;
   virtual int derived(double*, cudaStream_t) = 0;
+  virtual int wind_query(const double*, const int32_t*, int, float*, int64_t, cudaStream_t) = 0;
+  virtual int atmosphere_query(int, const double*, const int32_t*, double*, int64_t, cudaStream_t) = 0;
   virtual int set_decoder(const float* const*, const float* const*, cudaStream_t) = 0;
   virtual int decode(const float*, int64_t, float*, cudaStream_t) = 0;
   virtual int generate_fields(const uint64_t*, int64_t, int64_t, cudaStream_t) = 0;
@@ -1451,6 +1512,31 @@ struct Engine : EngineBase {
     return BLE_OK;
   }
 
+  int wind_query(const double* xyzt, const int32_t* env_idx, int with_noise, float* uv, int64_t m, cudaStream_t s) override {
+    if (m < 0 || (m > 0 && (xyzt == nullptr || env_idx == nullptr || uv == nullptr))) { err = "wind_query: bad argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    if (cfg.wind_model == BLE_WIND_GRID && !have_fields) { err = "wind_query: no wind fields (call ble_upload_fields first)"; return BLE_ERR_NOT_READY; }
+    if (with_noise && cfg.enable_noise && !have_noise) { err = "wind_query: noise enabled but not seeded"; return BLE_ERR_NOT_READY; }
+    if (m == 0) return BLE_OK;
+    BLE_DEVICE_GUARD();
+    k_wind_query<Real><<<grid_for(m, 128), 128, 0, s>>>(d, xyzt, env_idx, with_noise, reinterpret_cast<float2*>(uv), m);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
+  int atmosphere_query(int which, const double* q, const int32_t* env_idx, double* out, int64_t m, cudaStream_t s) override {
+    if (m < 0 || (which != 0 && which != 1) || (m > 0 && (q == nullptr || env_idx == nullptr || out == nullptr))) {
+      err = "atmosphere_query: bad argument"; return BLE_ERR_INVALID_ARGUMENT;
+    }
+    if (!have_state) { err = "atmosphere_query: no balloon state"; return BLE_ERR_NOT_READY; }
+    if (m == 0) return BLE_OK;
+    BLE_DEVICE_GUARD();
+    k_atmosphere_query<Real><<<grid_for(m, 128), 128, 0, s>>>(d, which, q, env_idx, out, m);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
+    return BLE_OK;
+  }
+
   int wind_gather(const float* xyzt, const int32_t* fidx, float* uv, int64_t m, cudaStream_t s) override {
     if (m < 0 || (m > 0 && (xyzt == nullptr || fidx == nullptr || uv == nullptr))) { err = "wind_gather: bad argument"; return BLE_ERR_INVALID_ARGUMENT; }
     if (!have_fields) { err = "wind_gather: no wind fields (call ble_upload_fields first)"; return BLE_ERR_NOT_READY; }
@@ -1613,6 +1699,14 @@ int ble_features_clear(ble_handle* h, void* stream) {
 }
 int ble_derived(ble_handle* h, double* out, void* stream) {
   BLE_H(h); return h->eng->derived(out, cudaStream_t(stream));
+}
+int ble_wind_query(ble_handle* h, const double* xyzt, const int32_t* env_idx, int32_t with_noise, float* uv, int64_t m,
+                   void* stream) {
+  BLE_H(h); return h->eng->wind_query(xyzt, env_idx, with_noise, uv, m, cudaStream_t(stream));
+}
+int ble_atmosphere_query(ble_handle* h, int32_t which, const double* q, const int32_t* env_idx, double* out, int64_t m,
+                         void* stream) {
+  BLE_H(h); return h->eng->atmosphere_query(which, q, env_idx, out, m, cudaStream_t(stream));
 }
 int ble_wind_gather(ble_handle* h, const float* xyzt, const int32_t* field_idx, float* uv, int64_t m, void* stream) {
   BLE_H(h); return h->eng->wind_gather(xyzt, field_idx, uv, m, cudaStream_t(stream));

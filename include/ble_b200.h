@@ -194,6 +194,20 @@ int ble_wind_at_balloon(ble_handle* h, float* wind_uv, void* stream);
 int ble_wind_gather(ble_handle* h, const float* xyzt, const int32_t* field_idx, float* uv,
                     int64_t m, void* stream);
 
+/* SimulatorState.wind_field for reference consumers (env/simulator_data.py:25-34): WindField.get_forecast
+ * (with_noise = 0; env/wind_field.py:69-87) or get_ground_truth (with_noise = 1; :125-145) at M arbitrary points of
+ * a BALLOON's own wind grid and noise generators.  xyzt float64 [M,4] = (x m, y m, pressure Pa, elapsed seconds) as
+ * the reference passes them, env_idx int32 [M] = balloon index, uv float32 [M,2]. */
+int ble_wind_query(ble_handle* h, const double* xyzt, const int32_t* env_idx, int32_t with_noise, float* uv,
+                   int64_t m, void* stream);
+
+/* SimulatorState.atmosphere: Atmosphere.at_pressure (which = 0, q = pressure Pa) / at_height (which = 1, q = metres)
+ * of balloon env_idx[i]'s atmosphere (env/balloon/standard_atmosphere.py:89-154).  out float64 [M,4] = (height m,
+ * temperature K, pressure Pa, density kg/m^3); a query outside the table, where the reference asserts (:95-96,
+ * :126-127), yields a NaN row. */
+int ble_atmosphere_query(ble_handle* h, int32_t which, const double* q, const int32_t* env_idx, double* out,
+                         int64_t m, void* stream);
+
 /* Observation surface: PerciatelliFeatureConstructor (env/features.py:269-581) for all balloons.
  * With enable_features = 1, ble_reset and ble_step end with the constructor's observe() of the new
  * state (env/balloon_arena.py:179-182, 201), i.e. the WindGP measurement history (env/wind_gp.py:98-119,
