@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from balloon_learning_environment_b200 import _lib
+from balloon_learning_environment_b200 import sharding
 
 # AltitudeControlCommand (env/balloon/control.py:21-25) and BalloonStatus (env/balloon/balloon.py:66-70)
 DOWN, STAY, UP = 0, 1, 2
@@ -142,8 +143,9 @@ class BatchedBalloonArena:
     ks, bs = [], []
     for i in range(4):
       layer = params[f'Dense_{i}']
-      ks.append(torch.as_tensor(np.asarray(layer['kernel'], np.float32)).to(self.device).contiguous())
-      bs.append(torch.as_tensor(np.asarray(layer['bias'], np.float32)).to(self.device).contiguous())
+      as_dev = lambda a: (a if torch.is_tensor(a) else torch.as_tensor(np.asarray(a, np.float32))).to(self.device, torch.float32).contiguous()
+      ks.append(as_dev(layer['kernel']))
+      bs.append(as_dev(layer['bias']))
     expected = [(64, 1000), (1000, 1000), (1000, 1000), (1000, 4410)]
     if [tuple(k.shape) for k in ks] != expected or [b.numel() for b in bs] != [1000, 1000, 1000, 4410]:
       raise ValueError('decoder weights do not have the vae.Decoder shapes')
@@ -415,11 +417,18 @@ class BatchedBalloonEnv:
   def __init__(self, num_envs: int, *, device: str = 'cuda:0', precision: str = 'fp32',
                wind_model: str = 'grid', enable_noise: bool = True, seed: int = 0,
                arena: Optional[BatchedBalloonArena] = None, observation: Optional[str] = None,
-               field_layout: str = 'x64', decoder_params=None):
+               field_layout: str = 'x64', decoder_params=None, shared_field_pool: Optional[torch.Tensor] = None,
+               first_env: int = 0, broadcast_src: Optional[int] = 0):
     """decoder_params (the flax tree of offlineskies22_decoder.msgpack['params']) switches the wind source
     to the reference's default GenerativeWindFieldSampler: every reset decodes one new field per balloon
     from that balloon's seed (env/generative_wind_field.py:52-62).  Without it the fields are whatever was
-    loaded with arena.set_wind_fields / write_wind_fields."""
+    loaded with arena.set_wind_fields / write_wind_fields, or `shared_field_pool` (float32 [F,21,21,10,9,2]):
+    balloon i of the JOB flies field (first_env + i) % F.
+
+    Under torch.distributed (one process per GPU, this rank holding the balloons [first_env, first_env + num_envs) of
+    the job) the constructor is a collective: rank `broadcast_src` hands its decoder weights / field pool to the others
+    over NCCL, so only one process reads them from disk (the others may pass None / an empty tensor of the right
+    shape).  broadcast_src=None switches that off (every rank brings its own)."""
     if observation not in (None, 'perciatelli'):
       raise ValueError("observation must be None or 'perciatelli'")
     self.arena = arena if arena is not None else BatchedBalloonArena(
@@ -434,6 +443,15 @@ class BatchedBalloonEnv:
                  if observation == 'perciatelli' else None)
     self._generator = torch.Generator(device='cpu')
     self.seed(seed)
+    if broadcast_src is not None and sharding.distributed_world() > 1:
+      decoder_params = sharding.broadcast_decoder_params(decoder_params, self.device, src=broadcast_src)
+      if shared_field_pool is not None:
+        shared_field_pool = sharding.broadcast_field_pool(shared_field_pool.to(self.device, torch.float32).contiguous(),
+                                                          src=broadcast_src)
+    if shared_field_pool is not None:
+      n_f = int(shared_field_pool.shape[0])
+      env_to_field = (torch.arange(self.num_envs, dtype=torch.int64) + int(first_env)) % n_f
+      self.arena.set_wind_fields(shared_field_pool, env_to_field.to(torch.int32))
     self._generative = decoder_params is not None
     if self._generative:
       self.arena.set_decoder(decoder_params)

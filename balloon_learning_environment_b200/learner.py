@@ -15,6 +15,7 @@ CUDA kernel behind the C ABI (csrc/ble_learner.cu).  Data-parallel training keep
 and sums the flat gradient buffer with ONE all-reduce per learner step (NCCL; gloo in the CPU tests
 of the host logic).  There is no CPU path for the kernels.
 """
+import contextlib
 import ctypes
 import dataclasses
 import math
@@ -47,6 +48,13 @@ def _check(rc: int, what: str):
     raise _lib.BleError(f'{what} failed (code {rc})')
 
 
+def _call(name: str, device, *args):
+  """One stateless learner entry point of the C ABI, launched with `device` current (the entry points take a stream
+  but no device ordinal; the stream belongs to `device`) and the caller's device restored afterwards."""
+  with torch.cuda.device(device):
+    _check(getattr(_lib.load(), name)(*args, _stream(device)), name)
+
+
 @dataclasses.dataclass
 class QrDqnConfig:
   """acme_utils.create_dqn (acme_utils.py:217-246) / agents/configs/quantile.gin."""
@@ -67,7 +75,10 @@ class QrDqnConfig:
   batch_size: int = 32                   # acme_utils.py:229 (per learner step, per GPU)
   samples_per_insert: float = 8.0        # batch_size / update_period, acme_utils.py:230
   max_replay_size: int = 2_000_000       # acme_utils.py:228 (transitions)
-  epsilon: float = 0.0                   # quantile.gin: epsilon_train = 0 (MarcoPolo explores instead)
+  epsilon: float = 0.05                  # acme_utils.py:225 builds dqn.DQNConfig(**params) without an epsilon, so the
+                                         # behaviour policy (:256-262) runs at Acme's DQNConfig default (0.05 in
+                                         # dm-acme 0.4, a dependency absent from the reference tree); quantile.gin's
+                                         # epsilon_train = 0 belongs to the dopamine agent, not to this path
   exploratory_episode_probability: float = 0.8   # acme_utils.py:207
   max_episode_length: int = 960          # train_acme_qrdqn.py:30-33
   tf32_matmul: bool = True               # dense layers on the tensor cores (TF32 in, fp32 accumulate): what
@@ -134,7 +145,7 @@ def greedy_actions(logits: torch.Tensor, with_q: bool = False):
   b, a, n = logits.shape
   actions = torch.empty(b, dtype=torch.int32, device=logits.device)
   q = torch.empty(b, a, dtype=torch.float32, device=logits.device) if with_q else None
-  _check(_lib.load().ble_qr_greedy(_ptr(logits), b, a, n, _ptr(actions), _ptr(q), _stream(logits.device)), 'ble_qr_greedy')
+  _call('ble_qr_greedy', logits.device, _ptr(logits), b, a, n, _ptr(actions), _ptr(q))
   return (actions, q) if with_q else actions
 
 
@@ -144,9 +155,8 @@ def target_distribution(next_logits: torch.Tensor, reward: torch.Tensor, discoun
   next_logits = next_logits.contiguous()
   b, a, n = next_logits.shape
   target = torch.empty(b, n, dtype=torch.float32, device=next_logits.device)
-  rc = _lib.load().ble_qr_target(_ptr(next_logits), _ptr(reward.contiguous()), _ptr(discount.contiguous()), b, a, n,
-                                 _ptr(target), _stream(next_logits.device))
-  _check(rc, 'ble_qr_target')
+  _call('ble_qr_target', next_logits.device, _ptr(next_logits), _ptr(reward.contiguous()), _ptr(discount.contiguous()),
+        b, a, n, _ptr(target))
   return target
 
 
@@ -160,10 +170,8 @@ class _QuantileHuberLoss(torch.autograd.Function):
     b, a, n = logits.shape
     loss = torch.empty(b, dtype=torch.float32, device=logits.device)
     grad = torch.empty_like(logits)
-    rc = _lib.load().ble_qr_loss(_ptr(logits), _ptr(actions.contiguous()), _ptr(target.contiguous()),
-                                 _ptr(weight.contiguous() if weight is not None else None), float(kappa), b, a, n,
-                                 1.0 / b, _ptr(loss), _ptr(grad), _stream(logits.device))
-    _check(rc, 'ble_qr_loss')
+    _call('ble_qr_loss', logits.device, _ptr(logits), _ptr(actions.contiguous()), _ptr(target.contiguous()),
+          _ptr(weight.contiguous() if weight is not None else None), float(kappa), b, a, n, 1.0 / b, _ptr(loss), _ptr(grad))
     ctx.save_for_backward(grad)
     ctx.mark_non_differentiable(loss)
     mean = (loss * weight).mean() if weight is not None else loss.mean()
@@ -183,9 +191,8 @@ def quantile_huber_loss(logits, actions, target, weight=None, kappa: float = 1.0
 def adam_step(params, grads, m, v, step: int, lr: float, b1=0.9, b2=0.999, eps=2e-5, grad_scale=1.0):
   """optax.adam on flat fp32 buffers, in place; step counts from 1."""
   _require_cuda(params, 'adam_step')
-  rc = _lib.load().ble_adam_step(_ptr(params), _ptr(grads), _ptr(m), _ptr(v), params.numel(), float(lr), float(b1),
-                                 float(b2), float(eps), int(step), float(grad_scale), _stream(params.device))
-  _check(rc, 'ble_adam_step')
+  _call('ble_adam_step', params.device, _ptr(params), _ptr(grads), _ptr(m), _ptr(v), params.numel(), float(lr), float(b1),
+        float(b2), float(eps), int(step), float(grad_scale))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -193,7 +200,14 @@ def adam_step(params, grads, m, v, step: int, lr: float, b1=0.9, b2=0.999, eps=2
 # ---------------------------------------------------------------------------------------------
 class DeviceReplay:
   """Time-major ring of whole N-balloon steps kept in HBM; n-step transitions are assembled at sampling
-  time by k_replay_sample.  capacity_steps * N transitions (the reference keeps 2,000,000)."""
+  time by k_replay_sample.  capacity_steps * N transitions (the reference keeps 2,000,000).
+
+  Known divergence (documented, not hidden): the ring stores the observation each action was CHOSEN on, so the
+  last observation of an episode cut by the step limit (StepLimitWrapper, acme_utils.py:72-73) is not kept, and
+  k_replay_sample rejects the n-step windows that cross such a truncation (`valid` = 0).  Acme's n-step adder
+  still emits those windows, bootstrapping from the final observation with discount gamma^k: here the last
+  n_step (5) of every 960 transitions of a truncated episode are not trained on (0.5 % of the data).  Windows that
+  end in a TERMINAL step are kept (discount 0, no bootstrap observation needed)."""
 
   def __init__(self, num_envs: int, capacity_steps: int, *, num_features: int = NUM_FEATURES, n_step: int = 5,
                gamma: float = 0.993, device='cuda:0', seed: int = 0):
@@ -245,10 +259,8 @@ class DeviceReplay:
     view = self.view()
     self._draws += 1
     seed = (self._seed * 0x9E3779B97F4A7C15 + self._draws) & 0xFFFFFFFFFFFFFFFF
-    rc = _lib.load().ble_replay_sample(ctypes.byref(view), _ptr(indices), seed, b, _ptr(out['state']),
-                                       _ptr(out['next_state']), _ptr(out['action']), _ptr(out['return']),
-                                       _ptr(out['discount']), _ptr(out['valid']), _ptr(out['indices']), _stream(dev))
-    _check(rc, 'ble_replay_sample')
+    _call('ble_replay_sample', dev, ctypes.byref(view), _ptr(indices), seed, b, _ptr(out['state']), _ptr(out['next_state']),
+          _ptr(out['action']), _ptr(out['return']), _ptr(out['discount']), _ptr(out['valid']), _ptr(out['indices']))
     return out
 
 
@@ -276,10 +288,9 @@ class MarcoPoloExploration:
     actions = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
     if begin is not None:
       begin = begin.to(self.device, torch.uint8).contiguous()
-    rc = _lib.load().ble_marco_polo_step(_ptr(obs.contiguous()), _ptr(rl_actions.to(torch.int32).contiguous()),
-                                         _ptr(begin), self.num_envs, _ptr(self.state), _ptr(self.walk_target),
-                                         _ptr(self.seeds), self._k, self.probability, _ptr(actions), _stream(self.device))
-    _check(rc, 'ble_marco_polo_step')
+    _call('ble_marco_polo_step', self.device, _ptr(obs.contiguous()), _ptr(rl_actions.to(torch.int32).contiguous()),
+          _ptr(begin), self.num_envs, _ptr(self.state), _ptr(self.walk_target), _ptr(self.seeds), self._k, self.probability,
+          _ptr(actions))
     self._k += 1
     return actions
 
@@ -307,7 +318,6 @@ class QrDqnLearner:
     self.device = torch.device(device)
     if self.device.type != 'cuda':
       raise _lib.BleError('QrDqnLearner needs a CUDA device (no CPU fallback exists)')
-    torch.backends.cuda.matmul.allow_tf32 = bool(config.tf32_matmul)
     torch.manual_seed(int(seed))                       # same seed on every rank -> identical initial replicas
     self.online = QuantileNetwork(config).to(self.device)
     self.target = QuantileNetwork(config).to(self.device)
@@ -321,10 +331,21 @@ class QrDqnLearner:
     self.steps = 0
     self.kernel_launches = 0
 
+  @contextlib.contextmanager
+  def _matmul_precision(self):
+    """config.tf32_matmul for THIS learner's GEMMs only: the process-wide torch flag is restored on exit."""
+    previous = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = bool(self.config.tf32_matmul)
+    try:
+      yield
+    finally:
+      torch.backends.cuda.matmul.allow_tf32 = previous
+
   @torch.no_grad()
   def act(self, obs: torch.Tensor, epsilon: Optional[float] = None, generator: Optional[torch.Generator] = None):
     """Behaviour policy (acme_utils.py:250-258): epsilon-greedy on the mean over atoms."""
-    actions = greedy_actions(self.online(obs))
+    with self._matmul_precision():
+      actions = greedy_actions(self.online(obs))
     self.kernel_launches += 1
     eps = self.config.epsilon if epsilon is None else epsilon
     if eps > 0.0:
@@ -337,13 +358,14 @@ class QrDqnLearner:
   def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
     """One SGD step on a sampled batch; returns the mean loss (device scalar)."""
     cfg = self.config
-    with torch.no_grad():
-      target = target_distribution(self.target(batch['next_state']), batch['return'], batch['discount'])
-    logits = self.online(batch['state'])
-    weight = batch['valid'].to(torch.float32) if 'valid' in batch else None
-    self.online.flat_grad.zero_()
-    mean_loss, _ = quantile_huber_loss(logits, batch['action'], target, weight, cfg.huber_param)
-    mean_loss.backward()
+    with self._matmul_precision():
+      with torch.no_grad():
+        target = target_distribution(self.target(batch['next_state']), batch['return'], batch['discount'])
+      logits = self.online(batch['state'])
+      weight = batch['valid'].to(torch.float32) if 'valid' in batch else None
+      self.online.flat_grad.zero_()
+      mean_loss, _ = quantile_huber_loss(logits, batch['action'], target, weight, cfg.huber_param)
+      mean_loss.backward()
     world = allreduce_sum_(self.online.flat_grad)
     self.steps += 1
     adam_step(self.flat, self.online.flat_grad, self.m, self.v, self.steps, cfg.learning_rate, cfg.adam_b1, cfg.adam_b2,

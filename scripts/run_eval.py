@@ -35,10 +35,13 @@ def main():
   if args.max_episode_length:
     suite.max_episode_length = args.max_episode_length
   device = f'cuda:{local}'
+  torch.cuda.set_device(local)
+  if world > 1:                       # rank 0 reads the decoder checkpoint; the others receive it over NCCL
+    torch.distributed.init_process_group('nccl', device_id=torch.device(device))
   n = len(suite.seeds)
   layout = 'x128' if n * 3686400 <= 60e9 else 'x64'
-  env = BatchedBalloonEnv(n, device=device, observation='perciatelli', decoder_params=models.load_decoder(args.decoder),
-                          field_layout=layout)
+  env = BatchedBalloonEnv(n, device=device, observation='perciatelli',
+                          decoder_params=models.load_decoder(args.decoder) if rank == 0 else None, field_layout=layout)
   agent = agents.create_agent(args.agent, env.action_space.n, env.observation_space.shape, env.arena)
   torch.cuda.synchronize()
   t0 = time.perf_counter()
@@ -58,6 +61,8 @@ def main():
                     'terminated': int(sum(r.out_of_power or r.envelope_burst or r.zeropressure for r in results))}),
         flush=True)
   env.close()
+  if world > 1:
+    torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -50,7 +50,7 @@ def main():
 
   layout = 'x128' if n * 3686400 <= 60e9 else 'x64'
   env = BatchedBalloonEnv(n, device=str(device), observation='perciatelli', field_layout=layout, seed=args.seed + rank,
-                          decoder_params=models.load_decoder(args.decoder))
+                          decoder_params=models.load_decoder(args.decoder) if rank == 0 else None)   # rank 0 reads, NCCL broadcast
   learner = learner_lib.QrDqnLearner(cfg, device=device, seed=args.seed)          # same seed: identical replicas
   explore = learner_lib.MarcoPoloExploration(n, exploratory_episode_probability=cfg.exploratory_episode_probability,
                                              seed=args.seed + 17 * rank, device=device)

@@ -28,7 +28,18 @@ def _worker(rank, world, port, out):
   stats = sharding.reduce_run_stats(elapsed_ms=10.0 + 5.0 * rank, env_steps=(e - b) * 3, launches=6)
   pool = torch.full((2, 3), float(rank + 1))
   sharding.broadcast_field_pool(pool, src=0)
-  out[rank] = (stats, pool.clone(), (b, e))
+  # decoder weights: only rank 0 "read the checkpoint"
+  params = None
+  if rank == 0:
+    g = torch.Generator().manual_seed(5)
+    params = {f'Dense_{l}': {'kernel': torch.randn(i, o, generator=g).numpy(), 'bias': torch.randn(o, generator=g).numpy()}
+              for l, (i, o) in enumerate(sharding.DECODER_SHAPES)}
+  got = sharding.broadcast_decoder_params(params, 'cpu', src=0)
+  checksum = sum(float(got[f'Dense_{l}']['kernel'].double().sum() + 3 * got[f'Dense_{l}']['bias'].double().sum())
+                 for l in range(4))
+  shapes = [tuple(got[f'Dense_{l}']['kernel'].shape) for l in range(4)]
+  none_everywhere = sharding.broadcast_decoder_params(None, 'cpu', src=0) is None
+  out[rank] = (stats, pool.clone(), (b, e), checksum, shapes, none_everywhere)
   dist.destroy_process_group()
 
 
@@ -39,7 +50,8 @@ def test_two_rank_reduction_and_broadcast():
   port = 29500 + (os.getpid() % 2000)
   mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
   for rank in range(world):
-    stats, pool, (b, e) = out[rank]
+    stats, pool, (b, e), checksum, shapes, none_everywhere = out[rank]
+    assert checksum == out[0][3] and shapes == list(sharding.DECODER_SHAPES) and none_everywhere
     assert stats == {'elapsed_ms': 15.0, 'env_steps': 65536 * 3, 'launches': 12}     # max time, summed work
     assert torch.equal(pool, torch.ones(2, 3))                                      # rank 0's pool everywhere
     assert e - b == 32768
