@@ -34,7 +34,7 @@ EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_u
            'ble_set_noise', 'ble_state_upload', 'ble_state_download', 'ble_reset', 'ble_init_derived',
            'ble_step', 'ble_step_ex', 'ble_rollout', 'ble_step_host', 'ble_wind_at_balloon', 'ble_wind_gather', 'ble_wind_query', 'ble_atmosphere_query', 'ble_derived',
            'ble_features_perciatelli', 'ble_features_observe', 'ble_features_clear', 'ble_features_track',
-           'ble_generate_fields', 'ble_generate_fields_at', 'ble_agent_station_seeker', 'ble_agent_random_walk',
+           'ble_generate_fields', 'ble_generate_fields_at', 'ble_sample_latents', 'ble_agent_station_seeker', 'ble_agent_random_walk',
            'ble_eval_begin', 'ble_eval_accumulate', 'ble_eval_results',
            'ble_launch_count',
            'ble_qr_greedy', 'ble_qr_target', 'ble_qr_loss', 'ble_replay_sample', 'ble_adam_step',
@@ -43,7 +43,7 @@ EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_u
 
 class BleConfig(_c.Structure):
   _fields_ = [('precision', _c.c_int32), ('wind_model', _c.c_int32), ('enable_noise', _c.c_int32),
-              ('field_layout', _c.c_int32), ('enable_features', _c.c_int32), ('decoder_tf32', _c.c_int32),
+              ('field_layout', _c.c_int32), ('enable_features', _c.c_int32), ('decoder_fp32', _c.c_int32),
               ('reserved', _c.c_int32 * 2)]
 
 
@@ -116,6 +116,7 @@ def load(build_if_missing=True):
   lib.ble_features_track.argtypes = [vp, i32]
   lib.ble_generate_fields.argtypes = [vp, vp, i64, i64, vp]
   lib.ble_generate_fields_at.argtypes = [vp, vp, vp, i64, vp]
+  lib.ble_sample_latents.argtypes = [vp, vp, i64, vp, vp]
   lib.ble_agent_station_seeker.argtypes = [vp, vp, vp, vp, vp]
   lib.ble_agent_random_walk.argtypes = [vp, vp, vp, i32, vp, vp]
   lib.ble_eval_begin.argtypes = [vp, vp]

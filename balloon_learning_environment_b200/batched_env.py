@@ -44,7 +44,7 @@ class BatchedBalloonArena:
 
   def __init__(self, num_envs: int, *, device: str = 'cuda:0', precision: str = 'fp32',
                wind_model: str = 'grid', enable_noise: bool = True, field_layout: str = 'x64',
-               enable_features: bool = False, decoder_tf32: bool = False):
+               enable_features: bool = False, decoder_precision: str = 'tf32'):
     if not torch.cuda.is_available():
       raise _lib.BleError('BatchedBalloonArena needs a CUDA device (no CPU fallback exists)')
     self._lib = _lib.load()
@@ -54,7 +54,7 @@ class BatchedBalloonArena:
     self.wind_model = wind_model
     self.enable_noise = bool(enable_noise)
     cfg = _lib.BleConfig(_lib.PRECISION[precision], _lib.WIND_MODEL[wind_model], int(enable_noise),
-                         _lib.FIELD_LAYOUT[field_layout], int(enable_features), int(decoder_tf32))
+                         _lib.FIELD_LAYOUT[field_layout], int(enable_features), {'tf32': 0, 'fp32': 1}[decoder_precision])
     self.enable_features = bool(enable_features)
     handle = ctypes.c_void_p()
     dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -180,6 +180,13 @@ class BatchedBalloonArena:
     seeds = seeds.to(self.device, torch.int64).contiguous()
     rc = self._lib.ble_generate_fields(self._h, _ptr(seeds), int(first_field), seeds.numel(), self._stream())
     self._check(rc, 'ble_generate_fields')
+
+  def sample_latents(self, seeds: torch.Tensor) -> torch.Tensor:
+    """The latents sample_wind_fields decodes for these seeds: int64 [K] -> float32 [K, 64], z ~ N(0, I)."""
+    seeds = seeds.to(self.device, torch.int64).contiguous()
+    out = torch.empty(seeds.numel(), 64, dtype=torch.float32, device=self.device)
+    self._check(self._lib.ble_sample_latents(self._h, _ptr(seeds), seeds.numel(), _ptr(out), self._stream()), 'ble_sample_latents')
+    return out
 
   def sample_wind_fields_at(self, seeds: torch.Tensor, field_index: torch.Tensor) -> None:
     """sample_wind_fields for a scattered set of fields: seeds int64 [K], field_index int32 [K] (distinct)."""

@@ -839,6 +839,7 @@ struct EngineBase {
   virtual int decode(const float*, int64_t, float*, cudaStream_t) = 0;
   virtual int generate_fields(const uint64_t*, int64_t, int64_t, cudaStream_t) = 0;
   virtual int generate_fields_at(const uint64_t*, int64_t, int64_t, const int32_t*, cudaStream_t) = 0;
+  virtual int sample_latents(const uint64_t*, int64_t, float*, cudaStream_t) = 0;
   virtual int agent_station_seeker(const float*, int32_t*, int32_t*, cudaStream_t) = 0;
   virtual int agent_random_walk(const float*, const uint64_t*, int32_t, int32_t*, cudaStream_t) = 0;
   virtual int eval_begin(cudaStream_t) = 0;
@@ -893,8 +894,10 @@ struct Engine : EngineBase {
   cublasLtHandle_t lt = nullptr;
   bool have_decoder = false;
   static constexpr int64_t kDecChunk = 4096;
-  static constexpr int64_t kGenChunk = 512;                 // fields decoded per pass of generate_fields
-  float* gen_latents = nullptr; float* gen_fields = nullptr;
+  static constexpr int64_t kGenChunk = 2048;                 // fields decoded per pass of generate_fields
+  float* gen_latents = nullptr; float* gen_flow[2] = {nullptr, nullptr};
+  cudaStream_t gen_stream = nullptr;
+  cudaEvent_t ev_flow[2] = {nullptr, nullptr}, ev_written[2] = {nullptr, nullptr}, ev_fork = nullptr;
   // evaluation surface
   EvalBuffers ev{nullptr, nullptr, nullptr, nullptr};
   double* walk_target = nullptr;
@@ -970,7 +973,10 @@ struct Engine : EngineBase {
     if (lt != nullptr) cublasLtDestroy(lt);
     cudaFree(gp_obs); cudaFree(gp_count); cudaFree(gp_chol); cudaFree(gp_m); cudaFree(feat_range);
     cudaFree(gp_first); cudaFree(gp_z); cudaFree(range_scratch);
-    cudaFree(gen_latents); cudaFree(gen_fields);
+    cudaFree(gen_latents); cudaFree(gen_flow[0]); cudaFree(gen_flow[1]);
+    for (int b = 0; b < 2; ++b) { if (ev_flow[b]) cudaEventDestroy(ev_flow[b]); if (ev_written[b]) cudaEventDestroy(ev_written[b]); }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (gen_stream) cudaStreamDestroy(gen_stream);
     cudaFree(ev.reward); cudaFree(ev.within); cudaFree(ev.steps); cudaFree(ev.active); cudaFree(walk_target);
     cudaFree(d_actions); cudaFree(d_reward);
     cudaFreeHost(h_actions); cudaFreeHost(h_reward);
@@ -1202,19 +1208,23 @@ struct Engine : EngineBase {
     if (kernels == nullptr || biases == nullptr) { err = "set_decoder: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
     BLE_DEVICE_GUARD();
     const int dims[5] = {kDecLatents, kDecHidden, kDecHidden, kDecHidden, kDecOut};
+    const int ld[5] = {kDecLatents, kDecHidden, kDecHidden, kDecHidden, kDecOutPad};     // row pitch of layer i's [in, out] weights
     if (lt == nullptr && cublasLtCreate(&lt) != CUBLAS_STATUS_SUCCESS) { err = "set_decoder: cublasLtCreate failed"; return BLE_ERR_CUDA; }
     for (int i = 0; i < 4; ++i) {
       if (kernels[i] == nullptr || biases[i] == nullptr) { err = "set_decoder: null layer"; return BLE_ERR_INVALID_ARGUMENT; }
       if (dec_w[i] == nullptr) {
-        BLE_CUDA(cudaMalloc(&dec_w[i], sizeof(float) * size_t(dims[i]) * dims[i + 1]));
-        BLE_CUDA(cudaMalloc(&dec_b[i], sizeof(float) * dims[i + 1]));
+        BLE_CUDA(cudaMalloc(&dec_w[i], sizeof(float) * size_t(dims[i]) * ld[i + 1]));
+        BLE_CUDA(cudaMalloc(&dec_b[i], sizeof(float) * ld[i + 1]));
+        BLE_CUDA(cudaMemsetAsync(dec_w[i], 0, sizeof(float) * size_t(dims[i]) * ld[i + 1], s));
+        BLE_CUDA(cudaMemsetAsync(dec_b[i], 0, sizeof(float) * ld[i + 1], s));
       }
-      BLE_CUDA(cudaMemcpyAsync(dec_w[i], kernels[i], sizeof(float) * size_t(dims[i]) * dims[i + 1], cudaMemcpyDeviceToDevice, s));
+      BLE_CUDA(cudaMemcpy2DAsync(dec_w[i], sizeof(float) * ld[i + 1], kernels[i], sizeof(float) * dims[i + 1],
+                                 sizeof(float) * dims[i + 1], dims[i], cudaMemcpyDeviceToDevice, s));
       BLE_CUDA(cudaMemcpyAsync(dec_b[i], biases[i], sizeof(float) * dims[i + 1], cudaMemcpyDeviceToDevice, s));
     }
     if (dec_act[0] == nullptr) {
-      BLE_CUDA(cudaMalloc(&dec_act[0], sizeof(float) * kDecChunk * kDecOut));
-      BLE_CUDA(cudaMalloc(&dec_act[1], sizeof(float) * kDecChunk * kDecOut));
+      BLE_CUDA(cudaMalloc(&dec_act[0], sizeof(float) * kDecChunk * kDecOutPad));
+      BLE_CUDA(cudaMalloc(&dec_act[1], sizeof(float) * kDecChunk * kDecOutPad));
       BLE_CUDA(cudaMalloc(&dec_workspace, kDecWorkspace));
     }
     have_decoder = true;
@@ -1233,7 +1243,7 @@ struct Engine : EngineBase {
       if (lc) cublasLtMatrixLayoutDestroy(lc);
       if (op) cublasLtMatmulDescDestroy(op);
     };
-    bool ok = cublasLtMatmulDescCreate(&op, cfg.decoder_tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F,
+    bool ok = cublasLtMatmulDescCreate(&op, cfg.decoder_fp32 ? CUBLAS_COMPUTE_32F : CUBLAS_COMPUTE_32F_FAST_TF32,
                                        CUDA_R_32F) == CUBLAS_STATUS_SUCCESS;
     const cublasLtEpilogue_t epi = relu ? CUBLASLT_EPILOGUE_RELU_BIAS : CUBLASLT_EPILOGUE_BIAS;
     const float* bias = dec_b[layer];
@@ -1257,6 +1267,15 @@ struct Engine : EngineBase {
     return BLE_OK;
   }
 
+  // the four GEMMs for c <= kDecChunk latents; the Dense_3 output [c, 4416] lands in `flow` (default dec_act[1])
+  int decoder_gemms(const float* latents, int64_t c, cudaStream_t s, float* flow = nullptr) {
+    int rc = dense(latents, dec_act[0], 0, c, kDecLatents, kDecHidden, true, s);
+    if (rc == BLE_OK) rc = dense(dec_act[0], dec_act[1], 1, c, kDecHidden, kDecHidden, true, s);
+    if (rc == BLE_OK) rc = dense(dec_act[1], dec_act[0], 2, c, kDecHidden, kDecHidden, true, s);
+    if (rc == BLE_OK) rc = dense(dec_act[0], flow != nullptr ? flow : dec_act[1], 3, c, kDecHidden, kDecOutPad, false, s);
+    return rc;
+  }
+
   int decode(const float* latents, int64_t f, float* fields, cudaStream_t s) override {
     if (latents == nullptr || fields == nullptr || f <= 0) { err = "decode: bad argument"; return BLE_ERR_INVALID_ARGUMENT; }
     if (!have_decoder) { err = "decode: no decoder weights (call ble_set_decoder first)"; return BLE_ERR_NOT_READY; }
@@ -1264,10 +1283,7 @@ struct Engine : EngineBase {
     const ResizeTaps taps = make_resize_taps();
     for (int64_t first = 0; first < f; first += kDecChunk) {
       const int64_t c = std::min<int64_t>(kDecChunk, f - first);
-      int rc = dense(latents + first * kDecLatents, dec_act[0], 0, c, kDecLatents, kDecHidden, true, s);
-      if (rc == BLE_OK) rc = dense(dec_act[0], dec_act[1], 1, c, kDecHidden, kDecHidden, true, s);
-      if (rc == BLE_OK) rc = dense(dec_act[1], dec_act[0], 2, c, kDecHidden, kDecHidden, true, s);
-      if (rc == BLE_OK) rc = dense(dec_act[0], dec_act[1], 3, c, kDecHidden, kDecOut, false, s);
+      const int rc = decoder_gemms(latents + first * kDecLatents, c, s);
       if (rc != BLE_OK) return rc;
       const int64_t threads = c * int64_t(kNX) * kNY * kDecFlows;
       k_decode_epilogue<<<grid_for(threads, 256), 256, 0, s>>>(dec_act[1], fields + first * kFieldFloats, taps, c);
@@ -1291,20 +1307,57 @@ struct Engine : EngineBase {
     BLE_DEVICE_GUARD();
     if (gen_latents == nullptr) {
       BLE_CUDA(cudaMalloc(&gen_latents, sizeof(float) * kGenChunk * kDecLatents));
-      BLE_CUDA(cudaMalloc(&gen_fields, sizeof(float) * kGenChunk * size_t(kFieldFloats)));
+      for (int b = 0; b < 2; ++b) {
+        BLE_CUDA(cudaMalloc(&gen_flow[b], sizeof(float) * kGenChunk * kDecOutPad));
+        BLE_CUDA(cudaEventCreateWithFlags(&ev_flow[b], cudaEventDisableTiming));
+        BLE_CUDA(cudaEventCreateWithFlags(&ev_written[b], cudaEventDisableTiming));
+      }
+      BLE_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      BLE_CUDA(cudaStreamCreateWithFlags(&gen_stream, cudaStreamNonBlocking));
+      BLE_CUDA(cudaFuncSetAttribute(k_flow_to_windows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(float) * kFlowSmemFloats)));
+      BLE_CUDA(cudaFuncSetAttribute(k_flow_to_windows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(float) * kFlowSmemFloats)));
     }
-    for (int64_t done_f = 0; done_f < count; done_f += kGenChunk) {
+    const ResizeTaps taps = make_resize_taps();
+    // Two streams: the decoder GEMMs of chunk k + 1 (tensor cores, caller's stream) run under the window writer of
+    // chunk k (HBM-write bound, gen_stream).  Dense_3 writes into one of two flow buffers; the writer's stream forks
+    // from the caller's stream here and joins it again below, so the caller sees ordinary stream semantics.
+    BLE_CUDA(cudaEventRecord(ev_fork, s));
+    BLE_CUDA(cudaStreamWaitEvent(gen_stream, ev_fork, 0));
+    int64_t chunk_no = 0;
+    for (int64_t done_f = 0; done_f < count; done_f += kGenChunk, ++chunk_no) {
       const int64_t c = std::min<int64_t>(kGenChunk, count - done_f);
+      const int b = int(chunk_no & 1);
+      if (chunk_no >= 2) BLE_CUDA(cudaStreamWaitEvent(s, ev_written[b], 0));          // flow buffer b is free again
       // The GEMMs always run on a full chunk (zero latents beyond c) so that cuBLASLt picks the same
       // algorithm whatever the batch: a seed's field is then bit-identical however a suite is sharded.
       if (c < kGenChunk) BLE_CUDA(cudaMemsetAsync(gen_latents, 0, sizeof(float) * kGenChunk * kDecLatents, s));
       k_sample_latents<<<grid_for(c * kDecLatents, 256), 256, 0, s>>>(seeds + done_f, c, gen_latents);
       ++launches;
       BLE_CUDA(cudaGetLastError());
-      int rc = decode(gen_latents, kGenChunk, gen_fields, s);
-      if (rc == BLE_OK) rc = write_fields_at(gen_fields, first + done_f, c, dst_index != nullptr ? dst_index + done_f : nullptr, s);
+      const int rc = decoder_gemms(gen_latents, kGenChunk, s, gen_flow[b]);
       if (rc != BLE_OK) return rc;
+      BLE_CUDA(cudaEventRecord(ev_flow[b], s));
+      BLE_CUDA(cudaStreamWaitEvent(gen_stream, ev_flow[b], 0));
+      // resize + curl + window layout in one pass: the windows are the only HBM traffic of the field writer
+      auto writer = d.layout.x_stride_floats == 32 ? k_flow_to_windows<true> : k_flow_to_windows<false>;
+      writer<<<unsigned(c * kYC), kFlowThreads, sizeof(float) * kFlowSmemFloats, gen_stream>>>(
+          gen_flow[b], cells, d.layout, taps, first + done_f, c, dst_index != nullptr ? dst_index + done_f : nullptr);
+      ++launches;
+      BLE_CUDA(cudaGetLastError());
+      BLE_CUDA(cudaEventRecord(ev_written[b], gen_stream));
+      have_fields = true;
     }
+    BLE_CUDA(cudaStreamWaitEvent(s, ev_written[0], 0));
+    if (chunk_no >= 2) BLE_CUDA(cudaStreamWaitEvent(s, ev_written[1], 0));
+    return BLE_OK;
+  }
+
+  int sample_latents(const uint64_t* seeds, int64_t count, float* latents, cudaStream_t s) override {
+    if (seeds == nullptr || latents == nullptr || count <= 0) { err = "sample_latents: bad argument"; return BLE_ERR_INVALID_ARGUMENT; }
+    BLE_DEVICE_GUARD();
+    k_sample_latents<<<grid_for(count * kDecLatents, 256), 256, 0, s>>>(seeds, count, latents);
+    ++launches;
+    BLE_CUDA(cudaGetLastError());
     return BLE_OK;
   }
 
@@ -1668,6 +1721,9 @@ int ble_generate_fields_at(ble_handle* h, const uint64_t* seeds, const int32_t* 
   BLE_H(h);
   if (field_index == nullptr) { h->eng->err = "generate_fields_at: null field_index"; return BLE_ERR_INVALID_ARGUMENT; }
   return h->eng->generate_fields_at(seeds, 0, count, field_index, cudaStream_t(stream));
+}
+int ble_sample_latents(ble_handle* h, const uint64_t* seeds, int64_t count, float* latents, void* stream) {
+  BLE_H(h); return h->eng->sample_latents(seeds, count, latents, cudaStream_t(stream));
 }
 int ble_agent_station_seeker(ble_handle* h, const float* obs, int32_t* actions, int32_t* best_level, void* stream) {
   BLE_H(h); return h->eng->agent_station_seeker(obs, actions, best_level, cudaStream_t(stream));

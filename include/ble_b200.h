@@ -63,8 +63,9 @@ typedef struct {
   int32_t enable_noise;        /* 1: ground truth = forecast + simplex noise (wind_field.py:125-145) */
   int32_t field_layout;        /* BLE_LAYOUT_*                                                      */
   int32_t enable_features;     /* 1: keep the WindGP history and allow ble_features_perciatelli      */
-  int32_t decoder_tf32;        /* 1: the decoder GEMMs run on the tensor cores (TF32 inputs, fp32
-                                * accumulate); 0 (default): fp32 FMA, used by the parity tests        */
+  int32_t decoder_fp32;        /* 0 (default): the decoder GEMMs run on the tensor cores (TF32 inputs, fp32
+                                * accumulate -- jax's default matmul precision on the reference's GPU
+                                * path); 1: fp32 FMA, what the reference computes on a CPU            */
   int32_t reserved[2];         /* must be 0                                                         */
 } ble_config;
 
@@ -263,6 +264,10 @@ int ble_generate_fields(ble_handle* h, const uint64_t* seeds, int64_t first_fiel
  * int32 [count], each entry in [0, n_fields) and distinct. */
 int ble_generate_fields_at(ble_handle* h, const uint64_t* seeds, const int32_t* field_index, int64_t count,
                            void* stream);
+/* The latents ble_generate_fields decodes for these seeds: device float32 [count, 64], z ~ N(0, I_64) per seed
+ * (env/generative_wind_field.py:57-58 draws jax.random.normal(key, (64,)); here Philox4x32-10 keyed by the seed).
+ * ble_decode_fields(latents) is the native-layout view of what ble_generate_fields writes into the bank. */
+int ble_sample_latents(ble_handle* h, const uint64_t* seeds, int64_t count, float* latents, void* stream);
 int ble_agent_station_seeker(ble_handle* h, const float* obs, int32_t* actions, int32_t* best_level, void* stream);
 int ble_agent_random_walk(ble_handle* h, const float* obs, const uint64_t* seeds, int32_t step_index,
                           int32_t* actions, void* stream);
