@@ -101,59 +101,45 @@ __device__ __forceinline__ void blocked_coords(int k, int* row, int* col) {
   *row = b * kGpBlk + r; *col = j * kGpBlk + c;
 }
 
-// Cholesky factor of the 8 x 8 diagonal block `blk` (A-fragment order, lower part valid) and its inverse, by one warp.
-// This is the serial part of the factorisation (15 of them per balloon, each waiting for the previous pivot), so it is
-// written for latency: lanes 0..7 own a row each during the factorisation (one shuffle for the pivot, seven pipelined
-// shuffles for the column), the reciprocal square roots come from an fp32 seed + ONE fp64 Newton step (2^-44), and the
-// triangular inverse and z_j = inv(L_jj) y'_j are ten independent forward substitutions -- lane c < 8 solves for column c
-// of the inverse, lanes 8 and 9 for the two target columns -- that multiply by the stored reciprocal diagonal.
-// On return the block holds inv(L_jj) (full 8 x 8, zeros above the diagonal) and yz[0..8) holds z_j.
-__device__ __forceinline__ void chol_diag_block(double* __restrict__ blk, double (*__restrict__ yz)[2], int lane) {
-  const int r = lane & 7;
-  double a[kGpBlk], dinv[kGpBlk];
-#pragma unroll
-  for (int c = 0; c < kGpBlk; ++c) a[c] = c <= r ? blk[blk_inner(r, c)] : 0.0;
-  const double rhs0 = yz[r][0], rhs1 = yz[r][1];
+// inv(L_jj) of the 8 x 8 diagonal block and z_j = inv(L_jj) y'_j, by one warp, for LATENCY: this is the serial part of
+// the factorisation (15 of them per balloon, each waiting for the previous pivot; the first version -- one row per lane,
+// a separate forward substitution for the inverse, ~1,100 dependent instructions -- held the other seven warps at the
+// barrier for 27 % of the kernel, profiles/r02_k_gp_posterior_source_report.txt).
+// The block arrives in the fp64 MMA's C-fragment layout (lane 4 g + tq holds (g, 2 tq), (g, 2 tq + 1)), i.e. straight
+// from the DMMA that applied the last trailing update, and never goes through shared memory.  Right-looking Cholesky
+// with the forward elimination of [I | y'] riding along: at pivot k every lane fetches a_kk, its row's a_gk and its two
+// columns' a_ck by four independent shuffles (column k lives in component k & 1 of the lanes with tq == k >> 1), scales
+// by 1 / l_kk (fp32 seed + one fp64 Newton step, 2^-44), updates its two entries of the trailing block, and applies the
+// same row operation to its two entries of W (-> inv(L_jj)) and, for tq < 2, to y'.  Eight pivots x ~100 cycles.
+// Entries above the diagonal are never read (they carry garbage).  On return blk holds inv(L_jj) (zeros above the
+// diagonal) in A-fragment order and yz[0..8) holds z_j.
+__device__ __forceinline__ void chol_diag_block(double a0, double a1, double* __restrict__ blk, double (*__restrict__ yz)[2], int lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const int g = lane >> 2, tq = lane & 3, quad = lane & ~3;
+  const int c0 = 2 * tq, c1 = c0 + 1;
+  double w0 = g == c0 ? 1.0 : 0.0, w1 = g == c1 ? 1.0 : 0.0;
+  double yv = tq < 2 ? yz[g][tq] : 0.0;
 #pragma unroll
   for (int k = 0; k < kGpBlk; ++k) {
-    const double dk = __shfl_sync(0xffffffffu, a[k], k);                 // pivot a_kk (held by lane k)
+    const double v = (k & 1) ? a1 : a0;
+    const int ks = k >> 1;
+    const double dk = __shfl_sync(kFull, v, 4 * k + ks);               // a_kk
+    const double agk = __shfl_sync(kFull, v, quad | ks);               // a_gk, own row
+    const double ac0 = __shfl_sync(kFull, v, 4 * c0 + ks);             // a_ck for the two columns this lane updates
+    const double ac1 = __shfl_sync(kFull, v, 4 * c1 + ks);
+    const double wk0 = __shfl_sync(kFull, w0, 4 * k + tq), wk1 = __shfl_sync(kFull, w1, 4 * k + tq);   // row k of W
+    const double yk = __shfl_sync(kFull, yv, 4 * k + tq);
     double inv = double(rsqrtf(float(dk)));
-    inv = inv * fma(-0.5 * dk * inv, inv, 1.5);
-    dinv[k] = inv;                                                        // 1 / l_kk
-    const double lrk = a[k] * inv;                                        // l_rk for r >= k (l_kk = sqrt(a_kk) on lane k)
-    a[k] = lrk;
-#pragma unroll
-    for (int c = k + 1; c < kGpBlk; ++c) {
-      const double lck = __shfl_sync(0xffffffffu, lrk, c);
-      if (r >= c) a[c] = fma(-lrk, lck, a[c]);
-    }
+    inv = inv * fma(-0.5 * dk * inv, inv, 1.5);                         // 1 / l_kk
+    const double lgk = agk * inv;
+    if (c0 > k) a0 = fma(-lgk, ac0 * inv, a0);
+    if (c1 > k) a1 = fma(-lgk, ac1 * inv, a1);
+    const double s0 = wk0 * inv, s1 = wk1 * inv, sy = yk * inv;         // row k of [W | y'] / l_kk
+    if (g == k) { w0 = s0; w1 = s1; yv = sy; }
+    else if (g > k) { w0 = fma(-lgk, s0, w0); w1 = fma(-lgk, s1, w1); yv = fma(-lgk, sy, yv); }
   }
-  __syncwarp();
-  if (lane < kGpBlk) {
-#pragma unroll
-    for (int c = 0; c < kGpBlk; ++c) blk[blk_inner(r, c)] = a[c];         // L_jj, zeros above the diagonal
-  }
-  __syncwarp();
-  // lane c < 8: column c of inv(L_jj) (right-hand side e_c); lanes 8, 9: z_j (right-hand sides y'_j); L entries are
-  // warp-wide broadcasts
-  double xcol[kGpBlk];
-  const int cidx = lane & 15;
-#pragma unroll
-  for (int i = 0; i < kGpBlk; ++i) {
-    const double yi0 = __shfl_sync(0xffffffffu, rhs0, i), yi1 = __shfl_sync(0xffffffffu, rhs1, i);   // row i of y'_j
-    double acc = cidx < kGpBlk ? (i == cidx ? 1.0 : 0.0) : (cidx == 8 ? yi0 : yi1);
-#pragma unroll
-    for (int k = 0; k < i; ++k) acc = fma(-blk[blk_inner(i, k)], xcol[k], acc);
-    xcol[i] = acc * dinv[i];
-  }
-  __syncwarp();
-  if (lane < kGpBlk) {
-#pragma unroll
-    for (int i = 0; i < kGpBlk; ++i) blk[blk_inner(i, lane)] = xcol[i];
-  } else if (lane < 10) {
-#pragma unroll
-    for (int i = 0; i < kGpBlk; ++i) yz[i][lane - 8] = xcol[i];
-  }
+  *reinterpret_cast<double2*>(blk + 4 * g + 2 * (tq & 1) + 32 * (tq >> 1)) = make_double2(w0, w1);
+  if (tq < 2) yz[g][tq] = yv;
   __syncwarp();
 }
 
@@ -322,7 +308,12 @@ __global__ void __launch_bounds__(kGpPThreads, 3) k_gp_posterior(DevState<Real> 
     __syncthreads();
 
     // ---- 2. blocked Cholesky (fp64), z = L^-1 y alongside ----
-    if (warp == 0) chol_diag_block(S.L + blk_offset(0, 0), &S.yz[0], lane);
+    const int cpos = 4 * g + 2 * (tq & 1) + 32 * (tq >> 1);                 // this lane's (g, 2 tq), (g, 2 tq + 1) of a C tile
+    if (warp == 0) {
+      const double2 a = *reinterpret_cast<const double2*>(S.L + blk_offset(0, 0) + cpos);
+      __syncwarp();
+      chol_diag_block(a.x, a.y, S.L + blk_offset(0, 0), &S.yz[0], lane);
+    }
     __syncthreads();
     for (int j = 0; j < nb; ++j) {
       const double* X = S.L + blk_offset(j, j);             // inv(L_jj)
@@ -347,7 +338,6 @@ __global__ void __launch_bounds__(kGpPThreads, 3) k_gp_posterior(DevState<Real> 
       // trailing update K_bb' -= L_bj L_b'j^T for j < b' <= b.  Warp 0 takes (j + 1, j + 1) and factors it at once
       // (look-ahead); warps 1..7 own block COLUMNS b' cyclically: the B operand L_b'j stays in registers while b runs down
       // the column, and the block addresses advance by increments.
-      const int cpos = 4 * g + 2 * (tq & 1) + 32 * (tq >> 1);               // this lane's (g, 2 tq), (g, 2 tq + 1) of a C tile
       if (warp == 0) {
         if (j + 1 < nb) {
           double* C = S.L + blk_offset(j + 1, j + 1);
@@ -355,9 +345,8 @@ __global__ void __launch_bounds__(kGpPThreads, 3) k_gp_posterior(DevState<Real> 
           double2 cc = *reinterpret_cast<double2*>(C + cpos);
           dmma884(cc.x, cc.y, -A[lane], A[lane]);
           dmma884(cc.x, cc.y, -A[32 + lane], A[32 + lane]);
-          *reinterpret_cast<double2*>(C + cpos) = cc;
           __syncwarp();
-          chol_diag_block(C, &S.yz[(j + 1) * kGpBlk], lane);
+          chol_diag_block(cc.x, cc.y, C, &S.yz[(j + 1) * kGpBlk], lane);     // the updated block stays in registers
         }
       } else {
         for (int b2 = j + 1 + (warp - 1); b2 < nb; b2 += kGpPWarps - 1) {
@@ -386,16 +375,19 @@ __global__ void __launch_bounds__(kGpPThreads, 3) k_gp_posterior(DevState<Real> 
     // LDS.128 each, landing in the register quad the MMA wants.  Diagonal blocks (the inverses) and the block right
     // under a diagonal block whose tile partner is that diagonal block stay element-wise {hi, lo} float2.
     {
+      // Work units of pivot column j, in order: u = 0 the diagonal block; then, if block row j + 1 is the BOTTOM of a tile
+      // (its tile partner is the diagonal block), that block alone; then the full tiles (b, b + 1), b = b0, b0 + 2, ...
+      // Unit u of column j belongs to warp (u + 3 j) mod 8, so a warp walks each column with stride 8 (the first version
+      // scanned all 120 (j, b) pairs in every warp: 17 % of the kernel's instructions).
       const int shift = nb & 1;
-      int unit = 0;
       for (int j = 0; j < nb; ++j) {
-        for (int b = j; b < nb; ++b) {
-          const bool top = ((b + shift) & 1) == 0;
-          const bool pair = b > j && top;                                  // (b, b + 1) is a full tile (b + 1 < nb always)
-          const bool single = b == j || (!top && b - 1 == j);              // diagonal block, or the block under it in its tile
-          if (!pair && !single) continue;
-          if ((unit++ & (kGpPWarps - 1)) != warp) continue;
-          if (pair) {
+        const bool under = j + 1 < nb && ((j + 1 + shift) & 1) != 0;          // (j + 1, j) is a single block
+        const int b0 = j + 1 + (under ? 1 : 0);                              // first full tile's top block row
+        const int n_units = 1 + (under ? 1 : 0) + (nb > b0 ? (nb - b0) >> 1 : 0);
+        for (int u = (warp - 3 * j) & (kGpPWarps - 1); u < n_units; u += kGpPWarps) {
+          const bool single = u == 0 || (under && u == 1);
+          if (!single) {
+            const int b = b0 + 2 * (u - 1 - (under ? 1 : 0));
             double* t0 = S.L + blk_offset(b, j);
             double* t1 = S.L + blk_offset(b + 1, j);
             const float e0 = float(-t0[lane]), e2 = float(-t0[32 + lane]), e1 = float(-t1[lane]), e3 = float(-t1[32 + lane]);
@@ -408,6 +400,7 @@ __global__ void __launch_bounds__(kGpPThreads, 3) k_gp_posterior(DevState<Real> 
             reinterpret_cast<float4*>(t0)[lane] = hi;
             reinterpret_cast<float4*>(t1)[lane] = lo4;
           } else {
+            const int b = j + u;
             double* t0 = S.L + blk_offset(b, j);
             const float sgn = b == j ? 1.f : -1.f;
             const float e0 = sgn * float(t0[lane]), e2 = sgn * float(t0[32 + lane]);
