@@ -444,10 +444,16 @@ k_step_roles(DevState<float> d, const int32_t* __restrict__ actions, FusedOut ou
 // =====================================================================================================================
 // Throughput shape
 // =====================================================================================================================
-constexpr int kWarpsPerCta = 4;
+// Warps per CTA.  The warps of a CTA share nothing, so the CTA is only the unit in which the hardware deals work to the
+// SMs: with one warp per CTA the 2,048 warps of a 65,536-balloon batch spread as 13 or 14 per SM instead of 12 or 16
+// (measured 117 vs 120 us per step at 65,536 and 88 vs 92 us at 32,768, gpurun_out r02p -> profiles/r02_step_timing_cta.jsonl).
+#ifndef BLE_WARPS_PER_CTA
+#define BLE_WARPS_PER_CTA 1
+#endif
+constexpr int kWarpsPerCta = BLE_WARPS_PER_CTA;
 
 #ifndef BLE_WARP_MIN_BLOCKS
-#define BLE_WARP_MIN_BLOCKS 4
+#define BLE_WARP_MIN_BLOCKS (16 / BLE_WARPS_PER_CTA)
 #endif
 __global__ void __launch_bounds__(32 * kWarpsPerCta, BLE_WARP_MIN_BLOCKS)
 k_step_warp(DevState<float> d, const int32_t* __restrict__ actions, FusedOut out, int noise_mode, int n_steps) {
