@@ -32,6 +32,8 @@
 // n_steps > 1 (ble_rollout): the same CTA runs the steps back to back on actions[step][N]; balloons do not
 // interact, so there is no grid-wide synchronisation and no launch gap between steps.
 #include "ble_step_fused.h"
+#include <algorithm>
+#include <cstdlib>
 
 #include "ble_step_roles.cuh"
 
@@ -588,11 +590,29 @@ static size_t warp_smem() { return size_t(kWarpsPerCta) * kPermStageBytes; }
 template <typename Kernel> static cudaError_t setup_kernel(Kernel kernel, int threads, size_t smem, int* blocks) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  // all of the unified L1 / shared storage as shared memory: the kernels' global traffic is streaming (state rows,
-  // one 128-byte window per balloon), what they need is resident CTAs
+  // Shared-memory carveout: exactly what the resident CTAs need, the rest of the unified storage stays L1.  The kernels'
+  // global traffic is streaming, but their register spills (152 B per thread in the sub-step loop) are not: with the
+  // whole storage carved out as shared memory the spill set (78 KB per SM) missed the 28 KB that was left of L1 on every
+  // reload; sized to fit, the step went from 117 to 111 us at 65,536 balloons (profiles/r02_step_timing_carveout.jsonl).
   e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, int(cudaSharedmemCarveoutMaxShared));
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kernel, threads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kernel, threads, smem);
+  if (e != cudaSuccess) return e;
+  int carveout = -2;
+  if (const char* env = std::getenv("BLE_STEP_CARVEOUT")) carveout = std::atoi(env);   // percent, A/B override
+  if (carveout == -2) {
+    constexpr size_t kUnified = 228 * 1024, kPerCtaReserve = 1024;
+    const size_t need = size_t(*blocks) * (smem + kPerCtaReserve + 128);
+    carveout = int(std::min<size_t>(100, (need * 100 + kUnified - 1) / kUnified));
+  }
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+  if (e != cudaSuccess) return e;
+  int fitted = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fitted, kernel, threads, smem);
+  if (e != cudaSuccess) return e;
+  if (fitted < *blocks)                                     // the hint cost residency: take the whole storage again
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, int(cudaSharedmemCarveoutMaxShared));
+  return e;
 }
 
 cudaError_t fused_setup(int blocks_per_sm[4]) {
