@@ -69,7 +69,7 @@ def rel_err(got, ref, key):
 
 # ------------------------------------------------------------------------------ wind gather
 
-@pytest.mark.parametrize('precision,tol', [('fp64', 1e-11), ('fp32', 3e-5)])
+@pytest.mark.parametrize('precision,tol', [('fp64', 1e-11), ('fp32', 1e-5)])
 def test_wind_gather_matches_oracle(ble, precision, tol):
   rng = np.random.default_rng(9)
   bank = golden_fields.field_bank()
@@ -86,8 +86,10 @@ def test_wind_gather_matches_oracle(ble, precision, tol):
   pts = wind_lib.prepare_points(xyzt[:, 0].astype(np.float64) * 1000, xyzt[:, 1].astype(np.float64) * 1000,
                                 xyzt[:, 2].astype(np.float64), xyzt[:, 3].astype(np.float64) * 3600.0)
   want = wind_lib.interpolate(bank, fidx, pts)
-  scale = 20.0 if precision == 'fp32' else 1.0
-  assert np.abs(uv - want).max() < max(tol * scale, 3e-6 if precision == 'fp64' else 0)  # fp32 output cast
+  err = float(np.abs(uv - want).max())
+  print(f'wind gather {precision}: worst |err| = {err:.2e} m/s over {m} lookups (max |wind| {np.abs(want).max():.1f} m/s)')
+  # fp64 engine: the only error is the float32 cast of the output; fp32 engine: fp32 weights and a 16-term fp32 blend
+  assert err < (3e-6 if precision == 'fp64' else tol)
   arena.close()
 
 
@@ -813,6 +815,47 @@ def test_incremental_gp_matches_full_refit(ble, monkeypatch):
   print('incremental vs refit: worst feature difference', worst)
   for a in arenas:
     a.close()
+
+
+def test_full_size_one_field_per_balloon(ble):
+  """BASELINE configs[2] as the bench flies it: 65,536 balloons, ONE generated wind field per balloon (127 GB of X64
+  windows), simplex noise on.  One step of the production kernel; a 512-balloon sample is checked against the oracle
+  flying the native-layout view of the same fields (ble_decode_fields(ble_sample_latents(seed)))."""
+  from oracle import vae as vae_oracle
+  n = 65536
+  free, _ = torch.cuda.mem_get_info()
+  if free < 150e9:
+    pytest.skip('needs 150 GB of free HBM')
+  rng = np.random.default_rng(21)
+  env = ble.BatchedBalloonEnv(n, precision='fp32', enable_noise=True, seed=5, decoder_params=vae_oracle.synthetic_params(6))
+  seeds = torch.arange(n, dtype=torch.int64) * 7919 + 3
+  env.reset(seeds=seeds)                                     # generates one field per balloon from its seed
+  noise_seeds = rng.integers(0, 1634753849, (n, 2, 5)); noise_offsets = rng.uniform(-1, 1, (n, 2, 5, 4)).astype(np.float32)
+  env.arena.set_wind_noise(torch.from_numpy(noise_seeds), torch.from_numpy(noise_offsets))
+  s0 = state_np(env.arena)
+  acts = torch.from_numpy(rng.integers(0, 3, n).astype(np.int32)).cuda()
+  _, reward, done, info = env.step(acts)
+  s1 = state_np(env.arena)
+  idx = np.sort(rng.choice(n, 512, replace=False))
+  fields = env.arena.decode_wind_fields(env.arena.sample_latents(seeds[idx])).cpu().numpy()
+  assert np.abs(fields).max() > 1.0
+  b = balloon_lib.BalloonBatch(**{k: s0[k][idx].copy() for k in balloon_lib.FLOAT_FIELDS + balloon_lib.INT_FIELDS})
+  oenv = env_lib.OracleEnv(env_lib.OracleArena(
+      b, atmosphere_lib.Atmosphere(s0['atmosphere_alpha'][idx]), fields=fields, field_idx=np.arange(512),
+      noise=wind_lib.SimplexWindNoise(noise_seeds[idx], noise_offsets[idx].astype(np.float64))))
+  want_r, want_done, _ = oenv.step(acts.cpu().numpy()[idx])
+  for k in balloon_lib.FLOAT_FIELDS:
+    assert rel_err(s1[k][idx], getattr(b, k), k) < 1e-4, k
+  for k in ('status', 'last_command', 'envelope_state', 'altitude_state', 'power_paused', 'time_elapsed', 'date_time'):
+    np.testing.assert_array_equal(s1[k][idx], getattr(b, k), err_msg=k)
+  assert np.abs(reward.cpu().numpy()[idx] - want_r).max() < 2e-4
+  np.testing.assert_array_equal(done.cpu().numpy()[idx] != 0, want_done)
+  assert int(info['time_elapsed'][idx[0]]) == 180
+  # every balloon flies its OWN field: the winds of two balloons at the same point differ
+  q = torch.tensor([[0.0, 0.0, 9000.0, 1.0]] * 4, dtype=torch.float32)
+  uv = env.arena.wind_forecast(q, torch.tensor([0, 1, 40000, 65535], dtype=torch.int32)).cpu().numpy()
+  assert len({tuple(np.round(r, 4)) for r in uv}) == 4
+  env.close()
 
 
 # ------------------------------------------------------------------------------ VAE decoder (reset path)
