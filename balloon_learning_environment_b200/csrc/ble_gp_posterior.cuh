@@ -123,7 +123,9 @@ __device__ __forceinline__ void chol_diag_block(double a0, double a1, double* __
   for (int k = 0; k < kGpBlk; ++k) {
     const double v = (k & 1) ? a1 : a0;
     const int ks = k >> 1;
-    const double dk = __shfl_sync(kFull, v, 4 * k + ks);               // a_kk
+    // a_kk.  In exact arithmetic every pivot of K + alpha I is >= alpha (a Schur complement of it); the clamp keeps a
+    // rounding accident from turning into a NaN that would fill the whole observation
+    const double dk = fmax(__shfl_sync(kFull, v, 4 * k + ks), kGpNoise);
     const double agk = __shfl_sync(kFull, v, quad | ks);               // a_gk, own row
     const double ac0 = __shfl_sync(kFull, v, 4 * c0 + ks);             // a_ck for the two columns this lane updates
     const double ac1 = __shfl_sync(kFull, v, 4 * c1 + ks);
