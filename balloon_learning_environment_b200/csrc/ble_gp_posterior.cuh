@@ -79,7 +79,6 @@ struct PosteriorSmem {
   double yz[kGpWindow][2];            // errors y, overwritten by z = L^-1 y
   float feat[kNumLevels * 3];
   unsigned char valid[kGpWindow];
-  unsigned char pair_bi[kGpNumBlk * (kGpNumBlk - 1) / 2], pair_bj[kGpNumBlk * (kGpNumBlk - 1) / 2];   // trailing-update pairs
   int lo, hi, n_invalid;
   unsigned long long bar;
 };
@@ -258,12 +257,6 @@ __global__ void __launch_bounds__(kGpPThreads, 3) k_gp_posterior(DevState<Real> 
   if (tid < kNumLevels) {
     const double pl = pressure_level(tid);
     if (!(pl < pmin || pl > pmax)) { atomicMin(&S.lo, tid); atomicMax(&S.hi, tid); }
-  }
-  if (tid < kGpNumBlk * (kGpNumBlk - 1) / 2) {              // pair index -> (bi >= bj); any trailing matrix uses a prefix
-    int bi = int((sqrtf(8.f * float(tid) + 1.f) - 1.f) * 0.5f);
-    while (((bi * (bi + 1)) >> 1) > tid) --bi;
-    while ((((bi + 1) * (bi + 2)) >> 1) <= tid) ++bi;
-    S.pair_bi[tid] = (unsigned char)bi; S.pair_bj[tid] = (unsigned char)(tid - ((bi * (bi + 1)) >> 1));
   }
   const double qx = x / kGpScaleXY, qy = y / kGpScaleXY, qt = double(t_elapsed) / kGpScaleT;
   if (tid < rows) {

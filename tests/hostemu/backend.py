@@ -81,7 +81,6 @@ class HostBackend:
     """Any valid state: the tests inject the state they compare from right after construction."""
     del seeds
     b = balloon_lib.make_batch(self.num_envs, center_lat=0.0, center_lng=0.0, date_time=1364203532, pressure=9000.0)
-    balloon_lib.init_power_safety(b)
     self._f, self._i = hostemu.pack_state(b, 0.5, True)
 
   # -- state --------------------------------------------------------------------------------------------------------
