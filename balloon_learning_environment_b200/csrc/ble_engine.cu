@@ -1,8 +1,9 @@
 // CUDA engine + C ABI (include/ble_b200.h) for the batched BLE transition function.
-// Target: sm_100a (B200).  One handle per GPU, one thread per balloon in the physics kernel,
-// one thread per (balloon, noise harmonic) in the noise kernel with TMA bulk staging of the
-// permutation tables.
+// Target: sm_100a (B200).  One handle per GPU.  The production step kernels live in ble_step_fused.cu (one launch per
+// BalloonEnv.step); this file holds the engine (memory, launches, error handling), the reset / IO / wind-query / feature
+// kernels, the generation path, the legacy step kernels (fp64 audit build, A/B) and the C entry points.
 #include <cublasLt.h>
+#include <cuda.h>           // CUtensorMap types only: the encoder is fetched with cudaGetDriverEntryPoint (no -lcuda)
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -873,6 +874,8 @@ struct Engine : EngineBase {
   ble_config cfg{};
   int device = 0;
   float* cells = nullptr; int64_t n_fields = 0;
+  CUtensorMap bank_map{};          // 5-D TMA view of the field bank (k_gp_posterior's column tile); valid iff tile_column
+  int tile_column = 0;
   int32_t* env_field = nullptr;
   uint8_t* perm = nullptr; float* offsets = nullptr;
   int64_t* noise_seeds = nullptr; float* noise_offsets_in = nullptr;
@@ -994,6 +997,35 @@ struct Engine : EngineBase {
       n_fields = nf;
     }
     d.cells = cells;
+    return encode_bank_map();
+  }
+
+  // TMA tensor map of the bank as [field][y-cell][p-cell][t-cell][row floats]: a box {128 B, 1, 9, 1, 1} is the forecast
+  // column of one (x, y, t) cell -- the 9 lookup windows every pressure level of a balloon's column interpolates in.
+  int encode_bank_map() {
+    tile_column = 0;
+    const char* env = std::getenv("BLE_COLUMN_TILE");            // "0": per-level gathers instead (A/B)
+    if (env != nullptr && std::strcmp(env, "0") == 0) return BLE_OK;
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult found;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &found) != cudaSuccess ||
+        found != cudaDriverEntryPointSuccess || fn == nullptr) {
+      err = "alloc_fields: the driver does not export cuTensorMapEncodeTiled";
+      return BLE_ERR_CUDA;
+    }
+    const cuuint64_t row = cuuint64_t(d.layout.row_floats);
+    const cuuint64_t dims[5] = {row, cuuint64_t(kTC), cuuint64_t(kPC), cuuint64_t(kYC), cuuint64_t(n_fields)};
+    const cuuint64_t strides[4] = {row * 4, row * 4 * kTC, row * 4 * kTC * kPC, cuuint64_t(d.layout.field_floats) * 4};   // bytes
+    const cuuint32_t box[5] = {32, 1, cuuint32_t(kPC), 1, 1};                                                           // 128 B x 9
+    const cuuint32_t elem[5] = {1, 1, 1, 1, 1};
+    const CUresult rc = reinterpret_cast<EncodeTiled>(fn)(&bank_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, cells, dims, strides, box, elem,
+                                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { err = "alloc_fields: cuTensorMapEncodeTiled failed (code " + std::to_string(int(rc)) + ")"; return BLE_ERR_CUDA; }
+    tile_column = 1;
     return BLE_OK;
   }
 
@@ -1503,7 +1535,7 @@ struct Engine : EngineBase {
       k_gp_factor<Real><<<unsigned(n), kFactorThreads, sizeof(double) * (kGpPacked + kGpWindow * 4), s>>>(d);
       k_gp_column<Real><<<unsigned(n), kColumnThreads, kColumnSmem, s>>>(d, obs);
     } else {
-      k_gp_posterior<Real><<<unsigned(n), kGpPThreads, sizeof(PosteriorSmem), s>>>(d, obs);
+      k_gp_posterior<Real><<<unsigned(n), kGpPThreads, sizeof(PosteriorSmem), s>>>(d, obs, bank_map, tile_column);
     }
     launches += gp_refit_every_step ? 5 : 4;
     BLE_CUDA(cudaGetLastError());

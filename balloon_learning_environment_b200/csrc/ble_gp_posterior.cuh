@@ -75,10 +75,14 @@ constexpr int kGpTiles = (kGpWindow + 15) / 16;            // 8 row tiles of 16 
 
 struct PosteriorSmem {
   double L[kGpBlockedLower];          // K -> L (fp64) -> {hi, lo} TF32 pairs; diagonal blocks hold inv(L_jj)
+  float4 col[kPC * 8];                // the balloon's forecast COLUMN: the 9 lookup windows (one per pressure cell) of its
+                                      // (x, y, t) cell, staged by ONE TMA tensor copy (box 128 B x 9 of the 5-D bank view);
+                                      // 128-byte aligned (L is 61,440 B)
   double cxy[kGpWindow], pz[kGpWindow];
   double yz[kGpWindow][2];            // errors y, overwritten by z = L^-1 y
   float feat[kNumLevels * 3];
   unsigned char valid[kGpWindow];
+  FieldCell<double> cell;             // the balloon's (x, y, t) cell and weights (the pressure axis varies per level)
   int lo, hi, n_invalid;
   unsigned long long bar;
 };
@@ -122,15 +126,16 @@ __device__ __forceinline__ void chol_diag_block(double a0, double a1, double* __
   for (int k = 0; k < kGpBlk; ++k) {
     const double v = (k & 1) ? a1 : a0;
     const int ks = k >> 1;
-    // a_kk.  In exact arithmetic every pivot of K + alpha I is >= alpha (a Schur complement of it); the clamp keeps a
-    // rounding accident from turning into a NaN that would fill the whole observation
-    const double dk = fmax(__shfl_sync(kFull, v, 4 * k + ks), kGpNoise);
+    const double dk = __shfl_sync(kFull, v, 4 * k + ks);               // a_kk
     const double agk = __shfl_sync(kFull, v, quad | ks);               // a_gk, own row
     const double ac0 = __shfl_sync(kFull, v, 4 * c0 + ks);             // a_ck for the two columns this lane updates
     const double ac1 = __shfl_sync(kFull, v, 4 * c1 + ks);
     const double wk0 = __shfl_sync(kFull, w0, 4 * k + tq), wk1 = __shfl_sync(kFull, w1, 4 * k + tq);   // row k of W
     const double yk = __shfl_sync(kFull, yv, 4 * k + tq);
-    double inv = double(rsqrtf(float(dk)));
+    // In exact arithmetic every pivot of K + alpha I is >= alpha (a Schur complement of it).  The fp32 seed is clamped
+    // there (one FMNMX; an fp64 clamp on dk itself cost 0.5 ms per 65,536 balloons on this dependent chain), so that a
+    // rounding accident yields a finite factor instead of a NaN that would fill the whole observation.
+    double inv = double(rsqrtf(fmaxf(float(dk), float(kGpNoise))));
     inv = inv * fma(-0.5 * dk * inv, inv, 1.5);                         // 1 / l_kk
     const double lgk = agk * inv;
     if (c0 > k) a0 = fma(-lgk, ac0 * inv, a0);
@@ -226,7 +231,8 @@ struct Sweep<kGpNumBlk, SHIFT> {
 };
 
 template <typename Real>
-__global__ void __launch_bounds__(kGpPThreads, 3) k_gp_posterior(DevState<Real> d, float* __restrict__ obs) {
+__global__ void __launch_bounds__(kGpPThreads, 3)
+k_gp_posterior(DevState<Real> d, float* __restrict__ obs, const __grid_constant__ CUtensorMap bank_map, int tile_column) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   PosteriorSmem& S = *reinterpret_cast<PosteriorSmem*>(s_raw);
   const int64_t e = blockIdx.x;
@@ -246,12 +252,28 @@ __global__ void __launch_bounds__(kGpPThreads, 3) k_gp_posterior(DevState<Real> 
     S.lo = kNumLevels; S.hi = -1; S.n_invalid = 0;
   }
   __syncthreads();
-  if (tid == 0 && nb > 0) {                                 // 1. the kernel matrix, one TMA bulk copy
-    const uint32_t bytes = uint32_t(blk_offset(nb, 0)) * 8u;
-    const double* src = d.gp_chol + e * int64_t(kGpFactorDoubles);
+  // The forecast column (features.py:457-497 asks the forecast at 181 pressure levels of ONE (x, y, t)): every level
+  // interpolates inside the same (x, y, t) cell, so the column's data is the 9 windows of that cell, 1,152 B.  They come
+  // as one box of the bank's 5-D tensor view [field][y-cell][p-cell][t-cell][row] (cp.async.bulk.tensor, UTMALDG in
+  // SASS) instead of one 128-byte gather per level (181 x 128 B requested for the same 1,152 B).
+  const bool use_tile = tile_column != 0 && d.wind_model != BLE_WIND_SIMPLE_STATIC;
+  if (tid == 0 && (nb > 0 || use_tile)) {                   // 1. the kernel matrix (one TMA bulk copy) and the column tile
+    const FieldCell<double> cell0 = locate<double>(make_field_point(x / 1000.0, y / 1000.0, p_b, double(t_elapsed) / 3600.0));
+    S.cell = cell0;
+    const uint32_t k_bytes = nb > 0 ? uint32_t(blk_offset(nb, 0)) * 8u : 0u;
+    const uint32_t bytes = k_bytes + (use_tile ? uint32_t(sizeof(S.col)) : 0u);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(S.L)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    if (nb > 0) {
+      const double* src = d.gp_chol + e * int64_t(kGpFactorDoubles);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(S.L)), "l"(src), "r"(k_bytes), "r"(bar) : "memory");
+    }
+    if (use_tile) {
+      const int c0 = cell0.ix * d.layout.x_stride_floats, c1 = cell0.tc, c2 = 0, c3 = cell0.iy, c4 = d.env_field[e];
+      asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                   ::"r"(smem_u32(S.col)), "l"(reinterpret_cast<uint64_t>(&bank_map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
+                     "r"(bar) : "memory");
+    }
   }
   // while it is in flight: reachable levels, validity of the slots, the query's distance terms, the targets
   if (tid < kNumLevels) {
@@ -280,12 +302,23 @@ __global__ void __launch_bounds__(kGpPThreads, 3) k_gp_posterior(DevState<Real> 
   const int n_act = hi >= lo ? hi - lo + 1 : 0;             // reachable levels lo .. hi
   const int m_valid = rows - S.n_invalid;
 
-  if (nb > 0) {
-    asm volatile(                                           // wait for the TMA transaction (phase 0)
+  if (nb > 0 || use_tile) {
+    asm volatile(                                           // wait for the TMA transactions (phase 0)
         "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
         "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar) : "memory");
   }
+  // forecast at level l: from the staged tile (same interp_window as every other lookup: bit-identical) or by a gather
+  auto column_forecast = [&](int l, double* fu, double* fv) {
+    if (use_tile) {
+      FieldCell<double> c = S.cell;                          // x, y, t axes: the balloon's; pressure axis: this level's
+      axis_cell<double>(make_field_point(0.0, 0.0, pressure_level(l), 0.0).p, 5000.f, 1000.f, kPC, &c.pc, &c.wp);
+      const float4* w = S.col + c.pc * 8;
+      interp_window<double>(c, [w](int j) { return w[j]; }, fu, fv);
+    } else {
+      forecast_at<double, DevState<Real>>(d, e, x, y, pressure_level(l), t_elapsed, fu, fv);
+    }
+  };
   if (m_valid > 0) {
     if (S.n_invalid > 0) {                                  // empty / expired slots: identity rows and columns
       for (int k = tid; k < blk_offset(nb, 0); k += kGpPThreads) {
@@ -460,7 +493,7 @@ __global__ void __launch_bounds__(kGpPThreads, 3) k_gp_posterior(DevState<Real> 
       const int l = lo + col;
       const double deviation = fmax(kGpSigma2 - norm2, 0.0) / kGpSigma2;             // wind_gp.py:186-193
       double fu, fv;
-      forecast_at<double, DevState<Real>>(d, e, x, y, pressure_level(l), t_elapsed, &fu, &fv);
+      column_forecast(l, &fu, &fv);
       wind_level_features(mean_u + fu, mean_v + fv, deviation, x, y, &S.feat[l * 3], &S.feat[l * 3 + 1], &S.feat[l * 3 + 2]);
     }
   }
@@ -468,7 +501,7 @@ __global__ void __launch_bounds__(kGpPThreads, 3) k_gp_posterior(DevState<Real> 
     for (int k = tid; k < n_act; k += kGpPThreads) {
       const int l = lo + k;
       double fu, fv;
-      forecast_at<double, DevState<Real>>(d, e, x, y, pressure_level(l), t_elapsed, &fu, &fv);
+      column_forecast(l, &fu, &fv);
       wind_level_features(fu, fv, 0.0, x, y, &S.feat[l * 3], &S.feat[l * 3 + 1], &S.feat[l * 3 + 2]);
     }
   }

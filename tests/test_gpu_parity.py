@@ -774,6 +774,46 @@ def test_features_batch_matches_oracle_after_reset(ble, steps, every_step):
   arena.close()
 
 
+@pytest.mark.parametrize('layout', ['x64', 'x128'])
+def test_column_tile_is_bit_identical_to_gathers(ble, monkeypatch, layout):
+  """The forecast column of the observation comes from ONE TMA tensor copy of the balloon's 9 lookup windows (the 5-D
+  tensor view of the field bank, `cp.async.bulk.tensor.5d`); with BLE_COLUMN_TILE=0 the same kernel gathers one
+  128-byte window per level.  Both feed the same interp_window, so the 1099 features must agree bit for bit -- across
+  cells (balloons drift over cell borders during 30 steps), both layouts, balloons at the clipped edges of the grid and
+  past the 48 h boomerang of the time axis."""
+  n = 64
+  bank = golden_fields.field_bank()
+  rng = np.random.default_rng(44)
+  fidx = torch.from_numpy(rng.integers(0, 4, n).astype(np.int32))
+  seeds = torch.arange(n, dtype=torch.int64) * 11 + 5
+  arenas = []
+  for tile in ('1', '0'):
+    monkeypatch.setenv('BLE_COLUMN_TILE', tile)
+    a = ble.BatchedBalloonArena(n, precision='fp32', enable_noise=True, enable_features=True, field_layout=layout)
+    a.set_wind_fields(torch.from_numpy(bank), fidx)
+    a.reset(seeds)
+    from balloon_learning_environment_b200 import _lib
+    f, i = a.get_state()
+    x, y, te = _lib.F_ROWS.index('x'), _lib.F_ROWS.index('y'), _lib.I_ROWS.index('time_elapsed')
+    f[x, :8] = torch.tensor([-499.9e3, 499.9e3, -650e3, 650e3, 0.0, 25e3, -25e3, 449.99e3], dtype=torch.float64)
+    f[y, :8] = torch.tensor([499.9e3, -499.9e3, 650e3, -650e3, 0.0, -475e3, 475e3, 0.01e3], dtype=torch.float64)
+    i[te, 8:12] = torch.tensor([47 * 3600 + 3000, 48 * 3600, 50 * 3600, 143 * 3600], dtype=torch.int64)
+    a.set_state(f, i)
+    a.features_clear(); a.features_observe()
+    arenas.append(a)
+  monkeypatch.delenv('BLE_COLUMN_TILE')
+  for t in range(30):
+    acts = torch.from_numpy(rng.integers(0, 3, n).astype(np.int32))
+    got, want = [], []
+    for a, out in zip(arenas, (got, want)):
+      a.step(acts)
+      out.append(a.features().cpu().numpy())
+    np.testing.assert_array_equal(got[0], want[0], err_msg=f'step {t}')
+  assert np.abs(got[0][:, 16:]).max() > 0.1
+  for a in arenas:
+    a.close()
+
+
 def test_incremental_gp_matches_full_refit(ble, monkeypatch):
   """k_gp_posterior (kernel matrix kept in ring-slot order in HBM, updated one row per observe; blocked fp64 Cholesky +
   3 x TF32 column sweep per call) against the first-generation kernels that rebuild K from the measurement ring at
