@@ -8,7 +8,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'balloon_learning_environment_b200', 'libble_b200.so')
-KEYS = ['UBLKCP', 'SYNCS', 'DMMA', 'LDG.E.128', 'LDG.E.64', 'SHFL', 'DFMA', 'FFMA', 'MUFU', 'BAR.SYNC', 'STL', 'LDL']
+KEYS = ['UBLKCP', 'UTMALDG', 'SYNCS', 'DMMA', 'HMMA', 'STG.E.EF.128', 'LDG.E.128', 'LDG.E.64', 'SHFL', 'DFMA', 'FFMA', 'MUFU', 'BAR.SYNC', 'STL', 'LDL']
 
 
 def main():
