@@ -75,21 +75,22 @@ __device__ __forceinline__ NoiseOffsets load_noise_offsets(const DevState<float>
   o.p = d.offsets[(int64_t(h10) * 4 + 2) * d.n + ec]; o.t = d.offsets[(int64_t(h10) * 4 + 3) * d.n + ec];
   return o;
 }
+// `tables_done()` runs (in every lane, converged) right after the last table read: the caller releases the staging
+// buffer there and starts the next copy.  Lanes beyond the batch evaluate on whatever their slot of the buffer holds
+// (the result is discarded) so that the warp stays converged through the callback.
+template <typename Done>
 __device__ __forceinline__ float noise_harmonic(int h10, const NoiseOffsets& off, int lane, double x, double y,
                                                 double p, int32_t t_elapsed, const uint8_t* stage, uint32_t bar,
-                                                uint32_t parity, bool valid) {
+                                                uint32_t parity, bool valid, Done tables_done) {
   const double* hp = kHarmonicsInvDev[h10];
   const double X = fma(x, hp[0], double(off.x));
   const double Y = fma(y, hp[1], double(off.y));
   const double Z = fma(p, hp[2], double(off.p));
   const double W = fma(double(t_elapsed), hp[3], double(off.t));
   mbar_wait(bar, parity);
-  float v = 0.f;
-  if (valid) {
-    RotatedPerm perm{stage + lane * 256, lane * 4};
-    v = simplex_noise4_v2<float>(perm, X, Y, Z, W);
-  }
-  return float(kNoiseMagnitude) * v;
+  RotatedPerm perm{stage + lane * 256, lane * 4};
+  const float v = simplex_noise4_v2<float>(perm, X, Y, Z, W, tables_done);
+  return valid ? float(kNoiseMagnitude) * v : 0.f;
 }
 
 // The three safety layers, once per agent step (balloon.py:305-313), and X = (p/P_i)^k at the pre-step pressure.
@@ -376,11 +377,14 @@ k_step_roles(DevState<float> d, const int32_t* __restrict__ actions, FusedOut ou
     for (int task = warp; task < kFusedTasks; task += kW) {
       if (task < 10) {
         if (noise_mode == 1) {
-          if (lane == 0) stage_perm_tables(d, task, e0, count, stage, bar);
-          sm.noise[task][lane] = noise_harmonic(task, load_noise_offsets(d, task, c.ec), lane, c.x_pre, c.y_pre, c.p_pre,
-                                                c.t_pre, stage, bar, bar_parity, c.valid);
+          if (task == warp && lane == 0) stage_perm_tables(d, task, e0, count, stage, bar);   // this warp's first harmonic
+          sm.noise[task][lane] = noise_harmonic(
+              task, load_noise_offsets(d, task, c.ec), lane, c.x_pre, c.y_pre, c.p_pre, c.t_pre, stage, bar, bar_parity, c.valid,
+              [&]() {                                       // tables read: the warp's next harmonic may overwrite them
+                __syncwarp();
+                if (task + kW < 10 && lane == 0) stage_perm_tables(d, task + kW, e0, count, stage, bar);
+              });
           bar_parity ^= 1u;
-          __syncwarp();                                     // every lane is done with the staging buffer
         } else {
           sm.noise[task][lane] = noise_mode == 2 ? d.noise_partial[int64_t(task) * d.n + c.ec] : 0.f;
         }
@@ -497,10 +501,11 @@ k_step_warp(DevState<float> d, const int32_t* __restrict__ actions, FusedOut out
         if (noise_mode == 1) {
           const NoiseOffsets cur = off;
           if (h + 1 < 10) off = load_noise_offsets(d, h + 1, ec);      // in flight while this harmonic is evaluated
-          nh = noise_harmonic(h, cur, lane, x_pre, y_pre, p_pre, t_pre, stage, bar, bar_parity, valid);
+          nh = noise_harmonic(h, cur, lane, x_pre, y_pre, p_pre, t_pre, stage, bar, bar_parity, valid, [&]() {
+            __syncwarp();                                   // every lane has read its table: the next copy may overwrite it
+            if (h + 1 < 10 && lane == 0) stage_perm_tables(d, h + 1, e0, count, stage, bar);
+          });
           bar_parity ^= 1u;
-          __syncwarp();                                     // every lane is done with the staging buffer
-          if (h + 1 < 10 && lane == 0) stage_perm_tables(d, h + 1, e0, count, stage, bar);
         } else {
           nh = d.noise_partial[int64_t(h) * d.n + ec];
         }

@@ -318,8 +318,14 @@ BLE_HD Real gradient_dot_fast(int hash, Real dx, Real dy, Real dz, Real dw) {
   return ((ax + ay) + (az + aw)) + Real(2) * pick;
 }
 
-template <typename Real, typename Perm>
-BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, double w) {
+// `tables_done()` is called once, after the LAST read of the permutation table: the fused step kernels release their
+// staging buffer there (and start the TMA copy of the next harmonic's tables), so that the copy runs under the 16 corner
+// evaluations instead of being waited for (the wait was 5.6 % of k_step_warp's stall samples).  Hence the order: all the
+// hashes of the 16 corners, the (few) extended neighbours completely, tables_done(), the corners' arithmetic.
+struct NoTablesDone { BLE_HD void operator()() const {} };
+
+template <typename Real, typename Perm, typename Done = NoTablesDone>
+BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, double w, Done tables_done = Done()) {
   const double s = (x + y + z + w) * kStretch4;
   const double xs = x + s, ys = y + s, zs = z + s, ws = w + s;
   const double fx = floor(xs), fy = floor(ys), fz = floor(zs), fw = floor(ws);
@@ -330,13 +336,8 @@ BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, do
   const int cb[4] = {int(int64_t(fx) & 255), int(int64_t(fy) & 255), int(int64_t(fz) & 255), int(int64_t(fw) & 255)};
   const Real sq = Real(kSquish4);
 
-  // ---- the 16 corners, unconditionally ----
-  Real e[4][2];                                        // real-space displacement per axis at offsets 0 / 1
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int a = 0; a < 4; ++a) { e[a][0] = d0[a]; e[a][1] = d0[a] - Real(1); }
-  int h1[2], h2[4], h3[8];
+  // ---- hashes of the 16 corners ----
+  int h1[2], h2[4], h3[8], hc[16];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -349,20 +350,10 @@ BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, do
 #pragma unroll
 #endif
   for (int i = 0; i < 8; ++i) h3[i] = perm[(h2[i & 3] + cb[2] + (i >> 2)) & 255];
-  Real value = Real(0);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int m = 0; m < 16; ++m) {
-    const int h = perm[(h3[m & 7] + cb[3] + (m >> 3)) & 255];
-    const int pc = (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + (m >> 3);
-    const Real t = Real(pc) * sq;
-    const Real dx = e[0][m & 1] - t, dy = e[1][(m >> 1) & 1] - t, dz = e[2][(m >> 2) & 1] - t, dw = e[3][m >> 3] - t;
-    Real attn = Real(2) - dx * dx - dy * dy - dz * dz - dw * dw;
-    attn = attn > Real(0) ? attn : Real(0);
-    attn *= attn;
-    value += attn * attn * gradient_dot_fast<Real>(h, dx, dy, dz, dw);
-  }
+  for (int m = 0; m < 16; ++m) hc[m] = perm[(h3[m & 7] + cb[3] + (m >> 3)) & 255];
 
   // ---- neighbours one step further out along one axis: range test in skewed coordinates, then a loop ----
   Real A[4][2], Ae[4];
@@ -406,6 +397,7 @@ BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, do
   }
   const uint32_t oe_packed = uint32_t(oe[0] & 255) | (uint32_t(oe[1] & 255) << 8) | (uint32_t(oe[2] & 255) << 16) |
                              (uint32_t(oe[3] & 255) << 24);
+  Real outer = Real(0);
   while (mask) {
 #if defined(__CUDA_ARCH__)
     const int c = __ffs(int(mask)) - 1;
@@ -431,9 +423,30 @@ BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, do
     h = perm[(h + cb[2] + o[2]) & 255];
     h = perm[(h + cb[3] + o[3]) & 255];
     attn *= attn;
-    value += attn * attn * gradient_dot_fast<Real>(h, dx, dy, dz, dw);
+    outer += attn * attn * gradient_dot_fast<Real>(h, dx, dy, dz, dw);
   }
-  return value / Real(30.0);
+  tables_done();
+
+  // ---- the 16 corners, unconditionally ----
+  Real e[4][2];                                        // real-space displacement per axis at offsets 0 / 1
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int a = 0; a < 4; ++a) { e[a][0] = d0[a]; e[a][1] = d0[a] - Real(1); }
+  Real value = Real(0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int m = 0; m < 16; ++m) {
+    const int pc = (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + (m >> 3);
+    const Real t = Real(pc) * sq;
+    const Real dx = e[0][m & 1] - t, dy = e[1][(m >> 1) & 1] - t, dz = e[2][(m >> 2) & 1] - t, dw = e[3][m >> 3] - t;
+    Real attn = Real(2) - dx * dx - dy * dy - dz * dz - dw * dw;
+    attn = attn > Real(0) ? attn : Real(0);
+    attn *= attn;
+    value += attn * attn * gradient_dot_fast<Real>(hc[m], dx, dy, dz, dw);
+  }
+  return (value + outer) / Real(30.0);
 }
 
 // OpenSimplex.__init__: 256-entry permutation from a 64-bit LCG (see oracle/opensimplex4.py).
