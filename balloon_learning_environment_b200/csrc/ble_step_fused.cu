@@ -478,6 +478,9 @@ k_step_warp(DevState<float> d, const int32_t* __restrict__ actions, FusedOut out
   if (lane == 0) mbar_init(bar);
   __syncwarp();
 
+  // the tables of harmonic 0 are requested before anything else; inside a rollout the request for the NEXT step goes out
+  // as soon as harmonic 9 has read its tables, so that the copy runs under the 18 sub-steps
+  if (noise_mode == 1 && lane == 0) stage_perm_tables(d, 0, e0, count, stage, bar);
   for (int step = 0; step < n_steps; ++step) {
     const uint32_t fl = d.flags[ec];
     const bool stepped = valid && (fl & 3u) == uint32_t(kOk);
@@ -489,7 +492,6 @@ k_step_warp(DevState<float> d, const int32_t* __restrict__ actions, FusedOut out
     action = action < 0 ? 0 : (action > 2 ? 2 : action);
 
     // ---- wind at the PRE-step state: forecast window + 10 noise harmonics ----
-    if (noise_mode == 1 && lane == 0) stage_perm_tables(d, 0, e0, count, stage, bar);
     float uf, vf;
     forecast_at<float, DevState<float>>(d, ec, x_pre, y_pre, p_pre, t_pre, &uf, &vf);
     if (noise_mode != 0) {
@@ -503,7 +505,8 @@ k_step_warp(DevState<float> d, const int32_t* __restrict__ actions, FusedOut out
           if (h + 1 < 10) off = load_noise_offsets(d, h + 1, ec);      // in flight while this harmonic is evaluated
           nh = noise_harmonic(h, cur, lane, x_pre, y_pre, p_pre, t_pre, stage, bar, bar_parity, valid, [&]() {
             __syncwarp();                                   // every lane has read its table: the next copy may overwrite it
-            if (h + 1 < 10 && lane == 0) stage_perm_tables(d, h + 1, e0, count, stage, bar);
+            const bool more = h + 1 < 10 || step + 1 < n_steps;
+            if (more && lane == 0) stage_perm_tables(d, h + 1 < 10 ? h + 1 : 0, e0, count, stage, bar);
           });
           bar_parity ^= 1u;
         } else {
