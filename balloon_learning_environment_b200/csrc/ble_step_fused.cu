@@ -461,7 +461,11 @@ constexpr int kWarpsPerCta = BLE_WARPS_PER_CTA;
 #ifndef BLE_WARP_MIN_BLOCKS
 #define BLE_WARP_MIN_BLOCKS (16 / BLE_WARPS_PER_CTA)
 #endif
+#ifdef BLE_WARP_MAXNREG
+__global__ void __maxnreg__(BLE_WARP_MAXNREG)
+#else
 __global__ void __launch_bounds__(32 * kWarpsPerCta, BLE_WARP_MIN_BLOCKS)
+#endif
 k_step_warp(DevState<float> d, const int32_t* __restrict__ actions, FusedOut out, int noise_mode, int n_steps) {
   extern __shared__ __align__(128) uint8_t warp_dyn[];
   __shared__ alignas(8) uint64_t s_bar[kWarpsPerCta];
