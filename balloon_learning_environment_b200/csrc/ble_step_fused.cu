@@ -62,8 +62,13 @@ __device__ __forceinline__ void stage_perm_tables(const DevState<float>& d, int 
   const uint32_t bytes = uint32_t(count) * 256u;
   const uint8_t* src = d.perm + (int64_t(h10) * d.n + e0) * 256;
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(stage)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  // the tables stream through once per step (168 MB at 65,536 balloons, more than the L2): evict-first keeps them from
+  // pushing the 26 MB of state rows, which every step re-reads, out of the L2 (81.0 -> 77.8 us at 32,768 balloons,
+  // 109.1 -> 108.3 us at 65,536; profiles/r02_step_timing_evict_first.jsonl)
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(stage)), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 
 // NoisyWindHarmonic.get_noise (simplex_wind_noise.py:116-146) for harmonic h10 of balloon ec; the warp's staging
