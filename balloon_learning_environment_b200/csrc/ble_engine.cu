@@ -16,6 +16,7 @@
 
 #include "../../include/ble_b200.h"
 #include "ble_devstate.cuh"
+#include "ble_fastmath.cuh"
 #include "ble_step_fused.h"
 #include "ble_agents.cuh"
 #include "ble_features.cuh"

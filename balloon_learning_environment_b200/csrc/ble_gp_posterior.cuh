@@ -78,7 +78,10 @@ struct PosteriorSmem {
   float4 col[kPC * 8];                // the balloon's forecast COLUMN: the 9 lookup windows (one per pressure cell) of its
                                       // (x, y, t) cell, staged by ONE TMA tensor copy (box 128 B x 9 of the 5-D bank view);
                                       // 128-byte aligned (L is 61,440 B)
-  double cxy[kGpWindow], pz[kGpWindow];
+  double pz[kGpWindow + 16];         // measurement pressures / scale, padded like cxf
+  float cxf[kGpWindow + 16];         // (x, y, t) part of the squared distance to the query, fp32; index = row + 8.  Rows that
+                                     // are invalid, beyond the window, or the phantom row of an odd block count hold 3e38, so that
+                                     // their K* entry evaluates to exactly 0 without a branch
   double yz[kGpWindow][2];            // errors y, overwritten by z = L^-1 y
   float feat[kNumLevels * 3];
   unsigned char valid[kGpWindow];
@@ -281,6 +284,7 @@ k_gp_posterior(DevState<Real> d, float* __restrict__ obs, const __grid_constant_
     if (!(pl < pmin || pl > pmax)) { atomicMin(&S.lo, tid); atomicMax(&S.hi, tid); }
   }
   const double qx = x / kGpScaleXY, qy = y / kGpScaleXY, qt = double(t_elapsed) / kGpScaleT;
+  if (tid < kGpWindow + 16 && (tid < 8 || tid >= rows + 8)) { S.cxf[tid] = 3e38f; S.pz[tid] = 0.0; }   // padding rows
   if (tid < rows) {
     double c = 0.0, pz = 0.0, eu = 0.0, ev = 0.0;
     bool ok = false;
@@ -294,7 +298,7 @@ k_gp_posterior(DevState<Real> d, float* __restrict__ obs, const __grid_constant_
         eu = o[4]; ev = o[5];
       }
     }
-    S.cxy[tid] = c; S.pz[tid] = pz; S.yz[tid][0] = eu; S.yz[tid][1] = ev; S.valid[tid] = ok ? 1 : 0;
+    S.cxf[tid + 8] = ok ? float(c) : 3e38f; S.pz[tid + 8] = pz; S.yz[tid][0] = eu; S.yz[tid][1] = ev; S.valid[tid] = ok ? 1 : 0;
     if (!ok) atomicAdd(&S.n_invalid, 1);
   }
   __syncthreads();
@@ -460,14 +464,16 @@ k_gp_posterior(DevState<Real> d, float* __restrict__ obs, const __grid_constant_
     for (int t = 0; t < kGpTiles; ++t) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int i = 8 * (2 * t + h - shift) + g;          // block row 2 t + h - shift (-1: the phantom row of an odd nb)
-        float k0 = 0.f, k1 = 0.f;
-        if (i >= 0 && i < rows && S.valid[i]) {
-          const double cx = S.cxy[i], pi = S.pz[i];
-          const float d0 = float(fma(pq0 - pi, pq0 - pi, cx)), d1 = float(fma(pq1 - pi, pq1 - pi, cx));
-          if (on0) k0 = float(kGpSigma2) * __expf(-sqrtf(d0));
-          if (on1) k1 = float(kGpSigma2) * __expf(-sqrtf(d1));
-        }
+        const int i = 8 * (2 * t + h - shift) + g + 8;      // padded index of block row 2 t + h - shift (7 + g: the phantom row)
+        // K*[i][l] = sigma^2 exp(-sqrt(c_i + (p_l - p_i)^2)): the pressure difference in fp64 (it cancels), the rest in fp32
+        // with the approximate root and exponential (the solve that consumes it is 3 x TF32: ~1e-7 relative either way)
+        const double pi = S.pz[i];
+        const float cx = S.cxf[i];
+        const float e0 = float(pq0 - pi), e1 = float(pq1 - pi);
+        float k0 = float(kGpSigma2) * fm::ex2f(-1.4426950408889634f * fm::sqrtf_pos(fmaf(e0, e0, cx)));
+        float k1 = float(kGpSigma2) * fm::ex2f(-1.4426950408889634f * fm::sqrtf_pos(fmaf(e1, e1, cx)));
+        if (!on0) k0 = 0.f;
+        if (!on1) k1 = 0.f;
         c[t][2 * h] = k0; c[t][2 * h + 1] = k1;
       }
     }
