@@ -381,22 +381,26 @@ k_gp_posterior(DevState<Real> d, float* __restrict__ obs, const __grid_constant_
           chol_diag_block(cc.x, cc.y, C, &S.yz[(j + 1) * kGpBlk], lane);     // the updated block stays in registers
         }
       } else {
-        // blocks (r, c), c <= r, of the (nb - j - 1)-block trailing triangle in row-major order, dealt round-robin to
-        // warps 1..7 (block (0, 0) is warp 0's): within 1 block of perfectly balanced, where owning whole block columns
-        // left the first warp 46 % above the mean at the early pivots
-        const int n_tr = nb - j - 1;
-        int r = 0, c = warp;                                               // q = warp: the first block after (0, 0)
-        while (c > r) { c -= r + 1; ++r; }
-        while (r < n_tr) {
-          const double* A = S.L + blk_offset(j + 1 + r, j);
-          const double* B = S.L + blk_offset(j + 1 + c, j);
-          double* C = S.L + blk_offset(j + 1 + r, j + 1 + c) + cpos;
-          double2 cc = *reinterpret_cast<double2*>(C);
-          dmma884(cc.x, cc.y, -A[lane], B[lane]);
-          dmma884(cc.x, cc.y, -A[32 + lane], B[32 + lane]);
-          *reinterpret_cast<double2*>(C) = cc;
-          c += kGpPWarps - 1;
-          while (c > r) { c -= r + 1; ++r; }
+        // Warps 1..7 own block COLUMNS b2 of the trailing matrix: the B operand L_b2j stays in registers while b runs down
+        // the column and the block addresses advance by increments (18 instructions per block; dealing single blocks
+        // round-robin balanced the warps perfectly but cost 41 instructions per block and no time).  The columns are
+        // dealt serpentine -- j + 1 .. j + 7 to warps 1 .. 7, j + 8 .. j + 14 to warps 7 .. 1 -- so every warp gets
+        // one long and one short column.
+#pragma unroll 1
+        for (int round = 0; round < 2; ++round) {
+          const int b2 = round == 0 ? j + warp : j + 15 - warp;
+          if (b2 >= nb) continue;
+          const double* B = S.L + blk_offset(b2, j);
+          const double bf0 = B[lane], bf1 = B[32 + lane];
+          int b = b2 == j + 1 ? b2 + 1 : b2;                                // (j + 1, j + 1) belongs to warp 0
+          int offA = blk_offset(b, j), offC = blk_offset(b, b2);
+          for (; b < nb; ++b) {
+            double2 cc = *reinterpret_cast<double2*>(S.L + offC + cpos);
+            dmma884(cc.x, cc.y, -S.L[offA + lane], bf0);
+            dmma884(cc.x, cc.y, -S.L[offA + 32 + lane], bf1);
+            *reinterpret_cast<double2*>(S.L + offC + cpos) = cc;
+            offA += (b + 1) * (kGpBlk * kGpBlk); offC += (b + 1) * (kGpBlk * kGpBlk);
+          }
         }
       }
       __syncthreads();
