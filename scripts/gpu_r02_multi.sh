@@ -1,7 +1,11 @@
 #!/bin/bash
 # N>1 evidence on one 8-GPU box: strong scaling of BASELINE configs[2] (65,536 balloons split over N GPUs; the weak number is a
-# side key of the same line), and the product path that broadcasts the decoder weights over NCCL at construction (run_eval).
+# side key of the same line), N = 1 on the same box for the ratio, configs[3] on 8 GPUs, and the product path that broadcasts
+# the decoder weights over NCCL at construction (run_eval).
 mkdir -p gpurun_out/r02multi
+timeout 400 python bench.py --steps 20 --warmup 5 --min-timed-ms 100 --no-cpu-baseline > gpurun_out/r02multi/bench_n1.json 2> gpurun_out/r02multi/bench_n1.err
+python -c "
+import json; d=json.loads(open('gpurun_out/r02multi/bench_n1.json').read().strip().splitlines()[-1]); print(1, d['value'], d['ms_per_step'])"
 for N in 2 4 8; do
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
   timeout 500 $TR --master-port $((29530 + N)) bench.py --gpus $N --steps 20 --warmup 5 --min-timed-ms 100 > gpurun_out/r02multi/bench_n${N}.json 2> gpurun_out/r02multi/bench_n${N}.err
@@ -14,6 +18,7 @@ except Exception as e:
   print('bench N=$N failed', e); print(open('gpurun_out/r02multi/bench_n${N}.err').read()[-1500:])
 PY
 done
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-NCCL_DEBUG=INFO timeout 500 $TR --master-port 29541 scripts/run_eval.py --agent station_seeker --suite small_eval --max-episode-length 120 --no-flight-path > gpurun_out/r02multi/run_eval_n2.log 2>&1
-grep -E "env_steps_per_s|NVLS|Broadcast|broadcast|Error|error" gpurun_out/r02multi/run_eval_n2.log | cut -c1-400 | tail -8
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+timeout 500 $TR --master-port 29551 bench.py --gpus 8 --num-envs 32768 --observation perciatelli --steps 10 --warmup 3 --min-timed-ms 50 --scaling weak > gpurun_out/r02multi/bench_obs_n8.json 2> gpurun_out/r02multi/bench_obs_n8.err
+python -c "
+import json; d=json.loads(open('gpurun_out/r02multi/bench_obs_n8.json').read().strip().splitlines()[-1]); print('obs8', d['value'], d['ms_per_step'], d['config']['num_envs'], d['e2e']['value'])"
