@@ -158,20 +158,49 @@ k_wind_gather(const float* __restrict__ cells, FieldLayout layout, const float4*
 // ---------------------------------------------------------------------------------------------
 // Noise: permutation tables (reset time) and the per-step noise kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void k_make_perms(int64_t n, const int64_t* __restrict__ seeds /*[n,2,5]*/,
-                             const float* __restrict__ offsets_in /*[n,2,5,4]*/, const uint8_t* __restrict__ mask,
-                             uint8_t* __restrict__ perm /*[10][n][256]*/, float* __restrict__ offsets /*[10][4][n]*/) {
-  const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (t >= n * 10) return;
-  const int64_t e = t / 10;
-  const int h10 = int(t - e * 10);
-  if (mask != nullptr && mask[e] == 0) return;
-  uint8_t table[256], scratch[256];
-  simplex_make_perm(seeds[e * 10 + h10], table, scratch);
-  uint8_t* dst = perm + (int64_t(h10) * n + e) * 256;
-  const int rot = int(e & 31) * 4;       // bank-conflict-free rotation, undone at lookup time
-  for (int j = 0; j < 256; ++j) dst[(j + rot) & 255] = table[j];
-  for (int c = 0; c < 4; ++c) offsets[(int64_t(h10) * 4 + c) * n + e] = offsets_in[(e * 10 + h10) * 4 + c];
+// One thread per table, 64 consecutive balloons of ONE harmonic per CTA: the 64 tables are built in shared memory (the
+// Fisher-Yates walk indexes its arrays dynamically; as per-thread local arrays they lived in local memory and the kernel
+// took 3.3 ms for 65,536 balloons) and leave as one contiguous, coalesced 16 KB block.  Lane-interleaved layout
+// (byte i of table t at i * 64 + t) for the scratch array; the finished table is written at its rotated position
+// (bank-conflict-free rotation by 4 (e mod 32) bytes, undone at lookup time) of a table-major staging area.
+constexpr int kPermCta = 64;
+__global__ void __launch_bounds__(kPermCta)
+k_make_perms(int64_t n, const int64_t* __restrict__ seeds /*[n,2,5]*/, const float* __restrict__ offsets_in /*[n,2,5,4]*/,
+             const uint8_t* __restrict__ mask, uint8_t* __restrict__ perm /*[10][n][256]*/, float* __restrict__ offsets /*[10][4][n]*/) {
+  __shared__ uint8_t s_source[256 * kPermCta];              // [i][t]
+  __shared__ __align__(16) uint8_t s_table[kPermCta * 256]; // [t][rotated j]
+  const int h10 = blockIdx.y, t = threadIdx.x;
+  const int64_t e0 = int64_t(blockIdx.x) * kPermCta, e = e0 + t;
+  const bool live = e < n && (mask == nullptr || mask[e] != 0);
+  if (live) {
+    const uint64_t A = 6364136223846793005ull, Cc = 1442695040888963407ull;
+    uint64_t s = uint64_t(seeds[e * 10 + h10]);
+    for (int i = 0; i < 256; ++i) s_source[i * kPermCta + t] = uint8_t(i);
+    s = s * A + Cc; s = s * A + Cc; s = s * A + Cc;
+    const int rot = int(e & 31) * 4;
+    uint8_t* table = s_table + t * 256;
+    for (int i = 255; i >= 0; --i) {
+      s = s * A + Cc;
+      // Python: r = (int64(s) + 31) % (i + 1), floor modulo (simplex_make_perm in ble_wind.cuh is the plain statement);
+      // here in 32-bit pieces: s = hi 2^32 + lo (unsigned) - 2^64 [s < 0]
+      const uint32_t m = uint32_t(i + 1);
+      const uint32_t hi = uint32_t(s >> 32), lo = uint32_t(s);
+      const uint32_t p32 = uint32_t((uint64_t(1) << 32) % m);          // 2^32 mod m
+      uint32_t r = ((hi % m) * p32 + lo % m + 31u) % m;                // < 256 * 256 + 256 + 31: no overflow
+      if (int64_t(s) < 0) { const uint32_t p64 = (p32 * p32) % m; r = (r + m - p64) % m; }
+      table[(i + rot) & 255] = s_source[r * kPermCta + t];
+      s_source[r * kPermCta + t] = s_source[i * kPermCta + t];
+    }
+    for (int c = 0; c < 4; ++c) offsets[(int64_t(h10) * 4 + c) * n + e] = offsets_in[(e * 10 + h10) * 4 + c];
+  }
+  __syncthreads();
+  // copy-out: the CTA's tables are contiguous in HBM; a masked-out table keeps what it had
+  uint4* dst = reinterpret_cast<uint4*>(perm + (int64_t(h10) * n + e0) * 256);
+  const uint4* src = reinterpret_cast<const uint4*>(s_table);
+  for (int k = t; k < kPermCta * 16; k += kPermCta) {
+    const int64_t ek = e0 + (k >> 4);
+    if (ek < n && (mask == nullptr || mask[ek] != 0)) dst[k] = src[k];
+  }
 }
 
 constexpr int kNoiseBlock = 128;
@@ -1079,7 +1108,7 @@ struct Engine : EngineBase {
     BLE_DEVICE_GUARD();
     int rc = ensure_noise_buffers();
     if (rc != BLE_OK) return rc;
-    k_make_perms<<<grid_for(n * 10, 64), 64, 0, s>>>(n, seeds, offs, mask, perm, offsets);
+    k_make_perms<<<dim3(grid_for(n, kPermCta), 10), kPermCta, 0, s>>>(n, seeds, offs, mask, perm, offsets);
     ++launches;
     BLE_CUDA(cudaGetLastError());
     have_noise = true;
@@ -1122,7 +1151,7 @@ struct Engine : EngineBase {
     k_reset<Real><<<grid_for(n, 128), 128, 0, s>>>(d, seeds, mask, noise_seeds, noise_offsets_in);
     ++launches;
     BLE_CUDA(cudaGetLastError());
-    k_make_perms<<<grid_for(n * 10, 64), 64, 0, s>>>(n, noise_seeds, noise_offsets_in, mask, perm, offsets);
+    k_make_perms<<<dim3(grid_for(n, kPermCta), 10), kPermCta, 0, s>>>(n, noise_seeds, noise_offsets_in, mask, perm, offsets);
     ++launches;
     BLE_CUDA(cudaGetLastError());
     have_state = true; have_noise = true;
