@@ -365,6 +365,8 @@ k_step_roles(DevState<float> d, const int32_t* __restrict__ actions, FusedOut ou
   uint32_t bar_parity = 0;
   if (lane == 0) mbar_init(bar);
   __syncwarp();
+  asm volatile("griddepcontrol.wait;" ::: "memory");        // the previous step (launch_step: PDL) has completed and flushed
+  asm volatile("griddepcontrol.launch_dependents;");        // the next step's grid may be placed from now on (it parks at its wait)
 
   for (int step = 0; step < n_steps; ++step) {
     c.fl = d.flags[c.ec];
@@ -487,6 +489,8 @@ k_step_warp(DevState<float> d, const int32_t* __restrict__ actions, FusedOut out
   if (lane == 0) mbar_init(bar);
   __syncwarp();
 
+  asm volatile("griddepcontrol.wait;" ::: "memory");        // the previous step (launch_step: PDL) has completed and flushed
+  asm volatile("griddepcontrol.launch_dependents;");        // the next step's grid may be placed from now on (it parks at its wait)
   // the tables of harmonic 0 are requested before anything else; inside a rollout the request for the NEXT step goes out
   // as soon as harmonic 9 has read its tables, so that the copy runs under the 18 sub-steps
   if (noise_mode == 1 && lane == 0) stage_perm_tables(d, 0, e0, count, stage, bar);
@@ -640,16 +644,37 @@ cudaError_t fused_setup(int blocks_per_sm[4]) {
   return e;
 }
 
+// Programmatic dependent launch: consecutive steps are consecutive launches of the same kernel on one stream.  With the
+// attribute set, the CTAs of step t + 1 are placed on an SM as soon as there is room (every CTA of step t signals
+// `griddepcontrol.launch_dependents` right after its own wait) and park at `griddepcontrol.wait` -- the first thing a step
+// kernel does before it touches global memory -- until step t has completed and flushed: the launch latency and the ramp
+// of the next grid run under the previous step.  Measured: 36.5 -> 34.7 us per step at 4,096 balloons, 41.6 -> 40.4 at
+// 8,192, 50.2 -> 48.8 at 16,384, unchanged at 65,536 (profiles/r02_step_timing_pdl.jsonl).  Rollouts are launched the
+// classic way: they are long, there is nothing to hide, and CTAs parked early unbalanced the SMs (29.2 -> 31.5 us).
+// BLE_STEP_PDL=0 launches the classic way (A/B).
+template <typename Kernel>
+static void launch_step(Kernel kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t s, const DevState<float>& d,
+                        const int32_t* actions, const FusedOut& out, int noise_mode, int n_steps) {
+  static const bool pdl = [] { const char* e = std::getenv("BLE_STEP_PDL"); return e == nullptr || std::atoi(e) != 0; }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr; cfg.numAttrs = (pdl && n_steps == 1) ? 1 : 0;   // rollouts are long: nothing to hide, and CTAs parked early unbalance the SMs
+  cudaLaunchKernelEx(&cfg, kernel, d, actions, out, noise_mode, n_steps);
+}
+
 void fused_launch(int shape, const DevState<float>& d, const int32_t* actions, const FusedOut& out, int noise_mode,
                   int n_steps, cudaStream_t s) {
   const unsigned grid = unsigned((d.n + 31) / 32);
   switch (shape) {
-    case 14: k_step_roles<14><<<grid, 32 * 14, roles_smem<14>(), s>>>(d, actions, out, noise_mode, n_steps); break;
-    case 8: k_step_roles<8><<<grid, 32 * 8, roles_smem<8>(), s>>>(d, actions, out, noise_mode, n_steps); break;
-    case 4: k_step_roles<4><<<grid, 32 * 4, roles_smem<4>(), s>>>(d, actions, out, noise_mode, n_steps); break;
+    case 14: launch_step(k_step_roles<14>, grid, 32 * 14, roles_smem<14>(), s, d, actions, out, noise_mode, n_steps); break;
+    case 8: launch_step(k_step_roles<8>, grid, 32 * 8, roles_smem<8>(), s, d, actions, out, noise_mode, n_steps); break;
+    case 4: launch_step(k_step_roles<4>, grid, 32 * 4, roles_smem<4>(), s, d, actions, out, noise_mode, n_steps); break;
     default:
-      k_step_warp<<<unsigned((d.n + 32 * kWarpsPerCta - 1) / (32 * kWarpsPerCta)), 32 * kWarpsPerCta, warp_smem(), s>>>(
-          d, actions, out, noise_mode, n_steps);
+      launch_step(k_step_warp, unsigned((d.n + 32 * kWarpsPerCta - 1) / (32 * kWarpsPerCta)), 32 * kWarpsPerCta, warp_smem(), s,
+                  d, actions, out, noise_mode, n_steps);
       break;
   }
 }
