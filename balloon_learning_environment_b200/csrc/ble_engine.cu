@@ -929,7 +929,8 @@ struct Engine : EngineBase {
   static constexpr int64_t kDecChunk = 4096;
   static constexpr int64_t kGenChunk = 2048;                 // fields decoded per pass of generate_fields
   float* gen_latents = nullptr; float* gen_flow[2] = {nullptr, nullptr};
-  cudaStream_t gen_stream = nullptr;
+  cudaStream_t gen_stream = nullptr, feat_stream = nullptr;
+  cudaEvent_t ev_feat_fork = nullptr, ev_feat_join = nullptr;
   cudaEvent_t ev_flow[2] = {nullptr, nullptr}, ev_written[2] = {nullptr, nullptr}, ev_fork = nullptr;
   // evaluation surface
   EvalBuffers ev{nullptr, nullptr, nullptr, nullptr};
@@ -1010,6 +1011,9 @@ struct Engine : EngineBase {
     for (int b = 0; b < 2; ++b) { if (ev_flow[b]) cudaEventDestroy(ev_flow[b]); if (ev_written[b]) cudaEventDestroy(ev_written[b]); }
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (gen_stream) cudaStreamDestroy(gen_stream);
+    if (feat_stream) cudaStreamDestroy(feat_stream);
+    if (ev_feat_fork) cudaEventDestroy(ev_feat_fork);
+    if (ev_feat_join) cudaEventDestroy(ev_feat_join);
     cudaFree(ev.reward); cudaFree(ev.within); cudaFree(ev.steps); cudaFree(ev.active); cudaFree(walk_target);
     cudaFree(d_actions); cudaFree(d_reward);
     cudaFreeHost(h_actions); cudaFreeHost(h_reward);
@@ -1558,7 +1562,17 @@ struct Engine : EngineBase {
     int rc = check_ready("features");
     if (rc != BLE_OK) return rc;
     BLE_DEVICE_GUARD();
-    k_feat_ambient<Real><<<grid_for(n, 128), 128, 0, s>>>(d, obs);
+    // The 16 ambient features (one latency-bound sunrise search per balloon, 0.4 ms at 65,536) touch nothing the wind
+    // column needs: they run on a side stream, forked from and joined to the caller's stream, under k_gp_posterior.
+    if (feat_stream == nullptr) {
+      BLE_CUDA(cudaStreamCreateWithFlags(&feat_stream, cudaStreamNonBlocking));
+      BLE_CUDA(cudaEventCreateWithFlags(&ev_feat_fork, cudaEventDisableTiming));
+      BLE_CUDA(cudaEventCreateWithFlags(&ev_feat_join, cudaEventDisableTiming));
+    }
+    BLE_CUDA(cudaEventRecord(ev_feat_fork, s));
+    BLE_CUDA(cudaStreamWaitEvent(feat_stream, ev_feat_fork, 0));
+    k_feat_ambient<Real><<<grid_for(n, 128), 128, 0, feat_stream>>>(d, obs);
+    BLE_CUDA(cudaEventRecord(ev_feat_join, feat_stream));
     k_feat_range_levels<Real><<<grid_for(n * kRangeLevels, 128), 128, 0, s>>>(d, range_scratch);
     k_feat_range<Real><<<grid_for(n, 128), 128, 0, s>>>(d, range_scratch);
     if (gp_refit_every_step) {
@@ -1567,6 +1581,7 @@ struct Engine : EngineBase {
     } else {
       k_gp_posterior<Real><<<unsigned(n), kGpPThreads, sizeof(PosteriorSmem), s>>>(d, obs, bank_map, tile_column);
     }
+    BLE_CUDA(cudaStreamWaitEvent(s, ev_feat_join, 0));
     launches += gp_refit_every_step ? 5 : 4;
     BLE_CUDA(cudaGetLastError());
     return BLE_OK;
