@@ -43,8 +43,8 @@ EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_u
 
 class BleConfig(_c.Structure):
   _fields_ = [('precision', _c.c_int32), ('wind_model', _c.c_int32), ('enable_noise', _c.c_int32),
-              ('field_layout', _c.c_int32), ('enable_features', _c.c_int32), ('decoder_fp32', _c.c_int32),
-              ('reserved', _c.c_int32 * 2)]
+              ('field_layout', _c.c_int32), ('enable_features', _c.c_int32), ('decoder_fp32', _c.c_int32), ('auto_reset', _c.c_int32),
+              ('reserved', _c.c_int32 * 1)]
 
 
 class BleReplayView(_c.Structure):

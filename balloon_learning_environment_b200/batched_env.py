@@ -44,7 +44,7 @@ class BatchedBalloonArena:
 
   def __init__(self, num_envs: int, *, device: str = 'cuda:0', precision: str = 'fp32',
                wind_model: str = 'grid', enable_noise: bool = True, field_layout: str = 'x64',
-               enable_features: bool = False, decoder_precision: str = 'tf32'):
+               enable_features: bool = False, decoder_precision: str = 'tf32', auto_reset: bool = False):
     if not torch.cuda.is_available():
       raise _lib.BleError('BatchedBalloonArena needs a CUDA device (no CPU fallback exists)')
     self._lib = _lib.load()
@@ -54,7 +54,9 @@ class BatchedBalloonArena:
     self.wind_model = wind_model
     self.enable_noise = bool(enable_noise)
     cfg = _lib.BleConfig(_lib.PRECISION[precision], _lib.WIND_MODEL[wind_model], int(enable_noise),
-                         _lib.FIELD_LAYOUT[field_layout], int(enable_features), {'tf32': 0, 'fp32': 1}[decoder_precision])
+                         _lib.FIELD_LAYOUT[field_layout], int(enable_features), {'tf32': 0, 'fp32': 1}[decoder_precision],
+                         int(bool(auto_reset)))
+    self.auto_reset = bool(auto_reset)
     self.enable_features = bool(enable_features)
     handle = ctypes.c_void_p()
     dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -425,7 +427,7 @@ class BatchedBalloonEnv:
                wind_model: str = 'grid', enable_noise: bool = True, seed: int = 0,
                arena: Optional[BatchedBalloonArena] = None, observation: Optional[str] = None,
                field_layout: str = 'x64', decoder_params=None, shared_field_pool: Optional[torch.Tensor] = None,
-               first_env: int = 0, broadcast_src: Optional[int] = 0):
+               first_env: int = 0, broadcast_src: Optional[int] = 0, auto_reset: bool = False):
     """decoder_params (the flax tree of offlineskies22_decoder.msgpack['params']) switches the wind source
     to the reference's default GenerativeWindFieldSampler: every reset decodes one new field per balloon
     from that balloon's seed (env/generative_wind_field.py:52-62).  Without it the fields are whatever was
@@ -435,12 +437,20 @@ class BatchedBalloonEnv:
     Under torch.distributed (one process per GPU, this rank holding the balloons [first_env, first_env + num_envs) of
     the job) the constructor is a collective: rank `broadcast_src` hands its decoder weights / field pool to the others
     over NCCL, so only one process reads them from disk (the others may pass None / an empty tensor of the right
-    shape).  broadcast_src=None switches that off (every rank brings its own)."""
+    shape).  broadcast_src=None switches that off (every rank brings its own).
+
+    auto_reset=True: a balloon whose step returned done starts a new episode before step() returns (reward / done /
+    info describe the step that ended the episode, the observation is the new episode's first one), the vector-env
+    convention; its seed continues a splitmix64 chain from the seed it was reset with.  With decoder_params the new
+    episode also gets a new wind field (one device -> host read of the done count per step); without, the C library
+    does it inside ble_step (ble_config.auto_reset) and the balloon keeps its field."""
     if observation not in (None, 'perciatelli'):
       raise ValueError("observation must be None or 'perciatelli'")
+    self._auto_reset_host = bool(auto_reset) and decoder_params is not None      # new field per episode: driven from here
     self.arena = arena if arena is not None else BatchedBalloonArena(
         num_envs, device=device, precision=precision, wind_model=wind_model, enable_noise=enable_noise,
-        field_layout=field_layout, enable_features=observation == 'perciatelli')
+        field_layout=field_layout, enable_features=observation == 'perciatelli',
+        auto_reset=bool(auto_reset) and decoder_params is None)
     if observation == 'perciatelli' and not self.arena.enable_features:
       raise ValueError("the arena was created without enable_features=True")
     self.observation = observation
@@ -513,7 +523,11 @@ class BatchedBalloonEnv:
 
   def step(self, actions: torch.Tensor):
     reward, done, _ = self.arena.step(actions)
-    return self._observe(), reward, done, self.arena.step_info()
+    info = self.arena.step_info()
+    if self._auto_reset_host and bool(done.any()):
+      reward, done = reward.clone(), done.clone()          # the arena's output buffers are reused by the reset's observe
+      return self.reset_where(done), reward, done, info
+    return self._observe(), reward, done, info
 
   def get_info(self) -> Dict[str, torch.Tensor]:
     """_get_info (env/balloon_env.py:280-290) for all balloons, from the CURRENT state (also valid before the first

@@ -203,6 +203,28 @@ k_make_perms(int64_t n, const int64_t* __restrict__ seeds /*[n,2,5]*/, const flo
   }
 }
 
+// ble_config.auto_reset: the balloons whose step returned done start a new episode; its seed continues a splitmix64 chain
+// from the seed of the episode that ended.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  uint64_t z = x + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void k_auto_reset_prepare(int64_t n, const uint8_t* __restrict__ done, uint64_t* __restrict__ episode_seed,
+                                     uint8_t* __restrict__ mask) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= n) return;
+  const bool m = done[e] != 0;
+  mask[e] = m ? 1 : 0;
+  if (m) episode_seed[e] = splitmix64(episode_seed[e]);
+}
+__global__ void k_keep_episode_seeds(int64_t n, const uint64_t* __restrict__ seeds, const uint8_t* __restrict__ mask,
+                                     uint64_t* __restrict__ episode_seed) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e < n && (mask == nullptr || mask[e] != 0)) episode_seed[e] = seeds[e];
+}
+
 constexpr int kNoiseBlock = 128;
 
 // One thread per (balloon, harmonic).  blockIdx.y = harmonic (0..9), blockIdx.x = block of 128
@@ -917,6 +939,7 @@ struct Engine : EngineBase {
   bool host_zero_copy = true;            // BLE_HOST_ZERO_COPY=0: staged copies in ble_step_host instead of mapped pinned memory
   bool host_prefetch_noise = true;       // BLE_HOST_PREFETCH_NOISE=0: ble_step_host does not queue the next step's noise kernel
   bool track_measurements = true;        // ble_features_track: append a WindGP measurement after every reset / step
+  uint64_t* episode_seed = nullptr; uint8_t* auto_mask = nullptr;   // ble_config.auto_reset: seed chain and the done mask of the last step
   bool gp_refit_every_step = false;      // BLE_GP_REFIT=1: the first-generation kernels (full refit per call), kept for A/B checks
   double* feat_range = nullptr;
   // VAE decoder (reset path)
@@ -1007,7 +1030,7 @@ struct Engine : EngineBase {
     if (lt != nullptr) cublasLtDestroy(lt);
     cudaFree(gp_obs); cudaFree(gp_count); cudaFree(gp_chol); cudaFree(gp_m); cudaFree(feat_range);
     cudaFree(gp_first); cudaFree(gp_z); cudaFree(range_scratch);
-    cudaFree(gen_latents); cudaFree(gen_flow[0]); cudaFree(gen_flow[1]);
+    cudaFree(gen_latents); cudaFree(gen_flow[0]); cudaFree(gen_flow[1]); cudaFree(episode_seed); cudaFree(auto_mask);
     for (int b = 0; b < 2; ++b) { if (ev_flow[b]) cudaEventDestroy(ev_flow[b]); if (ev_written[b]) cudaEventDestroy(ev_written[b]); }
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (gen_stream) cudaStreamDestroy(gen_stream);
@@ -1152,6 +1175,16 @@ struct Engine : EngineBase {
       BLE_CUDA(cudaMalloc(&noise_seeds, sizeof(int64_t) * 10 * n));
       BLE_CUDA(cudaMalloc(&noise_offsets_in, sizeof(float) * 40 * n));
     }
+    if (cfg.auto_reset) {
+      if (episode_seed == nullptr) {
+        BLE_CUDA(cudaMalloc(&episode_seed, sizeof(uint64_t) * n));
+        BLE_CUDA(cudaMalloc(&auto_mask, n));
+      }
+      if (seeds != episode_seed) {
+        k_keep_episode_seeds<<<grid_for(n, 256), 256, 0, s>>>(n, seeds, mask, episode_seed);
+        ++launches;
+      }
+    }
     k_reset<Real><<<grid_for(n, 128), 128, 0, s>>>(d, seeds, mask, noise_seeds, noise_offsets_in);
     ++launches;
     BLE_CUDA(cudaGetLastError());
@@ -1223,6 +1256,8 @@ struct Engine : EngineBase {
       err = "rollout: the WindGP measurement history cannot be tracked inside a multi-step launch (ble_features_track(0) first)";
       return BLE_ERR_UNSUPPORTED;
     }
+    if (cfg.auto_reset && n_steps > 1) { err = "rollout: not available with ble_config.auto_reset"; return BLE_ERR_UNSUPPORTED; }
+    if (cfg.auto_reset && episode_seed == nullptr) { err = "step: auto_reset needs a ble_reset first (it continues that seed chain)"; return BLE_ERR_NOT_READY; }
     BLE_DEVICE_GUARD();
     FusedOut fo{o->reward, o->done, reinterpret_cast<float2*>(o->wind_uv), o->status, o->time_elapsed, o->sim_error};
     if (use_fused()) {
@@ -1254,6 +1289,14 @@ struct Engine : EngineBase {
         ++launches;
         BLE_CUDA(cudaGetLastError());
       }
+    }
+    if (cfg.auto_reset) {
+      // the balloons that just returned done = 1 start a new episode; the masked reset ends with the measurement append
+      // for EVERY balloon (post-step state of the ones that fly on, first state of the new episodes), so nothing more here
+      k_auto_reset_prepare<<<grid_for(n, 256), 256, 0, s>>>(n, fo.done, episode_seed, auto_mask);
+      ++launches;
+      BLE_CUDA(cudaGetLastError());
+      return reset(episode_seed, auto_mask, s);
     }
     // arena.step ends with feature_constructor.observe(get_measurements()) (env/balloon_arena.py:201):
     // the noise evaluated for it at the post-step state is also next step's pre-step wind.

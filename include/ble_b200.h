@@ -66,7 +66,16 @@ typedef struct {
   int32_t decoder_fp32;        /* 0 (default): the decoder GEMMs run on the tensor cores (TF32 inputs, fp32
                                 * accumulate -- jax's default matmul precision on the reference's GPU
                                 * path); 1: fp32 FMA, what the reference computes on a CPU            */
-  int32_t reserved[2];         /* must be 0                                                         */
+  int32_t auto_reset;          /* 1: a balloon whose step returned done = 1 (terminal status, or stepped while already
+                                * finished) starts a new episode before ble_step returns control of the stream: reward /
+                                * done / info describe the step that ended the episode, the state (and the WindGP history)
+                                * is the new episode's.  Its seed is splitmix64 of the seed of the episode that ended (the
+                                * chain starts at the seed given to ble_reset), so runs are reproducible.  The balloon keeps
+                                * its wind field; a caller that wants a new field per episode regenerates it with
+                                * ble_generate_fields_at for the balloons whose done flag it saw.  Not available inside
+                                * ble_rollout.  0 (default): a finished balloon is frozen (stepping it is a no-op with
+                                * reward 0, done 1; the reference asserts, env/balloon/balloon.py:288).              */
+  int32_t reserved[1];         /* must be 0                                                         */
 } ble_config;
 
 /* State exchange: two row-major device matrices, one row per field, N columns.

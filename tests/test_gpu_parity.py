@@ -465,6 +465,61 @@ def test_reset_distributions_ks_against_reference_samples(ble):
   arena.close()
 
 
+def test_auto_reset_restarts_finished_balloons_inside_the_step(ble):
+  """ble_config.auto_reset: a balloon whose step returns done = 1 starts a new episode before the call returns control of
+  the stream -- exactly the masked ble_reset a caller would issue, with the seed chain splitmix64(previous seed); the
+  others fly on untouched.  reward / done / info describe the step that ended the episode."""
+  from balloon_learning_environment_b200 import _lib
+
+  def splitmix64(x):
+    m = (1 << 64) - 1
+    z = (x + 0x9E3779B97F4A7C15) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return z ^ (z >> 31)
+
+  n = 96
+  seeds = torch.arange(n, dtype=torch.int64) * 1009 + 77
+  rng = np.random.default_rng(2)
+  auto = ble.BatchedBalloonArena(n, precision='fp32', wind_model='simple_static', enable_noise=True, auto_reset=True)
+  manual = ble.BatchedBalloonArena(n, precision='fp32', wind_model='simple_static', enable_noise=True)
+  ended = np.zeros(n, bool); ended[[3, 17, 40, 41, 95]] = True
+  for a in (auto, manual):
+    a.reset(seeds)
+    f, i = a.get_state()
+    i[_lib.I_ROWS.index('status'), torch.from_numpy(ended)] = 2          # BURST: the next step returns done = 1 for these
+    a.set_state(f, i)
+  acts = torch.from_numpy(rng.integers(0, 3, n).astype(np.int32))
+  r_auto, d_auto, _ = auto.step(acts); r_auto, d_auto = r_auto.clone(), d_auto.clone()
+  info = auto.step_info()
+  r_man, d_man, _ = manual.step(acts)
+  np.testing.assert_array_equal(d_auto.cpu().numpy() != 0, ended)
+  np.testing.assert_array_equal(d_auto.cpu().numpy(), d_man.cpu().numpy())
+  np.testing.assert_array_equal(r_auto.cpu().numpy(), r_man.cpu().numpy())
+  np.testing.assert_array_equal(info['envelope_burst'].cpu().numpy(), ended)           # info of the step that ended them
+  next_seeds = np.array([splitmix64(int(s)) for s in seeds.numpy()], np.uint64).view(np.int64)
+  manual.reset(torch.from_numpy(next_seeds), torch.from_numpy(ended.astype(np.uint8)))
+  sa, sm = state_np(auto), state_np(manual)
+  for k in sa:
+    np.testing.assert_array_equal(sa[k], sm[k], err_msg=k)
+  assert (sa['status'] == 0).all() and (sa['time_elapsed'][ended] == 0).all() and (sa['time_elapsed'][~ended] == 180).all()
+  # the chain continues: a second episode end of balloon 3 uses splitmix64 of the second seed
+  for a in (auto, manual):
+    f, i = a.get_state()
+    i[_lib.I_ROWS.index('status'), 3] = 1
+    a.set_state(f, i)
+  auto.step(acts); manual.step(acts)
+  again = np.zeros(n, np.uint8); again[3] = 1
+  third = next_seeds.copy(); third[3] = np.array([splitmix64(int(next_seeds.view(np.uint64)[3]))], np.uint64).view(np.int64)[0]
+  manual.reset(torch.from_numpy(third), torch.from_numpy(again))
+  sa, sm = state_np(auto), state_np(manual)
+  for k in sa:
+    np.testing.assert_array_equal(sa[k], sm[k], err_msg=k)
+  with pytest.raises(_lib.BleError):
+    auto.rollout(acts[None].repeat(2, 1))
+  auto.close(); manual.close()
+
+
 # ------------------------------------------------------------------------------ fp32 rollout vs oracle
 
 def test_fp32_rollout_tracks_oracle(ble):
