@@ -42,7 +42,13 @@ namespace ble {
 constexpr int kFusedTasks = 13;
 constexpr int kPermStageBytes = 32 * 256;
 
-__device__ __forceinline__ void role_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Named barrier of the four role warps.  `bar.sync` is an ALIGNED barrier: every thread of a warp has to execute it
+// together, and after an `if (live) { ... }` whose condition differs between lanes nothing makes the lanes reconverge by
+// themselves (compute-sanitizer --tool synccheck: "divergent thread(s) in block") -- hence the __syncwarp() first.
+__device__ __forceinline__ void role_barrier() {
+  __syncwarp();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
