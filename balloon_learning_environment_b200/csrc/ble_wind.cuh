@@ -199,12 +199,14 @@ BLE_HD Real gradient_dot(int hash, Real dx, Real dy, Real dz, Real dw) {
   return (ax + ay) + (az + aw);
 }
 
-// noise4d(x, y, z, w) summed over every lattice vertex whose kernel (2 - |d|^2)^4 is non-zero.
+// ---- A/B form: noise4d(x, y, z, w) summed over EVERY lattice vertex whose kernel (2 - |d|^2)^4 is non-zero --------
+// (round-1 definition, oracle form='all'; the production kernels use the decision-tree selection further down and
+// fall back to this sum only when built with -DBLE_NOISE_ALL_VERTICES).
 // Candidate c in [0, 80): m = c / 5 is the cube corner (bit k of m = offset along axis k),
 // e = c % 5: 0 = the corner itself, 1..4 = step one further out along axis e-1
 // (offset 1 -> 2, offset 0 -> -1).  `perm` is this generator's 256-entry table.
 template <typename Real, typename Perm>
-BLE_HD Real simplex_noise4(const Perm& perm, double x, double y, double z, double w) {
+BLE_HD Real simplex_noise4_all(const Perm& perm, double x, double y, double z, double w) {
   const double s = (x + y + z + w) * kStretch4;
   const double fx = floor(x + s), fy = floor(y + s), fz = floor(z + s), fw = floor(w + s);
   const double q = (fx + fy + fz + fw) * kSquish4;
@@ -296,8 +298,8 @@ BLE_HD Real simplex_noise4(const Perm& perm, double x, double y, double z, doubl
   return value / Real(30.0);
 }
 
-// ---- second-generation evaluation of the same sum (production fp32 kernels) ---------------------------------
-// simplex_noise4 above spends ~620 instructions deciding which of the 80 candidates are in range and then loops
+// ---- second-generation evaluation of the same all-vertices sum (A/B form) ------------------------------------
+// simplex_noise4_all above spends ~620 instructions deciding which of the 80 candidates are in range and then loops
 // over them one at a time (a warp iterates max-over-lanes ~12 times at ~105 instructions).  Two facts make it
 // cheaper.  (1) In the skewed lattice coordinates u = x + STRETCH * sum(x) the kernel argument separates:
 //     |d|^2 = sum_a (u_a - o_a)^2 + (sum(u) - sum(o))^2,
@@ -306,7 +308,7 @@ BLE_HD Real simplex_noise4(const Perm& perm, double x, double y, double z, doubl
 //   and branch-free -- compile-time offsets, the permutation look-ups shared as a binary tree (30 instead of 64) --
 //   and only the "one step further out" neighbours (1.2 in range on average, never more than one direction per axis:
 //   (u_a + 1)^2 < 2 needs u_a < 0.414, (u_a - 2)^2 < 2 needs u_a > 0.586) go through a mask + loop.
-// Same definition, different summation order: agrees with simplex_noise4 to fp32 rounding.
+// Same definition, different summation order: agrees with simplex_noise4_all to fp32 rounding.
 template <typename Real>
 BLE_HD Real gradient_dot_fast(int hash, Real dx, Real dy, Real dz, Real dw) {
   // hash bits: [7..4] negate component 3..0, [3..2] position of the "3"
@@ -325,7 +327,7 @@ BLE_HD Real gradient_dot_fast(int hash, Real dx, Real dy, Real dz, Real dw) {
 struct NoTablesDone { BLE_HD void operator()() const {} };
 
 template <typename Real, typename Perm, typename Done = NoTablesDone>
-BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, double w, Done tables_done = Done()) {
+BLE_HD Real simplex_noise4_v2_all(const Perm& perm, double x, double y, double z, double w, Done tables_done = Done()) {
   const double s = (x + y + z + w) * kStretch4;
   const double xs = x + s, ys = y + s, zs = z + s, ws = w + s;
   const double fx = floor(xs), fy = floor(ys), fz = floor(zs), fw = floor(ws);
@@ -447,6 +449,193 @@ BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, do
     value += attn * attn * gradient_dot_fast<Real>(hc[m], dx, dy, dz, dw);
   }
   return (value + outer) / Real(30.0);
+}
+
+// ---- the package's vertex selection (oracle form='tree', the default) ------------------------------------------
+// opensimplex.noise4d does not visit every in-range vertex: a decision tree on the position inside the unit cell
+// picks the BASE vertices of one of four regions plus THREE extras (oracle/opensimplex4.py spells the rule out and
+// cites what it restates).  Here the tree is evaluated branch-free:
+//   * regions B / D (inSum > 2) are the point reflection v -> 1 - v of A / C, so the selection runs in the lower frame
+//     u = 1 - ins and the result is reflected back;
+//   * a vertex is an 8-bit code, 2 bits per axis holding offset + 1 (offsets are -1 .. 2), so that "lower a zero axis
+//     to -1" clears one bit, "(0,0,0,2) on axis k" sets one bit, and the reflection is a bitwise NOT;
+//   * the base vertices are cube corners: a 16-bit mask over the corner index m (bit a of m = offset along axis a).
+BLE_HD uint32_t simplex_spread2(uint32_t m) {           // bit a of m -> bit 2a
+  uint32_t t = (m | (m << 2)) & 0x33u;
+  return (t | (t << 1)) & 0x55u;
+}
+
+template <typename Real>
+struct SimplexTop2 {                                     // the two closest candidates so far
+  Real a_sc, b_sc;
+  uint32_t a_po, b_po;
+  bool a_big, b_big;
+  BLE_HD void offer(Real score, uint32_t point, bool big) {
+    const bool into_b = (a_sc >= b_sc) && (score > b_sc);
+    const bool into_a = (a_sc < b_sc) && (score > a_sc);
+    b_sc = into_b ? score : b_sc; b_po = into_b ? point : b_po; b_big = into_b ? big : b_big;
+    a_sc = into_a ? score : a_sc; a_po = into_a ? point : a_po; a_big = into_a ? big : a_big;
+  }
+};
+
+// in[4] = position inside the unit cell.  Returns the corner mask of the region's base vertices and writes the three
+// extras as codes (see above).
+template <typename Real>
+BLE_HD uint32_t simplex_tree_select(const Real in[4], uint32_t ext[3]) {
+  const Real S = ((in[0] + in[1]) + in[2]) + in[3];
+  const bool refl = S > Real(2);
+  const bool penta = (S <= Real(1)) || (S >= Real(3));
+  const Real u0 = refl ? Real(1) - in[0] : in[0], u1 = refl ? Real(1) - in[1] : in[1];
+  const Real u2 = refl ? Real(1) - in[2] : in[2], u3 = refl ? Real(1) - in[3] : in[3];
+  const Real T = ((u0 + u1) + u2) + u3;
+  uint32_t cc, third_code;
+  bool keep_first, three_lowered;
+  if (penta) {
+    // two closest of the unit vertices; is the origin closer than one of them?
+    SimplexTop2<Real> t{u0, u1, 1u, 2u, true, true};
+    t.offer(u2, 4u, true);
+    t.offer(u3, 8u, true);
+    const Real un = Real(1) - T;
+    const bool origin_close = (un > t.a_sc) || (un > t.b_sc);
+    cc = origin_close ? (t.b_sc > t.a_sc ? t.b_po : t.a_po) : (t.a_po | t.b_po);
+    keep_first = !origin_close;        // extras = {cc, cc - e_z0, cc - e_z1}  or  {cc - e_z0, cc - e_z1, cc - e_z2}
+    three_lowered = origin_close;
+    third_code = 0;
+  } else {
+    // the closer of each complementary two-ones pair, then the unit vertices (scores as the package defines them)
+    const bool p0 = (u0 + u1) > (u2 + u3), p1 = (u0 + u2) > (u1 + u3), p2 = (u0 + u3) > (u1 + u2);
+    SimplexTop2<Real> t{p0 ? u0 + u1 : u2 + u3, p1 ? u0 + u2 : u1 + u3, p0 ? 0x3u : 0xCu, p1 ? 0x5u : 0xAu, true, true};
+    t.offer(p2 ? u0 + u3 : u1 + u2, p2 ? 0x9u : 0x6u, true);
+    const Real r = Real(2) - T;
+    t.offer(r + u0, 1u, false);
+    t.offer(r + u1, 2u, false);
+    t.offer(r + u2, 4u, false);
+    t.offer(r + u3, 8u, false);
+    const bool both_big = t.a_big && t.b_big, both_small = !t.a_big && !t.b_big;
+    const uint32_t big_po = t.a_big ? t.a_po : t.b_po, small_po = t.a_big ? t.b_po : t.a_po;
+    cc = (both_big || both_small) ? (t.a_po | t.b_po) : big_po;
+    keep_first = both_big;             // extras = {cc, cc - e_z0, 2 e_k}  or  {cc - e_z0, cc - e_z1, 2 e_k | origin}
+    three_lowered = false;
+    const uint32_t k = both_big ? (t.a_po & t.b_po) : small_po;          // one-hot axis of the (0,0,0,2) vertex
+    third_code = both_small ? 0x55u : (0x55u | ((k * k) << 1));
+  }
+  const uint32_t code = 0x55u + simplex_spread2(cc);
+  const uint32_t z = ~cc & 15u;
+  const uint32_t h0 = z & (0u - z), zr = z ^ h0, h1 = zr & (0u - zr), h2 = zr ^ h1;   // one-hot zero axes, ascending
+  const uint32_t l0 = code & ~(h0 * h0), l1 = code & ~(h1 * h1), l2 = code & ~(h2 * h2);
+  uint32_t e0 = keep_first ? code : l0;
+  uint32_t e1 = keep_first ? l0 : l1;
+  uint32_t e2 = three_lowered ? l2 : (penta ? l1 : third_code);
+  if (refl) { e0 = ~e0 & 0xFFu; e1 = ~e1 & 0xFFu; e2 = ~e2 & 0xFFu; }
+  ext[0] = e0; ext[1] = e1; ext[2] = e2;
+  return penta ? (refl ? 0xE880u : 0x0117u) : (refl ? 0x7EE8u : 0x177Eu);
+}
+
+// One selected vertex with run-time offsets (the extras): 4 dependent table reads + the kernel.
+template <typename Real, typename Perm>
+BLE_HD Real simplex_vertex(const Perm& perm, const int cb[4], const Real d0[4], uint32_t code) {
+  const int o0 = int(code & 3u) - 1, o1 = int((code >> 2) & 3u) - 1, o2 = int((code >> 4) & 3u) - 1,
+            o3 = int((code >> 6) & 3u) - 1;
+  const Real t = Real(o0 + o1 + o2 + o3) * Real(kSquish4);
+  const Real dx = d0[0] - Real(o0) - t, dy = d0[1] - Real(o1) - t, dz = d0[2] - Real(o2) - t, dw = d0[3] - Real(o3) - t;
+  Real attn = Real(2) - dx * dx - dy * dy - dz * dz - dw * dw;
+  attn = attn > Real(0) ? attn : Real(0);
+  int h = perm[(cb[0] + o0) & 255];
+  h = perm[(h + cb[1] + o1) & 255];
+  h = perm[(h + cb[2] + o2) & 255];
+  h = perm[(h + cb[3] + o3) & 255];
+  attn *= attn;
+  return attn * attn * gradient_dot_fast<Real>(h, dx, dy, dz, dw);
+}
+
+// Plain evaluation of the tree form (audit / host replay): base corners in index order, then the extras.
+template <typename Real, typename Perm>
+BLE_HD Real simplex_noise4(const Perm& perm, double x, double y, double z, double w) {
+  const double s = (x + y + z + w) * kStretch4;
+  const double xs = x + s, ys = y + s, zs = z + s, ws = w + s;
+  const double fx = floor(xs), fy = floor(ys), fz = floor(zs), fw = floor(ws);
+  const double q = (fx + fy + fz + fw) * kSquish4;
+  const Real d0[4] = {Real(x - (fx + q)), Real(y - (fy + q)), Real(z - (fz + q)), Real(w - (fw + q))};
+  const Real in[4] = {Real(xs - fx), Real(ys - fy), Real(zs - fz), Real(ws - fw)};
+  const int cb[4] = {int(int64_t(fx) & 255), int(int64_t(fy) & 255), int(int64_t(fz) & 255), int(int64_t(fw) & 255)};
+  uint32_t ext[3];
+  const uint32_t cmask = simplex_tree_select<Real>(in, ext);
+  Real value = Real(0);
+  for (uint32_t m = 0; m < 16; ++m)
+    if ((cmask >> m) & 1u) value += simplex_vertex<Real>(perm, cb, d0, 0x55u + simplex_spread2(m));
+  for (int k = 0; k < 3; ++k) value += simplex_vertex<Real>(perm, cb, d0, ext[k]);
+  return value / Real(30.0);
+}
+
+// Production evaluation of the tree form.  The 16 cube corners are evaluated unconditionally and branch-free
+// (compile-time offsets, the permutation look-ups shared as a binary tree: 30 reads instead of 64) and the ones the
+// region does not select are masked out; the three extras follow with run-time offsets.  Order as in the A/B form so
+// that the fused kernels can release the staged tables early: corner hashes, the extras completely, tables_done(),
+// the corners' arithmetic.
+template <typename Real, typename Perm, typename Done = NoTablesDone>
+BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, double w, Done tables_done = Done()) {
+#if defined(BLE_NOISE_ALL_VERTICES)
+  return simplex_noise4_v2_all<Real, Perm, Done>(perm, x, y, z, w, tables_done);
+#else
+  const double s = (x + y + z + w) * kStretch4;
+  const double xs = x + s, ys = y + s, zs = z + s, ws = w + s;
+  const double fx = floor(xs), fy = floor(ys), fz = floor(zs), fw = floor(ws);
+  const double q = (fx + fy + fz + fw) * kSquish4;
+  const Real d0[4] = {Real(x - (fx + q)), Real(y - (fy + q)), Real(z - (fz + q)), Real(w - (fw + q))};
+  const Real in[4] = {Real(xs - fx), Real(ys - fy), Real(zs - fz), Real(ws - fw)};   // inside the unit cell
+  const int cb[4] = {int(int64_t(fx) & 255), int(int64_t(fy) & 255), int(int64_t(fz) & 255), int(int64_t(fw) & 255)};
+  const Real sq = Real(kSquish4);
+
+  // ---- hashes of the 16 corners ----
+  int h1[2], h2[4], h3[8], hc[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 2; ++i) h1[i] = perm[(cb[0] + i) & 255];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 4; ++i) h2[i] = perm[(h1[i & 1] + cb[1] + (i >> 1)) & 255];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 8; ++i) h3[i] = perm[(h2[i & 3] + cb[2] + (i >> 2)) & 255];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int m = 0; m < 16; ++m) hc[m] = perm[(h3[m & 7] + cb[3] + (m >> 3)) & 255];
+
+  // ---- vertex selection, then the three extras ----
+  uint32_t ext[3];
+  const uint32_t cmask = simplex_tree_select<Real>(in, ext);
+  Real outer = Real(0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 3; ++k) outer += simplex_vertex<Real>(perm, cb, d0, ext[k]);
+  tables_done();
+
+  // ---- the 16 corners ----
+  Real e[4][2];                                        // real-space displacement per axis at offsets 0 / 1
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int a = 0; a < 4; ++a) { e[a][0] = d0[a]; e[a][1] = d0[a] - Real(1); }
+  Real value = Real(0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int m = 0; m < 16; ++m) {
+    const int pc = (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + (m >> 3);
+    const Real t = Real(pc) * sq;
+    const Real dx = e[0][m & 1] - t, dy = e[1][(m >> 1) & 1] - t, dz = e[2][(m >> 2) & 1] - t, dw = e[3][m >> 3] - t;
+    Real attn = Real(2) - dx * dx - dy * dy - dz * dz - dw * dw;
+    attn = (attn > Real(0) && ((cmask >> m) & 1u)) ? attn : Real(0);
+    attn *= attn;
+    value += attn * attn * gradient_dot_fast<Real>(hc[m], dx, dy, dz, dw);
+  }
+  return (value + outer) / Real(30.0);
+#endif
 }
 
 // OpenSimplex.__init__: 256-entry permutation from a 64-bit LCG (see oracle/opensimplex4.py).

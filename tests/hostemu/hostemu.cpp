@@ -136,7 +136,22 @@ void emu_noise(int precision, int64_t n, const int64_t* seeds, const double* xyz
   }
 }
 
-// second-generation evaluation (production fp32 kernels); precision as emu_noise
+// the A/B all-vertices forms (oracle form='all'): which = 0 round-1 evaluation, 1 second generation
+void emu_noise_all(int precision, int which, int64_t n, const int64_t* seeds, const double* xyzw, double* out) {
+  uint8_t perm[256], scratch[256];
+  for (int64_t i = 0; i < n; ++i) {
+    simplex_make_perm(seeds[i], perm, scratch);
+    const double* p = xyzw + 4 * i;
+    const uint8_t* pm = perm;
+    if (precision == BLE_PRECISION_FP64)
+      out[i] = which ? simplex_noise4_v2_all<double>(pm, p[0], p[1], p[2], p[3]) : simplex_noise4_all<double>(pm, p[0], p[1], p[2], p[3]);
+    else
+      out[i] = which ? double(simplex_noise4_v2_all<float>(pm, p[0], p[1], p[2], p[3]))
+                     : double(simplex_noise4_all<float>(pm, p[0], p[1], p[2], p[3]));
+  }
+}
+
+// production evaluation (tree form, corners unrolled); precision as emu_noise
 void emu_noise_v2(int precision, int64_t n, const int64_t* seeds, const double* xyzw, double* out) {
   uint8_t perm[256], scratch[256];
   for (int64_t i = 0; i < n; ++i) {
