@@ -1,0 +1,369 @@
+// Dense layers of the QR-DQN network (agents/networks.py:63-98: 8 x Dense(600) + ReLU) on the 5th-generation tensor
+// cores: ONE hand-written GEMM kernel, D[M, N] = A[M, K] . B[N, K]^T with both operands K-contiguous in HBM, serves
+// the forward pass, the input gradient and the weight gradient of every layer (the caller keeps transposed copies so
+// that every product has this shape; see learner.py DenseStack).
+//
+//   * operands: fp32 in HBM, read as TF32 by the tensor core (`tcgen05.mma.cta_group::1.kind::tf32`, fp32 accumulate
+//     in tensor memory) -- the precision jax's default matmul has on the reference's GPU path;
+//   * tile 128 x 128 x 32 (one 128-byte swizzle row of K per stage row), operands brought by TMA tensor copies
+//     (`cp.async.bulk.tensor.2d`, 128-byte swizzle, out-of-range rows / columns zero-filled) into a 3-stage ring,
+//     4 MMAs (K = 8) per stage issued by one elected thread, accumulator = 128 lanes x 128 columns of TMEM;
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue, warps 2-5 = epilogue (each reads its
+//     32 TMEM lanes with `tcgen05.ld.32x32b.x32`: a thread holds 32 consecutive columns of one output row);
+//   * fused epilogues: + bias, + bias and ReLU, x (forward activation > 0) for the input gradient, atomic accumulation
+//     for the split-K weight gradient; every mode can also write the TRANSPOSED tile (a register column is 32
+//     consecutive rows across the lanes, so the transposed store is the coalesced one), which is what the next
+//     product along the backward pass reads as its K-contiguous operand.
+//
+// Two CTAs per SM (97 KB of shared memory and 128 TMEM columns each) so that one tile's epilogue overlaps the other's
+// main loop.  mbarrier waits are bounded (trap after ~2 s) so that a protocol error surfaces as a CUDA error instead
+// of a hung device.
+#include <cuda.h>           // CUtensorMap types only: the encoder is fetched with cudaGetDriverEntryPoint (no -lcuda)
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/ble_b200.h"
+
+namespace ble {
+namespace {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32;           // kBK floats = 128 B = the swizzle span
+constexpr int kUmmaK = 8;                               // tf32: 32 B of K per MMA
+constexpr int kStages = 3;
+constexpr int kABytes = kBM * kBK * 4, kBBytes = kBN * kBK * 4, kStageBytes = kABytes + kBBytes;
+constexpr int kTmemCols = 128;
+constexpr int kThreads = 192;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+struct DenseArgs {
+  int64_t m, n, k;
+  int k_blocks_per_split;
+  const float* aux; int64_t ld_aux;                     // bias [N] (modes 0, 1) or forward activation [M, N] (mode 2)
+  float* d; int64_t ldd;                                // row-major output (may be null when only dt is wanted)
+  float* dt; int64_t ldt;                               // transposed output [N, M] or null
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000ll) __trap();        // ~2 s: a pipeline protocol error, not a slow copy
+  }
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major tile stored as rows of 128 B with the 128-byte swizzle: start address,
+// stride between 8-row groups = 1024 B, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+
+// Instruction descriptor: D = fp32, A = B = TF32, both K-major, N = 128, M = 128.
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kBN >> 3) << 17) | (uint32_t(kBM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_load_32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// kMode: 0 = + bias, 1 = + bias then ReLU, 2 = x (aux[m, n] > 0), 3 = atomic accumulation (split-K)
+template <int kMode>
+__global__ void __launch_bounds__(kThreads, 2)
+k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, DenseArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // swizzled tiles need 1024-byte alignment
+  const uint32_t bars = base + kStages * kStageBytes;                      // full[kStages], empty[kStages], tmem_full
+  const uint32_t tmem_slot = bars + (2 * kStages + 1) * 8;
+  uint8_t* generic_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(generic_base + kStages * kStageBytes + (2 * kStages + 1) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;
+  const int total_kb = int((args.k + kBK - 1) / kBK);
+  const int kb0 = blockIdx.z * args.k_blocks_per_split;
+  const int kb1 = min(total_kb, kb0 + args.k_blocks_per_split);
+  const int num_kb = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (kStages + s), 1); }
+    mbar_init(bars + 8 * 2 * kStages, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {                                                       // ---- TMA producer ----
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kStages;
+        const uint32_t parity = uint32_t(i / kStages) & 1u;
+        mbar_wait(bars + 8 * (kStages + s), parity ^ 1u);                  // slot free (passes at once the first round)
+        const uint32_t full = bars + 8 * s;
+        mbar_expect_tx(full, kStageBytes);
+        const uint32_t sa = base + s * kStageBytes;
+        tma_load_2d(&map_a, full, sa, (kb0 + i) * kBK, m0);
+        tma_load_2d(&map_b, full, sa + kABytes, (kb0 + i) * kBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                                       // ---- MMA issue ----
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kStages;
+        const uint32_t parity = uint32_t(i / kStages) & 1u;
+        mbar_wait(bars + 8 * s, parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * kStageBytes;
+#pragma unroll
+        for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+          umma_tf32(tmem_base, umma_desc(sa + kk * kUmmaK * 4), umma_desc(sa + kABytes + kk * kUmmaK * 4),
+                    (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(bars + 8 * (kStages + s));                             // slot reusable once these MMAs have read it
+      }
+      umma_commit(bars + 8 * 2 * kStages);                                 // accumulator complete
+    }
+  } else {                                                                 // ---- epilogue: warps 2..5 ----
+    const int q = warp & 3;                                                // the TMEM lane quarter this warp may read
+    const int64_t m = int64_t(m0) + q * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(bars + 8 * 2 * kStages, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+#pragma unroll 1
+    for (int c = 0; c < kBN / 32; ++c) {
+      float v[32];
+      if (num_kb > 0) {
+        tmem_load_32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      const int64_t nc = int64_t(n0) + c * 32;
+      if (nc >= args.n) break;
+      const bool row_ok = m < args.m;
+      const bool full_chunk = nc + 32 <= args.n;
+      if (kMode == 0 || kMode == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float b = (nc + j < args.n) ? __ldg(args.aux + nc + j) : 0.f;
+          v[j] += b;
+          if (kMode == 1) v[j] = fmaxf(v[j], 0.f);
+        }
+      } else if (kMode == 2) {
+        if (row_ok) {
+          const float* h = args.aux + m * args.ld_aux + nc;
+          if (full_chunk && (args.ld_aux & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 hv = __ldg(reinterpret_cast<const float4*>(h + j));
+              v[j] = hv.x > 0.f ? v[j] : 0.f; v[j + 1] = hv.y > 0.f ? v[j + 1] : 0.f;
+              v[j + 2] = hv.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = hv.w > 0.f ? v[j + 3] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (nc + j < args.n && __ldg(h + j) > 0.f) ? v[j] : 0.f;
+          }
+        }
+      }
+      if (kMode == 3) {
+        if (row_ok) {
+          float* out = args.d + m * args.ldd + nc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nc + j < args.n) atomicAdd(out + j, v[j]);
+        }
+        continue;
+      }
+      if (args.d != nullptr && row_ok) {
+        float* out = args.d + m * args.ldd + nc;
+        if (full_chunk && (args.ldd & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nc + j < args.n) out[j] = v[j];
+        }
+      }
+      if (args.dt != nullptr && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nc + j < args.n) args.dt[(nc + j) * args.ldt + m] = v[j];  // lanes = consecutive m: coalesced
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ---- small companions ---------------------------------------------------------------------------------------
+// dst[c, r] = src[r, c] (32 x 32 tiles through shared memory, both sides coalesced)
+__global__ void __launch_bounds__(256)
+k_transpose(const float* __restrict__ src, int64_t lds, int64_t rows, int64_t cols, float* __restrict__ dst, int64_t ldd) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = int64_t(blockIdx.y) * 32, c0 = int64_t(blockIdx.x) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    tile[i][tx] = (r0 + i < rows && c0 + tx < cols) ? src[(r0 + i) * lds + c0 + tx] : 0.f;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < cols && r0 + tx < rows) dst[(c0 + i) * ldd + r0 + tx] = tile[tx][i];
+}
+
+// out[r] (+)= sum_c src[r, c]: one warp per row (bias gradient = row sums of the transposed output gradient)
+__global__ void __launch_bounds__(256)
+k_row_sum(const float* __restrict__ src, int64_t lds, int64_t rows, int64_t cols, float* __restrict__ out, int accumulate) {
+  const int64_t r = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* p = src + r * lds;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int64_t c = lane;
+  for (; c + 96 < cols; c += 128) { acc[0] += p[c]; acc[1] += p[c + 32]; acc[2] += p[c + 64]; acc[3] += p[c + 96]; }
+  for (; c < cols; c += 32) acc[0] += p[c];
+  float s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[r] = accumulate ? out[r] + s : s;
+}
+
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiled tensor_map_encoder() {
+  static EncodeTiled cached = []() -> EncodeTiled {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult found;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &found) != cudaSuccess ||
+        found != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiled>(fn);
+  }();
+  return cached;
+}
+
+// [rows, k] fp32, row pitch ld floats -> box {32 floats, 128 rows}, 128-byte swizzle, zero fill out of range
+bool operand_map(CUtensorMap* map, const float* p, int64_t rows, int64_t k, int64_t ld) {
+  EncodeTiled enc = tensor_map_encoder();
+  if (enc == nullptr) return false;
+  const cuuint64_t dims[2] = {cuuint64_t(k), cuuint64_t(rows)};
+  const cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
+  const cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(kBM)};
+  const cuuint32_t elem[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, elem,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int kMode>
+int launch_dense(const CUtensorMap& ma, const CUtensorMap& mb, const DenseArgs& args, dim3 grid, cudaStream_t s) {
+  static bool configured[16] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return BLE_ERR_CUDA;
+  if (!configured[dev]) {
+    if (cudaFuncSetAttribute(k_dense_tf32<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+      return BLE_ERR_CUDA;
+    configured[dev] = true;
+  }
+  k_dense_tf32<kMode><<<grid, kThreads, kSmemBytes, s>>>(ma, mb, args);
+  return cudaGetLastError() == cudaSuccess ? BLE_OK : BLE_ERR_CUDA;
+}
+
+}  // namespace
+}  // namespace ble
+
+extern "C" {
+
+int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int64_t n, int64_t k, int32_t mode,
+                   const float* aux, int64_t ld_aux, float* d, int64_t ldd, float* dt, int64_t ldt, int32_t split_k,
+                   void* stream) {
+  using namespace ble;
+  if (a == nullptr || b == nullptr || m <= 0 || n <= 0 || k <= 0 || mode < 0 || mode > 3 || lda < k || ldb < k ||
+      (lda & 3) != 0 || (ldb & 3) != 0 || (reinterpret_cast<uintptr_t>(a) & 15) != 0 || (reinterpret_cast<uintptr_t>(b) & 15) != 0 ||
+      (d == nullptr && dt == nullptr) || (d != nullptr && ldd < n) || (dt != nullptr && ldt < m) ||
+      (mode <= 2 && aux == nullptr) || (mode == 2 && ld_aux < n) || (mode == 3 && (d == nullptr || dt != nullptr)) ||
+      split_k < 1 || (mode != 3 && split_k != 1)) {
+    return BLE_ERR_INVALID_ARGUMENT;
+  }
+  CUtensorMap ma, mb;
+  if (!operand_map(&ma, a, m, k, lda) || !operand_map(&mb, b, n, k, ldb)) return BLE_ERR_CUDA;
+  const int total_kb = int((k + kBK - 1) / kBK);
+  const int splits = split_k > total_kb ? total_kb : split_k;
+  DenseArgs args{m, n, k, (total_kb + splits - 1) / splits, aux, ld_aux, d, ldd, dt, ldt};
+  const dim3 grid(unsigned((n + kBN - 1) / kBN), unsigned((m + kBM - 1) / kBM), unsigned(splits));
+  cudaStream_t s = cudaStream_t(stream);
+  switch (mode) {
+    case 0: return launch_dense<0>(ma, mb, args, grid, s);
+    case 1: return launch_dense<1>(ma, mb, args, grid, s);
+    case 2: return launch_dense<2>(ma, mb, args, grid, s);
+    default: return launch_dense<3>(ma, mb, args, grid, s);
+  }
+}
+
+int ble_transpose_f32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* dst, int64_t ld_dst, void* stream) {
+  if (src == nullptr || dst == nullptr || rows <= 0 || cols <= 0 || ld_src < cols || ld_dst < rows) return BLE_ERR_INVALID_ARGUMENT;
+  const dim3 grid(unsigned((cols + 31) / 32), unsigned((rows + 31) / 32));
+  ble::k_transpose<<<grid, 256, 0, cudaStream_t(stream)>>>(src, ld_src, rows, cols, dst, ld_dst);
+  return cudaGetLastError() == cudaSuccess ? BLE_OK : BLE_ERR_CUDA;
+}
+
+int ble_row_sum_f32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* out, int32_t accumulate, void* stream) {
+  if (src == nullptr || out == nullptr || rows <= 0 || cols <= 0 || ld_src < cols) return BLE_ERR_INVALID_ARGUMENT;
+  ble::k_row_sum<<<unsigned((rows + 7) / 8), 256, 0, cudaStream_t(stream)>>>(src, ld_src, rows, cols, out, accumulate);
+  return cudaGetLastError() == cudaSuccess ? BLE_OK : BLE_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -567,11 +567,14 @@ BLE_HD Real simplex_noise4(const Perm& perm, double x, double y, double z, doubl
   return value / Real(30.0);
 }
 
-// Production evaluation of the tree form.  The 16 cube corners are evaluated unconditionally and branch-free
-// (compile-time offsets, the permutation look-ups shared as a binary tree: 30 reads instead of 64) and the ones the
-// region does not select are masked out; the three extras follow with run-time offsets.  Order as in the A/B form so
-// that the fused kernels can release the staged tables early: corner hashes, the extras completely, tables_done(),
-// the corners' arithmetic.
+// Production evaluation of the tree form.  Everything runs in the LOWER frame (the unit cell reflected when inSum > 2,
+// see simplex_tree_select): there the base vertices are always among 11 cube corners -- the 4 unit corners (every
+// region), the 6 two-ones corners (regions C / D) and the origin (regions A / B) -- so 11 corners are evaluated
+// branch-free with compile-time lower-frame offsets (the reflection only swaps which of two precomputed values an
+// offset bit selects), the permutation look-ups shared as a pruned binary tree (24 reads), and the ones the region
+// does not use masked out; the three extras follow with run-time offsets.  Order as in the A/B form so that the fused
+// kernels can release the staged tables early: corner hashes, the extras completely, tables_done(), the corners'
+// arithmetic.
 template <typename Real, typename Perm, typename Done = NoTablesDone>
 BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, double w, Done tables_done = Done()) {
 #if defined(BLE_NOISE_ALL_VERTICES)
@@ -586,28 +589,37 @@ BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, do
   const int cb[4] = {int(int64_t(fx) & 255), int(int64_t(fy) & 255), int(int64_t(fz) & 255), int(int64_t(fw) & 255)};
   const Real sq = Real(kSquish4);
 
-  // ---- hashes of the 16 corners ----
-  int h1[2], h2[4], h3[8], hc[16];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = 0; i < 2; ++i) h1[i] = perm[(cb[0] + i) & 255];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = 0; i < 4; ++i) h2[i] = perm[(h1[i & 1] + cb[1] + (i >> 1)) & 255];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = 0; i < 8; ++i) h3[i] = perm[(h2[i & 3] + cb[2] + (i >> 2)) & 255];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int m = 0; m < 16; ++m) hc[m] = perm[(h3[m & 7] + cb[3] + (m >> 3)) & 255];
-
-  // ---- vertex selection, then the three extras ----
+  // ---- vertex selection ----
   uint32_t ext[3];
   const uint32_t cmask = simplex_tree_select<Real>(in, ext);
+  const bool refl = (cmask & 0x8000u) != 0 || cmask == 0x7EE8u;   // regions B / D
+  const bool penta = (cmask & 0x8001u) != 0;                      // regions A / B (the only masks with corner 0 or 15)
+
+  // ---- hashes of the 11 lower-frame corners: lower-frame offset bit b of axis a is the real offset b ^ refl ----
+  int ca[4][2];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int a = 0; a < 4; ++a) { ca[a][0] = cb[a] + (refl ? 1 : 0); ca[a][1] = cb[a] + (refl ? 0 : 1); }
+  int h1[2], h2[4], h3[7];
+  h1[0] = perm[ca[0][0] & 255]; h1[1] = perm[ca[0][1] & 255];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 4; ++i) h2[i] = perm[(h1[i & 1] + ca[1][i >> 1]) & 255];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 7; ++i) h3[i] = perm[(h2[i & 3] + ca[2][i >> 2]) & 255];
+  // corner list: origin, 4 units, 6 two-ones (lower-frame index m, bit a = offset along axis a)
+  constexpr int kCorner[11] = {0, 1, 2, 4, 8, 3, 5, 6, 9, 10, 12};
+  int hc[11];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int c = 0; c < 11; ++c) hc[c] = perm[(h3[kCorner[c] & 7] + ca[3][kCorner[c] >> 3]) & 255];
+
+  // ---- the three extras ----
   Real outer = Real(0);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -615,24 +627,27 @@ BLE_HD Real simplex_noise4_v2(const Perm& perm, double x, double y, double z, do
   for (int k = 0; k < 3; ++k) outer += simplex_vertex<Real>(perm, cb, d0, ext[k]);
   tables_done();
 
-  // ---- the 16 corners ----
-  Real e[4][2];                                        // real-space displacement per axis at offsets 0 / 1
+  // ---- the corners ----
+  Real e[4][2];                                        // real-space displacement per axis at lower-frame offsets 0 / 1
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int a = 0; a < 4; ++a) { e[a][0] = d0[a]; e[a][1] = d0[a] - Real(1); }
+  for (int a = 0; a < 4; ++a) { e[a][0] = refl ? d0[a] - Real(1) : d0[a]; e[a][1] = refl ? d0[a] : d0[a] - Real(1); }
+  const Real tv[3] = {refl ? Real(4) * sq : Real(0), refl ? Real(3) * sq : sq, Real(2) * sq};   // by lower-frame popcount
   Real value = Real(0);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int m = 0; m < 16; ++m) {
+  for (int c = 0; c < 11; ++c) {
+    const int m = kCorner[c];
     const int pc = (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + (m >> 3);
-    const Real t = Real(pc) * sq;
+    const Real t = tv[pc];
     const Real dx = e[0][m & 1] - t, dy = e[1][(m >> 1) & 1] - t, dz = e[2][(m >> 2) & 1] - t, dw = e[3][m >> 3] - t;
     Real attn = Real(2) - dx * dx - dy * dy - dz * dz - dw * dw;
-    attn = (attn > Real(0) && ((cmask >> m) & 1u)) ? attn : Real(0);
+    const bool used = pc == 1 ? true : (pc == 0 ? penta : !penta);
+    attn = (attn > Real(0) && used) ? attn : Real(0);
     attn *= attn;
-    value += attn * attn * gradient_dot_fast<Real>(hc[m], dx, dy, dz, dw);
+    value += attn * attn * gradient_dot_fast<Real>(hc[c], dx, dy, dz, dw);
   }
   return (value + outer) / Real(30.0);
 #endif
