@@ -12,7 +12,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.environ.get('BLE_B200_LIB') or os.path.join(PKG_DIR, 'libble_b200.so')
-SOURCES = [os.path.join(CSRC, f) for f in ('ble_engine.cu', 'ble_step_fused.cu', 'ble_learner.cu')]
+SOURCES = [os.path.join(CSRC, f) for f in ('ble_engine.cu', 'ble_step_fused.cu', 'ble_learner.cu', 'ble_dense.cu')]
 HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))) + [
            os.path.join(PKG_DIR, '..', 'include', 'ble_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

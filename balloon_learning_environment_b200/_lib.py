@@ -38,7 +38,7 @@ EXPORTS = ('ble_create', 'ble_destroy', 'ble_last_error', 'ble_num_envs', 'ble_u
            'ble_eval_begin', 'ble_eval_accumulate', 'ble_eval_results',
            'ble_launch_count',
            'ble_qr_greedy', 'ble_qr_target', 'ble_qr_loss', 'ble_replay_sample', 'ble_adam_step',
-           'ble_marco_polo_step')
+           'ble_marco_polo_step', 'ble_dense_tf32', 'ble_transpose_f32', 'ble_row_sum_f32')
 
 
 class BleConfig(_c.Structure):
@@ -129,6 +129,9 @@ def load(build_if_missing=True):
   lib.ble_replay_sample.argtypes = [_c.POINTER(BleReplayView), vp, u64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
   lib.ble_adam_step.argtypes = [vp, vp, vp, vp, i64, f64, f64, f64, f64, i64, f32, vp]
   lib.ble_marco_polo_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, f32, vp, vp]
+  lib.ble_dense_tf32.argtypes = [vp, i64, vp, i64, i64, i64, i64, i32, vp, i64, vp, i64, vp, i64, i32, vp]
+  lib.ble_transpose_f32.argtypes = [vp, i64, i64, i64, vp, i64, vp]
+  lib.ble_row_sum_f32.argtypes = [vp, i64, i64, i64, vp, i32, vp]
   for name in EXPORTS:
     if name not in ('ble_last_error', 'ble_num_envs', 'ble_launch_count'):
       getattr(lib, name).restype = _c.c_int

@@ -5,9 +5,10 @@
 //
 //   * operands: fp32 in HBM, read as TF32 by the tensor core (`tcgen05.mma.cta_group::1.kind::tf32`, fp32 accumulate
 //     in tensor memory) -- the precision jax's default matmul has on the reference's GPU path;
-//   * tile 128 x 128 x 32 (one 128-byte swizzle row of K per stage row), operands brought by TMA tensor copies
-//     (`cp.async.bulk.tensor.2d`, 128-byte swizzle, out-of-range rows / columns zero-filled) into a 3-stage ring,
-//     4 MMAs (K = 8) per stage issued by one elected thread, accumulator = 128 lanes x 128 columns of TMEM;
+//   * tile 128 x 160 x 32 (one 128-byte swizzle row of K per stage row; N = 160 covers the 600-wide layers in 4 tiles, so
+//     the 8,192-sample products are 256 CTAs = ONE wave at 2 CTAs per SM, and the 153 logits in one), operands brought by
+//     TMA tensor copies (`cp.async.bulk.tensor.2d`, 128-byte swizzle, out-of-range rows / columns zero-filled) into a
+//     3-stage ring, 4 MMAs (K = 8) per stage issued by one elected thread, accumulator = 128 lanes x 160 TMEM columns;
 //   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue, warps 2-5 = epilogue (each reads its
 //     32 TMEM lanes with `tcgen05.ld.32x32b.x32`: a thread holds 32 consecutive columns of one output row);
 //   * fused epilogues: + bias, + bias and ReLU, x (forward activation > 0) for the input gradient, atomic accumulation
@@ -15,7 +16,7 @@
 //     consecutive rows across the lanes, so the transposed store is the coalesced one), which is what the next
 //     product along the backward pass reads as its K-contiguous operand.
 //
-// Two CTAs per SM (97 KB of shared memory and 128 TMEM columns each) so that one tile's epilogue overlaps the other's
+// Two CTAs per SM (109 KB of shared memory and 256 TMEM columns each) so that one tile's epilogue overlaps the other's
 // main loop.  mbarrier waits are bounded (trap after ~2 s) so that a protocol error surfaces as a CUDA error instead
 // of a hung device.
 #include <cuda.h>           // CUtensorMap types only: the encoder is fetched with cudaGetDriverEntryPoint (no -lcuda)
@@ -28,11 +29,11 @@
 namespace ble {
 namespace {
 
-constexpr int kBM = 128, kBN = 128, kBK = 32;           // kBK floats = 128 B = the swizzle span
+constexpr int kBM = 128, kBN = 160, kBK = 32;           // kBK floats = 128 B = the swizzle span
 constexpr int kUmmaK = 8;                               // tf32: 32 B of K per MMA
 constexpr int kStages = 3;
 constexpr int kABytes = kBM * kBK * 4, kBBytes = kBN * kBK * 4, kStageBytes = kABytes + kBBytes;
-constexpr int kTmemCols = 128;
+constexpr int kTmemCols = 256;                          // power of two >= kBN
 constexpr int kThreads = 192;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
@@ -79,7 +80,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
          (uint64_t(2) << 61);
 }
 
-// Instruction descriptor: D = fp32, A = B = TF32, both K-major, N = 128, M = 128.
+// Instruction descriptor: D = fp32, A = B = TF32, both K-major, N = kBN, M = kBM.
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kBN >> 3) << 17) | (uint32_t(kBM >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
@@ -215,12 +216,11 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           }
         }
       }
-      if (kMode == 3) {
-        if (row_ok) {
-          float* out = args.d + m * args.ldd + nc;
+      if (kMode == 3) {                                 // split-K: accumulate into the TRANSPOSED result, where the 32 lanes
+        if (row_ok) {                                   // of a reduction are 32 consecutive floats
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (nc + j < args.n) atomicAdd(out + j, v[j]);
+            if (nc + j < args.n) atomicAdd(args.dt + (nc + j) * args.ldt + m, v[j]);
         }
         continue;
       }
@@ -264,20 +264,34 @@ k_transpose(const float* __restrict__ src, int64_t lds, int64_t rows, int64_t co
     if (c0 + i < cols && r0 + tx < rows) dst[(c0 + i) * ldd + r0 + tx] = tile[tx][i];
 }
 
-// out[r] (+)= sum_c src[r, c]: one warp per row (bias gradient = row sums of the transposed output gradient)
+// out[r] (+)= sum_c src[r, c]: one CTA per row, 16-byte loads (bias gradient = row sums of the transposed output
+// gradient; rows start 16-byte aligned because the pitch is a multiple of 4 floats)
 __global__ void __launch_bounds__(256)
 k_row_sum(const float* __restrict__ src, int64_t lds, int64_t rows, int64_t cols, float* __restrict__ out, int accumulate) {
-  const int64_t r = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
+  __shared__ float part[8];
+  const int64_t r = blockIdx.x;
   const float* p = src + r * lds;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int64_t c = lane;
-  for (; c + 96 < cols; c += 128) { acc[0] += p[c]; acc[1] += p[c + 32]; acc[2] += p[c + 64]; acc[3] += p[c + 96]; }
-  for (; c < cols; c += 32) acc[0] += p[c];
-  float s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  float s = 0.f;
+  if ((lds & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int64_t vec = cols >> 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t c = threadIdx.x; c < vec; c += 256) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p) + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    s = (acc.x + acc.y) + (acc.z + acc.w);
+    for (int64_t c = (vec << 2) + threadIdx.x; c < cols; c += 256) s += p[c];
+  } else {
+    for (int64_t c = threadIdx.x; c < cols; c += 256) s += p[c];
+  }
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) out[r] = accumulate ? out[r] + s : s;
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += part[i];
+    out[r] = accumulate ? out[r] + t : t;
+  }
 }
 
 typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -295,13 +309,13 @@ EncodeTiled tensor_map_encoder() {
   return cached;
 }
 
-// [rows, k] fp32, row pitch ld floats -> box {32 floats, 128 rows}, 128-byte swizzle, zero fill out of range
-bool operand_map(CUtensorMap* map, const float* p, int64_t rows, int64_t k, int64_t ld) {
+// [rows, k] fp32, row pitch ld floats -> box {32 floats, box_rows rows}, 128-byte swizzle, zero fill out of range
+bool operand_map(CUtensorMap* map, const float* p, int64_t rows, int64_t k, int64_t ld, int box_rows) {
   EncodeTiled enc = tensor_map_encoder();
   if (enc == nullptr) return false;
   const cuuint64_t dims[2] = {cuuint64_t(k), cuuint64_t(rows)};
   const cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
-  const cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(kBM)};
+  const cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(box_rows)};
   const cuuint32_t elem[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, elem,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -334,12 +348,12 @@ int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int
   if (a == nullptr || b == nullptr || m <= 0 || n <= 0 || k <= 0 || mode < 0 || mode > 3 || lda < k || ldb < k ||
       (lda & 3) != 0 || (ldb & 3) != 0 || (reinterpret_cast<uintptr_t>(a) & 15) != 0 || (reinterpret_cast<uintptr_t>(b) & 15) != 0 ||
       (d == nullptr && dt == nullptr) || (d != nullptr && ldd < n) || (dt != nullptr && ldt < m) ||
-      (mode <= 2 && aux == nullptr) || (mode == 2 && ld_aux < n) || (mode == 3 && (d == nullptr || dt != nullptr)) ||
+      (mode <= 2 && aux == nullptr) || (mode == 2 && ld_aux < n) || (mode == 3 && (dt == nullptr || d != nullptr)) ||
       split_k < 1 || (mode != 3 && split_k != 1)) {
     return BLE_ERR_INVALID_ARGUMENT;
   }
   CUtensorMap ma, mb;
-  if (!operand_map(&ma, a, m, k, lda) || !operand_map(&mb, b, n, k, ldb)) return BLE_ERR_CUDA;
+  if (!operand_map(&ma, a, m, k, lda, kBM) || !operand_map(&mb, b, n, k, ldb, kBN)) return BLE_ERR_CUDA;
   const int total_kb = int((k + kBK - 1) / kBK);
   const int splits = split_k > total_kb ? total_kb : split_k;
   DenseArgs args{m, n, k, (total_kb + splits - 1) / splits, aux, ld_aux, d, ldd, dt, ldt};
@@ -362,7 +376,7 @@ int ble_transpose_f32(const float* src, int64_t ld_src, int64_t rows, int64_t co
 
 int ble_row_sum_f32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* out, int32_t accumulate, void* stream) {
   if (src == nullptr || out == nullptr || rows <= 0 || cols <= 0 || ld_src < cols) return BLE_ERR_INVALID_ARGUMENT;
-  ble::k_row_sum<<<unsigned((rows + 7) / 8), 256, 0, cudaStream_t(stream)>>>(src, ld_src, rows, cols, out, accumulate);
+  ble::k_row_sum<<<unsigned(rows), 256, 0, cudaStream_t(stream)>>>(src, ld_src, rows, cols, out, accumulate);
   return cudaGetLastError() == cudaSuccess ? BLE_OK : BLE_ERR_CUDA;
 }
 

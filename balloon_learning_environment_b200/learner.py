@@ -83,6 +83,13 @@ class QrDqnConfig:
   max_episode_length: int = 960          # train_acme_qrdqn.py:30-33
   tf32_matmul: bool = True               # dense layers on the tensor cores (TF32 in, fp32 accumulate): what
                                          # jax's default matmul precision does on an Ampere+ GPU
+  dense_backend: str = 'tcgen05'         # 'tcgen05': forward AND backward of the dense layers by the hand-written
+                                         # ble_dense_tf32 kernel (DenseStack, no autograd); 'cublas': nn.Linear +
+                                         # autograd on library GEMMs (A/B reference; the only choice for the fp32
+                                         # audit setting tf32_matmul = False)
+  cuda_graph: bool = True                # tcgen05 backend: the ~60 launches of one SGD step (target forward, online
+                                         # forward, loss, backward) and the operand refresh are captured once per batch
+                                         # size and replayed (the eager sequence is bound by host launch overhead)
 
 
 class QuantileNetwork(nn.Module):
@@ -193,6 +200,130 @@ def adam_step(params, grads, m, v, step: int, lr: float, b1=0.9, b2=0.999, eps=2
   _require_cuda(params, 'adam_step')
   _call('ble_adam_step', params.device, _ptr(params), _ptr(grads), _ptr(m), _ptr(v), params.numel(), float(lr), float(b1),
         float(b2), float(eps), int(step), float(grad_scale))
+
+
+def _pitch4(n: int) -> int:
+  return (int(n) + 3) // 4 * 4
+
+
+def dense_tf32(a, lda, b, ldb, m, n, k, mode, aux=None, ld_aux=0, d=None, ldd=0, dt=None, ldt=0, split_k=1):
+  """D[m, n] = A[m, k] . B[n, k]^T on the tcgen05 tensor cores (include/ble_b200.h: ble_dense_tf32)."""
+  _require_cuda(a, 'dense_tf32')
+  _call('ble_dense_tf32', a.device, _ptr(a), int(lda), _ptr(b), int(ldb), int(m), int(n), int(k), int(mode), _ptr(aux),
+        int(ld_aux), _ptr(d), int(ldd), _ptr(dt), int(ldt), int(split_k))
+
+
+def transpose_f32(src, ld_src, rows, cols, dst, ld_dst):
+  _call('ble_transpose_f32', src.device, _ptr(src), int(ld_src), int(rows), int(cols), _ptr(dst), int(ld_dst))
+
+
+def row_sum_f32(src, ld_src, rows, cols, out, accumulate=False):
+  _call('ble_row_sum_f32', src.device, _ptr(src), int(ld_src), int(rows), int(cols), _ptr(out), int(bool(accumulate)))
+
+
+class DenseStack:
+  """Forward and backward pass of a QuantileNetwork's dense layers WITHOUT autograd: every product is one launch of
+  ble_dense_tf32 (D = A . B^T, both operands K-contiguous), with bias / ReLU / ReLU-mask / split-K accumulation fused
+  into its epilogue.  To give every product that shape the stack keeps, next to the parameters (which stay the flat
+  fp32 buffer of `flatten_parameters`):
+
+    w_t[l]   [in_l, out_l]  transposed weights (input gradient:  dH = dY . W       = dY [B, out] . (W^T [in, out])^T)
+    h_t[l]   [out_l, B]     transposed activations, written by the forward epilogue
+    g_t[l]   [out_l, B]     transposed output gradients, written by the input-gradient epilogue
+                            (weight gradient: dW^T = H^T . dY = H^T [in, B] . (dY^T [out, B])^T, split over K = B)
+
+  Pitches are rounded up to 4 floats (TMA needs 16-byte row pitches); `refresh()` re-derives the weight copies after
+  the parameters changed.  Gradients land in the parameters' .grad views of the flat gradient buffer."""
+
+  SPLIT_TARGET_CTAS = 296                               # 2 CTAs per SM x 148 SMs
+
+  def __init__(self, net: QuantileNetwork, device):
+    self.net, self.device = net, torch.device(device)
+    self.dims = [(l.in_features, l.out_features) for l in net.layers]
+    self.w_fwd, self.w_t = [], []
+    for l, (fin, fout) in enumerate(self.dims):
+      self.w_fwd.append(None if fin % 4 == 0 else torch.zeros(fout, _pitch4(fin), dtype=torch.float32, device=self.device))
+      self.w_t.append(None if l == 0 else torch.zeros(fin, _pitch4(fout), dtype=torch.float32, device=self.device))
+    self._work = {}
+    self.launches = 0
+    self.refresh()
+
+  def refresh(self) -> None:
+    with torch.no_grad():
+      for l, layer in enumerate(self.net.layers):
+        fin, fout = self.dims[l]
+        if self.w_fwd[l] is not None:
+          self.w_fwd[l][:, :fin].copy_(layer.weight)
+        if self.w_t[l] is not None:
+          transpose_f32(layer.weight, fin, fout, fin, self.w_t[l], self.w_t[l].shape[1])
+          self.launches += 1
+
+  def _buffers(self, batch: int, keep: bool):
+    key = (batch, keep)
+    if key not in self._work:
+      bp = _pitch4(batch)
+      z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=self.device)
+      w = {'bp': bp, 'x': z(batch, _pitch4(self.dims[0][0])), 'h': [z(batch, fout) for _, fout in self.dims]}
+      if keep:
+        w['x_t'] = z(self.dims[0][0], bp)
+        w['h_t'] = [z(fout, bp) for _, fout in self.dims[:-1]]
+        w['g'] = [z(batch, _pitch4(fout)) for _, fout in self.dims]
+        w['g_t'] = [z(fout, bp) for _, fout in self.dims]
+      self._work[key] = w
+    return self._work[key]
+
+  @torch.no_grad()
+  def forward(self, x: torch.Tensor, keep: bool = False) -> torch.Tensor:
+    """x [B, F] -> logits [B, A * N] (a buffer owned by the stack, overwritten by the next call with the same B)."""
+    batch, feat = x.shape
+    assert feat == self.dims[0][0], (feat, self.dims[0][0])
+    w = self._buffers(batch, keep)
+    if (x.dtype == torch.float32 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.stride(0) >= feat and
+        x.data_ptr() % 16 == 0):
+      a, lda = x, x.stride(0)                              # already a TMA-able operand (e.g. the learner's padded buffers)
+    else:
+      w['x'][:, :feat].copy_(x)
+      a, lda = w['x'], w['x'].shape[1]
+    if keep:
+      transpose_f32(a, lda, batch, feat, w['x_t'], w['bp'])
+      self.launches += 1
+    last = len(self.dims) - 1
+    for l, (fin, fout) in enumerate(self.dims):
+      layer = self.net.layers[l]
+      b = layer.weight if self.w_fwd[l] is None else self.w_fwd[l]
+      dt = w['h_t'][l] if keep and l < last else None
+      dense_tf32(a, lda, b, _pitch4(fin), batch, fout, fin, 0 if l == last else 1, aux=layer.bias, d=w['h'][l], ldd=fout,
+                 dt=dt, ldt=w['bp'])
+      self.launches += 1
+      a, lda = w['h'][l], fout
+    return w['h'][last]
+
+  @torch.no_grad()
+  def backward(self, grad_logits: torch.Tensor) -> None:
+    """grad_logits [B, A * N] = dLoss / dlogits of the LAST forward(keep=True) call with this batch size; ACCUMULATES the
+    parameter gradients into the .grad views (the caller zeroes the flat gradient buffer)."""
+    batch = grad_logits.shape[0]
+    w = self._buffers(batch, True)
+    bp, last = w['bp'], len(self.dims) - 1
+    fout = self.dims[last][1]
+    w['g'][last][:, :fout].copy_(grad_logits.reshape(batch, fout))
+    transpose_f32(w['g'][last], w['g'][last].shape[1], batch, fout, w['g_t'][last], bp)
+    self.launches += 1
+    for l in range(last, -1, -1):
+      fin, fout = self.dims[l]
+      layer = self.net.layers[l]
+      prev_t = w['x_t'] if l == 0 else w['h_t'][l - 1]
+      # dW^T [in, out] = H^T [in, B] . (dY^T [out, B])^T, accumulated through the kernel's transposed output: the
+      # reductions of a warp then fall on consecutive floats of dW [out, in]
+      tiles = ((fin + 127) // 128) * ((fout + 159) // 160)     # the kernel's 128 x 160 tiles
+      split = max(1, min((batch + 31) // 32, self.SPLIT_TARGET_CTAS // tiles))
+      dense_tf32(prev_t, bp, w['g_t'][l], bp, fin, fout, batch, 3, dt=layer.weight.grad, ldt=fin, split_k=split)
+      row_sum_f32(w['g_t'][l], bp, fout, batch, layer.bias.grad, accumulate=True)
+      self.launches += 2
+      if l > 0:
+        dense_tf32(w['g'][l], w['g'][l].shape[1], self.w_t[l], self.w_t[l].shape[1], batch, fin, fout, 2,
+                   aux=w['h'][l - 1], ld_aux=fin, d=w['g'][l - 1], ldd=w['g'][l - 1].shape[1], dt=w['g_t'][l - 1], ldt=bp)
+        self.launches += 1
 
 
 # ---------------------------------------------------------------------------------------------
@@ -330,6 +461,13 @@ class QrDqnLearner:
     self.v = torch.zeros_like(self.flat)
     self.steps = 0
     self.kernel_launches = 0
+    if config.dense_backend not in ('tcgen05', 'cublas'):
+      raise ValueError(f'unknown dense_backend {config.dense_backend!r}')
+    self.hand_written_dense = config.dense_backend == 'tcgen05' and config.tf32_matmul
+    if self.hand_written_dense:
+      self.dense = DenseStack(self.online, self.device)
+      self.dense_target = DenseStack(self.target, self.device)
+      self._io = {}
 
   @contextlib.contextmanager
   def _matmul_precision(self):
@@ -344,8 +482,12 @@ class QrDqnLearner:
   @torch.no_grad()
   def act(self, obs: torch.Tensor, epsilon: Optional[float] = None, generator: Optional[torch.Generator] = None):
     """Behaviour policy (acme_utils.py:250-258): epsilon-greedy on the mean over atoms."""
-    with self._matmul_precision():
-      actions = greedy_actions(self.online(obs))
+    if self.hand_written_dense:
+      logits = self.dense.forward(obs.to(torch.float32))
+      actions = greedy_actions(logits.view(-1, self.config.num_actions, self.config.num_atoms))
+    else:
+      with self._matmul_precision():
+        actions = greedy_actions(self.online(obs))
     self.kernel_launches += 1
     eps = self.config.epsilon if epsilon is None else epsilon
     if eps > 0.0:
@@ -358,6 +500,8 @@ class QrDqnLearner:
   def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
     """One SGD step on a sampled batch; returns the mean loss (device scalar)."""
     cfg = self.config
+    if self.hand_written_dense:
+      return self._step_hand_written(batch)
     with self._matmul_precision():
       with torch.no_grad():
         target = target_distribution(self.target(batch['next_state']), batch['return'], batch['discount'])
@@ -375,6 +519,83 @@ class QrDqnLearner:
       self.flat_target.copy_(self.flat)
     return mean_loss.detach()
 
+  def _sgd_pass(self, io: Dict[str, torch.Tensor]) -> None:
+    """target forward -> target distribution -> online forward -> loss + dL/dlogits -> backward, on the buffers of `io`
+    (every launch goes to the current stream: this is the body that is captured into a CUDA graph)."""
+    cfg = self.config
+    b = io['state'].shape[0]
+    shape = (b, cfg.num_actions, cfg.num_atoms)
+    target = target_distribution(self.dense_target.forward(io['next_state']).view(shape), io['return'], io['discount'])
+    logits = self.dense.forward(io['state'], keep=True).view(shape)
+    _call('ble_qr_loss', self.device, _ptr(logits), _ptr(io['action']), _ptr(target), _ptr(io['weight']),
+          float(cfg.huber_param), b, cfg.num_actions, cfg.num_atoms, 1.0 / b, _ptr(io['loss']), _ptr(io['grad']))
+    io['mean'].copy_((io['loss'] * io['weight']).mean())
+    self.online.flat_grad.zero_()
+    self.dense.backward(io['grad'].view(b, -1))
+
+  def _step_io(self, b: int) -> Dict[str, torch.Tensor]:
+    """Static buffers (and, with config.cuda_graph, the captured graphs) of the hand-written step for batch size b."""
+    if b in self._io:
+      return self._io[b]
+    cfg, dev = self.config, self.device
+    f32 = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+    pitch = _pitch4(cfg.num_features)                       # padded rows: the dense kernel reads these buffers in place
+    io = {'state': f32(b, pitch)[:, :cfg.num_features], 'next_state': f32(b, pitch)[:, :cfg.num_features],
+          'action': torch.zeros(b, dtype=torch.int32, device=dev), 'return': f32(b), 'discount': f32(b), 'weight': f32(b),
+          'loss': f32(b), 'grad': f32(b, cfg.num_actions, cfg.num_atoms), 'mean': f32(())}
+    if cfg.cuda_graph:
+      snapshot = (self.online.flat_grad.clone(),)
+      side = torch.cuda.Stream(device=dev)
+      side.wait_stream(torch.cuda.current_stream(dev))
+      with torch.cuda.stream(side):                       # warm-up off the capture: allocates every work buffer
+        self._sgd_pass(io)
+        self.dense.refresh()
+      torch.cuda.current_stream(dev).wait_stream(side)
+      io['pass_graph'], io['refresh_graph'] = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+      with torch.cuda.graph(io['pass_graph']):
+        self._sgd_pass(io)
+      with torch.cuda.graph(io['refresh_graph']):
+        self.dense.refresh()
+      self.online.flat_grad.copy_(snapshot[0])
+    self._io[b] = io
+    return io
+
+  @torch.no_grad()
+  def _step_hand_written(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """The same SGD step with every dense product on ble_dense_tf32 (no autograd graph)."""
+    cfg = self.config
+    b = batch['state'].shape[0]
+    io = self._step_io(b)
+    for k in ('state', 'next_state', 'action', 'return', 'discount'):
+      io[k].copy_(batch[k])
+    if 'valid' in batch:
+      io['weight'].copy_(batch['valid'])
+    else:
+      io['weight'].fill_(1.0)
+    if cfg.cuda_graph:
+      io['pass_graph'].replay()
+    else:
+      self._sgd_pass(io)
+    world = allreduce_sum_(self.online.flat_grad)
+    self.steps += 1
+    adam_step(self.flat, self.online.flat_grad, self.m, self.v, self.steps, cfg.learning_rate, cfg.adam_b1, cfg.adam_b2,
+              cfg.adam_eps, 1.0 / world)
+    if cfg.cuda_graph:
+      io['refresh_graph'].replay()
+    else:
+      self.dense.refresh()
+    self.kernel_launches += 3
+    if self.steps % cfg.target_update_period == 0:
+      self.flat_target.copy_(self.flat)
+      self.dense_target.refresh()
+    return io['mean'].clone()
+
+  def parameters_changed(self) -> None:
+    """Call after writing the parameters from outside (load_flax_params, a manual copy into .flat): re-derives the
+    operand copies the hand-written dense path keeps."""
+    if self.hand_written_dense:
+      self.dense.refresh(); self.dense_target.refresh()
+
   def state_dict(self) -> Dict[str, torch.Tensor]:
     return {'params': self.flat.clone(), 'target': self.flat_target.clone(), 'm': self.m.clone(), 'v': self.v.clone(),
             'steps': torch.tensor(self.steps)}
@@ -383,6 +604,8 @@ class QrDqnLearner:
     self.flat.copy_(state['params']); self.flat_target.copy_(state['target'])
     self.m.copy_(state['m']); self.v.copy_(state['v'])
     self.steps = int(state['steps'])
+    if self.hand_written_dense:
+      self.dense.refresh(); self.dense_target.refresh()
 
 
 class TrainingLoop:

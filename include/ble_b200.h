@@ -341,6 +341,21 @@ int ble_marco_polo_step(const float* obs, const int32_t* rl_actions, const uint8
                         int32_t* state, double* walk_target, const uint64_t* seeds, int64_t step_index,
                         float exploratory_episode_probability, int32_t* actions, void* stream);
 
+/* Dense layers of the QuantileNetwork (agents/networks.py:63-98; the reference evaluates them as flax nn.Dense inside
+ * dopamine's / acme's jitted train step, agents/quantile_agent.py:122-139, acme_utils.py:217-277) on the tcgen05
+ * tensor cores (TF32 operands, fp32 accumulation).  Stateless; every pointer is caller-owned device memory.
+ *   ble_dense_tf32: D[m, n] = A[m, k] . B[n, k]^T, A and B row-major with K contiguous (pitches lda, ldb in floats,
+ *     multiples of 4; base addresses 16-byte aligned).  mode 0: D += aux[n] (bias); 1: bias then ReLU; 2: D *= (aux[m, n]
+ *     > 0) with aux row-major of pitch ld_aux (the ReLU mask of the backward pass); 3: the TRANSPOSED result dt is ACCUMULATED
+ *     atomically and the K range is split over split_k CTAs per tile (weight gradient; the caller zeroes dt).  d (pitch
+ *     ldd) and / or the transposed result dt [n, m] (pitch ldt) are written (mode 3: dt only).
+ *   ble_transpose_f32: dst[c, r] = src[r, c].   ble_row_sum_f32: out[r] (+)= sum_c src[r, c] (bias gradient). */
+int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int64_t n, int64_t k, int32_t mode,
+                   const float* aux, int64_t ld_aux, float* d, int64_t ldd, float* dt, int64_t ldt, int32_t split_k,
+                   void* stream);
+int ble_transpose_f32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* dst, int64_t ld_dst, void* stream);
+int ble_row_sum_f32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* out, int32_t accumulate, void* stream);
+
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t ble_launch_count(const ble_handle* h);
 

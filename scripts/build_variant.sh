@@ -7,6 +7,6 @@ name=$1; shift
 pkg=balloon_learning_environment_b200
 mkdir -p $pkg/variants
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c -o $pkg/variants/fused_$name.o $pkg/csrc/ble_step_fused.cu
-nvcc -gencode arch=compute_100a,code=sm_100a --shared -o $pkg/variants/libble_$name.so $pkg/build/ble_engine.o $pkg/variants/fused_$name.o $pkg/build/ble_learner.o -lcublasLt -Xlinker -rpath=/usr/local/cuda/lib64
+nvcc -gencode arch=compute_100a,code=sm_100a --shared -o $pkg/variants/libble_$name.so $pkg/build/ble_engine.o $pkg/variants/fused_$name.o $pkg/build/ble_learner.o $pkg/build/ble_dense.o -lcublasLt -Xlinker -rpath=/usr/local/cuda/lib64
 rm -f $pkg/variants/fused_$name.o
 echo $pkg/variants/libble_$name.so

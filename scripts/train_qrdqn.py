@@ -34,6 +34,8 @@ def main():
   ap.add_argument('--max-episode-length', type=int, default=960)
   ap.add_argument('--seed', type=int, default=0)
   ap.add_argument('--fp32-matmul', action='store_true', help='dense layers in fp32 FMA instead of TF32 tensor cores')
+  ap.add_argument('--dense-backend', default='tcgen05', choices=('tcgen05', 'cublas'),
+                  help="tcgen05: the hand-written ble_dense_tf32 kernel for forward and backward; cublas: nn.Linear + autograd (A/B)")
   args = ap.parse_args()
   rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
   local = int(os.environ.get('LOCAL_RANK', 0))
@@ -46,7 +48,7 @@ def main():
   learner_steps = max(1, args.learner_steps)
   batch = args.batch_size or max(32, 8 * n // learner_steps)
   cfg = learner_lib.QrDqnConfig(batch_size=batch, max_episode_length=args.max_episode_length, min_replay_size=8 * n,
-                                tf32_matmul=not args.fp32_matmul)
+                                tf32_matmul=not args.fp32_matmul, dense_backend=args.dense_backend)
 
   layout = 'x128' if n * 3686400 <= 60e9 else 'x64'
   env = BatchedBalloonEnv(n, device=str(device), observation='perciatelli', field_layout=layout, seed=args.seed + rank,
@@ -88,6 +90,7 @@ def main():
         'n_gpus': world, 'envs_per_gpu': n, 'iterations': args.iterations, 'ms_per_iteration': red['elapsed_ms'] / args.iterations,
         'env_steps_per_s': red['env_steps'] / (red['elapsed_ms'] * 1e-3),
         'learner_steps_per_iteration': learner_steps, 'batch_size_per_gpu': batch,
+        'dense_backend': args.dense_backend if not args.fp32_matmul else 'cublas',
         'learner_samples_per_s': sgd * batch * world / (red['elapsed_ms'] * 1e-3),
         'samples_per_insert': sgd * batch / (n * args.iterations),
         'last_loss': stats['last_loss'], 'mean_reward': stats['mean_reward'], 'episodes_rank0': stats['episodes'],
