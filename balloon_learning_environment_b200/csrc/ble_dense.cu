@@ -43,6 +43,7 @@ struct DenseArgs {
   const float* aux; int64_t ld_aux;                     // bias [N] (modes 0, 1) or forward activation [M, N] (mode 2)
   float* d; int64_t ldd;                                // row-major output (may be null when only dt is wanted)
   float* dt; int64_t ldt;                               // transposed output [N, M] or null
+  int tma_store;                                        // 1: the row-major tile leaves through shared memory + TMA stores
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -91,6 +92,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate) : "memory");
 }
 
+// Row-major output: 32 x 32 boxes staged in shared memory with the 128-byte swizzle, written by TMA (clipped at the
+// tensor's edges), so that the HBM writes are whole lines instead of 32 half-filled sectors per store instruction.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -112,7 +120,8 @@ __device__ __forceinline__ void tmem_load_32(uint32_t taddr, float* v) {
 // kMode: 0 = + bias, 1 = + bias then ReLU, 2 = x (aux[m, n] > 0), 3 = atomic accumulation (split-K)
 template <int kMode>
 __global__ void __launch_bounds__(kThreads, 2)
-k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, DenseArgs args) {
+k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+             const __grid_constant__ CUtensorMap map_d, DenseArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // swizzled tiles need 1024-byte alignment
   const uint32_t bars = base + kStages * kStageBytes;                      // full[kStages], empty[kStages], tmem_full
@@ -224,7 +233,15 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         }
         continue;
       }
-      if (args.d != nullptr && row_ok) {
+      if (args.tma_store) {
+        // the operand ring is idle once the accumulator is complete: warp q stages its 32 x 32 box of chunk c there
+        const uint32_t row = base + uint32_t(q) * (kBN / 32) * 4096u + uint32_t(c) * 4096u + uint32_t(lane) * 128u;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + (uint32_t(g ^ (lane & 7)) << 4)),
+                       "f"(v[4 * g]), "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3]) : "memory");
+        }
+      } else if (args.d != nullptr && row_ok) {
         float* out = args.d + m * args.ldd + nc;
         if (full_chunk && (args.ldd & 3) == 0) {
 #pragma unroll
@@ -240,6 +257,19 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         for (int j = 0; j < 32; ++j)
           if (nc + j < args.n) args.dt[(nc + j) * args.ldt + m] = v[j];  // lanes = consecutive m: coalesced
       }
+    }
+  }
+  if (kMode != 3 && args.tma_store && warp >= 2) {
+    const int q = warp & 3;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the TMA
+    __syncwarp();
+    if (lane == 0 && int64_t(m0) + q * 32 < args.m) {
+      for (int c = 0; c < kBN / 32; ++c) {
+        if (int64_t(n0) + c * 32 >= args.n) break;
+        tma_store_2d(&map_d, base + uint32_t(q) * (kBN / 32) * 4096u + uint32_t(c) * 4096u, n0 + c * 32, m0 + q * 32);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the reads
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -311,6 +341,7 @@ EncodeTiled tensor_map_encoder() {
 
 // [rows, k] fp32, row pitch ld floats -> box {32 floats, box_rows rows}, 128-byte swizzle, zero fill out of range
 bool operand_map(CUtensorMap* map, const float* p, int64_t rows, int64_t k, int64_t ld, int box_rows) {
+  if (p == nullptr) { *map = CUtensorMap{}; return true; }
   EncodeTiled enc = tensor_map_encoder();
   if (enc == nullptr) return false;
   const cuuint64_t dims[2] = {cuuint64_t(k), cuuint64_t(rows)};
@@ -323,7 +354,8 @@ bool operand_map(CUtensorMap* map, const float* p, int64_t rows, int64_t k, int6
 }
 
 template <int kMode>
-int launch_dense(const CUtensorMap& ma, const CUtensorMap& mb, const DenseArgs& args, dim3 grid, cudaStream_t s) {
+int launch_dense(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const DenseArgs& args, dim3 grid,
+                 cudaStream_t s) {
   static bool configured[16] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return BLE_ERR_CUDA;
@@ -332,7 +364,7 @@ int launch_dense(const CUtensorMap& ma, const CUtensorMap& mb, const DenseArgs& 
       return BLE_ERR_CUDA;
     configured[dev] = true;
   }
-  k_dense_tf32<kMode><<<grid, kThreads, kSmemBytes, s>>>(ma, mb, args);
+  k_dense_tf32<kMode><<<grid, kThreads, kSmemBytes, s>>>(ma, mb, md, args);
   return cudaGetLastError() == cudaSuccess ? BLE_OK : BLE_ERR_CUDA;
 }
 
@@ -352,18 +384,23 @@ int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int
       split_k < 1 || (mode != 3 && split_k != 1)) {
     return BLE_ERR_INVALID_ARGUMENT;
   }
-  CUtensorMap ma, mb;
-  if (!operand_map(&ma, a, m, k, lda, kBM) || !operand_map(&mb, b, n, k, ldb, kBN)) return BLE_ERR_CUDA;
+  // row-major output through TMA stores when its rows can be a tensor map (16-byte pitch and base) and end on a 16-byte
+  // boundary (the TMA writes whole 16-byte granules: measured, a 257-column tensor had columns 257..259 overwritten);
+  // else direct stores
+  const bool tma_store = mode != 3 && d != nullptr && (ldd & 3) == 0 && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0;
+  CUtensorMap ma, mb, md;
+  if (!operand_map(&ma, a, m, k, lda, kBM) || !operand_map(&mb, b, n, k, ldb, kBN) ||
+      !operand_map(&md, tma_store ? d : nullptr, m, n, ldd, 32)) return BLE_ERR_CUDA;
   const int total_kb = int((k + kBK - 1) / kBK);
   const int splits = split_k > total_kb ? total_kb : split_k;
-  DenseArgs args{m, n, k, (total_kb + splits - 1) / splits, aux, ld_aux, d, ldd, dt, ldt};
+  DenseArgs args{m, n, k, (total_kb + splits - 1) / splits, aux, ld_aux, d, ldd, dt, ldt, tma_store ? 1 : 0};
   const dim3 grid(unsigned((n + kBN - 1) / kBN), unsigned((m + kBM - 1) / kBM), unsigned(splits));
   cudaStream_t s = cudaStream_t(stream);
   switch (mode) {
-    case 0: return launch_dense<0>(ma, mb, args, grid, s);
-    case 1: return launch_dense<1>(ma, mb, args, grid, s);
-    case 2: return launch_dense<2>(ma, mb, args, grid, s);
-    default: return launch_dense<3>(ma, mb, args, grid, s);
+    case 0: return launch_dense<0>(ma, mb, md, args, grid, s);
+    case 1: return launch_dense<1>(ma, mb, md, args, grid, s);
+    case 2: return launch_dense<2>(ma, mb, md, args, grid, s);
+    default: return launch_dense<3>(ma, mb, md, args, grid, s);
   }
 }
 

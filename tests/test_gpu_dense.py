@@ -38,7 +38,7 @@ def alloc(rows, cols, pitch, gen, exact):
 
 
 @pytest.mark.parametrize('m,n,k', [(128, 128, 32), (256, 128, 64), (1000, 153, 600), (8192, 600, 600), (333, 600, 1099),
-                                   (64, 8, 4), (130, 257, 36)])
+                                   (64, 8, 4), (130, 257, 36), (130, 260, 36)])
 @pytest.mark.parametrize('exact', [True, False])
 def test_dense_forward_modes(lrn, m, n, k, exact):
   gen = torch.Generator(device='cuda'); gen.manual_seed(m * 7 + n * 3 + k)
