@@ -1630,6 +1630,13 @@ struct Engine : EngineBase {
     return BLE_OK;
   }
 
+  // Device-side alias of a page-locked, mapped host allocation; nullptr for pageable memory.
+  static const void* mapped_host_pointer(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+  }
+
   int step_host(const int32_t* actions_host, float* reward_host, uint8_t* done_host, cudaStream_t s) override {
     if (actions_host == nullptr || reward_host == nullptr || done_host == nullptr) { err = "step_host: null argument"; return BLE_ERR_INVALID_ARGUMENT; }
     int rc = check_ready("step_host");
@@ -1637,6 +1644,19 @@ struct Engine : EngineBase {
     BLE_DEVICE_GUARD();
     rc = launch_noise(s);                  // needs no actions: runs while the host stages them (no-op when prefetched)
     if (rc != BLE_OK) return rc;
+    if (host_zero_copy) {
+      // caller's buffers already page-locked and mapped (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory):
+      // the step kernel reads / writes THEM over PCIe and the two staging copies drop out
+      const void* da = mapped_host_pointer(actions_host);
+      void* dr = const_cast<void*>(mapped_host_pointer(reward_host));
+      void* dd = const_cast<void*>(mapped_host_pointer(done_host));
+      if (da != nullptr && dr != nullptr && dd != nullptr) {
+        rc = step(static_cast<const int32_t*>(da), static_cast<float*>(dr), static_cast<uint8_t*>(dd), nullptr, s);
+        if (rc != BLE_OK) return rc;
+        BLE_CUDA(cudaStreamSynchronize(s));
+        return host_prefetch_noise ? launch_noise(s) : BLE_OK;
+      }
+    }
     std::memcpy(h_actions, actions_host, sizeof(int32_t) * n);
     if (host_zero_copy) {
       // pinned host memory is device-accessible under UVA: the step kernel reads the actions and writes reward /

@@ -598,6 +598,8 @@ def test_host_step_sequence_matches_device_steps(ble):
     arenas.append(a)
   host, dev = arenas
   r_host = np.zeros(n, np.float32); d_host = np.zeros(n, np.uint8)
+  # page-locked caller buffers take the no-staging path (the kernel reads / writes them in place): steps 4 and 5
+  pinned = [torch.zeros(n, dtype=dt).pin_memory().numpy() for dt in (torch.int32, torch.float32, torch.uint8)]
   for t in range(6):
     if t == 3:                                   # move every balloon: the wind queued for the old position is stale
       for a in arenas:
@@ -605,7 +607,13 @@ def test_host_step_sequence_matches_device_steps(ble):
         f = f.clone(); f[0] += 25000.0; f[1] -= 40000.0
         a.set_state(f, i)
     acts = rng.integers(0, 3, n).astype(np.int32)
-    host.step_host(acts, r_host, d_host)
+    if t >= 4:
+      pinned[0][:] = acts
+      pinned[1][:] = -1.0; pinned[2][:] = 7
+      host.step_host(pinned[0], pinned[1], pinned[2])
+      r_host, d_host = pinned[1], pinned[2]
+    else:
+      host.step_host(acts, r_host, d_host)
     r_dev, d_dev, _ = dev.step(torch.from_numpy(acts))
     np.testing.assert_array_equal(r_host, r_dev.cpu().numpy())
     np.testing.assert_array_equal(d_host, d_dev.cpu().numpy())
