@@ -50,7 +50,7 @@ class BleConfig(_c.Structure):
 class BleReplayView(_c.Structure):
   _fields_ = [('obs', _c.c_void_p), ('action', _c.c_void_p), ('reward', _c.c_void_p), ('terminal', _c.c_void_p),
               ('truncated', _c.c_void_p), ('capacity', _c.c_int64), ('num_envs', _c.c_int64), ('count', _c.c_int64),
-              ('n_step', _c.c_int32), ('num_features', _c.c_int32), ('gamma', _c.c_float), ('reserved', _c.c_int32)]
+              ('n_step', _c.c_int32), ('num_features', _c.c_int32), ('gamma', _c.c_float), ('out_pitch', _c.c_int32)]
 
 
 class BleStepOut(_c.Structure):

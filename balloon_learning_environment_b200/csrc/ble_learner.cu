@@ -160,7 +160,7 @@ __device__ int nstep_at(const ReplayView& r, int64_t t, int64_t e, float* ret, f
 // observation rows (coalesced 4-byte lanes; rows are 4,396 B so only 4-byte alignment is guaranteed).
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 k_replay_sample(ReplayView r, const int64_t* __restrict__ forced /*[B,2] (t, e) or nullptr*/, uint64_t seed, int64_t b,
-                int features, float* __restrict__ state, float* __restrict__ next_state, int32_t* __restrict__ action,
+                int features, int pitch, float* __restrict__ state, float* __restrict__ next_state, int32_t* __restrict__ action,
                 float* __restrict__ ret_out, float* __restrict__ disc_out, uint8_t* __restrict__ valid,
                 int64_t* __restrict__ picked /*[B,2] or nullptr*/) {
   const int64_t s = blockIdx.x * int64_t(kWarpsPerBlock) + (threadIdx.x >> 5);
@@ -193,8 +193,8 @@ k_replay_sample(ReplayView r, const int64_t* __restrict__ forced /*[B,2] (t, e) 
   n_used = __shfl_sync(0xffffffffu, n_used, 0);
   const float* src0 = r.obs + ((t % r.capacity) * r.envs + e) * features;
   const float* src1 = r.obs + ((t_next % r.capacity) * r.envs + e) * features;
-  float* dst0 = state + s * features;
-  float* dst1 = next_state + s * features;
+  float* dst0 = state + s * pitch;
+  float* dst1 = next_state + s * pitch;
   for (int f = lane; f < features; f += 32) { dst0[f] = src0[f]; dst1[f] = src1[f]; }
   if (lane == 0) {
     action[s] = r.action[(t % r.capacity) * r.envs + e];
@@ -298,7 +298,8 @@ int ble_replay_sample(const ble_replay_view* view, const int64_t* forced_indices
                       uint8_t* valid, int64_t* picked, void* stream) {
   if (view == nullptr || view->obs == nullptr || view->action == nullptr || view->reward == nullptr ||
       view->terminal == nullptr || view->truncated == nullptr || view->capacity <= 0 || view->num_envs <= 0 ||
-      view->count < 0 || view->n_step <= 0 || view->num_features <= 0 || state == nullptr || next_state == nullptr ||
+      view->count < 0 || view->n_step <= 0 || view->num_features <= 0 ||
+      (view->out_pitch != 0 && view->out_pitch < view->num_features) || state == nullptr || next_state == nullptr ||
       action == nullptr || n_step_return == nullptr || discount == nullptr || valid == nullptr || batch < 0) {
     return BLE_ERR_INVALID_ARGUMENT;
   }
@@ -306,7 +307,8 @@ int ble_replay_sample(const ble_replay_view* view, const int64_t* forced_indices
   ble::ReplayView r{view->obs, view->action, view->reward, view->terminal, view->truncated,
                     view->capacity, view->num_envs, view->count, view->n_step, view->gamma};
   ble::k_replay_sample<<<ble::warp_grid(batch), 32 * ble::kWarpsPerBlock, 0, cudaStream_t(stream)>>>(
-      r, forced_indices, seed, batch, view->num_features, state, next_state, action, n_step_return, discount, valid, picked);
+      r, forced_indices, seed, batch, view->num_features, view->out_pitch > 0 ? view->out_pitch : view->num_features, state,
+      next_state, action, n_step_return, discount, valid, picked);
   return ble::finish();
 }
 

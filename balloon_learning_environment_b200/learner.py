@@ -370,24 +370,32 @@ class DeviceReplay:
     self.truncated[slot].copy_(truncated)
     self.count += 1
 
-  def view(self) -> _lib.BleReplayView:
+  def view(self, out_pitch: int = 0) -> _lib.BleReplayView:
     return _lib.BleReplayView(self.obs.data_ptr(), self.action.data_ptr(), self.reward.data_ptr(),
                               self.terminal.data_ptr(), self.truncated.data_ptr(), self.capacity, self.num_envs,
-                              self.count, self.n_step, self.num_features, self.gamma, 0)
+                              self.count, self.n_step, self.num_features, self.gamma, int(out_pitch))
 
-  def sample(self, batch_size: int, indices: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-    """batch_size n-step transitions; indices (int64 [B, 2] = absolute step, balloon) forces the picks."""
+  def sample(self, batch_size: int, indices: Optional[torch.Tensor] = None,
+             out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """batch_size n-step transitions; indices (int64 [B, 2] = absolute step, balloon) forces the picks.  `out`
+    (QrDqnLearner.sample_buffers): write the batch straight into the learner's own (row-padded) input buffers."""
     b, dev = int(batch_size), self.device
-    out = {'state': torch.empty(b, self.num_features, dtype=torch.float32, device=dev),
-           'next_state': torch.empty(b, self.num_features, dtype=torch.float32, device=dev),
-           'action': torch.empty(b, dtype=torch.int32, device=dev),
-           'return': torch.empty(b, dtype=torch.float32, device=dev),
-           'discount': torch.empty(b, dtype=torch.float32, device=dev),
-           'valid': torch.empty(b, dtype=torch.uint8, device=dev),
-           'indices': torch.empty(b, 2, dtype=torch.int64, device=dev)}
+    if out is not None:
+      pitch = out['state'].stride(0)
+      assert out['state'].shape == (b, self.num_features) and out['next_state'].stride(0) == pitch
+      out = dict(out)
+    else:
+      pitch = 0
+      out = {'state': torch.empty(b, self.num_features, dtype=torch.float32, device=dev),
+             'next_state': torch.empty(b, self.num_features, dtype=torch.float32, device=dev),
+             'action': torch.empty(b, dtype=torch.int32, device=dev),
+             'return': torch.empty(b, dtype=torch.float32, device=dev),
+             'discount': torch.empty(b, dtype=torch.float32, device=dev),
+             'valid': torch.empty(b, dtype=torch.uint8, device=dev)}
+    out['indices'] = torch.empty(b, 2, dtype=torch.int64, device=dev)
     if indices is not None:
       indices = indices.to(dev, torch.int64).contiguous()
-    view = self.view()
+    view = self.view(pitch)
     self._draws += 1
     seed = (self._seed * 0x9E3779B97F4A7C15 + self._draws) & 0xFFFFFFFFFFFFFFFF
     _call('ble_replay_sample', dev, ctypes.byref(view), _ptr(indices), seed, b, _ptr(out['state']), _ptr(out['next_state']),
@@ -542,7 +550,8 @@ class QrDqnLearner:
     pitch = _pitch4(cfg.num_features)                       # padded rows: the dense kernel reads these buffers in place
     io = {'state': f32(b, pitch)[:, :cfg.num_features], 'next_state': f32(b, pitch)[:, :cfg.num_features],
           'action': torch.zeros(b, dtype=torch.int32, device=dev), 'return': f32(b), 'discount': f32(b), 'weight': f32(b),
-          'loss': f32(b), 'grad': f32(b, cfg.num_actions, cfg.num_atoms), 'mean': f32(())}
+          'loss': f32(b), 'grad': f32(b, cfg.num_actions, cfg.num_atoms), 'mean': f32(()),
+          'valid': torch.zeros(b, dtype=torch.uint8, device=dev)}
     if cfg.cuda_graph:
       snapshot = (self.online.flat_grad.clone(),)
       side = torch.cuda.Stream(device=dev)
@@ -560,6 +569,16 @@ class QrDqnLearner:
     self._io[b] = io
     return io
 
+  def sample_buffers(self, batch_size: int) -> Optional[Dict[str, torch.Tensor]]:
+    """The learner's own input buffers for DeviceReplay.sample(out=...): the batch is then sampled where the dense kernel
+    reads it (row pitch padded to 16 bytes) and step() copies nothing.  None on the library-GEMM path."""
+    if not self.hand_written_dense:
+      return None
+    io = self._step_io(int(batch_size))
+    out = {k: io[k] for k in ('state', 'next_state', 'action', 'return', 'discount')}
+    out['valid'] = io['valid']
+    return out
+
   @torch.no_grad()
   def _step_hand_written(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
     """The same SGD step with every dense product on ble_dense_tf32 (no autograd graph)."""
@@ -567,7 +586,8 @@ class QrDqnLearner:
     b = batch['state'].shape[0]
     io = self._step_io(b)
     for k in ('state', 'next_state', 'action', 'return', 'discount'):
-      io[k].copy_(batch[k])
+      if batch[k].data_ptr() != io[k].data_ptr():       # a batch sampled into sample_buffers() is already in place
+        io[k].copy_(batch[k])
     if 'valid' in batch:
       io['weight'].copy_(batch['valid'])
     else:
@@ -670,7 +690,7 @@ class TrainingLoop:
       mark('replay_add_and_resets')
       if replay.num_transitions >= cfg.min_replay_size and replay.count > cfg.n_step:
         for _ in range(self.learner_steps_per_iteration):
-          batch = replay.sample(cfg.batch_size)
+          batch = replay.sample(cfg.batch_size, out=learner.sample_buffers(cfg.batch_size))
           mark('replay_sample')
           self.last_loss = learner.step(batch)
           mark('learner_step')
@@ -754,7 +774,7 @@ class QuantileAgent:
     cfg = self.learner.config
     if self.replay.num_transitions >= cfg.min_replay_size and self.replay.count > cfg.n_step:
       for _ in range(self.learner_steps_per_step):
-        self.last_loss = self.learner.step(self.replay.sample(cfg.batch_size))
+        self.last_loss = self.learner.step(self.replay.sample(cfg.batch_size, out=self.learner.sample_buffers(cfg.batch_size)))
 
   def step(self, reward: torch.Tensor, observation: torch.Tensor, done: Optional[torch.Tensor] = None) -> torch.Tensor:
     """done (uint8 / bool [N], optional): balloons whose episode ended with this reward (terminal status)."""

@@ -323,7 +323,7 @@ typedef struct ble_replay_view {
   int32_t n_step;              /* update horizon (5)                                                 */
   int32_t num_features;        /* 1099                                                               */
   float gamma;                 /* 0.993                                                              */
-  int32_t reserved;
+  int32_t out_pitch;           /* row pitch (floats) of the state / next_state outputs; 0 = num_features */
 } ble_replay_view;
 int ble_qr_greedy(const float* logits, int64_t batch, int32_t num_actions, int32_t num_atoms, int32_t* actions,
                   float* q_values, void* stream);

@@ -13,7 +13,7 @@ def test_library_exports_every_declared_symbol():
   from balloon_learning_environment_b200 import _lib
   lib = _lib.load()
   header = open(os.path.join(ROOT, 'include', 'ble_b200.h')).read()
-  declared = sorted(set(re.findall(r'\b(ble_[a-z_]+)\s*\(', header)))
+  declared = sorted(set(re.findall(r'\b(ble_[a-z0-9_]+)\s*\(', header)))
   assert len(declared) >= 15
   for name in declared:
     assert hasattr(lib, name), f'{name} declared in include/ble_b200.h but not exported'

@@ -129,6 +129,19 @@ def test_replay_sample_matches_oracle(lrn):
   # empty ring: nothing to sample
   empty = lrn.DeviceReplay(4, 8, num_features=feat)
   assert int(empty.sample(16)['valid'].sum()) == 0
+  # sampling into the learner's own row-padded input buffers (out_pitch of the replay view): same rows, padding untouched
+  cfg = lrn.QrDqnConfig(num_layers=2, hidden_units=16, num_features=feat)
+  learner = lrn.QrDqnLearner(cfg, seed=0)
+  sel = dev(idx[valid.astype(bool)][:40])
+  plain = rep.sample(len(sel), indices=sel)
+  bufs = learner.sample_buffers(len(sel))
+  assert bufs['state'].stride(0) == 24 and bufs['state'].shape == (len(sel), feat)
+  placed = rep.sample(len(sel), indices=sel, out=bufs)
+  for k in ('state', 'next_state', 'action', 'return', 'discount', 'valid'):
+    assert placed[k].data_ptr() == bufs[k].data_ptr()
+    assert torch.equal(placed[k], plain[k]), k
+  loss = learner.step(placed)                         # consumed in place (no copy): a finite loss and a parameter update
+  assert np.isfinite(float(loss))
 
 
 def test_adam_kernel_matches_oracle(lrn):
