@@ -1,5 +1,6 @@
 """Counts the SASS mnemonics that identify the hardware paths each kernel uses (TMA bulk copies = UBLKCP +
-SYNCS mbarrier ops, fp64 tensor cores = DMMA, 128-bit loads, shuffles, spills = STL / LDL) in the built
+SYNCS mbarrier ops, tcgen05 tensor cores = UTCHMMA with TMEM loads LDTM and commits UTCBAR, TMA tensor loads / stores =
+UTMALDG / UTMASTG, fp64 tensor cores = DMMA, 128-bit loads, shuffles, spills = STL / LDL) in the built
 libble_b200.so.  CPU only:   python scripts/sass_mnemonics.py > profiles/r01c_sass_mnemonics.txt"""
 import collections
 import os
@@ -8,7 +9,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'balloon_learning_environment_b200', 'libble_b200.so')
-KEYS = ['UBLKCP', 'UTMALDG', 'SYNCS', 'DMMA', 'HMMA', 'STG.E.EF.128', 'LDG.E.128', 'LDG.E.64', 'SHFL', 'DFMA', 'FFMA', 'MUFU', 'BAR.SYNC', 'STL', 'LDL']
+KEYS = ['UTCHMMA', 'LDTM', 'UTCBAR', 'UTMASTG', 'UBLKCP', 'UTMALDG', 'SYNCS', 'DMMA', 'HMMA', 'STG.E.EF.128', 'LDG.E.128', 'LDG.E.64', 'SHFL', 'DFMA', 'FFMA', 'MUFU', 'BAR.SYNC', 'STL', 'LDL']
 
 
 def main():
@@ -25,7 +26,7 @@ def main():
   names = subprocess.run(['c++filt'], input='\n'.join(counts), capture_output=True, text=True).stdout.splitlines()
   print('%-40s %7s ' % ('kernel (sm_100a SASS)', 'instrs') + ' '.join('%9s' % k for k in KEYS))
   for (fn, c), name in zip(counts.items(), names):
-    short = re.sub(r'^void ', '', re.sub(r'\(.*', '', name))
+    short = re.sub(r'^void ', '', re.sub(r'\(.*', '', name.replace('(anonymous namespace)::', '')))
     if not re.match(r'ble::k_', short):
       continue
     row = [sum(v for o, v in c.items() if o.startswith(k)) for k in KEYS]
