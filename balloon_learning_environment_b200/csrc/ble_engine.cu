@@ -1270,8 +1270,7 @@ struct Engine : EngineBase {
           mode = 2;
         }
       }
-      launch_fused(actions, fo, mode, n_steps, s);
-      ++launches;
+      launches += launch_fused(actions, fo, mode, n_steps, s);
       BLE_CUDA(cudaGetLastError());
       noise_valid = false;
     } else {
@@ -1564,8 +1563,9 @@ struct Engine : EngineBase {
     }
     return 0;
   }
-  void launch_fused(const int32_t* actions, const FusedOut& fo, int mode, int n_steps, cudaStream_t s) {
-    if constexpr (std::is_same<Real, float>::value) fused_launch(fused_shape(), d, actions, fo, mode, n_steps, s);
+  int launch_fused(const int32_t* actions, const FusedOut& fo, int mode, int n_steps, cudaStream_t s) {
+    if constexpr (std::is_same<Real, float>::value) return fused_launch(fused_shape(), d, actions, fo, mode, n_steps, s);
+    return 0;
   }
 
   int features_observe(cudaStream_t s) override {

@@ -671,9 +671,26 @@ static void launch_step(Kernel kernel, unsigned grid, unsigned block, size_t sme
   cudaLaunchKernelEx(&cfg, kernel, d, actions, out, noise_mode, n_steps);
 }
 
-void fused_launch(int shape, const DevState<float>& d, const int32_t* actions, const FusedOut& out, int noise_mode,
-                  int n_steps, cudaStream_t s) {
+int fused_launch(int shape, const DevState<float>& d, const int32_t* actions, const FusedOut& out, int noise_mode,
+                 int n_steps, cudaStream_t s) {
   const unsigned grid = unsigned((d.n + 31) / 32);
+  if (shape == 0 && n_steps > 1) {
+    // Throughput shape (the batch fills the GPU): K launches of one step beat one launch of K steps -- inside a long
+    // launch the warps of an SM drift apart and the 130 KB of SASS stop sharing instruction-cache lines (101 us per
+    // step against 134 us at 65,536 balloons, 72 against 86 us at 32,768; profiles/r02b_step_timing.jsonl) -- so a
+    // rollout is issued as K programmatic-dependent launches.  Bit-identical by construction.
+    static const bool split = [] { const char* e = std::getenv("BLE_ROLLOUT_SPLIT"); return e == nullptr || std::atoi(e) != 0; }();
+    if (split) {
+      for (int k = 0; k < n_steps; ++k) {
+        FusedOut o = out;
+        o.reward += int64_t(k) * d.n; o.done += int64_t(k) * d.n;
+        if (k + 1 < n_steps) { o.wind_uv = nullptr; o.status = nullptr; o.time_elapsed = nullptr; o.sim_error = nullptr; }
+        launch_step(k_step_warp, unsigned((d.n + 32 * kWarpsPerCta - 1) / (32 * kWarpsPerCta)), 32 * kWarpsPerCta, warp_smem(), s,
+                    d, actions + int64_t(k) * d.n, o, noise_mode, 1);
+      }
+      return n_steps;
+    }
+  }
   switch (shape) {
     case 14: launch_step(k_step_roles<14>, grid, 32 * 14, roles_smem<14>(), s, d, actions, out, noise_mode, n_steps); break;
     case 8: launch_step(k_step_roles<8>, grid, 32 * 8, roles_smem<8>(), s, d, actions, out, noise_mode, n_steps); break;
@@ -683,6 +700,7 @@ void fused_launch(int shape, const DevState<float>& d, const int32_t* actions, c
                   d, actions, out, noise_mode, n_steps);
       break;
   }
+  return 1;
 }
 
 }  // namespace ble

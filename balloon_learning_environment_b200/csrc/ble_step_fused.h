@@ -23,7 +23,8 @@ constexpr int kFusedShapes[4] = {0, 4, 8, 14};
 // Opts every shape into its dynamic shared memory and reports how many of its CTAs one SM holds (same order).
 cudaError_t fused_setup(int blocks_per_sm[4]);
 // noise_mode: 0 = no noise, 1 = evaluate the 10 harmonics in the kernel, 2 = read d.noise_partial (k_noise ran ahead)
-void fused_launch(int shape, const DevState<float>& d, const int32_t* actions, const FusedOut& out, int noise_mode,
-                  int n_steps, cudaStream_t stream);
+// returns the number of kernel launches issued (a rollout at the throughput shape is n_steps dependent launches)
+int fused_launch(int shape, const DevState<float>& d, const int32_t* actions, const FusedOut& out, int noise_mode,
+                 int n_steps, cudaStream_t stream);
 
 }  // namespace ble
