@@ -227,9 +227,16 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       }
       if (kMode == 3) {                                 // split-K: accumulate into the TRANSPOSED result, where the 32 lanes
         if (row_ok) {                                   // of a reduction are 32 consecutive floats
+          // aux != null: the LAST row of A is the caller's row of ones, so its products are the column sums of B^T --
+          // the bias gradient -- and go to aux[n] instead of the (m x n) weight-gradient block
+          const bool bias_row = args.aux != nullptr && m == args.m - 1;
+          float* p = bias_row ? const_cast<float*>(args.aux) + nc : args.dt + nc * args.ldt + m;
+          const int64_t step = bias_row ? 1 : args.ldt;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nc + j < args.n) atomicAdd(args.dt + (nc + j) * args.ldt + m, v[j]);
+          for (int j = 0; j < 32; ++j) {
+            if (nc + j < args.n) atomicAdd(p, v[j]);
+            p += step;
+          }
         }
         continue;
       }
@@ -253,9 +260,12 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         }
       }
       if (args.dt != nullptr && row_ok) {
+        float* pt = args.dt + nc * args.ldt + m;                         // lanes = consecutive m: coalesced
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nc + j < args.n) args.dt[(nc + j) * args.ldt + m] = v[j];  // lanes = consecutive m: coalesced
+        for (int j = 0; j < 32; ++j) {
+          if (nc + j < args.n) *pt = v[j];
+          pt += args.ldt;
+        }
       }
     }
   }
@@ -379,7 +389,7 @@ int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int
   using namespace ble;
   if (a == nullptr || b == nullptr || m <= 0 || n <= 0 || k <= 0 || mode < 0 || mode > 3 || lda < k || ldb < k ||
       (lda & 3) != 0 || (ldb & 3) != 0 || (reinterpret_cast<uintptr_t>(a) & 15) != 0 || (reinterpret_cast<uintptr_t>(b) & 15) != 0 ||
-      (d == nullptr && dt == nullptr) || (d != nullptr && ldd < n) || (dt != nullptr && ldt < m) ||
+      (d == nullptr && dt == nullptr) || (d != nullptr && ldd < n) || (dt != nullptr && ldt < (mode == 3 && aux != nullptr ? m - 1 : m)) ||
       (mode <= 2 && aux == nullptr) || (mode == 2 && ld_aux < n) || (mode == 3 && (dt == nullptr || d != nullptr)) ||
       split_k < 1 || (mode != 3 && split_k != 1)) {
     return BLE_ERR_INVALID_ARGUMENT;

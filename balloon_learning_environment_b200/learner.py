@@ -19,6 +19,7 @@ import contextlib
 import ctypes
 import dataclasses
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -236,6 +237,7 @@ class DenseStack:
   the parameters changed.  Gradients land in the parameters' .grad views of the flat gradient buffer."""
 
   SPLIT_TARGET_CTAS = 296                               # 2 CTAs per SM x 148 SMs
+  FUSE_BIAS_GRADIENT = os.environ.get('BLE_DENSE_FUSE_BIAS', '1') != '0'
 
   def __init__(self, net: QuantileNetwork, device):
     self.net, self.device = net, torch.device(device)
@@ -265,8 +267,12 @@ class DenseStack:
       z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=self.device)
       w = {'bp': bp, 'x': z(batch, _pitch4(self.dims[0][0])), 'h': [z(batch, fout) for _, fout in self.dims]}
       if keep:
-        w['x_t'] = z(self.dims[0][0], bp)
-        w['h_t'] = [z(fout, bp) for _, fout in self.dims[:-1]]
+        # transposed inputs of every layer carry ONE extra row of ones: the weight-gradient product then yields the bias
+        # gradient as its last output row (ble_dense_tf32 mode 3 with aux)
+        w['x_t'] = z(self.dims[0][0] + 1, bp)
+        w['h_t'] = [z(fout + 1, bp) for _, fout in self.dims[:-1]]
+        for t in [w['x_t']] + w['h_t']:
+          t[-1].fill_(1.0)
         w['g'] = [z(batch, _pitch4(fout)) for _, fout in self.dims]
         w['g_t'] = [z(fout, bp) for _, fout in self.dims]
       self._work[key] = w
@@ -315,11 +321,16 @@ class DenseStack:
       prev_t = w['x_t'] if l == 0 else w['h_t'][l - 1]
       # dW^T [in, out] = H^T [in, B] . (dY^T [out, B])^T, accumulated through the kernel's transposed output: the
       # reductions of a warp then fall on consecutive floats of dW [out, in]
-      tiles = ((fin + 127) // 128) * ((fout + 159) // 160)     # the kernel's 128 x 160 tiles
+      tiles = ((fin + 1 + 127) // 128) * ((fout + 159) // 160)     # the kernel's 128 x 160 tiles (+ the row of ones)
       split = max(1, min((batch + 31) // 32, self.SPLIT_TARGET_CTAS // tiles))
-      dense_tf32(prev_t, bp, w['g_t'][l], bp, fin, fout, batch, 3, dt=layer.weight.grad, ldt=fin, split_k=split)
-      row_sum_f32(w['g_t'][l], bp, fout, batch, layer.bias.grad, accumulate=True)
-      self.launches += 2
+      if self.FUSE_BIAS_GRADIENT:
+        dense_tf32(prev_t, bp, w['g_t'][l], bp, fin + 1, fout, batch, 3, aux=layer.bias.grad, dt=layer.weight.grad, ldt=fin,
+                   split_k=split)
+        self.launches += 1
+      else:                                                # A/B: bias gradient as row sums of dY^T in its own launch
+        dense_tf32(prev_t, bp, w['g_t'][l], bp, fin, fout, batch, 3, dt=layer.weight.grad, ldt=fin, split_k=split)
+        row_sum_f32(w['g_t'][l], bp, fout, batch, layer.bias.grad, accumulate=True)
+        self.launches += 2
       if l > 0:
         dense_tf32(w['g'][l], w['g'][l].shape[1], self.w_t[l], self.w_t[l].shape[1], batch, fin, fout, 2,
                    aux=w['h'][l - 1], ld_aux=fin, d=w['g'][l - 1], ldd=w['g'][l - 1].shape[1], dt=w['g_t'][l - 1], ldt=bp)

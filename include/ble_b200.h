@@ -347,7 +347,9 @@ int ble_marco_polo_step(const float* obs, const int32_t* rl_actions, const uint8
  *   ble_dense_tf32: D[m, n] = A[m, k] . B[n, k]^T, A and B row-major with K contiguous (pitches lda, ldb in floats,
  *     multiples of 4; base addresses 16-byte aligned).  mode 0: D += aux[n] (bias); 1: bias then ReLU; 2: D *= (aux[m, n]
  *     > 0) with aux row-major of pitch ld_aux (the ReLU mask of the backward pass); 3: the TRANSPOSED result dt is ACCUMULATED
- *     atomically and the K range is split over split_k CTAs per tile (weight gradient; the caller zeroes dt).  d (pitch
+ *     atomically and the K range is split over split_k CTAs per tile (weight gradient; the caller zeroes dt; if aux is not
+ *     NULL the LAST row of A is taken to be a row of ones appended by the caller and its results -- the column sums of
+ *     B^T, i.e. the bias gradient -- are accumulated into aux[n] instead of dt).  d (pitch
  *     ldd) and / or the transposed result dt [n, m] (pitch ldt) are written (mode 3: dt only).
  *   ble_transpose_f32: dst[c, r] = src[r, c].   ble_row_sum_f32: out[r] (+)= sum_c src[r, c] (bias gradient). */
 int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int64_t n, int64_t k, int32_t mode,

@@ -83,6 +83,14 @@ def test_dense_split_k_accumulates(lrn, m, n, k, split):
   scale = (a[:, :k].double().abs() @ b[:, :k].double().abs().t()).t() + 1.0
   assert ((dt[:, :m].double() - want).abs() / scale).max().item() < 1e-5
   assert torch.equal(dt[:, m:], start[:, m:])
+  # with aux: the last row of A is the caller's row of ones and its results (column sums of B^T) go to aux
+  a[m - 1, :k] = 1.0
+  dt2 = start.clone(); bias = torch.full((n,), 0.5, device='cuda')
+  lrn.dense_tf32(a, ld, b, ld, m, n, k, 3, aux=bias, dt=dt2, ldt=m + 2, split_k=split)
+  assert ((dt2[:, :m - 1].double() - want[:, :m - 1]).abs() / scale[:, :m - 1]).max().item() < 1e-5
+  assert torch.equal(dt2[:, m - 1:], start[:, m - 1:])                            # the last row went elsewhere
+  col = b[:, :k].double().sum(1)
+  assert ((bias.double() - 0.5 - col).abs() / (b[:, :k].double().abs().sum(1) + 1.0)).max().item() < 1e-5
 
 
 def test_transpose_and_row_sum(lrn):
@@ -133,15 +141,15 @@ def test_dense_stack_matches_autograd(lrn, layers, hidden, features, batch):
     z = q(inputs[l]) @ q(ws[l]).t() + net.layers[l].bias.detach().double()
     assert rel(w['h'][l], z.clamp_min(0) if l + 1 < layers else z) < tight, ('forward', l)
     if l + 1 < layers:
-      assert torch.equal(w['h_t'][l][:, :batch].t().contiguous(), w['h'][l])
-  assert torch.equal(w['x_t'][:, :batch].t().contiguous(), x)
+      assert torch.equal(w['h_t'][l][:-1, :batch].t().contiguous(), w['h'][l]) and (w['h_t'][l][-1, :batch] == 1).all()
+  assert torch.equal(w['x_t'][:-1, :batch].t().contiguous(), x) and (w['x_t'][-1, :batch] == 1).all()
   fouts = [o for _, o in stack.dims]
   assert torch.equal(w['g'][-1][:, :fouts[-1]], gl)
   for l in range(layers - 1, -1, -1):                           # backward products on the stack's own gradients
     g = w['g'][l][:, :fouts[l]]
     assert torch.equal(w['g_t'][l][:, :batch].t().contiguous(), g.contiguous())
     assert rel(net.layers[l].weight.grad, q(g.t()) @ q(inputs[l].t()).t()) < tight, ('weight gradient', l)
-    assert rel(net.layers[l].bias.grad, g.double().sum(0)) < tight, ('bias gradient', l)
+    assert rel(net.layers[l].bias.grad, q(g).sum(0)) < tight, ('bias gradient', l)     # TF32 g x exact ones
     if l > 0:
       want = (q(g) @ q(ws[l].t()).t()) * (inputs[l].double() > 0)
       assert rel(w['g'][l - 1][:, :fouts[l - 1]], want) < tight, ('input gradient', l)
