@@ -1,10 +1,11 @@
 """Small end-to-end exercise of the CUDA paths for compute-sanitizer (memcheck / racecheck / synccheck):
-generation, reset, steps of every kernel shape, rollout, features, auto-reset, wind / atmosphere queries."""
+generation, reset, steps of every kernel shape, rollout, features, auto-reset, wind / atmosphere queries, and the
+learner's tcgen05 dense path (forward, backward and one SGD step at ragged sizes)."""
 import os, sys
 import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from balloon_learning_environment_b200 import batched_env, models
+from balloon_learning_environment_b200 import batched_env, learner, models
 
 
 def main():
@@ -38,6 +39,17 @@ def main():
     b.step(torch.randint(0, 3, (n,), dtype=torch.int32, device=dev))
   torch.cuda.synchronize()
   b.close()
+  # learner: every epilogue mode of ble_dense_tf32 at ragged sizes, DenseStack forward / backward, one eager SGD step
+  cfg = learner.QrDqnConfig(num_layers=3, hidden_units=200, num_features=1099, cuda_graph=False)
+  lrn = learner.QrDqnLearner(cfg, seed=0)
+  bsz = 70
+  batch = {'state': torch.rand(bsz, 1099, device=dev), 'next_state': torch.rand(bsz, 1099, device=dev),
+           'action': torch.randint(0, 3, (bsz,), dtype=torch.int32, device=dev), 'return': torch.rand(bsz, device=dev),
+           'discount': torch.full((bsz,), 0.96, device=dev), 'valid': torch.ones(bsz, dtype=torch.uint8, device=dev)}
+  loss = lrn.step(batch)
+  acts2 = lrn.act(torch.rand(n, 1099, device=dev))
+  torch.cuda.synchronize()
+  assert torch.isfinite(loss) and acts2.shape == (n,)
   print('sanitizer probe ok')
 
 
