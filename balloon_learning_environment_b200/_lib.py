@@ -129,7 +129,7 @@ def load(build_if_missing=True):
   lib.ble_replay_sample.argtypes = [_c.POINTER(BleReplayView), vp, u64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
   lib.ble_adam_step.argtypes = [vp, vp, vp, vp, i64, f64, f64, f64, f64, i64, f32, vp]
   lib.ble_marco_polo_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, f32, vp, vp]
-  lib.ble_dense_tf32.argtypes = [vp, i64, vp, i64, i64, i64, i64, i32, vp, i64, vp, i64, vp, i64, i32, vp]
+  lib.ble_dense_tf32.argtypes = [vp, i64, vp, i64, i64, i64, i64, i32, vp, i64, vp, i64, vp, i64, i32, vp, i64, vp]
   lib.ble_transpose_f32.argtypes = [vp, i64, i64, i64, vp, i64, vp]
   lib.ble_row_sum_f32.argtypes = [vp, i64, i64, i64, vp, i32, vp]
   for name in EXPORTS:

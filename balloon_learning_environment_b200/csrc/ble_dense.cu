@@ -11,7 +11,8 @@
 //     3-stage ring, 4 MMAs (K = 8) per stage issued by one elected thread, accumulator = 128 lanes x 160 TMEM columns;
 //   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue, warps 2-5 = epilogue (each reads its
 //     32 TMEM lanes with `tcgen05.ld.32x32b.x32`: a thread holds 32 consecutive columns of one output row);
-//   * fused epilogues: + bias, + bias and ReLU, x (forward activation > 0) for the input gradient, atomic accumulation
+//   * fused epilogues: + bias, + bias and ReLU (which can also leave the ReLU mask packed 32 columns per word), x mask
+//     for the input gradient (from that packed mask, or from the forward activation itself), atomic accumulation
 //     for the split-K weight gradient; every mode can also write the TRANSPOSED tile (a register column is 32
 //     consecutive rows across the lanes, so the transposed store is the coalesced one), which is what the next
 //     product along the backward pass reads as its K-contiguous operand.
@@ -44,6 +45,7 @@ struct DenseArgs {
   float* d; int64_t ldd;                                // row-major output (may be null when only dt is wanted)
   float* dt; int64_t ldt;                               // transposed output [N, M] or null
   int tma_store;                                        // 1: the row-major tile leaves through shared memory + TMA stores
+  uint32_t* relu_bits; int64_t ld_bits;                 // packed ReLU mask [M, ld_bits words]: written by mode 1, read by mode 2
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -209,6 +211,20 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           v[j] += b;
           if (kMode == 1) v[j] = fmaxf(v[j], 0.f);
         }
+        if (kMode == 1 && args.relu_bits != nullptr && row_ok) {
+          // the ReLU mask of this row's 32 columns as ONE word: what the input gradient of the backward pass reads back
+          // instead of 32 activations (tiles start at multiples of 160 columns, so the chunk is word-aligned)
+          uint32_t word = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) word |= (v[j] > 0.f ? 1u : 0u) << j;
+          args.relu_bits[m * args.ld_bits + (nc >> 5)] = word;
+        }
+      } else if (kMode == 2 && args.relu_bits != nullptr) {
+        if (row_ok) {
+          const uint32_t word = __ldg(args.relu_bits + m * args.ld_bits + (nc >> 5));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((word >> j) & 1u) ? v[j] : 0.f;
+        }
       } else if (kMode == 2) {
         if (row_ok) {
           const float* h = args.aux + m * args.ld_aux + nc;
@@ -282,6 +298,7 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the reads
     }
   }
+  __syncwarp();                                                            // the single-lane roles reconverge their warps
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -385,12 +402,13 @@ extern "C" {
 
 int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int64_t n, int64_t k, int32_t mode,
                    const float* aux, int64_t ld_aux, float* d, int64_t ldd, float* dt, int64_t ldt, int32_t split_k,
-                   void* stream) {
+                   uint32_t* relu_bits, int64_t ld_bits, void* stream) {
   using namespace ble;
   if (a == nullptr || b == nullptr || m <= 0 || n <= 0 || k <= 0 || mode < 0 || mode > 3 || lda < k || ldb < k ||
       (lda & 3) != 0 || (ldb & 3) != 0 || (reinterpret_cast<uintptr_t>(a) & 15) != 0 || (reinterpret_cast<uintptr_t>(b) & 15) != 0 ||
       (d == nullptr && dt == nullptr) || (d != nullptr && ldd < n) || (dt != nullptr && ldt < (mode == 3 && aux != nullptr ? m - 1 : m)) ||
-      (mode <= 2 && aux == nullptr) || (mode == 2 && ld_aux < n) || (mode == 3 && (dt == nullptr || d != nullptr)) ||
+      (mode <= 1 && aux == nullptr) || (mode == 2 && aux == nullptr && relu_bits == nullptr) ||
+      (relu_bits != nullptr && (mode == 0 || mode == 3 || ld_bits < (n + 31) / 32)) || (mode == 2 && aux != nullptr && ld_aux < n) || (mode == 3 && (dt == nullptr || d != nullptr)) ||
       split_k < 1 || (mode != 3 && split_k != 1)) {
     return BLE_ERR_INVALID_ARGUMENT;
   }
@@ -403,7 +421,7 @@ int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int
       !operand_map(&md, tma_store ? d : nullptr, m, n, ldd, 32)) return BLE_ERR_CUDA;
   const int total_kb = int((k + kBK - 1) / kBK);
   const int splits = split_k > total_kb ? total_kb : split_k;
-  DenseArgs args{m, n, k, (total_kb + splits - 1) / splits, aux, ld_aux, d, ldd, dt, ldt, tma_store ? 1 : 0};
+  DenseArgs args{m, n, k, (total_kb + splits - 1) / splits, aux, ld_aux, d, ldd, dt, ldt, tma_store ? 1 : 0, relu_bits, ld_bits};
   const dim3 grid(unsigned((n + kBN - 1) / kBN), unsigned((m + kBM - 1) / kBM), unsigned(splits));
   cudaStream_t s = cudaStream_t(stream);
   switch (mode) {

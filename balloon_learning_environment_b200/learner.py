@@ -207,11 +207,13 @@ def _pitch4(n: int) -> int:
   return (int(n) + 3) // 4 * 4
 
 
-def dense_tf32(a, lda, b, ldb, m, n, k, mode, aux=None, ld_aux=0, d=None, ldd=0, dt=None, ldt=0, split_k=1):
-  """D[m, n] = A[m, k] . B[n, k]^T on the tcgen05 tensor cores (include/ble_b200.h: ble_dense_tf32)."""
+def dense_tf32(a, lda, b, ldb, m, n, k, mode, aux=None, ld_aux=0, d=None, ldd=0, dt=None, ldt=0, split_k=1, relu_bits=None):
+  """D[m, n] = A[m, k] . B[n, k]^T on the tcgen05 tensor cores (include/ble_b200.h: ble_dense_tf32).  relu_bits: int32
+  [m, >= ceil(n / 32)], the packed ReLU mask mode 1 writes and mode 2 reads."""
   _require_cuda(a, 'dense_tf32')
   _call('ble_dense_tf32', a.device, _ptr(a), int(lda), _ptr(b), int(ldb), int(m), int(n), int(k), int(mode), _ptr(aux),
-        int(ld_aux), _ptr(d), int(ldd), _ptr(dt), int(ldt), int(split_k))
+        int(ld_aux), _ptr(d), int(ldd), _ptr(dt), int(ldt), int(split_k), _ptr(relu_bits),
+        0 if relu_bits is None else int(relu_bits.stride(0)))
 
 
 def transpose_f32(src, ld_src, rows, cols, dst, ld_dst):
@@ -273,6 +275,7 @@ class DenseStack:
         w['h_t'] = [z(fout + 1, bp) for _, fout in self.dims[:-1]]
         for t in [w['x_t']] + w['h_t']:
           t[-1].fill_(1.0)
+        w['bits'] = [torch.zeros(batch, (fout + 31) // 32, dtype=torch.int32, device=self.device) for _, fout in self.dims[:-1]]
         w['g'] = [z(batch, _pitch4(fout)) for _, fout in self.dims]
         w['g_t'] = [z(fout, bp) for _, fout in self.dims]
       self._work[key] = w
@@ -299,7 +302,7 @@ class DenseStack:
       b = layer.weight if self.w_fwd[l] is None else self.w_fwd[l]
       dt = w['h_t'][l] if keep and l < last else None
       dense_tf32(a, lda, b, _pitch4(fin), batch, fout, fin, 0 if l == last else 1, aux=layer.bias, d=w['h'][l], ldd=fout,
-                 dt=dt, ldt=w['bp'])
+                 dt=dt, ldt=w['bp'], relu_bits=w['bits'][l] if keep and l < last else None)
       self.launches += 1
       a, lda = w['h'][l], fout
     return w['h'][last]
@@ -333,7 +336,7 @@ class DenseStack:
         self.launches += 2
       if l > 0:
         dense_tf32(w['g'][l], w['g'][l].shape[1], self.w_t[l], self.w_t[l].shape[1], batch, fin, fout, 2,
-                   aux=w['h'][l - 1], ld_aux=fin, d=w['g'][l - 1], ldd=w['g'][l - 1].shape[1], dt=w['g_t'][l - 1], ldt=bp)
+                   relu_bits=w['bits'][l - 1], d=w['g'][l - 1], ldd=w['g'][l - 1].shape[1], dt=w['g_t'][l - 1], ldt=bp)
         self.launches += 1
 
 

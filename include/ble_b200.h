@@ -351,10 +351,12 @@ int ble_marco_polo_step(const float* obs, const int32_t* rl_actions, const uint8
  *     NULL the LAST row of A is taken to be a row of ones appended by the caller and its results -- the column sums of
  *     B^T, i.e. the bias gradient -- are accumulated into aux[n] instead of dt).  d (pitch
  *     ldd) and / or the transposed result dt [n, m] (pitch ldt) are written (mode 3: dt only).
+ *     relu_bits (or NULL): the ReLU mask packed 32 columns per word, [m, ld_bits] -- mode 1 WRITES it (bit j of word w of
+ *     row r = D[r, 32 w + j] > 0), mode 2 READS it instead of aux when it is not NULL.
  *   ble_transpose_f32: dst[c, r] = src[r, c].   ble_row_sum_f32: out[r] (+)= sum_c src[r, c] (bias gradient). */
 int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int64_t n, int64_t k, int32_t mode,
                    const float* aux, int64_t ld_aux, float* d, int64_t ldd, float* dt, int64_t ldt, int32_t split_k,
-                   void* stream);
+                   uint32_t* relu_bits, int64_t ld_bits, void* stream);
 int ble_transpose_f32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* dst, int64_t ld_dst, void* stream);
 int ble_row_sum_f32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* out, int32_t accumulate, void* stream);
 

@@ -11,7 +11,7 @@ from balloon_learning_environment_b200 import batched_env, learner, models
 def main():
   n = 100                                              # ragged: not a multiple of 32
   dev = torch.device('cuda:0')
-  for layout in ('x64', 'x128'):
+  for layout in (() if '--dense-only' in sys.argv else ('x64', 'x128')):
     a = batched_env.BatchedBalloonArena(n, precision='fp32', enable_noise=True, enable_features=True, field_layout=layout)
     a.set_decoder(models.load_decoder(''))
     a.alloc_wind_fields(n)
@@ -33,12 +33,13 @@ def main():
     torch.cuda.synchronize()
     assert torch.isfinite(obs).all()
     a.close()
-  b = batched_env.BatchedBalloonArena(n, precision='fp32', wind_model='simple_static', enable_noise=True, auto_reset=True)
-  b.reset(torch.arange(n, dtype=torch.int64))
-  for t in range(3):
-    b.step(torch.randint(0, 3, (n,), dtype=torch.int32, device=dev))
-  torch.cuda.synchronize()
-  b.close()
+  if '--dense-only' not in sys.argv:
+    b = batched_env.BatchedBalloonArena(n, precision='fp32', wind_model='simple_static', enable_noise=True, auto_reset=True)
+    b.reset(torch.arange(n, dtype=torch.int64))
+    for t in range(3):
+      b.step(torch.randint(0, 3, (n,), dtype=torch.int32, device=dev))
+    torch.cuda.synchronize()
+    b.close()
   # learner: every epilogue mode of ble_dense_tf32 at ragged sizes, DenseStack forward / backward, one eager SGD step
   cfg = learner.QrDqnConfig(num_layers=3, hidden_units=200, num_features=1099, cuda_graph=False)
   lrn = learner.QrDqnLearner(cfg, seed=0)

@@ -59,6 +59,18 @@ def test_dense_forward_modes(lrn, m, n, k, exact):
     assert err < tol, (mode, err)
     assert torch.equal(d[:, :n].t().contiguous(), dt[:, :m].contiguous())        # the transposed copy is the same numbers
     assert (d[:, n:] == -7.0).all() and (dt[:, m:] == -7.0).all()                 # nothing written past the edges
+  # mode 1 can leave the ReLU mask packed 32 columns per word; mode 2 reads it back instead of the activations
+  words = (n + 31) // 32
+  bits = torch.full((m, words + 1), 0x55555555, dtype=torch.int32, device='cuda')
+  lrn.dense_tf32(a, lda, b, ldb, m, n, k, 1, aux=bias, d=d, ldd=n + 3, relu_bits=bits)
+  cols = torch.arange(words * 32, device='cuda')
+  got_bits = ((bits[:, :words].unsqueeze(-1) >> torch.arange(32, device='cuda', dtype=torch.int32)) & 1).reshape(m, -1)[:, :n]
+  assert torch.equal(got_bits.bool(), d[:, :n] > 0) and (bits[:, words] == 0x55555555).all()
+  d_bits = torch.empty(m, n, device='cuda')
+  lrn.dense_tf32(a, lda, b, ldb, m, n, k, 2, d=d_bits, ldd=n, relu_bits=bits)
+  d_act = torch.empty(m, n, device='cuda')
+  lrn.dense_tf32(a, lda, b, ldb, m, n, k, 2, aux=d, ld_aux=n + 3, d=d_act, ldd=n)
+  assert torch.equal(d_bits, d_act)
   # mode 2: ReLU mask of the backward pass; only the transposed output requested
   h = torch.randn(m, n, device='cuda', generator=gen)
   d = torch.empty(m, n, device='cuda')
