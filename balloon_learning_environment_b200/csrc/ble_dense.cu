@@ -83,15 +83,29 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
          (uint64_t(2) << 61);
 }
 
+// The same for an MN-major tile (mode 4): the operand arrives as rows of K holding 32 consecutive M (or N) elements --
+// TMA boxes {32 elements of MN, 32 rows of K} of 4096 B.  For 32-bit MN-major operands the tensor core accepts ONE layout,
+// the 128-byte swizzle with a 32-byte atom (descriptor layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; with the plain
+// 128-byte swizzle the MMA returned zeros): the swizzle pattern spans 4 rows of K, so consecutive K are 128 B apart,
+// groups of 4 K are 512 B apart (stride byte offset; one K = 8 MMA reads two of them), and the next 32 elements of MN
+// are one box = 4096 B further (leading byte offset).
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(4096 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(1) << 61);
+}
+
 // Instruction descriptor: D = fp32, A = B = TF32, both K-major, N = kBN, M = kBM.
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kBN >> 3) << 17) | (uint32_t(kBM >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+constexpr uint32_t kInstrDescMN = kInstrDesc | (1u << 15) | (1u << 16);       // A and B MN-major
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate,
+                                          uint32_t idesc = kInstrDesc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate) : "memory");
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 // Row-major output: 32 x 32 boxes staged in shared memory with the 128-byte swizzle, written by TMA (clipped at the
@@ -119,11 +133,13 @@ __device__ __forceinline__ void tmem_load_32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// kMode: 0 = + bias, 1 = + bias then ReLU, 2 = x (aux[m, n] > 0), 3 = atomic accumulation (split-K)
+// kMode: 0 = + bias, 1 = + bias then ReLU, 2 = x ReLU mask, 3 = atomic accumulation (split-K), 4 = 3 with MN-major operands
 template <int kMode>
 __global__ void __launch_bounds__(kThreads, 2)
 k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
              const __grid_constant__ CUtensorMap map_d, DenseArgs args) {
+  constexpr bool kAccumulate = kMode >= 3;              // split-K epilogue
+  constexpr bool kMnMajor = kMode == 4;                 // operands row-major [K, M] / [K, N] instead of [M, K] / [N, K]
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // swizzled tiles need 1024-byte alignment
   const uint32_t bars = base + kStages * kStageBytes;                      // full[kStages], empty[kStages], tmem_full
@@ -163,8 +179,15 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const uint32_t full = bars + 8 * s;
         mbar_expect_tx(full, kStageBytes);
         const uint32_t sa = base + s * kStageBytes;
-        tma_load_2d(&map_a, full, sa, (kb0 + i) * kBK, m0);
-        tma_load_2d(&map_b, full, sa + kABytes, (kb0 + i) * kBK, n0);
+        if (kMnMajor) {
+#pragma unroll
+          for (int c = 0; c < kBM / 32; ++c) tma_load_2d(&map_a, full, sa + c * 4096, m0 + 32 * c, (kb0 + i) * kBK);
+#pragma unroll
+          for (int c = 0; c < kBN / 32; ++c) tma_load_2d(&map_b, full, sa + kABytes + c * 4096, n0 + 32 * c, (kb0 + i) * kBK);
+        } else {
+          tma_load_2d(&map_a, full, sa, (kb0 + i) * kBK, m0);
+          tma_load_2d(&map_b, full, sa + kABytes, (kb0 + i) * kBK, n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -177,8 +200,13 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const uint32_t sa = base + s * kStageBytes;
 #pragma unroll
         for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-          umma_tf32(tmem_base, umma_desc(sa + kk * kUmmaK * 4), umma_desc(sa + kABytes + kk * kUmmaK * 4),
-                    (i > 0 || kk > 0) ? 1u : 0u);
+          if (kMnMajor) {
+            umma_tf32(tmem_base, umma_desc_mn(sa + kk * 1024), umma_desc_mn(sa + kABytes + kk * 1024),
+                      (i > 0 || kk > 0) ? 1u : 0u, kInstrDescMN);
+          } else {
+            umma_tf32(tmem_base, umma_desc(sa + kk * kUmmaK * 4), umma_desc(sa + kABytes + kk * kUmmaK * 4),
+                      (i > 0 || kk > 0) ? 1u : 0u);
+          }
         }
         umma_commit(bars + 8 * (kStages + s));                             // slot reusable once these MMAs have read it
       }
@@ -241,7 +269,7 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           }
         }
       }
-      if (kMode == 3) {                                 // split-K: accumulate into the TRANSPOSED result, where the 32 lanes
+      if (kAccumulate) {                                // split-K: accumulate into the TRANSPOSED result, where the 32 lanes
         if (row_ok) {                                   // of a reduction are 32 consecutive floats
           // aux != null: the LAST row of A is the caller's row of ones, so its products are the column sums of B^T --
           // the bias gradient -- and go to aux[n] instead of the (m x n) weight-gradient block
@@ -285,7 +313,7 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       }
     }
   }
-  if (kMode != 3 && args.tma_store && warp >= 2) {
+  if (!kAccumulate && args.tma_store && warp >= 2) {
     const int q = warp & 3;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the TMA
     __syncwarp();
@@ -367,7 +395,8 @@ EncodeTiled tensor_map_encoder() {
 }
 
 // [rows, k] fp32, row pitch ld floats -> box {32 floats, box_rows rows}, 128-byte swizzle, zero fill out of range
-bool operand_map(CUtensorMap* map, const float* p, int64_t rows, int64_t k, int64_t ld, int box_rows) {
+bool operand_map(CUtensorMap* map, const float* p, int64_t rows, int64_t k, int64_t ld, int box_rows,
+                 CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   if (p == nullptr) { *map = CUtensorMap{}; return true; }
   EncodeTiled enc = tensor_map_encoder();
   if (enc == nullptr) return false;
@@ -376,7 +405,7 @@ bool operand_map(CUtensorMap* map, const float* p, int64_t rows, int64_t k, int6
   const cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(box_rows)};
   const cuuint32_t elem[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, elem,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -404,21 +433,25 @@ int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int
                    const float* aux, int64_t ld_aux, float* d, int64_t ldd, float* dt, int64_t ldt, int32_t split_k,
                    uint32_t* relu_bits, int64_t ld_bits, void* stream) {
   using namespace ble;
-  if (a == nullptr || b == nullptr || m <= 0 || n <= 0 || k <= 0 || mode < 0 || mode > 3 || lda < k || ldb < k ||
+  const bool mn = mode == 4;                            // operands [k, m] / [k, n] row-major
+  const bool acc = mode >= 3;
+  if (a == nullptr || b == nullptr || m <= 0 || n <= 0 || k <= 0 || mode < 0 || mode > 4 || lda < (mn ? m : k) || ldb < (mn ? n : k) ||
       (lda & 3) != 0 || (ldb & 3) != 0 || (reinterpret_cast<uintptr_t>(a) & 15) != 0 || (reinterpret_cast<uintptr_t>(b) & 15) != 0 ||
-      (d == nullptr && dt == nullptr) || (d != nullptr && ldd < n) || (dt != nullptr && ldt < (mode == 3 && aux != nullptr ? m - 1 : m)) ||
+      (d == nullptr && dt == nullptr) || (d != nullptr && ldd < n) || (dt != nullptr && ldt < (acc && aux != nullptr ? m - 1 : m)) ||
       (mode <= 1 && aux == nullptr) || (mode == 2 && aux == nullptr && relu_bits == nullptr) ||
-      (relu_bits != nullptr && (mode == 0 || mode == 3 || ld_bits < (n + 31) / 32)) || (mode == 2 && aux != nullptr && ld_aux < n) || (mode == 3 && (dt == nullptr || d != nullptr)) ||
-      split_k < 1 || (mode != 3 && split_k != 1)) {
+      (relu_bits != nullptr && (mode == 0 || acc || ld_bits < (n + 31) / 32)) || (mode == 2 && aux != nullptr && ld_aux < n) || (acc && (dt == nullptr || d != nullptr)) ||
+      split_k < 1 || (!acc && split_k != 1)) {
     return BLE_ERR_INVALID_ARGUMENT;
   }
   // row-major output through TMA stores when its rows can be a tensor map (16-byte pitch and base) and end on a 16-byte
   // boundary (the TMA writes whole 16-byte granules: measured, a 257-column tensor had columns 257..259 overwritten);
   // else direct stores
-  const bool tma_store = mode != 3 && d != nullptr && (ldd & 3) == 0 && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0;
+  const bool tma_store = !acc && d != nullptr && (ldd & 3) == 0 && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0;
   CUtensorMap ma, mb, md;
-  if (!operand_map(&ma, a, m, k, lda, kBM) || !operand_map(&mb, b, n, k, ldb, kBN) ||
-      !operand_map(&md, tma_store ? d : nullptr, m, n, ldd, 32)) return BLE_ERR_CUDA;
+  const bool maps_ok = mn ? operand_map(&ma, a, k, m, lda, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&          // boxes {32 of MN, 32 of K}
+                            operand_map(&mb, b, k, n, ldb, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                          : operand_map(&ma, a, m, k, lda, kBM) && operand_map(&mb, b, n, k, ldb, kBN);    // boxes {32 of K, tile rows}
+  if (!maps_ok || !operand_map(&md, tma_store ? d : nullptr, m, n, ldd, 32)) return BLE_ERR_CUDA;
   const int total_kb = int((k + kBK - 1) / kBK);
   const int splits = split_k > total_kb ? total_kb : split_k;
   DenseArgs args{m, n, k, (total_kb + splits - 1) / splits, aux, ld_aux, d, ldd, dt, ldt, tma_store ? 1 : 0, relu_bits, ld_bits};
@@ -428,7 +461,8 @@ int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int
     case 0: return launch_dense<0>(ma, mb, md, args, grid, s);
     case 1: return launch_dense<1>(ma, mb, md, args, grid, s);
     case 2: return launch_dense<2>(ma, mb, md, args, grid, s);
-    default: return launch_dense<3>(ma, mb, md, args, grid, s);
+    case 3: return launch_dense<3>(ma, mb, md, args, grid, s);
+    default: return launch_dense<4>(ma, mb, md, args, grid, s);
   }
 }
 

@@ -207,6 +207,12 @@ def _pitch4(n: int) -> int:
   return (int(n) + 3) // 4 * 4
 
 
+def _pitch32(n: int) -> int:
+  """Row pitch of the dense path's own buffers: a multiple of 32 floats, so that every row starts on a 128-byte line and a
+  TMA box row never straddles two (measured: 27 -> 23 us per 8,192 x 600 x 600 forward product against a 604-float pitch)."""
+  return (int(n) + 31) // 32 * 32
+
+
 def dense_tf32(a, lda, b, ldb, m, n, k, mode, aux=None, ld_aux=0, d=None, ldd=0, dt=None, ldt=0, split_k=1, relu_bits=None):
   """D[m, n] = A[m, k] . B[n, k]^T on the tcgen05 tensor cores (include/ble_b200.h: ble_dense_tf32).  relu_bits: int32
   [m, >= ceil(n / 32)], the packed ReLU mask mode 1 writes and mode 2 reads."""
@@ -226,29 +232,29 @@ def row_sum_f32(src, ld_src, rows, cols, out, accumulate=False):
 
 class DenseStack:
   """Forward and backward pass of a QuantileNetwork's dense layers WITHOUT autograd: every product is one launch of
-  ble_dense_tf32 (D = A . B^T, both operands K-contiguous), with bias / ReLU / ReLU-mask / split-K accumulation fused
-  into its epilogue.  To give every product that shape the stack keeps, next to the parameters (which stay the flat
-  fp32 buffer of `flatten_parameters`):
+  ble_dense_tf32, with bias / ReLU (+ packed mask) / ReLU-mask / split-K accumulation fused into its epilogue.
 
-    w_t[l]   [in_l, out_l]  transposed weights (input gradient:  dH = dY . W       = dY [B, out] . (W^T [in, out])^T)
-    h_t[l]   [out_l, B]     transposed activations, written by the forward epilogue
-    g_t[l]   [out_l, B]     transposed output gradients, written by the input-gradient epilogue
-                            (weight gradient: dW^T = H^T . dY = H^T [in, B] . (dY^T [out, B])^T, split over K = B)
+    forward          H' = relu(H . W^T + b)      A = H [B, in], B = W [out, in]            both K-contiguous (mode 1 / 0)
+    input gradient   dH = (dY . W) * mask        A = dY [B, out], B = W^T [in, out] (a copy kept by refresh())   (mode 2)
+    weight gradient  dW^T = H^T . dY             A = H [B, in], B = dY [B, out] read as MN-MAJOR operands        (mode 4):
+                     the row-major activations and output gradients as they are, split over K = batch and accumulated
+                     through the kernel's transposed output so that a warp's reductions fall on consecutive floats of dW.
 
-  Pitches are rounded up to 4 floats (TMA needs 16-byte row pitches); `refresh()` re-derives the weight copies after
-  the parameters changed.  Gradients land in the parameters' .grad views of the flat gradient buffer."""
+  Every activation buffer carries one extra column of ones, so the weight-gradient product's last output row is the
+  bias gradient.  Pitches are rounded up to 4 floats (TMA needs 16-byte row pitches); `refresh()` re-derives the weight
+  copies after the parameters changed.  Gradients land in the parameters' .grad views of the flat gradient buffer."""
 
   SPLIT_TARGET_CTAS = 296                               # 2 CTAs per SM x 148 SMs
-  FUSE_BIAS_GRADIENT = os.environ.get('BLE_DENSE_FUSE_BIAS', '1') != '0'
 
   def __init__(self, net: QuantileNetwork, device):
     self.net, self.device = net, torch.device(device)
     self.dims = [(l.in_features, l.out_features) for l in net.layers]
     self.w_fwd, self.w_t = [], []
     for l, (fin, fout) in enumerate(self.dims):
-      self.w_fwd.append(None if fin % 4 == 0 else torch.zeros(fout, _pitch4(fin), dtype=torch.float32, device=self.device))
-      self.w_t.append(None if l == 0 else torch.zeros(fin, _pitch4(fout), dtype=torch.float32, device=self.device))
+      self.w_fwd.append(torch.zeros(fout, _pitch32(fin), dtype=torch.float32, device=self.device))      # line-aligned rows
+      self.w_t.append(None if l == 0 else torch.zeros(fin, _pitch32(fout), dtype=torch.float32, device=self.device))
     self._work = {}
+    self._ones_inputs = set()
     self.launches = 0
     self.refresh()
 
@@ -256,28 +262,34 @@ class DenseStack:
     with torch.no_grad():
       for l, layer in enumerate(self.net.layers):
         fin, fout = self.dims[l]
-        if self.w_fwd[l] is not None:
-          self.w_fwd[l][:, :fin].copy_(layer.weight)
+        self.w_fwd[l][:, :fin].copy_(layer.weight)
         if self.w_t[l] is not None:
           transpose_f32(layer.weight, fin, fout, fin, self.w_t[l], self.w_t[l].shape[1])
           self.launches += 1
 
+  def _with_ones(self, batch: int, width: int) -> torch.Tensor:
+    """[batch, pitch] zeros with column `width` set to one (the bias-gradient column); use t[:, :width]."""
+    t = torch.zeros(batch, _pitch32(width + 1), dtype=torch.float32, device=self.device)
+    t[:, width].fill_(1.0)
+    return t
+
+  def input_buffer(self, batch: int) -> torch.Tensor:
+    """A network input buffer forward(keep=True) can use IN PLACE: [batch, features] view of a row-padded allocation whose
+    column `features` holds the ones the weight gradient of the first layer needs."""
+    t = self._with_ones(batch, self.dims[0][0])
+    self._ones_inputs.add(t.data_ptr())
+    return t[:, :self.dims[0][0]]
+
   def _buffers(self, batch: int, keep: bool):
     key = (batch, keep)
     if key not in self._work:
-      bp = _pitch4(batch)
       z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=self.device)
-      w = {'bp': bp, 'x': z(batch, _pitch4(self.dims[0][0])), 'h': [z(batch, fout) for _, fout in self.dims]}
+      last = len(self.dims) - 1
+      w = {'x': self.input_buffer(batch),
+           'h': [self._with_ones(batch, fout) if l < last else z(batch, fout) for l, (_, fout) in enumerate(self.dims)]}
       if keep:
-        # transposed inputs of every layer carry ONE extra row of ones: the weight-gradient product then yields the bias
-        # gradient as its last output row (ble_dense_tf32 mode 3 with aux)
-        w['x_t'] = z(self.dims[0][0] + 1, bp)
-        w['h_t'] = [z(fout + 1, bp) for _, fout in self.dims[:-1]]
-        for t in [w['x_t']] + w['h_t']:
-          t[-1].fill_(1.0)
         w['bits'] = [torch.zeros(batch, (fout + 31) // 32, dtype=torch.int32, device=self.device) for _, fout in self.dims[:-1]]
-        w['g'] = [z(batch, _pitch4(fout)) for _, fout in self.dims]
-        w['g_t'] = [z(fout, bp) for _, fout in self.dims]
+        w['g'] = [z(batch, _pitch32(fout)) for _, fout in self.dims]
       self._work[key] = w
     return self._work[key]
 
@@ -287,24 +299,23 @@ class DenseStack:
     batch, feat = x.shape
     assert feat == self.dims[0][0], (feat, self.dims[0][0])
     w = self._buffers(batch, keep)
-    if (x.dtype == torch.float32 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.stride(0) >= feat and
-        x.data_ptr() % 16 == 0):
-      a, lda = x, x.stride(0)                              # already a TMA-able operand (e.g. the learner's padded buffers)
+    tma_able = (x.dtype == torch.float32 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.stride(0) >= feat and
+                x.data_ptr() % 16 == 0)
+    if tma_able and (not keep or x.data_ptr() in self._ones_inputs):
+      a, lda = x, x.stride(0)                              # read in place (keep: one of input_buffer()'s allocations)
     else:
-      w['x'][:, :feat].copy_(x)
-      a, lda = w['x'], w['x'].shape[1]
-    if keep:
-      transpose_f32(a, lda, batch, feat, w['x_t'], w['bp'])
-      self.launches += 1
+      w['x'].copy_(x)
+      a, lda = w['x'], w['x'].stride(0)
+    w['input'] = (a, lda)
     last = len(self.dims) - 1
     for l, (fin, fout) in enumerate(self.dims):
       layer = self.net.layers[l]
-      b = layer.weight if self.w_fwd[l] is None else self.w_fwd[l]
-      dt = w['h_t'][l] if keep and l < last else None
-      dense_tf32(a, lda, b, _pitch4(fin), batch, fout, fin, 0 if l == last else 1, aux=layer.bias, d=w['h'][l], ldd=fout,
-                 dt=dt, ldt=w['bp'], relu_bits=w['bits'][l] if keep and l < last else None)
+      b = self.w_fwd[l]
+      h = w['h'][l]
+      dense_tf32(a, lda, b, b.stride(0), batch, fout, fin, 0 if l == last else 1, aux=layer.bias, d=h, ldd=h.stride(0),
+                 relu_bits=w['bits'][l] if keep and l < last else None)
       self.launches += 1
-      a, lda = w['h'][l], fout
+      a, lda = h, h.stride(0)
     return w['h'][last]
 
   @torch.no_grad()
@@ -313,30 +324,23 @@ class DenseStack:
     parameter gradients into the .grad views (the caller zeroes the flat gradient buffer)."""
     batch = grad_logits.shape[0]
     w = self._buffers(batch, True)
-    bp, last = w['bp'], len(self.dims) - 1
-    fout = self.dims[last][1]
-    w['g'][last][:, :fout].copy_(grad_logits.reshape(batch, fout))
-    transpose_f32(w['g'][last], w['g'][last].shape[1], batch, fout, w['g_t'][last], bp)
-    self.launches += 1
+    last = len(self.dims) - 1
+    w['g'][last][:, :self.dims[last][1]].copy_(grad_logits.reshape(batch, -1))
     for l in range(last, -1, -1):
       fin, fout = self.dims[l]
       layer = self.net.layers[l]
-      prev_t = w['x_t'] if l == 0 else w['h_t'][l - 1]
-      # dW^T [in, out] = H^T [in, B] . (dY^T [out, B])^T, accumulated through the kernel's transposed output: the
-      # reductions of a warp then fall on consecutive floats of dW [out, in]
-      tiles = ((fin + 1 + 127) // 128) * ((fout + 159) // 160)     # the kernel's 128 x 160 tiles (+ the row of ones)
+      g = w['g'][l]
+      prev, ld_prev = w['input'] if l == 0 else (w['h'][l - 1], w['h'][l - 1].stride(0))
+      # dW^T [in + 1, out] = [H, 1]^T . dY: rows 0 .. in-1 accumulate into dW (transposed output), row `in` into db
+      tiles = ((fin + 1 + 127) // 128) * ((fout + 159) // 160)     # the kernel's 128 x 160 tiles
       split = max(1, min((batch + 31) // 32, self.SPLIT_TARGET_CTAS // tiles))
-      if self.FUSE_BIAS_GRADIENT:
-        dense_tf32(prev_t, bp, w['g_t'][l], bp, fin + 1, fout, batch, 3, aux=layer.bias.grad, dt=layer.weight.grad, ldt=fin,
-                   split_k=split)
-        self.launches += 1
-      else:                                                # A/B: bias gradient as row sums of dY^T in its own launch
-        dense_tf32(prev_t, bp, w['g_t'][l], bp, fin, fout, batch, 3, dt=layer.weight.grad, ldt=fin, split_k=split)
-        row_sum_f32(w['g_t'][l], bp, fout, batch, layer.bias.grad, accumulate=True)
-        self.launches += 2
+      dense_tf32(prev, ld_prev, g, g.stride(0), fin + 1, fout, batch, 4, aux=layer.bias.grad, dt=layer.weight.grad, ldt=fin,
+                 split_k=split)
+      self.launches += 1
       if l > 0:
-        dense_tf32(w['g'][l], w['g'][l].shape[1], self.w_t[l], self.w_t[l].shape[1], batch, fin, fout, 2,
-                   relu_bits=w['bits'][l - 1], d=w['g'][l - 1], ldd=w['g'][l - 1].shape[1], dt=w['g_t'][l - 1], ldt=bp)
+        gp = w['g'][l - 1]
+        dense_tf32(g, g.stride(0), self.w_t[l], self.w_t[l].shape[1], batch, fin, fout, 2, relu_bits=w['bits'][l - 1],
+                   d=gp, ldd=gp.stride(0))
         self.launches += 1
 
 
@@ -561,8 +565,8 @@ class QrDqnLearner:
       return self._io[b]
     cfg, dev = self.config, self.device
     f32 = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
-    pitch = _pitch4(cfg.num_features)                       # padded rows: the dense kernel reads these buffers in place
-    io = {'state': f32(b, pitch)[:, :cfg.num_features], 'next_state': f32(b, pitch)[:, :cfg.num_features],
+    # row-padded buffers the dense kernel reads in place (the online one with the column of ones the backward pass needs)
+    io = {'state': self.dense.input_buffer(b), 'next_state': self.dense_target.input_buffer(b),
           'action': torch.zeros(b, dtype=torch.int32, device=dev), 'return': f32(b), 'discount': f32(b), 'weight': f32(b),
           'loss': f32(b), 'grad': f32(b, cfg.num_actions, cfg.num_atoms), 'mean': f32(()),
           'valid': torch.zeros(b, dtype=torch.uint8, device=dev)}

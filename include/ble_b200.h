@@ -351,6 +351,9 @@ int ble_marco_polo_step(const float* obs, const int32_t* rl_actions, const uint8
  *     NULL the LAST row of A is taken to be a row of ones appended by the caller and its results -- the column sums of
  *     B^T, i.e. the bias gradient -- are accumulated into aux[n] instead of dt).  d (pitch
  *     ldd) and / or the transposed result dt [n, m] (pitch ldt) are written (mode 3: dt only).
+ *     mode 4 = mode 3 with the operands given the other way round in memory: a = [k, m] and b = [k, n] row-major
+ *     (pitches lda >= m, ldb >= n), i.e. D = A^T . B for row-major A [k, m], B [k, n] -- the weight gradient straight from
+ *     the row-major activations and output gradients (MN-major tensor-core operands), no transposed copies.
  *     relu_bits (or NULL): the ReLU mask packed 32 columns per word, [m, ld_bits] -- mode 1 WRITES it (bit j of word w of
  *     row r = D[r, 32 w + j] > 0), mode 2 READS it instead of aux when it is not NULL.
  *   ble_transpose_f32: dst[c, r] = src[r, c].   ble_row_sum_f32: out[r] (+)= sum_c src[r, c] (bias gradient). */

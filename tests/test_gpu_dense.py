@@ -105,6 +105,31 @@ def test_dense_split_k_accumulates(lrn, m, n, k, split):
   assert ((bias.double() - 0.5 - col).abs() / (b[:, :k].double().abs().sum(1) + 1.0)).max().item() < 1e-5
 
 
+@pytest.mark.parametrize('m,n,k,split', [(601, 600, 8192, 14), (154, 600, 1000, 4), (1100, 600, 4096, 6), (40, 24, 100, 3),
+                                         (128, 160, 32, 1), (33, 153, 70, 2)])
+def test_dense_mn_major_operands(lrn, m, n, k, split):
+  """mode 4: D^T += A^T . B for ROW-MAJOR A [k, m], B [k, n] (MN-major tensor-core operands), the last column of A being
+  the caller's column of ones whose products go to aux -- the weight + bias gradient straight from activations and
+  output gradients."""
+  gen = torch.Generator(device='cuda'); gen.manual_seed(k + m)
+  lda, ldb = lrn._pitch4(m) + 4, lrn._pitch4(n)
+  a, b = alloc(k, m, lda, gen, True), alloc(k, n, ldb, gen, True)
+  a[:, m - 1] = 1.0
+  start = torch.randn(n, m + 1, device='cuda', generator=gen)
+  dt = start.clone(); bias = torch.full((n,), -2.0, device='cuda')
+  lrn.dense_tf32(a, lda, b, ldb, m, n, k, 4, aux=bias, dt=dt, ldt=m + 1, split_k=split)
+  full = b[:, :n].double().t() @ a[:, :m].double()                      # [n, m]
+  scale = b[:, :n].double().abs().t() @ a[:, :m].double().abs() + 1.0
+  err = ((dt[:, :m - 1].double() - start[:, :m - 1].double() - full[:, :m - 1]).abs() / scale[:, :m - 1]).max().item()
+  assert err < 1e-5, err
+  assert torch.equal(dt[:, m - 1:], start[:, m - 1:])
+  assert ((bias.double() + 2.0 - full[:, m - 1]).abs() / scale[:, m - 1]).max().item() < 1e-5
+  # without aux every row of A^T lands in dt
+  dt2 = start.clone()
+  lrn.dense_tf32(a, lda, b, ldb, m, n, k, 4, dt=dt2, ldt=m + 1, split_k=split)
+  assert ((dt2[:, :m].double() - start[:, :m].double() - full).abs() / scale).max().item() < 1e-5
+
+
 def test_transpose_and_row_sum(lrn):
   gen = torch.Generator(device='cuda'); gen.manual_seed(1)
   src = torch.randn(77, 1099 + 5, device='cuda', generator=gen)
@@ -147,19 +172,21 @@ def test_dense_stack_matches_autograd(lrn, layers, hidden, features, batch):
   rel = lambda got, want: ((got.double() - want).norm() / (want.norm() + 1e-30)).item()
   w = stack._work[(batch, True)]
   ws = [l.weight.detach() for l in net.layers]
-  tight = 5e-6
-  inputs = [x] + [w['h'][l] for l in range(layers - 1)]
-  for l in range(layers):                                       # forward products, and the transposed copies
-    z = q(inputs[l]) @ q(ws[l]).t() + net.layers[l].bias.detach().double()
-    assert rel(w['h'][l], z.clamp_min(0) if l + 1 < layers else z) < tight, ('forward', l)
-    if l + 1 < layers:
-      assert torch.equal(w['h_t'][l][:-1, :batch].t().contiguous(), w['h'][l]) and (w['h_t'][l][-1, :batch] == 1).all()
-  assert torch.equal(w['x_t'][:-1, :batch].t().contiguous(), x) and (w['x_t'][-1, :batch] == 1).all()
   fouts = [o for _, o in stack.dims]
+  tight = 5e-6
+  acts = [w['h'][l][:, :fouts[l]] for l in range(layers)]         # views without the column of ones
+  inputs = [x] + acts[:-1]
+  for l in range(layers):                                       # forward products, the ones columns, the packed masks
+    z = q(inputs[l]) @ q(ws[l]).t() + net.layers[l].bias.detach().double()
+    assert rel(acts[l], z.clamp_min(0) if l + 1 < layers else z) < tight, ('forward', l)
+    if l + 1 < layers:
+      assert (w['h'][l][:, fouts[l]] == 1).all()
+      bits = ((w['bits'][l].unsqueeze(-1) >> torch.arange(32, device='cuda', dtype=torch.int32)) & 1).reshape(batch, -1)
+      assert torch.equal(bits[:, :fouts[l]].bool(), acts[l] > 0)
+  assert torch.equal(w['input'][0][:, :features], x) and (w['x'].storage_offset() == 0)
   assert torch.equal(w['g'][-1][:, :fouts[-1]], gl)
   for l in range(layers - 1, -1, -1):                           # backward products on the stack's own gradients
     g = w['g'][l][:, :fouts[l]]
-    assert torch.equal(w['g_t'][l][:, :batch].t().contiguous(), g.contiguous())
     assert rel(net.layers[l].weight.grad, q(g.t()) @ q(inputs[l].t()).t()) < tight, ('weight gradient', l)
     assert rel(net.layers[l].bias.grad, q(g).sum(0)) < tight, ('bias gradient', l)     # TF32 g x exact ones
     if l > 0:

@@ -135,7 +135,7 @@ def test_replay_sample_matches_oracle(lrn):
   sel = dev(idx[valid.astype(bool)][:40])
   plain = rep.sample(len(sel), indices=sel)
   bufs = learner.sample_buffers(len(sel))
-  assert bufs['state'].stride(0) == 24 and bufs['state'].shape == (len(sel), feat)
+  assert bufs['state'].stride(0) == 32 and bufs['state'].shape == (len(sel), feat)
   placed = rep.sample(len(sel), indices=sel, out=bufs)
   for k in ('state', 'next_state', 'action', 'return', 'discount', 'valid'):
     assert placed[k].data_ptr() == bufs[k].data_ptr()
