@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/ble_b200.h"
 
@@ -32,11 +33,19 @@ namespace {
 
 constexpr int kBM = 128, kBN = 160, kBK = 32;           // kBK floats = 128 B = the swizzle span
 constexpr int kUmmaK = 8;                               // tf32: 32 B of K per MMA
-constexpr int kStages = 3;
-constexpr int kABytes = kBM * kBK * 4, kBBytes = kBN * kBK * 4, kStageBytes = kABytes + kBBytes;
-constexpr int kTmemCols = 256;                          // power of two >= kBN
+constexpr int kBBytes = kBN * kBK * 4;
 constexpr int kThreads = 192;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+// kAcc = 1 (default): one 128 x 160 accumulator per CTA, 3 stages, 2 CTAs per SM.  kAcc = 2 (BLE_DENSE_ROWS=256, A/B): TWO
+// accumulators (a 256 x 160 tile whose halves share every B tile in shared memory: a third less operand traffic per FLOP),
+// 4 stages, the whole TMEM, 1 CTA per SM -- measured slower (see ble_dense_tf32).
+template <int kAcc> struct Tile {
+  static constexpr int kRows = kBM * kAcc;
+  static constexpr int kABytes = kRows * kBK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kAcc == 1 ? 3 : 4;
+  static constexpr int kTmemCols = kAcc == 1 ? 256 : 512;          // power of two >= kAcc * kBN
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
 
 struct DenseArgs {
   int64_t m, n, k;
@@ -134,12 +143,14 @@ __device__ __forceinline__ void tmem_load_32(uint32_t taddr, float* v) {
 }
 
 // kMode: 0 = + bias, 1 = + bias then ReLU, 2 = x ReLU mask, 3 = atomic accumulation (split-K), 4 = 3 with MN-major operands
-template <int kMode>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int kMode, int kAcc>
+__global__ void __launch_bounds__(kThreads, kAcc == 1 ? 2 : 1)
 k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
              const __grid_constant__ CUtensorMap map_d, DenseArgs args) {
   constexpr bool kAccumulate = kMode >= 3;              // split-K epilogue
   constexpr bool kMnMajor = kMode == 4;                 // operands row-major [K, M] / [K, N] instead of [M, K] / [N, K]
+  constexpr int kStages = Tile<kAcc>::kStages, kStageBytes = Tile<kAcc>::kStageBytes, kABytes = Tile<kAcc>::kABytes;
+  constexpr int kTmemCols = Tile<kAcc>::kTmemCols, kRows = Tile<kAcc>::kRows;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // swizzled tiles need 1024-byte alignment
   const uint32_t bars = base + kStages * kStageBytes;                      // full[kStages], empty[kStages], tmem_full
@@ -148,7 +159,7 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(generic_base + kStages * kStageBytes + (2 * kStages + 1) * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;
+  const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kRows;
   const int total_kb = int((args.k + kBK - 1) / kBK);
   const int kb0 = blockIdx.z * args.k_blocks_per_split;
   const int kb1 = min(total_kb, kb0 + args.k_blocks_per_split);
@@ -181,7 +192,7 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const uint32_t sa = base + s * kStageBytes;
         if (kMnMajor) {
 #pragma unroll
-          for (int c = 0; c < kBM / 32; ++c) tma_load_2d(&map_a, full, sa + c * 4096, m0 + 32 * c, (kb0 + i) * kBK);
+          for (int c = 0; c < kRows / 32; ++c) tma_load_2d(&map_a, full, sa + c * 4096, m0 + 32 * c, (kb0 + i) * kBK);
 #pragma unroll
           for (int c = 0; c < kBN / 32; ++c) tma_load_2d(&map_b, full, sa + kABytes + c * 4096, n0 + 32 * c, (kb0 + i) * kBK);
         } else {
@@ -200,12 +211,16 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const uint32_t sa = base + s * kStageBytes;
 #pragma unroll
         for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-          if (kMnMajor) {
-            umma_tf32(tmem_base, umma_desc_mn(sa + kk * 1024), umma_desc_mn(sa + kABytes + kk * 1024),
-                      (i > 0 || kk > 0) ? 1u : 0u, kInstrDescMN);
-          } else {
-            umma_tf32(tmem_base, umma_desc(sa + kk * kUmmaK * 4), umma_desc(sa + kABytes + kk * kUmmaK * 4),
-                      (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+          for (int acc = 0; acc < kAcc; ++acc) {            // the accumulators of a 256-row tile share the B tile
+            const uint32_t td = tmem_base + uint32_t(acc * kBN), sa_acc = sa + acc * (kBM * kBK * 4);
+            if (kMnMajor) {
+              umma_tf32(td, umma_desc_mn(sa_acc + kk * 1024), umma_desc_mn(sa + kABytes + kk * 1024),
+                        (i > 0 || kk > 0) ? 1u : 0u, kInstrDescMN);
+            } else {
+              umma_tf32(td, umma_desc(sa_acc + kk * kUmmaK * 4), umma_desc(sa + kABytes + kk * kUmmaK * 4),
+                        (i > 0 || kk > 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(bars + 8 * (kStages + s));                             // slot reusable once these MMAs have read it
@@ -214,22 +229,23 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
   } else {                                                                 // ---- epilogue: warps 2..5 ----
     const int q = warp & 3;                                                // the TMEM lane quarter this warp may read
-    const int64_t m = int64_t(m0) + q * 32 + lane;
     if (num_kb > 0) {
       mbar_wait(bars + 8 * 2 * kStages, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
+    for (int ac = 0; ac < kAcc * (kBN / 32); ++ac) {
+      const int acc = ac / (kBN / 32), c = ac - acc * (kBN / 32);
+      const int64_t m = int64_t(m0) + acc * kBM + q * 32 + lane;
       float v[32];
       if (num_kb > 0) {
-        tmem_load_32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
+        tmem_load_32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kBN + c * 32), v);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
       const int64_t nc = int64_t(n0) + c * 32;
-      if (nc >= args.n) break;
+      if (nc >= args.n) continue;
       const bool row_ok = m < args.m;
       const bool full_chunk = nc + 32 <= args.n;
       if (kMode == 0 || kMode == 1) {
@@ -286,7 +302,8 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       }
       if (args.tma_store) {
         // the operand ring is idle once the accumulator is complete: warp q stages its 32 x 32 box of chunk c there
-        const uint32_t row = base + uint32_t(q) * (kBN / 32) * 4096u + uint32_t(c) * 4096u + uint32_t(lane) * 128u;
+        const uint32_t row = base + uint32_t(acc) * (kBM * kBN * 4) + uint32_t(q) * (kBN / 32) * 4096u + uint32_t(c) * 4096u +
+                             uint32_t(lane) * 128u;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + (uint32_t(g ^ (lane & 7)) << 4)),
@@ -317,10 +334,14 @@ k_dense_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const int q = warp & 3;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the TMA
     __syncwarp();
-    if (lane == 0 && int64_t(m0) + q * 32 < args.m) {
-      for (int c = 0; c < kBN / 32; ++c) {
-        if (int64_t(n0) + c * 32 >= args.n) break;
-        tma_store_2d(&map_d, base + uint32_t(q) * (kBN / 32) * 4096u + uint32_t(c) * 4096u, n0 + c * 32, m0 + q * 32);
+    if (lane == 0) {
+      for (int acc = 0; acc < kAcc; ++acc) {
+        if (int64_t(m0) + acc * kBM + q * 32 >= args.m) break;
+        for (int c = 0; c < kBN / 32; ++c) {
+          if (int64_t(n0) + c * 32 >= args.n) break;
+          tma_store_2d(&map_d, base + uint32_t(acc) * (kBM * kBN * 4) + uint32_t(q) * (kBN / 32) * 4096u + uint32_t(c) * 4096u,
+                       n0 + c * 32, m0 + acc * kBM + q * 32);
+        }
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the reads
@@ -409,18 +430,19 @@ bool operand_map(CUtensorMap* map, const float* p, int64_t rows, int64_t k, int6
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int kMode>
+template <int kMode, int kAcc>
 int launch_dense(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const DenseArgs& args, dim3 grid,
                  cudaStream_t s) {
+  constexpr int kSmemBytes = Tile<kAcc>::kSmemBytes;
   static bool configured[16] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return BLE_ERR_CUDA;
   if (!configured[dev]) {
-    if (cudaFuncSetAttribute(k_dense_tf32<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_dense_tf32<kMode, kAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
       return BLE_ERR_CUDA;
     configured[dev] = true;
   }
-  k_dense_tf32<kMode><<<grid, kThreads, kSmemBytes, s>>>(ma, mb, md, args);
+  k_dense_tf32<kMode, kAcc><<<grid, kThreads, kSmemBytes, s>>>(ma, mb, md, args);
   return cudaGetLastError() == cudaSuccess ? BLE_OK : BLE_ERR_CUDA;
 }
 
@@ -448,21 +470,27 @@ int ble_dense_tf32(const float* a, int64_t lda, const float* b, int64_t ldb, int
   // else direct stores
   const bool tma_store = !acc && d != nullptr && (ldd & 3) == 0 && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0;
   CUtensorMap ma, mb, md;
+  // BLE_DENSE_ROWS=256 (A/B): 256-row tiles, two accumulators sharing every B tile -- a third less operand traffic per FLOP,
+  // but one CTA per SM (no epilogue / main-loop overlap between CTAs) and 128 CTAs for 148 SMs: measured 0.872 ms per
+  // 8,192-sample SGD step against 0.781 ms with the 128-row tiles, so the 128-row kernel is the default
+  static const bool allow_256 = [] { const char* e = std::getenv("BLE_DENSE_ROWS"); return e != nullptr && std::atoi(e) == 256; }();
+  const bool rows256 = allow_256 && !acc && ((m + 255) / 256) * ((n + kBN - 1) / kBN) >= 120;
+  const int tile_rows = rows256 ? 256 : kBM;
   const bool maps_ok = mn ? operand_map(&ma, a, k, m, lda, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&          // boxes {32 of MN, 32 of K}
                             operand_map(&mb, b, k, n, ldb, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
-                          : operand_map(&ma, a, m, k, lda, kBM) && operand_map(&mb, b, n, k, ldb, kBN);    // boxes {32 of K, tile rows}
+                          : operand_map(&ma, a, m, k, lda, tile_rows) && operand_map(&mb, b, n, k, ldb, kBN);   // boxes {32 of K, tile rows}
   if (!maps_ok || !operand_map(&md, tma_store ? d : nullptr, m, n, ldd, 32)) return BLE_ERR_CUDA;
   const int total_kb = int((k + kBK - 1) / kBK);
   const int splits = split_k > total_kb ? total_kb : split_k;
   DenseArgs args{m, n, k, (total_kb + splits - 1) / splits, aux, ld_aux, d, ldd, dt, ldt, tma_store ? 1 : 0, relu_bits, ld_bits};
-  const dim3 grid(unsigned((n + kBN - 1) / kBN), unsigned((m + kBM - 1) / kBM), unsigned(splits));
+  const dim3 grid(unsigned((n + kBN - 1) / kBN), unsigned((m + tile_rows - 1) / tile_rows), unsigned(splits));
   cudaStream_t s = cudaStream_t(stream);
   switch (mode) {
-    case 0: return launch_dense<0>(ma, mb, md, args, grid, s);
-    case 1: return launch_dense<1>(ma, mb, md, args, grid, s);
-    case 2: return launch_dense<2>(ma, mb, md, args, grid, s);
-    case 3: return launch_dense<3>(ma, mb, md, args, grid, s);
-    default: return launch_dense<4>(ma, mb, md, args, grid, s);
+    case 0: return rows256 ? launch_dense<0, 2>(ma, mb, md, args, grid, s) : launch_dense<0, 1>(ma, mb, md, args, grid, s);
+    case 1: return rows256 ? launch_dense<1, 2>(ma, mb, md, args, grid, s) : launch_dense<1, 1>(ma, mb, md, args, grid, s);
+    case 2: return rows256 ? launch_dense<2, 2>(ma, mb, md, args, grid, s) : launch_dense<2, 1>(ma, mb, md, args, grid, s);
+    case 3: return launch_dense<3, 1>(ma, mb, md, args, grid, s);
+    default: return launch_dense<4, 1>(ma, mb, md, args, grid, s);
   }
 }
 

@@ -38,9 +38,25 @@ def alloc(rows, cols, pitch, gen, exact):
 
 
 @pytest.mark.parametrize('m,n,k', [(128, 128, 32), (256, 128, 64), (1000, 153, 600), (8192, 600, 600), (333, 600, 1099),
-                                   (64, 8, 4), (130, 257, 36), (130, 260, 36)])
+                                   (64, 8, 4), (130, 257, 36), (130, 260, 36), (7003, 700, 100)])   # the last: ragged 256-row tiles
 @pytest.mark.parametrize('exact', [True, False])
 def test_dense_forward_modes(lrn, m, n, k, exact):
+  _dense_forward_modes(lrn, m, n, k, exact)
+
+
+def test_dense_forward_modes_256_row_tiles():
+  """The two-accumulator variant (BLE_DENSE_ROWS=256, read once per process) on the shapes that select it."""
+  import os, subprocess, sys
+  if not torch.cuda.is_available():
+    pytest.skip('no CUDA device')
+  code = ('import tests.test_gpu_dense as t; from balloon_learning_environment_b200 import learner as l;'
+          '[t._dense_forward_modes(l, m, n, k, e) for (m, n, k) in ((8192, 600, 600), (7003, 700, 100)) for e in (True, False)]; print("ok256")')
+  env = dict(os.environ, BLE_DENSE_ROWS='256')
+  out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+  assert 'ok256' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def _dense_forward_modes(lrn, m, n, k, exact):
   gen = torch.Generator(device='cuda'); gen.manual_seed(m * 7 + n * 3 + k)
   lda, ldb = lrn._pitch4(k) + 4, lrn._pitch4(k)
   a, b = alloc(m, k, lda, gen, exact), alloc(n, k, ldb, gen, exact)
