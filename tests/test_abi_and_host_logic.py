@@ -88,6 +88,39 @@ def test_create_without_gpu_fails_loudly():
     batched_env.BatchedBalloonArena(4)
 
 
+def test_stateless_learner_entry_points_reject_bad_arguments():
+  """The stateless entry points validate their arguments before they touch the device: null pointers, pitches that are
+  not TMA-able, inconsistent modes -> BLE_ERR_INVALID_ARGUMENT (no GPU needed to get there)."""
+  import numpy as np
+  from balloon_learning_environment_b200 import _lib
+  lib = _lib.load()
+  buf = np.zeros(4096, np.float32)
+  base = buf.ctypes.data + (-buf.ctypes.data) % 16                 # a 16-byte aligned host address: never dereferenced
+  p = ctypes.c_void_p(base)
+  null = ctypes.c_void_p(0)
+  inv = -1                                                         # BLE_ERR_INVALID_ARGUMENT (include/ble_b200.h)
+
+  def dense(a=p, lda=32, b=p, ldb=32, m=8, n=8, k=32, mode=0, aux=p, ld_aux=0, d=p, ldd=8, dt=null, ldt=0, split=1,
+            bits=null, ld_bits=0):
+    return lib.ble_dense_tf32(a, lda, b, ldb, m, n, k, mode, aux, ld_aux, d, ldd, dt, ldt, split, bits, ld_bits, null)
+
+  assert dense(a=null) == inv and dense(b=null) == inv
+  assert dense(lda=30) == inv                                      # pitch not a multiple of 4 floats (16-byte TMA rows)
+  assert dense(lda=16) == inv                                      # pitch shorter than K
+  assert dense(a=ctypes.c_void_p(base + 4)) == inv                 # base not 16-byte aligned
+  assert dense(mode=5) == inv and dense(mode=-1) == inv
+  assert dense(aux=null) == inv                                    # bias missing
+  assert dense(d=null) == inv                                      # no output at all
+  assert dense(ldd=4) == inv                                       # output pitch shorter than N
+  assert dense(split=2) == inv                                     # split-K only with the accumulating modes
+  assert dense(mode=3, d=p, dt=null) == inv and dense(mode=3, d=p, dt=p, ldt=8) == inv   # accumulates into dt only
+  assert dense(mode=2, aux=null, bits=null) == inv                 # a mask from somewhere
+  assert dense(mode=1, bits=p, ld_bits=0) == inv                   # mask pitch shorter than ceil(n / 32) words
+  assert dense(mode=4, d=null, dt=p, ldt=8, lda=4) == inv          # MN-major: pitch must cover M
+  assert lib.ble_transpose_f32(null, 8, 8, 8, p, 8, null) == inv and lib.ble_transpose_f32(p, 4, 8, 8, p, 8, null) == inv
+  assert lib.ble_row_sum_f32(p, 8, 8, 8, null, 0, null) == inv and lib.ble_row_sum_f32(p, 4, 8, 8, p, 0, null) == inv
+
+
 def test_row_order_matches_header_enums():
   from balloon_learning_environment_b200 import _lib
   header = open(os.path.join(ROOT, 'include', 'ble_b200.h')).read()
