@@ -1,5 +1,7 @@
 #!/bin/bash
-# 11 lower-frame corners (main) vs 16 masked corners (variants/libble_c16.so): parity suite on main, A/B timing, ncu instruction count
+# 11 lower-frame corners (main) vs 16 masked corners: parity suite on main, A/B timing, ncu instruction count.
+# variants/libble_c16.so = the library of commit e32193b (tree form, 16 masked corners); the all-vertices A/B library is
+# `scripts/build_variant.sh allv -DBLE_NOISE_ALL_VERTICES` (substitute it for libble_c16.so to reproduce r02b_step_timing_noise_all_vertices.jsonl)
 O=gpurun_out/r02noise2; mkdir -p $O
 timeout 1200 python -m pytest tests -m gpu -q -x > $O/pytest_gpu.log 2>&1; tail -3 $O/pytest_gpu.log
 for rep in 1 2; do
